@@ -1,0 +1,759 @@
+// fg_api.cu -- C ABI (include/fg_abi.h): graph store, device upload, Levenberg-Marquardt control.
+//
+// The LM control flow restates gtsam::LevenbergMarquardtOptimizer with default parameters as invoked by
+// CGraphGT::optimizeGraphBatch (gtsam/gtsam_graph.cpp:1784-1788); see SURVEY.md A.7.  All arithmetic over
+// factors and variables runs in the CUDA kernels of fg_kernels.cu / fg_chol.cu; the host only takes the
+// accept/reject decision from four scalars per trial.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include "fg_internal.h"
+
+using namespace fg;
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf[512];                                                                     \
+      snprintf(buf, sizeof buf, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      if (c) c->err = buf;                                                               \
+      return FG_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+static int fail(fg_ctx* c, int code, const char* msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------ NCCL (loaded at run time; single-GPU use needs no NCCL)
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*p_ncclGetUniqueId)(nccl_uid*);
+typedef int (*p_ncclCommInitRank)(void**, int, nccl_uid, int);
+typedef int (*p_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*p_ncclCommDestroy)(void*);
+struct NcclApi {
+  void* h = nullptr;
+  p_ncclGetUniqueId GetUniqueId = nullptr;
+  p_ncclCommInitRank CommInitRank = nullptr;
+  p_ncclAllReduce AllReduce = nullptr;
+  p_ncclCommDestroy CommDestroy = nullptr;
+} g_nccl;
+bool load_nccl() {
+  if (g_nccl.h) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return false;
+  g_nccl.GetUniqueId = (p_ncclGetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (p_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.AllReduce = (p_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.CommDestroy = (p_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
+  return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+const int kNcclDouble = 8, kNcclSum = 0;   // ncclFloat64, ncclSum
+}  // namespace
+
+// ------------------------------------------------------------------ device memory helpers
+template <typename T>
+static int dev_upload(fg_ctx* c, T** dst, const T* src, size_t n) {
+  *dst = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void**)dst, n * sizeof(T)));
+  c->allocs.push_back(*dst);
+  if (src) CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  else CK(cudaMemsetAsync(*dst, 0, n * sizeof(T), c->stream));
+  return FG_OK;
+}
+template <typename T>
+static int dev_upload(fg_ctx* c, T** dst, const std::vector<T>& v) {
+  return dev_upload(c, dst, v.empty() ? (const T*)nullptr : v.data(), v.size());
+}
+static void dev_free_all(fg_ctx* c) {
+  for (void* p : c->allocs) cudaFree(p);
+  c->allocs.clear();
+  c->d = DevGraph();
+}
+
+static int pull_values(fg_ctx* c) {
+  if (!c->device_newer) return FG_OK;
+  for (int t = 0; t < T_COUNT; ++t)
+    if (c->d.n[t]) CK(cudaMemcpyAsync(c->h.val[t].data(), c->d.val[t], sizeof(double) * c->h.val[t].size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->device_newer = false;
+  return FG_OK;
+}
+static int push_values(fg_ctx* c) {
+  if (!c->finalized || !c->values_dirty) return FG_OK;
+  for (int t = 0; t < T_COUNT; ++t)
+    if (c->d.n[t]) CK(cudaMemcpyAsync(c->d.val[t], c->h.val[t].data(), sizeof(double) * c->h.val[t].size(), cudaMemcpyHostToDevice, c->stream));
+  c->values_dirty = false;
+  return FG_OK;
+}
+
+// ------------------------------------------------------------------ lifetime
+extern "C" fg_ctx* fg_create(int device, int rank, int nranks) {
+  if (device == -1) {
+    // detached context: graph construction and symbolic analysis only (host logic tests);
+    // every numeric entry point fails with FG_ERR_CUDA -- there is no CPU solver in this library.
+    fg_ctx* c = new fg_ctx();
+    c->device = -1; c->rank = rank; c->nranks = nranks < 1 ? 1 : nranks;
+    c->h.calib.assign(9, 0.0);
+    c->h.sensor = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    return c;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  fg_ctx* c = new fg_ctx();
+  c->device = device; c->rank = rank; c->nranks = nranks < 1 ? 1 : nranks;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  c->h.calib.assign(9, 0.0);
+  c->h.sensor = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  return c;
+}
+extern "C" void fg_destroy(fg_ctx* c) {
+  if (!c) return;
+  if (c->device < 0) { delete c; return; }
+  cudaSetDevice(c->device);
+  if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+  dev_free_all(c);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+extern "C" const char* fg_last_error(fg_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int fg_abi_version(void) { return 1; }
+
+// ------------------------------------------------------------------ values
+static int add_value(fg_ctx* c, fg_key key, int type, const double* v) {
+  if (!c || !v) return fail(c, FG_ERR_INVALID, "null argument");
+  if (c->h.index.count(key)) return fail(c, FG_ERR_DUPLICATE_KEY, "key already exists in Values");
+  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  int idx = (int)c->h.keys[type].size();
+  c->h.index[key] = VarRef{type, idx};
+  c->h.keys[type].push_back(key);
+  c->h.val[type].insert(c->h.val[type].end(), v, v + kStore[type]);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_pose(fg_ctx* c, fg_key k, const double T[12]) { return add_value(c, k, T_POSE, T); }
+extern "C" int fg_add_vec3(fg_ctx* c, fg_key k, const double v[3]) { return add_value(c, k, T_VEC3, v); }
+extern "C" int fg_add_bias(fg_ctx* c, fg_key k, const double b[6]) { return add_value(c, k, T_BIAS, b); }
+extern "C" int fg_add_point(fg_ctx* c, fg_key k, const double p[3]) { return add_value(c, k, T_POINT, p); }
+extern "C" int fg_add_plane(fg_ctx* c, fg_key k, const double pl[4]) {
+  if (!pl) return fail(c, FG_ERR_INVALID, "null argument");
+  double n = std::sqrt(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2]);
+  if (!(n > 0)) return fail(c, FG_ERR_INVALID, "zero plane normal");
+  double q[4] = {pl[0] / n, pl[1] / n, pl[2] / n, pl[3]};   // OrientedPlane3(a,b,c,d): Unit3(a,b,c), d kept
+  return add_value(c, k, T_PLANE, q);
+}
+extern "C" int fg_add_points(fg_ctx* c, int64_t n, const fg_key* keys, const double* p3) {
+  if (!c || !keys || !p3 || n < 0) return fail(c, FG_ERR_INVALID, "bad argument");
+  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  c->h.index.reserve(c->h.index.size() + (size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (c->h.index.count(keys[i])) return fail(c, FG_ERR_DUPLICATE_KEY, "key already exists in Values");
+    c->h.index[keys[i]] = VarRef{T_POINT, (int)c->h.keys[T_POINT].size()};
+    c->h.keys[T_POINT].push_back(keys[i]);
+  }
+  c->h.val[T_POINT].insert(c->h.val[T_POINT].end(), p3, p3 + 3 * n);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_update_value(fg_ctx* c, fg_key key, const double* v) {
+  if (!c || !v) return fail(c, FG_ERR_INVALID, "null argument");
+  auto it = c->h.index.find(key);
+  if (it == c->h.index.end()) return fail(c, FG_ERR_UNKNOWN_KEY, "key does not exist in Values");
+  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  int t = it->second.type;
+  std::copy(v, v + kStore[t], c->h.val[t].begin() + (size_t)it->second.idx * kStore[t]);
+  c->values_dirty = true;
+  return FG_OK;
+}
+extern "C" int fg_exists(fg_ctx* c, fg_key key) { return (c && c->h.index.count(key)) ? 1 : 0; }
+extern "C" int fg_get_value(fg_ctx* c, fg_key key, double* out, int* n_out) {
+  if (!c || !out) return fail(c, FG_ERR_INVALID, "null argument");
+  auto it = c->h.index.find(key);
+  if (it == c->h.index.end()) return fail(c, FG_ERR_UNKNOWN_KEY, "key does not exist in Values");
+  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  int t = it->second.type;
+  const double* src = c->h.val[t].data() + (size_t)it->second.idx * kStore[t];
+  std::copy(src, src + kStore[t], out);
+  if (n_out) *n_out = kStore[t];
+  return FG_OK;
+}
+extern "C" int64_t fg_num_values(fg_ctx* c, int type) {
+  if (!c || type < 0 || type >= T_COUNT) return -1;
+  return c->h.count(type);
+}
+extern "C" int fg_get_values(fg_ctx* c, int type, double* out) {
+  if (!c || !out || type < 0 || type >= T_COUNT) return fail(c, FG_ERR_INVALID, "bad argument");
+  size_t nb = sizeof(double) * c->h.val[type].size();
+  if (c->finalized && c->device_newer && c->d.n[type]) {
+    CK(cudaMemcpyAsync(out, c->d.val[type], nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  } else {
+    std::memcpy(out, c->h.val[type].data(), nb);
+  }
+  return FG_OK;
+}
+extern "C" int fg_set_values(fg_ctx* c, int type, const double* in) {
+  if (!c || !in || type < 0 || type >= T_COUNT) return fail(c, FG_ERR_INVALID, "bad argument");
+  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  size_t nb = sizeof(double) * c->h.val[type].size();
+  std::memcpy(c->h.val[type].data(), in, nb);
+  if (c->finalized && c->d.n[type] && !c->values_dirty) {
+    // fast path: straight host -> device copy of this one array (the caller's buffer may be pinned)
+    CK(cudaMemcpyAsync(c->d.val[type], in, nb, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    c->values_dirty = true;
+  }
+  return FG_OK;
+}
+
+// ------------------------------------------------------------------ factors
+static int find_var(fg_ctx* c, fg_key key, int type, int* idx) {
+  auto it = c->h.index.find(key);
+  if (it == c->h.index.end()) return fail(c, FG_ERR_UNKNOWN_KEY, "factor refers to a key that is not in Values");
+  if (it->second.type != type) return fail(c, FG_ERR_INVALID, "factor key has the wrong value type");
+  *idx = it->second.idx;
+  return FG_OK;
+}
+#define FIND(key, type, out) do { int rc_ = find_var(c, key, type, out); if (rc_ != FG_OK) return rc_; } while (0)
+
+extern "C" int fg_add_prior_pose(fg_ctx* c, fg_key key, const double T[12], const double info[36]) {
+  if (!c || !T || !info) return fail(c, FG_ERR_INVALID, "null argument");
+  int v; FIND(key, T_POSE, &v);
+  c->h.pp_var.push_back(v);
+  c->h.pp_mean.insert(c->h.pp_mean.end(), T, T + 12);
+  c->h.pp_info.insert(c->h.pp_info.end(), info, info + 36);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_prior_vec3(fg_ctx* c, fg_key key, const double m[3], const double info[9]) {
+  if (!c || !m || !info) return fail(c, FG_ERR_INVALID, "null argument");
+  int v; FIND(key, T_VEC3, &v);
+  c->h.pv_var.push_back(v);
+  c->h.pv_mean.insert(c->h.pv_mean.end(), m, m + 3);
+  c->h.pv_info.insert(c->h.pv_info.end(), info, info + 9);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_prior_bias(fg_ctx* c, fg_key key, const double m[6], const double info[36]) {
+  if (!c || !m || !info) return fail(c, FG_ERR_INVALID, "null argument");
+  int v; FIND(key, T_BIAS, &v);
+  c->h.pb_var.push_back(v);
+  c->h.pb_mean.insert(c->h.pb_mean.end(), m, m + 6);
+  c->h.pb_info.insert(c->h.pb_info.end(), info, info + 36);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_prior_point(fg_ctx* c, fg_key key, const double m[3], double sigma) {
+  if (!c || !m || !(sigma > 0)) return fail(c, FG_ERR_INVALID, "bad argument");
+  int v; FIND(key, T_POINT, &v);
+  c->h.pq_var.push_back(v);
+  c->h.pq_mean.insert(c->h.pq_mean.end(), m, m + 3);
+  c->h.pq_w.push_back(1.0 / (sigma * sigma));
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_prior_points(fg_ctx* c, int64_t n, const fg_key* keys, const double* m3, double sigma) {
+  if (!c || !keys || !m3 || n < 0 || !(sigma > 0)) return fail(c, FG_ERR_INVALID, "bad argument");
+  for (int64_t i = 0; i < n; ++i) {
+    int v; FIND(keys[i], T_POINT, &v);
+    c->h.pq_var.push_back(v);
+  }
+  c->h.pq_mean.insert(c->h.pq_mean.end(), m3, m3 + 3 * n);
+  c->h.pq_w.insert(c->h.pq_w.end(), (size_t)n, 1.0 / (sigma * sigma));
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_between(fg_ctx* c, fg_key k1, fg_key k2, const double T[12], const double info[36]) {
+  if (!c || !T || !info) return fail(c, FG_ERR_INVALID, "null argument");
+  int a, b; FIND(k1, T_POSE, &a); FIND(k2, T_POSE, &b);
+  c->h.bt_i.push_back(a); c->h.bt_j.push_back(b);
+  c->h.bt_meas.insert(c->h.bt_meas.end(), T, T + 12);
+  c->h.bt_info.insert(c->h.bt_info.end(), info, info + 36);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_set_calibration(fg_ctx* c, int id, const double K[9]) {
+  if (!c || !K || id < 0) return fail(c, FG_ERR_INVALID, "bad argument");
+  if ((size_t)(id + 1) * 9 > c->h.calib.size()) c->h.calib.resize((size_t)(id + 1) * 9, 0.0);
+  std::copy(K, K + 9, c->h.calib.begin() + (size_t)id * 9);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_set_sensor(fg_ctx* c, int id, const double T[12]) {
+  if (!c || !T || id < 0) return fail(c, FG_ERR_INVALID, "bad argument");
+  if ((size_t)(id + 1) * 12 > c->h.sensor.size()) c->h.sensor.resize((size_t)(id + 1) * 12, 0.0);
+  std::copy(T, T + 12, c->h.sensor.begin() + (size_t)id * 12);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_projections(fg_ctx* c, int64_t n, const fg_key* kp, const fg_key* kq, const double* uv2,
+                                  double sigma, int calib_id, int sensor_id) {
+  if (!c || !kp || !kq || !uv2 || n < 0 || !(sigma > 0) || calib_id < 0 || sensor_id < 0)
+    return fail(c, FG_ERR_INVALID, "bad argument");
+  if ((size_t)(calib_id + 1) * 9 > c->h.calib.size() || (size_t)(sensor_id + 1) * 12 > c->h.sensor.size())
+    return fail(c, FG_ERR_INVALID, "unknown calibration or sensor id");
+  size_t base = c->h.pj_pose.size();
+  c->h.pj_pose.resize(base + n); c->h.pj_point.resize(base + n);
+  for (int64_t i = 0; i < n; ++i) {
+    int a, b;
+    int rc = find_var(c, kp[i], T_POSE, &a);
+    if (rc == FG_OK) rc = find_var(c, kq[i], T_POINT, &b);
+    if (rc != FG_OK) { c->h.pj_pose.resize(base); c->h.pj_point.resize(base); return rc; }
+    c->h.pj_pose[base + i] = a; c->h.pj_point[base + i] = b;
+  }
+  c->h.pj_uv.insert(c->h.pj_uv.end(), uv2, uv2 + 2 * n);
+  c->h.pj_w.insert(c->h.pj_w.end(), (size_t)n, 1.0 / (sigma * sigma));
+  c->h.pj_calib.insert(c->h.pj_calib.end(), (size_t)n, calib_id);
+  c->h.pj_sensor.insert(c->h.pj_sensor.end(), (size_t)n, sensor_id);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_add_projection(fg_ctx* c, fg_key kp, fg_key kq, const double uv[2], double sigma, int calib_id, int sensor_id) {
+  return fg_add_projections(c, 1, &kp, &kq, uv, sigma, calib_id, sensor_id);
+}
+
+// symmetric positive definite inverse by Cholesky (host, n <= 15)
+static bool spd_inverse(const double* A, int n, double* Ai) {
+  double L[225], Li[225];
+  for (int i = 0; i < n * n; ++i) { L[i] = 0; Li[i] = 0; }
+  for (int j = 0; j < n; ++j) {
+    double s = A[j * n + j];
+    for (int k = 0; k < j; ++k) s -= L[j * n + k] * L[j * n + k];
+    if (!(s > 0)) return false;
+    L[j * n + j] = std::sqrt(s);
+    for (int i = j + 1; i < n; ++i) {
+      double t = 0.5 * (A[i * n + j] + A[j * n + i]);
+      for (int k = 0; k < j; ++k) t -= L[i * n + k] * L[j * n + k];
+      L[i * n + j] = t / L[j * n + j];
+    }
+  }
+  for (int j = 0; j < n; ++j) {       // Li = L^-1 (lower), column by column
+    Li[j * n + j] = 1.0 / L[j * n + j];
+    for (int i = j + 1; i < n; ++i) {
+      double t = 0;
+      for (int k = j; k < i; ++k) t -= L[i * n + k] * Li[k * n + j];
+      Li[i * n + j] = t / L[i * n + i];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double t = 0;
+      for (int k = i; k < n; ++k) t += Li[k * n + i] * Li[k * n + j];
+      Ai[i * n + j] = t; Ai[j * n + i] = t;
+    }
+  return true;
+}
+
+extern "C" int fg_add_plane_factor(fg_ctx* c, fg_key kpose, fg_key kplane, const double z[4], const double cov[9]) {
+  if (!c || !z || !cov) return fail(c, FG_ERR_INVALID, "null argument");
+  int a, b; FIND(kpose, T_POSE, &a); FIND(kplane, T_PLANE, &b);
+  double info[9];
+  if (!spd_inverse(cov, 3, info)) return fail(c, FG_ERR_INVALID, "plane covariance is not positive definite");
+  double n = std::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+  if (!(n > 0)) return fail(c, FG_ERR_INVALID, "zero plane normal");
+  double q[4] = {z[0] / n, z[1] / n, z[2] / n, z[3]};
+  c->h.pl_pose.push_back(a); c->h.pl_plane.push_back(b);
+  c->h.pl_meas.insert(c->h.pl_meas.end(), q, q + 4);
+  c->h.pl_info.insert(c->h.pl_info.end(), info, info + 9);
+  c->finalized = false;
+  return FG_OK;
+}
+
+extern "C" int fg_add_imu(fg_ctx* c, const fg_key keys[6], const fg_pim* pim) {
+  if (!c || !keys || !pim) return fail(c, FG_ERR_INVALID, "null argument");
+  int v[6];
+  FIND(keys[0], T_POSE, &v[0]); FIND(keys[1], T_VEC3, &v[1]); FIND(keys[2], T_POSE, &v[2]);
+  FIND(keys[3], T_VEC3, &v[3]); FIND(keys[4], T_BIAS, &v[4]); FIND(keys[5], T_BIAS, &v[5]);
+  ImuRec r;
+  r.dt = pim->dt;
+  std::copy(pim->preint, pim->preint + 9, r.preint);
+  std::copy(pim->H_ba, pim->H_ba + 27, r.Hba);
+  std::copy(pim->H_bg, pim->H_bg + 27, r.Hbg);
+  std::copy(pim->bias_hat, pim->bias_hat + 6, r.bias_hat);
+  std::copy(pim->gravity, pim->gravity + 3, r.gravity);
+  if (!spd_inverse(pim->cov, 15, r.info)) return fail(c, FG_ERR_INVALID, "preintMeasCov is not positive definite");
+  c->h.imu_var.insert(c->h.imu_var.end(), v, v + 6);
+  c->h.imu_rec.push_back(r);
+  c->finalized = false;
+  return FG_OK;
+}
+
+// ------------------------------------------------------------------ IMU preintegration
+extern "C" int fg_preintegrate(fg_ctx* c, int n, const int* offsets, const double* imu6, double dt,
+                               const fg_imu_params* params, const double* bias_hat6, fg_pim* out) {
+  if (n < 0 || !offsets || !imu6 || !params || !bias_hat6 || !out || !(dt > 0)) return fail(c, FG_ERR_INVALID, "bad argument");
+  if (n == 0) return FG_OK;
+  if (c && c->device < 0) return fail(c, FG_ERR_CUDA, "detached context (device -1): no CUDA device");
+  cudaStream_t st = c ? c->stream : (cudaStream_t)0;
+  if (c) cudaSetDevice(c->device);
+  int ns = offsets[n];
+  ImuParamsDev hp;
+  std::memcpy(hp.acc_cov, params->acc_cov, sizeof hp.acc_cov);
+  std::memcpy(hp.gyro_cov, params->gyro_cov, sizeof hp.gyro_cov);
+  std::memcpy(hp.int_cov, params->int_cov, sizeof hp.int_cov);
+  std::memcpy(hp.bias_acc_cov, params->bias_acc_cov, sizeof hp.bias_acc_cov);
+  std::memcpy(hp.bias_gyro_cov, params->bias_gyro_cov, sizeof hp.bias_gyro_cov);
+  std::memcpy(hp.bint, params->bias_acc_omega_int, sizeof hp.bint);
+  std::memcpy(hp.gravity, params->gravity, sizeof hp.gravity);
+  int* d_off = nullptr; double* d_imu = nullptr; ImuParamsDev* d_par = nullptr; double* d_bias = nullptr; fg_pim* d_out = nullptr;
+  int rc = FG_OK;
+  cudaError_t e;
+  e = cudaMalloc((void**)&d_off, sizeof(int) * (n + 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_imu, sizeof(double) * 6 * (size_t)(ns > 0 ? ns : 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_par, sizeof(ImuParamsDev));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_bias, sizeof(double) * 6 * n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, sizeof(fg_pim) * n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offsets, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && ns > 0) e = cudaMemcpyAsync(d_imu, imu6, sizeof(double) * 6 * (size_t)ns, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, &hp, sizeof hp, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_bias, bias_hat6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    launch_preintegrate(n, d_off, d_imu, dt, d_par, d_bias, d_out, st);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(fg_pim) * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { if (c) c->err = cudaGetErrorString(e); rc = FG_ERR_CUDA; }
+  cudaFree(d_off); cudaFree(d_imu); cudaFree(d_par); cudaFree(d_bias); cudaFree(d_out);
+  return rc;
+}
+
+extern "C" int fg_pim_predict(const fg_pim* pim, const double Xi[12], const double vi[3], const double bi[6],
+                              double Xj[12], double vj[3]) {
+  if (!pim || !Xi || !vi || !bi || !Xj || !vj) return FG_ERR_INVALID;
+  double inc[6], bc[9];
+  for (int i = 0; i < 6; ++i) inc[i] = bi[i] - pim->bias_hat[i];
+  for (int i = 0; i < 9; ++i)
+    bc[i] = pim->preint[i] + pim->H_ba[3 * i] * inc[0] + pim->H_ba[3 * i + 1] * inc[1] + pim->H_ba[3 * i + 2] * inc[2]
+          + pim->H_bg[3 * i] * inc[3] + pim->H_bg[3 * i + 1] * inc[4] + pim->H_bg[3 * i + 2] * inc[5];
+  double dt = pim->dt, dt22 = 0.5 * dt * dt, Rtv[3], Rtg[3], xp[3], xv[3], dR[9], t[3];
+  m3_tvec(Xi, vi, Rtv);
+  m3_tvec(Xi, pim->gravity, Rtg);
+  for (int i = 0; i < 3; ++i) { xp[i] = bc[3 + i] + dt * Rtv[i] + dt22 * Rtg[i]; xv[i] = bc[6 + i] + dt * Rtg[i]; }
+  so3_exp(bc, dR);
+  m3_mul(Xi, dR, Xj);
+  m3_vec(Xi, xp, t);
+  for (int i = 0; i < 3; ++i) Xj[9 + i] = Xi[9 + i] + t[i];
+  m3_vec(Xi, xv, t);
+  for (int i = 0; i < 3; ++i) vj[i] = vi[i] + t[i];
+  return FG_OK;
+}
+
+// ------------------------------------------------------------------ finalize: symbolic + upload
+extern "C" int fg_finalize(fg_ctx* c) {
+  if (!c) return FG_ERR_INVALID;
+  if (c->device < 0) return fail(c, FG_ERR_CUDA, "detached context (device -1): no CUDA device, and there is no CPU solver");
+  if (c->finalized) return push_values(c);
+  CK(cudaSetDevice(c->device));
+  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  HostGraph& h = c->h;
+  if (h.count(T_POSE) + h.count(T_VEC3) + h.count(T_BIAS) + h.count(T_PLANE) == 0)
+    return fail(c, FG_ERR_STATE, "graph has no pose-side variables");
+  dev_free_all(c);
+  int rc = build_symbolic(c);
+  if (rc != FG_OK) return fail(c, rc, "symbolic analysis failed");
+  Symbolic& S = c->sym;
+  DevGraph& d = c->d;
+  // values
+  for (int t = 0; t < T_COUNT; ++t) {
+    d.n[t] = h.count(t);
+    if ((rc = dev_upload(c, &d.val[t], h.val[t])) != FG_OK) return rc;
+    if ((rc = dev_upload<double>(c, &d.val_new[t], nullptr, h.val[t].size())) != FG_OK) return rc;
+    if (t != T_POINT) if ((rc = dev_upload(c, &d.off[t], S.off[t])) != FG_OK) return rc;
+  }
+  // pose-side factors
+  d.n_pp = (int)h.pp_var.size(); d.n_pv = (int)h.pv_var.size(); d.n_pb = (int)h.pb_var.size();
+  d.n_bt = (int)h.bt_i.size(); d.n_imu = (int)h.imu_rec.size(); d.n_pl = (int)h.pl_pose.size();
+  if ((rc = dev_upload(c, &d.pp_var, h.pp_var)) || (rc = dev_upload(c, &d.pp_mean, h.pp_mean)) || (rc = dev_upload(c, &d.pp_info, h.pp_info))) return rc;
+  if ((rc = dev_upload(c, &d.pv_var, h.pv_var)) || (rc = dev_upload(c, &d.pv_mean, h.pv_mean)) || (rc = dev_upload(c, &d.pv_info, h.pv_info))) return rc;
+  if ((rc = dev_upload(c, &d.pb_var, h.pb_var)) || (rc = dev_upload(c, &d.pb_mean, h.pb_mean)) || (rc = dev_upload(c, &d.pb_info, h.pb_info))) return rc;
+  if ((rc = dev_upload(c, &d.bt_i, h.bt_i)) || (rc = dev_upload(c, &d.bt_j, h.bt_j)) || (rc = dev_upload(c, &d.bt_meas, h.bt_meas)) || (rc = dev_upload(c, &d.bt_info, h.bt_info))) return rc;
+  if ((rc = dev_upload(c, &d.imu_var, h.imu_var)) || (rc = dev_upload(c, &d.imu_rec, h.imu_rec))) return rc;
+  if ((rc = dev_upload(c, &d.pl_pose, h.pl_pose)) || (rc = dev_upload(c, &d.pl_plane, h.pl_plane)) || (rc = dev_upload(c, &d.pl_meas, h.pl_meas)) || (rc = dev_upload(c, &d.pl_info, h.pl_info))) return rc;
+  // landmarks: sort observations by landmark (stable), CSR by pose
+  const int64_t L = h.count(T_POINT), M = (int64_t)h.pj_pose.size(), P = h.count(T_POSE);
+  d.n_obs = M;
+  if (L) {
+    for (size_t i = 1; i < h.pj_calib.size(); ++i)
+      if (h.pj_calib[i] != h.pj_calib[0] || h.pj_sensor[i] != h.pj_sensor[0])
+        return fail(c, FG_ERR_INVALID, "projection factors must share one calibration and one body_P_sensor");
+    int cid = M ? h.pj_calib[0] : 0, sid = M ? h.pj_sensor[0] : 0;
+    std::vector<int64_t> lm_ptr(L + 1, 0), pose_ptr(P + 1, 0);
+    for (int64_t o = 0; o < M; ++o) { lm_ptr[h.pj_point[o] + 1]++; pose_ptr[h.pj_pose[o] + 1]++; }
+    for (int64_t l = 0; l < L; ++l) lm_ptr[l + 1] += lm_ptr[l];
+    for (int64_t p = 0; p < P; ++p) pose_ptr[p + 1] += pose_ptr[p];
+    std::vector<int> s_pose(M), s_point(M);
+    std::vector<double> s_uv(2 * M), s_w(M);
+    {
+      std::vector<int64_t> cur(lm_ptr.begin(), lm_ptr.end() - 1);
+      for (int64_t o = 0; o < M; ++o) {
+        int64_t k = cur[h.pj_point[o]]++;
+        s_pose[k] = h.pj_pose[o]; s_point[k] = h.pj_point[o];
+        s_uv[2 * k] = h.pj_uv[2 * o]; s_uv[2 * k + 1] = h.pj_uv[2 * o + 1]; s_w[k] = h.pj_w[o];
+      }
+    }
+    std::vector<int64_t> pose_obs(M);
+    {
+      std::vector<int64_t> cur(pose_ptr.begin(), pose_ptr.end() - 1);
+      for (int64_t k = 0; k < M; ++k) pose_obs[cur[s_pose[k]]++] = k;
+    }
+    std::vector<double> pm(3 * L, 0.0), pw(L, 0.0);
+    for (size_t i = 0; i < h.pq_var.size(); ++i) {
+      int l = h.pq_var[i];
+      if (pw[l] != 0.0) return fail(c, FG_ERR_INVALID, "more than one PriorFactor<Point3> on a landmark");
+      pw[l] = h.pq_w[i];
+      pm[3 * l] = h.pq_mean[3 * i]; pm[3 * l + 1] = h.pq_mean[3 * i + 1]; pm[3 * l + 2] = h.pq_mean[3 * i + 2];
+    }
+    if ((rc = dev_upload(c, &d.lm_ptr, lm_ptr)) || (rc = dev_upload(c, &d.obs_pose, s_pose)) || (rc = dev_upload(c, &d.obs_point, s_point)) ||
+        (rc = dev_upload(c, &d.obs_uv, s_uv)) || (rc = dev_upload(c, &d.obs_w, s_w)) || (rc = dev_upload(c, &d.pose_obs_ptr, pose_ptr)) ||
+        (rc = dev_upload(c, &d.pose_obs, pose_obs)) || (rc = dev_upload(c, &d.lm_prior_mean, pm)) || (rc = dev_upload(c, &d.lm_prior_w, pw))) return rc;
+    if ((rc = dev_upload<double>(c, &d.W, nullptr, (size_t)18 * M)) || (rc = dev_upload<double>(c, &d.V, nullptr, (size_t)6 * L)) ||
+        (rc = dev_upload<double>(c, &d.gl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Vinv, nullptr, (size_t)6 * L)) ||
+        (rc = dev_upload<double>(c, &d.tl, nullptr, (size_t)3 * L))) return rc;
+    if ((rc = dev_upload(c, &d.calib, h.calib.data() + 9 * cid, 9)) || (rc = dev_upload(c, &d.sensor, h.sensor.data() + 12 * sid, 12))) return rc;
+    CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
+  }
+  // reduced system
+  if ((rc = dev_upload<double>(c, &d.L, nullptr, (size_t)S.nnz + 8)) || (rc = dev_upload<double>(c, &d.U0, nullptr, (size_t)S.nnz + 8)) ||
+      (rc = dev_upload<double>(c, &d.g_r, nullptr, S.n_r)) || (rc = dev_upload<double>(c, &d.delta, nullptr, S.n_r)) ||
+      (rc = dev_upload<double>(c, &d.scal, nullptr, 8)) || (rc = dev_upload<int>(c, &d.flags, nullptr, S.n_sn)) ||
+      (rc = dev_upload<int>(c, &d.status, nullptr, 1))) return rc;
+  if ((rc = dev_upload(c, &d.col2sn, S.col2sn)) || (rc = dev_upload(c, &d.sn_col0, S.sn_col0)) || (rc = dev_upload(c, &d.sn_ncols, S.sn_ncols)) ||
+      (rc = dev_upload(c, &d.sn_nrows, S.sn_nrows)) || (rc = dev_upload(c, &d.sn_rowptr, S.sn_rowptr)) || (rc = dev_upload(c, &d.sn_valptr, S.sn_valptr)) ||
+      (rc = dev_upload(c, &d.rowidx, S.rowidx)) || (rc = dev_upload(c, &d.upd_ptr, S.upd_ptr)) || (rc = dev_upload(c, &d.upd_d, S.upd_d)) ||
+      (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b))) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  c->epoch = 0;
+  c->finalized = true;
+  c->values_dirty = false;
+  c->device_newer = false;
+  return FG_OK;
+}
+
+// ------------------------------------------------------------------ optimise
+extern "C" void fg_lm_params_default(fg_lm_params* p) {
+  if (!p) return;
+  p->lambda_initial = 1e-5; p->lambda_factor = 10.0; p->lambda_upper = 1e5; p->lambda_lower = 0.0;
+  p->min_model_fidelity = 1e-3; p->max_iterations = 100; p->relative_error_tol = 1e-5;
+  p->absolute_error_tol = 1e-5; p->error_tol = 0.0; p->force_iterations = 0; p->verbosity = 0;
+}
+
+static int allreduce(fg_ctx* c, double* buf, size_t n) {
+  if (c->nranks <= 1) return FG_OK;
+  if (!c->nccl_comm) return fail(c, FG_ERR_NCCL, "nranks > 1 but fg_comm_init was not called");
+  int r = g_nccl.AllReduce(buf, buf, n, kNcclDouble, kNcclSum, c->nccl_comm, c->stream);
+  return r == 0 ? FG_OK : fail(c, FG_ERR_NCCL, "ncclAllReduce failed");
+}
+
+static int read_scalars(fg_ctx* c, double* hs, int* status) {
+  CK(cudaMemcpyAsync(hs, c->d.scal, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (status) CK(cudaMemcpyAsync(status, c->d.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FG_OK;
+}
+
+extern "C" int fg_error(fg_ctx* c, double* error) {
+  if (!c || !error) return fail(c, FG_ERR_INVALID, "null argument");
+  int rc = fg_finalize(c);
+  if (rc != FG_OK) return rc;
+  CK(cudaSetDevice(c->device));
+  launch_error_only(c, false);
+  if ((rc = allreduce(c, c->d.scal, 1)) != FG_OK) return rc;
+  double hs[4];
+  if ((rc = read_scalars(c, hs, nullptr)) != FG_OK) return rc;
+  CK(cudaGetLastError());
+  *error = 0.5 * hs[0];
+  return FG_OK;
+}
+
+extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_report* rep) {
+  if (!c) return FG_ERR_INVALID;
+  fg_lm_params p;
+  if (params) p = *params; else fg_lm_params_default(&p);
+  fg_lm_report local;
+  if (!rep) rep = &local;
+  std::memset(rep, 0, sizeof *rep);
+  int rc = fg_finalize(c);
+  if (rc != FG_OK) { rep->status = rc; return rc; }
+  CK(cudaSetDevice(c->device));
+  DevGraph& d = c->d;
+  cudaEvent_t ev[6];
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  auto cleanup = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
+
+  double err;
+  if ((rc = fg_error(c, &err)) != FG_OK) { cleanup(); rep->status = rc; return rc; }
+  rep->initial_error = err;
+  rep->n_reduced_dims = c->sym.n_r; rep->n_supernodes = c->sym.n_sn; rep->nnz_L = c->sym.nnz;
+  rep->n_projections = d.n_obs; rep->n_landmarks = d.n[T_POINT];
+  double lam = p.lambda_initial;
+  const double inf = std::numeric_limits<double>::infinity();
+  int it = 0;
+  cudaEvent_t ev_begin, ev_end;
+  CK(cudaEventCreate(&ev_begin)); CK(cudaEventCreate(&ev_end));
+  CK(cudaEventRecord(ev_begin, c->stream));
+  while (true) {
+    const double cur = err;
+    // ---- LevenbergMarquardtOptimizer::iterate()
+    CK(cudaEventRecord(ev[0], c->stream));
+    launch_linearize(c);
+    CK(cudaEventRecord(ev[1], c->stream));
+    bool first = true;
+    while (true) {
+      if (!first) CK(cudaEventRecord(ev[1], c->stream));
+      launch_build_and_schur(c, lam);
+      if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) break;
+      CK(cudaEventRecord(ev[2], c->stream));
+      launch_factor(c);
+      CK(cudaEventRecord(ev[3], c->stream));
+      launch_backsolve(c);
+      CK(cudaEventRecord(ev[4], c->stream));
+      launch_retract_error(c, lam);
+      if ((rc = allreduce(c, d.scal + 1, 3)) != FG_OK) break;
+      CK(cudaEventRecord(ev[5], c->stream));
+      double hs[4]; int st = 0;
+      if ((rc = read_scalars(c, hs, &st)) != FG_OK) break;
+      CK(cudaGetLastError());
+      float ms;
+      if (first) { cudaEventElapsedTime(&ms, ev[0], ev[1]); rep->ms_linearize += ms; }
+      cudaEventElapsedTime(&ms, ev[1], ev[2]); rep->ms_schur += ms;
+      cudaEventElapsedTime(&ms, ev[2], ev[3]); rep->ms_factor += ms;
+      cudaEventElapsedTime(&ms, ev[3], ev[4]); rep->ms_solve += ms;
+      cudaEventElapsedTime(&ms, ev[4], ev[5]); rep->ms_retract_error += ms;
+      first = false;
+      rep->trials++;
+
+      const double gTd = hs[1], dd = hs[2];
+      double new_err = 0.5 * hs[3];
+      bool solved = (st == 0) && std::isfinite(gTd) && std::isfinite(dd);
+      bool step_ok = false, stop = false;
+      if (solved) {
+        // linear.error(delta) = err + g^T d + 1/2 d^T H d with (H + lam I) d = -g
+        const double lin_change = -0.5 * gTd + 0.5 * lam * dd;
+        if (lin_change >= 0) {
+          const double cost_change = err - new_err;
+          if (lin_change > 1e-20) step_ok = (cost_change / lin_change) > p.min_model_fidelity;
+          else stop = true;
+          if (std::fabs(cost_change) < p.relative_error_tol * err) stop = true;
+        } else {
+          new_err = inf;
+        }
+      } else {
+        new_err = inf;
+      }
+      if (rep->trace_len < FG_TRACE_MAX) {
+        int k = rep->trace_len++;
+        rep->trace_lambda[k] = lam; rep->trace_error[k] = err; rep->trace_new_error[k] = new_err; rep->trace_accepted[k] = step_ok;
+      }
+      if (p.verbosity > 0)
+        fprintf(stderr, "[fg] iter %d lambda %.3e error %.9e -> %.9e %s\n", it, lam, err, new_err, step_ok ? "accepted" : "rejected");
+      if (step_ok) {
+        for (int t = 0; t < T_COUNT; ++t) std::swap(d.val[t], d.val_new[t]);
+        c->device_newer = true;
+        err = new_err;
+        lam = std::max(p.lambda_lower, lam / p.lambda_factor);
+        break;
+      } else if (!stop) {
+        lam *= p.lambda_factor;
+        if (lam >= p.lambda_upper) break;
+      } else {
+        break;
+      }
+    }
+    if (rc != FG_OK) break;
+    ++it;
+    if (it >= p.max_iterations || !std::isfinite(err)) break;
+    if (!p.force_iterations) {
+      if (p.error_tol >= err) break;
+      const double absdec = cur - err, reldec = cur != 0.0 ? absdec / cur : 0.0;
+      if ((p.relative_error_tol != 0.0 && reldec <= p.relative_error_tol) || absdec <= p.absolute_error_tol) break;
+    }
+  }
+  cudaEventRecord(ev_end, c->stream);
+  cudaEventSynchronize(ev_end);
+  float total = 0;
+  cudaEventElapsedTime(&total, ev_begin, ev_end);
+  cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+  cleanup();
+  rep->ms_total = total;
+  rep->iterations = it;
+  rep->final_error = err;
+  rep->lambda = lam;
+  rep->status = rc;
+  return rc;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+extern "C" int fg_comm_unique_id(char id[128]) {
+  if (!id) return FG_ERR_INVALID;
+  if (!load_nccl()) return FG_ERR_NCCL;
+  nccl_uid u;
+  if (g_nccl.GetUniqueId(&u) != 0) return FG_ERR_NCCL;
+  std::memcpy(id, u.internal, 128);
+  return FG_OK;
+}
+extern "C" int fg_comm_init(fg_ctx* c, const char id[128]) {
+  if (!c || !id) return FG_ERR_INVALID;
+  if (!load_nccl()) return fail(c, FG_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  CK(cudaSetDevice(c->device));
+  nccl_uid u;
+  std::memcpy(u.internal, id, 128);
+  if (g_nccl.CommInitRank(&c->nccl_comm, c->nranks, u, c->rank) != 0) return fail(c, FG_ERR_NCCL, "ncclCommInitRank failed");
+  return FG_OK;
+}
+
+// Host-only symbolic analysis for tests: fills `out` (capacity cap int64 entries) with array `which` and
+// returns the array length (or a negative status).  Works on a detached context (fg_create(-1, ...)).
+extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t cap) {
+  if (!c) return FG_ERR_INVALID;
+  if (which == 0) {
+    int rc = build_symbolic(c);
+    if (rc != FG_OK) return rc;
+  }
+  const Symbolic& S = c->sym;
+  std::vector<int64_t> v;
+  auto put = [&](const std::vector<int>& a) { v.assign(a.begin(), a.end()); };
+  switch (which) {
+    case 0: v = {S.n_r, S.n_sn, S.nnz, S.max_nrows, S.max_ncols, (int64_t)S.flops_factor}; break;
+    case 1: put(S.sn_col0); break;
+    case 2: put(S.sn_ncols); break;
+    case 3: put(S.sn_nrows); break;
+    case 4: put(S.sn_rowptr); break;
+    case 5: v.assign(S.sn_valptr.begin(), S.sn_valptr.end()); break;
+    case 6: put(S.rowidx); break;
+    case 7: put(S.upd_ptr); break;
+    case 8: put(S.upd_d); break;
+    case 9: put(S.upd_a); break;
+    case 10: put(S.upd_b); break;
+    case 11: put(S.off[T_POSE]); break;
+    case 12: put(S.off[T_VEC3]); break;
+    case 13: put(S.off[T_BIAS]); break;
+    case 14: put(S.off[T_PLANE]); break;
+    default: return FG_ERR_INVALID;
+  }
+  if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];
+  return (int64_t)v.size();
+}
+
+extern "C" int fg_debug_sizes(fg_ctx* c, int64_t out[8]) {
+  if (!c || !out) return FG_ERR_INVALID;
+  int rc = fg_finalize(c);
+  if (rc != FG_OK) return rc;
+  out[0] = c->sym.n_r; out[1] = c->sym.n_sn; out[2] = c->sym.nnz; out[3] = c->sym.max_nrows;
+  out[4] = c->sym.max_ncols; out[5] = (int64_t)c->sym.flops_factor; out[6] = c->d.n_obs; out[7] = c->d.n[T_POINT];
+  return FG_OK;
+}

@@ -1,0 +1,187 @@
+// fg_internal.h -- host-side graph store, symbolic structure and device views (not part of the ABI).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/fg_abi.h"
+#include "fg_factors.cuh"
+
+namespace fg {
+
+enum VarType { T_POSE = 0, T_VEC3 = 1, T_BIAS = 2, T_POINT = 3, T_PLANE = 4, T_COUNT = 5 };
+static const int kStore[T_COUNT] = {12, 3, 6, 3, 4};   // doubles stored per value
+static const int kDim[T_COUNT] = {6, 3, 6, 3, 3};      // tangent dimension
+
+struct VarRef { int type; int idx; };
+
+// ------------------------------------------------------------------ host graph store
+struct HostGraph {
+  std::unordered_map<fg_key, VarRef> index;
+  std::vector<double> val[T_COUNT];          // kStore[t] doubles per value
+  std::vector<fg_key> keys[T_COUNT];
+
+  // factor SoA (host)
+  std::vector<int> pp_var;  std::vector<double> pp_mean, pp_info;                 // prior pose: 12, 36
+  std::vector<int> pv_var;  std::vector<double> pv_mean, pv_info;                 // prior vec3: 3, 9
+  std::vector<int> pb_var;  std::vector<double> pb_mean, pb_info;                 // prior bias: 6, 36
+  std::vector<int> pq_var;  std::vector<double> pq_mean, pq_w;                    // prior point: 3, 1 (1/sigma^2)
+  std::vector<int> bt_i, bt_j; std::vector<double> bt_meas, bt_info;             // between: 12, 36
+  std::vector<int> imu_var;                                                       // 6 per factor (pose_i, vel_i, pose_j, vel_j, bias_i, bias_j)
+  std::vector<ImuRec> imu_rec;
+  std::vector<int> pj_pose, pj_point; std::vector<double> pj_uv; std::vector<double> pj_w;  // projection: uv 2, w = 1/sigma^2
+  std::vector<int> pj_calib, pj_sensor;
+  std::vector<int> pl_pose, pl_plane; std::vector<double> pl_meas, pl_info;      // plane factor: 4, 9
+  std::vector<double> calib;    // 9 per id
+  std::vector<double> sensor;   // 12 per id
+
+  int64_t count(int t) const { return (int64_t)keys[t].size(); }
+};
+
+// ------------------------------------------------------------------ symbolic structure of the reduced system
+struct Symbolic {
+  int n_r = 0;                       // reduced scalar dimension (poses, vels, biases, planes)
+  int n_sn = 0;                      // supernodes
+  int64_t nnz = 0;                   // doubles in panel storage (incl. rhs rows)
+  std::vector<int> off[T_COUNT];     // scalar offset of each reduced variable (T_POINT unused)
+  std::vector<int> sn_col0, sn_ncols, sn_nrows, sn_rowptr;  // nrows includes diag rows and the rhs row
+  std::vector<int64_t> sn_valptr;
+  std::vector<int> rowidx;           // concatenated row lists (global scalar rows; last = n_r = rhs row)
+  std::vector<int> col2sn;           // scalar column -> supernode
+  std::vector<int> upd_ptr, upd_d, upd_a, upd_b;   // per target supernode: (descendant, row range [a,b) in d)
+  int max_nrows = 0, max_ncols = 0;
+  double flops_factor = 0;
+};
+
+// ------------------------------------------------------------------ device view passed to kernels
+struct SysView {
+  double* L;                 // panel storage (values)
+  const int* col2sn;
+  const int* sn_col0;
+  const int* sn_ncols;
+  const int* sn_nrows;
+  const int* sn_rowptr;
+  const int64_t* sn_valptr;
+  const int* rowidx;
+  int n_r;
+};
+
+// offset of entry (row R, col C), R >= C, in panel storage; ld returned through *ld
+__device__ __forceinline__ int64_t sys_find(const SysView& s, int R, int C, int* ld) {
+  int sn = s.col2sn[C];
+  int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
+  *ld = nr;
+  int r;
+  if (R < c0 + nc) {
+    r = R - c0;
+  } else {
+    const int* rows = s.rowidx + s.sn_rowptr[sn];
+    int lo = nc, hi = nr - 1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (rows[mid] < R) lo = mid + 1; else hi = mid;
+    }
+    r = lo;
+  }
+  return s.sn_valptr[sn] + r + (int64_t)(C - c0) * nr;
+}
+
+// add a dense block H (da x db, row-major, ld ldh) coupling reduced offsets oa (rows of H) and ob (cols of H)
+// into the lower-triangular panel storage.  For oa == ob only the lower triangle is written.
+__device__ __forceinline__ void sys_add_block(const SysView& s, int oa, int da, int ob, int db,
+                                              const double* H, int ldh) {
+  int ld;
+  if (oa == ob) {
+    int64_t base = sys_find(s, oa, oa, &ld);
+    for (int i = 0; i < da; ++i)
+      for (int j = 0; j <= i; ++j) atomicAdd(&s.L[base + i + (int64_t)j * ld], H[i * ldh + j]);
+  } else if (oa > ob) {
+    int64_t base = sys_find(s, oa, ob, &ld);
+    for (int i = 0; i < da; ++i)
+      for (int j = 0; j < db; ++j) atomicAdd(&s.L[base + i + (int64_t)j * ld], H[i * ldh + j]);
+  } else {
+    int64_t base = sys_find(s, ob, oa, &ld);   // transposed block: rows = ob.., cols = oa..
+    for (int i = 0; i < da; ++i)
+      for (int j = 0; j < db; ++j) atomicAdd(&s.L[base + j + (int64_t)i * ld], H[i * ldh + j]);
+  }
+}
+
+// ------------------------------------------------------------------ device graph (raw pointers owned by the ctx)
+struct DevGraph {
+  // values, current and trial
+  double* val[T_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* val_new[T_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t n[T_COUNT] = {0, 0, 0, 0, 0};
+  int* off[T_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // reduced offsets (not for points)
+  // factors
+  int n_pp = 0; int* pp_var = nullptr; double* pp_mean = nullptr; double* pp_info = nullptr;
+  int n_pv = 0; int* pv_var = nullptr; double* pv_mean = nullptr; double* pv_info = nullptr;
+  int n_pb = 0; int* pb_var = nullptr; double* pb_mean = nullptr; double* pb_info = nullptr;
+  int n_bt = 0; int* bt_i = nullptr; int* bt_j = nullptr; double* bt_meas = nullptr; double* bt_info = nullptr;
+  int n_imu = 0; int* imu_var = nullptr; ImuRec* imu_rec = nullptr;
+  int n_pl = 0; int* pl_pose = nullptr; int* pl_plane = nullptr; double* pl_meas = nullptr; double* pl_info = nullptr;
+  // landmarks: observations sorted by landmark (CSR), plus CSR by pose
+  int64_t n_obs = 0;
+  int64_t* lm_ptr = nullptr;        // L+1
+  int* obs_pose = nullptr;          // M
+  double* obs_uv = nullptr;         // 2M
+  double* obs_w = nullptr;          // M  (1/sigma^2)
+  int64_t* pose_obs_ptr = nullptr;  // P+1
+  int64_t* pose_obs = nullptr;      // M  observation ids grouped by pose
+  int* obs_point = nullptr;         // M
+  double* lm_prior_mean = nullptr;  // 3L (NaN weight = no prior)
+  double* lm_prior_w = nullptr;     // L
+  double* W = nullptr;              // 18 M : Jp^T Jl * w
+  double* V = nullptr;              // 6 L  : upper of sum Jl^T Jl w + prior
+  double* gl = nullptr;             // 3 L
+  double* Vinv = nullptr;           // 6 L
+  double* tl = nullptr;             // 3 L  : sum_o W_o^T delta_p (back-substitution scratch)
+  double* calib = nullptr;          // 9
+  double* sensor = nullptr;         // 12
+  // reduced system
+  double* L = nullptr;              // panels being factored
+  double* U0 = nullptr;             // undamped pose-side Hessian in panel layout (lambda independent)
+  double* g_r = nullptr;            // reduced gradient J^T Omega r  (n_r)
+  double* delta = nullptr;          // n_r
+  double* scal = nullptr;           // scalars: [0] chi2, [1] g^T delta, [2] |delta|^2, [3] new chi2
+  int* flags = nullptr;             // per supernode epoch flags
+  int* status = nullptr;            // factorisation status (0 ok)
+  // symbolic on device
+  int *col2sn = nullptr, *sn_col0 = nullptr, *sn_ncols = nullptr, *sn_nrows = nullptr, *sn_rowptr = nullptr, *rowidx = nullptr;
+  int64_t* sn_valptr = nullptr;
+  int *upd_ptr = nullptr, *upd_d = nullptr, *upd_a = nullptr, *upd_b = nullptr;
+};
+
+}  // namespace fg
+
+// ------------------------------------------------------------------ the context
+struct fg_ctx {
+  int device = 0, rank = 0, nranks = 1;
+  std::string err;
+  fg::HostGraph h;
+  fg::Symbolic sym;
+  fg::DevGraph d;
+  bool finalized = false;
+  bool values_dirty = false;     // host values newer than device
+  bool device_newer = false;     // device values newer than host
+  cudaStream_t stream = nullptr;
+  int epoch = 0;
+  int num_sms = 148;
+  void* nccl_comm = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace fg {
+// host.cpp
+int build_symbolic(fg_ctx* c);
+// kernels (launch wrappers), all asynchronous on c->stream
+void launch_linearize(fg_ctx* c);                         // U0, g_r, V, gl, W, chi2 -> scal[0]
+void launch_build_and_schur(fg_ctx* c, double lambda);    // L = U0 + lambda I - W V'^-1 W^T ; rhs row = -(g_red)
+void launch_factor(fg_ctx* c);                            // cholesky; the rhs row makes it the forward solve too
+void launch_backsolve(fg_ctx* c);                         // backward solve -> delta
+void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
+void launch_error_only(fg_ctx* c, bool trial);            // chi2 of val (or val_new) -> scal[0] (or scal[3])
+void launch_preintegrate(int n, const int* d_off, const double* d_imu, double dt, const ImuParamsDev* d_par,
+                         const double* d_bias, fg_pim* d_out, cudaStream_t st);
+}  // namespace fg

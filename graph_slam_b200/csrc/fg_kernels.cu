@@ -1,0 +1,812 @@
+// fg_kernels.cu -- hand-written sm_100a CUDA for the Gauss-Newton / LM inner loop (fp64).
+//
+// Kernels (names follow SURVEY.md section 7):
+//   K2  k_prior_pose / k_prior_vec<D>     priors                      (gtsam_graph.cpp:341,362-367)
+//   K1  k_between                         BetweenFactor<Pose3>        (gtsam_graph.cpp:691-692)
+//   K4  k_imu                             CombinedImuFactor           (test_vro_imu_graph.cpp:191-196)
+//   K5  k_plane                           OrientedPlane3Factor        (gtsam_graph.cpp:1265)
+//   K6  k_lm_prior / k_proj_obs / k_proj_pose / k_schur   projection factors + landmark Schur complement
+//                                                                     (gtsam_graph.cpp:370-448)
+//   K9  k_lm_backsub_obs / k_lm_update    landmark back-substitution + retraction
+//   K10 k_retract_reduced                 SE3 / vector / plane retraction (Values::retract)
+//   K3  k_preintegrate                    PreintegratedCombinedMeasurements::integrateMeasurement loop
+//                                                                     (imu_base.cpp:76-85)
+// All kernels are templated on JAC: JAC=true linearises and assembles, JAC=false evaluates chi2 only
+// (graph.error, gtsam_graph.cpp:173-176).
+#include <cstdio>
+#include "fg_internal.h"
+
+namespace fg {
+
+struct Vals { const double* v[T_COUNT]; };
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  return v;
+}
+// every thread of the block must call; one atomic per warp
+__device__ __forceinline__ void chi2_accumulate(double e, double* target) {
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(target, e);
+}
+
+// 128-bit loads of a pose record (12 doubles, 96 B, 16 B aligned)
+__device__ __forceinline__ void load_pose(const double* __restrict__ base, int idx, double* X) {
+  const double2* p = reinterpret_cast<const double2*>(base + (int64_t)idx * 12);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { double2 v = __ldg(p + i); X[2 * i] = v.x; X[2 * i + 1] = v.y; }
+}
+
+// sym mat-vec helpers on row-major dense
+template <int M, int N>
+__device__ __forceinline__ void matvec(const double* A, const double* x, double* y) {
+#pragma unroll
+  for (int i = 0; i < M; ++i) { double s = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += A[i * N + j] * x[j]; y[i] = s; }
+}
+
+// ------------------------------------------------------------------ priors
+template <bool JAC>
+__global__ void k_prior_pose(int n, const int* __restrict__ var, const double* __restrict__ mean,
+                             const double* __restrict__ info, Vals vals, const int* __restrict__ off,
+                             SysView sys, double* g_r, double* chi2) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (f < n) {
+    double X[12], Pm[12], r[6], wr[6];
+    load_pose(vals.v[T_POSE], var[f], X);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Pm[i] = mean[12 * f + i];
+    prior_pose_eval(X, Pm, r);
+    const double* Om = info + 36 * f;
+    matvec<6, 6>(Om, r, wr);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e += r[i] * wr[i];
+    if (JAC) {
+      int o = off[var[f]];
+      sys_add_block(sys, o, 6, o, 6, Om, 6);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) atomicAdd(&g_r[o + i], wr[i]);
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+
+template <bool JAC, int D, int TYPE>
+__global__ void k_prior_vec(int n, const int* __restrict__ var, const double* __restrict__ mean,
+                            const double* __restrict__ info, Vals vals, const int* __restrict__ off,
+                            SysView sys, double* g_r, double* chi2) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (f < n) {
+    double r[D], wr[D];
+    const double* x = vals.v[TYPE] + (int64_t)var[f] * D;
+#pragma unroll
+    for (int i = 0; i < D; ++i) r[i] = x[i] - mean[D * f + i];
+    const double* Om = info + D * D * f;
+    matvec<D, D>(Om, r, wr);
+#pragma unroll
+    for (int i = 0; i < D; ++i) e += r[i] * wr[i];
+    if (JAC) {
+      int o = off[var[f]];
+      sys_add_block(sys, o, D, o, D, Om, D);
+#pragma unroll
+      for (int i = 0; i < D; ++i) atomicAdd(&g_r[o + i], wr[i]);
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+
+// ------------------------------------------------------------------ K1 between
+template <bool JAC>
+__global__ void k_between(int n, const int* __restrict__ vi, const int* __restrict__ vj,
+                          const double* __restrict__ meas, const double* __restrict__ info, Vals vals,
+                          const int* __restrict__ off, SysView sys, double* g_r, double* chi2) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (f < n) {
+    double X1[12], X2[12], Z[12], r[6], J1[36], wr[6];
+    load_pose(vals.v[T_POSE], vi[f], X1);
+    load_pose(vals.v[T_POSE], vj[f], X2);
+    load_pose(meas, f, Z);
+    between_eval<JAC>(X1, X2, Z, r, J1);
+    const double* Om = info + 36 * (int64_t)f;
+    double O[36];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      double2 v = __ldg(reinterpret_cast<const double2*>(Om) + i);
+      O[2 * i] = v.x; O[2 * i + 1] = v.y;
+    }
+    matvec<6, 6>(O, r, wr);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e += r[i] * wr[i];
+    if (JAC) {
+      int o1 = off[vi[f]], o2 = off[vj[f]];
+      double M[36], H11[36], g1[6];
+      // M = Omega J1 ; H11 = J1^T M ; H21 = M ; H22 = Omega
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          double s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += O[6 * i + k] * J1[6 * k + j];
+          M[6 * i + j] = s;
+        }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          double s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += J1[6 * k + i] * M[6 * k + j];
+          H11[6 * i + j] = s;
+        }
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += J1[6 * k + i] * wr[k];
+        g1[i] = s;
+      }
+      sys_add_block(sys, o1, 6, o1, 6, H11, 6);
+      sys_add_block(sys, o2, 6, o1, 6, M, 6);
+      sys_add_block(sys, o2, 6, o2, 6, O, 6);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { atomicAdd(&g_r[o1 + i], g1[i]); atomicAdd(&g_r[o2 + i], wr[i]); }
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+
+// ------------------------------------------------------------------ K5 plane
+template <bool JAC>
+__global__ void k_plane(int n, const int* __restrict__ vp, const int* __restrict__ vl,
+                        const double* __restrict__ meas, const double* __restrict__ info, Vals vals,
+                        const int* __restrict__ off_pose, const int* __restrict__ off_plane, SysView sys,
+                        double* g_r, double* chi2) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (f < n) {
+    double X[12], pl[4], z[4], r[3], Hr[18], Hp[9], wr[3];
+    load_pose(vals.v[T_POSE], vp[f], X);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pl[i] = vals.v[T_PLANE][4 * (int64_t)vl[f] + i]; z[i] = meas[4 * (int64_t)f + i]; }
+    plane_eval<JAC>(X, pl, z, r, Hr, Hp);
+    const double* Om = info + 9 * (int64_t)f;
+    matvec<3, 3>(Om, r, wr);
+    e = r[0] * wr[0] + r[1] * wr[1] + r[2] * wr[2];
+    if (JAC) {
+      int op = off_pose[vp[f]], ol = off_plane[vl[f]];
+      double Mr[18], Mp[9];   // Omega Hr (3x6), Omega Hp (3x3)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Mr[6 * i + j] = Om[3 * i] * Hr[j] + Om[3 * i + 1] * Hr[6 + j] + Om[3 * i + 2] * Hr[12 + j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Mp[3 * i + j] = Om[3 * i] * Hp[j] + Om[3 * i + 1] * Hp[3 + j] + Om[3 * i + 2] * Hp[6 + j];
+      }
+      double Hpp[36], Hlp[18], Hll[9];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Hpp[6 * i + j] = Hr[i] * Mr[j] + Hr[6 + i] * Mr[6 + j] + Hr[12 + i] * Mr[12 + j];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Hlp[6 * i + j] = Hp[i] * Mr[j] + Hp[3 + i] * Mr[6 + j] + Hp[6 + i] * Mr[12 + j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Hll[3 * i + j] = Hp[i] * Mp[j] + Hp[3 + i] * Mp[3 + j] + Hp[6 + i] * Mp[6 + j];
+      }
+      sys_add_block(sys, op, 6, op, 6, Hpp, 6);
+      sys_add_block(sys, ol, 3, op, 6, Hlp, 6);
+      sys_add_block(sys, ol, 3, ol, 3, Hll, 3);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) atomicAdd(&g_r[op + i], Hr[i] * wr[0] + Hr[6 + i] * wr[1] + Hr[12 + i] * wr[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) atomicAdd(&g_r[ol + i], Hp[i] * wr[0] + Hp[3 + i] * wr[1] + Hp[6 + i] * wr[2]);
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+
+// ------------------------------------------------------------------ K4 imu: one warp per factor
+#define IMU_WPB 4
+template <bool JAC>
+__global__ void __launch_bounds__(32 * IMU_WPB) k_imu(int n, const int* __restrict__ var, const ImuRec* __restrict__ rec,
+                                                      Vals vals, const int* __restrict__ off_pose,
+                                                      const int* __restrict__ off_vel, const int* __restrict__ off_bias,
+                                                      SysView sys, double* g_r, double* chi2) {
+  __shared__ double sJ[IMU_WPB][450];
+  __shared__ double sM[IMU_WPB][450];
+  __shared__ double sr[IMU_WPB][16];
+  __shared__ double swr[IMU_WPB][16];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int f = blockIdx.x * IMU_WPB + w;
+  double e = 0.0;
+  bool act = f < n;
+  const ImuRec* F = rec + (act ? f : 0);
+  const int* v = var + 6 * (int64_t)(act ? f : 0);
+  if (act && lane == 0) {
+    double Xi[12], Xj[12];
+    load_pose(vals.v[T_POSE], v[0], Xi);
+    load_pose(vals.v[T_POSE], v[2], Xj);
+    const double* vi = vals.v[T_VEC3] + 3 * (int64_t)v[1];
+    const double* vj = vals.v[T_VEC3] + 3 * (int64_t)v[3];
+    const double* bi = vals.v[T_BIAS] + 6 * (int64_t)v[4];
+    const double* bj = vals.v[T_BIAS] + 6 * (int64_t)v[5];
+    imu_eval<JAC>(Xi, vi, Xj, vj, bi, bj, F, sr[w], sJ[w]);
+  }
+  __syncwarp();
+  if (act) {
+    // wr = Omega r (lanes 0..14)
+    if (lane < 15) {
+      double s = 0;
+      for (int k = 0; k < 15; ++k) s += F->info[15 * lane + k] * sr[w][k];
+      swr[w][lane] = s;
+      e = s * sr[w][lane];
+    }
+  }
+  if (JAC) {
+    __syncwarp();
+    if (act && lane < 30) {
+      // column `lane` of M = Omega J
+      double col[15];
+      for (int k = 0; k < 15; ++k) col[k] = sJ[w][30 * k + lane];
+      for (int i = 0; i < 15; ++i) {
+        double s = 0;
+        for (int k = 0; k < 15; ++k) s += F->info[15 * i + k] * col[k];
+        sM[w][30 * i + lane] = s;
+      }
+    }
+    __syncwarp();
+    if (act && lane < 30) {
+      // gradient entry and Hessian column `lane`: H[:, lane] = J^T M[:, lane]
+      const int seg_start[6] = {0, 6, 9, 15, 18, 24};
+      const int seg_dim[6] = {6, 3, 6, 3, 6, 6};
+      int offs[6] = {off_pose[v[0]], off_vel[v[1]], off_pose[v[2]], off_vel[v[3]], off_bias[v[4]], off_bias[v[5]]};
+      int myseg = 0;
+      for (int s = 0; s < 6; ++s) if (lane >= seg_start[s]) myseg = s;
+      int C = offs[myseg] + (lane - seg_start[myseg]);   // global reduced column of this lane
+      double gsum = 0;
+      for (int k = 0; k < 15; ++k) gsum += sJ[w][30 * k + lane] * swr[w][k];
+      atomicAdd(&g_r[C], gsum);
+      for (int s = 0; s < 6; ++s) {
+        for (int i = 0; i < seg_dim[s]; ++i) {
+          int row_local = seg_start[s] + i;
+          int R = offs[s] + i;
+          if (R < C) continue;              // lower triangle only (R >= C)
+          double h = 0;
+          for (int k = 0; k < 15; ++k) h += sJ[w][30 * k + row_local] * sM[w][30 * k + lane];
+          int ld;
+          int64_t idx = sys_find(sys, R, C, &ld);
+          atomicAdd(&sys.L[idx], h);
+        }
+      }
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+
+// ------------------------------------------------------------------ K6 projection + Schur
+// per landmark: initialise V, gl with the point prior (PriorFactor<Point3>, gtsam_graph.cpp:394)
+template <bool JAC>
+__global__ void k_lm_prior(int64_t L, const double* __restrict__ pts, const double* __restrict__ mean,
+                           const double* __restrict__ w, double* V, double* gl, double* chi2) {
+  int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (l < L) {
+    double wl = w[l];
+    double r0 = 0, r1 = 0, r2 = 0;
+    if (wl > 0) {
+      r0 = pts[3 * l] - mean[3 * l]; r1 = pts[3 * l + 1] - mean[3 * l + 1]; r2 = pts[3 * l + 2] - mean[3 * l + 2];
+      e = wl * (r0 * r0 + r1 * r1 + r2 * r2);
+    }
+    if (JAC) {
+      V[6 * l + 0] = wl; V[6 * l + 1] = 0; V[6 * l + 2] = 0; V[6 * l + 3] = wl; V[6 * l + 4] = 0; V[6 * l + 5] = wl;
+      gl[3 * l] = wl * r0; gl[3 * l + 1] = wl * r1; gl[3 * l + 2] = wl * r2;
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+
+// segmented (by key) inclusive-suffix reduction inside a warp: head lane of each run gets the run sum
+__device__ __forceinline__ double seg_sum(double v, int key, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double o = __shfl_down_sync(0xffffffffu, v, d);
+    int k2 = __shfl_down_sync(0xffffffffu, key, d);
+    if (lane + d < 32 && k2 == key) v += o;
+  }
+  return v;
+}
+
+// one thread per observation (observations sorted by landmark): residual, Jp, Jl; W = w Jp^T Jl stored SoA;
+// V_l, g_l by warp-segmented reduction.
+template <bool JAC>
+__global__ void __launch_bounds__(256) k_proj_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+                                                  const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
+                                                  Vals vals, const double* __restrict__ calib, const double* __restrict__ sensor,
+                                                  double* __restrict__ W, double* V, double* gl, double* chi2) {
+  int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int lane = threadIdx.x & 31;
+  double e = 0.0;
+  bool act = o < M;
+  int l = act ? obs_point[o] : -1;
+  double r[2], Jp[12], Jl[6], w = 0.0;
+  if (act) {
+    double X[12], K[9], S[12], p[3];
+    load_pose(vals.v[T_POSE], obs_pose[o], X);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) K[i] = __ldg(calib + i);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) S[i] = __ldg(sensor + i);
+    p[0] = vals.v[T_POINT][3 * (int64_t)l]; p[1] = vals.v[T_POINT][3 * (int64_t)l + 1]; p[2] = vals.v[T_POINT][3 * (int64_t)l + 2];
+    double2 uvv = __ldg(reinterpret_cast<const double2*>(obs_uv) + o);
+    double uv[2] = {uvv.x, uvv.y};
+    w = obs_w[o];
+    projection_eval<JAC>(X, p, uv, K, S, r, Jp, Jl);
+    e = w * (r[0] * r[0] + r[1] * r[1]);
+  }
+  if (JAC) {
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          W[(int64_t)(3 * i + c) * M + o] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
+    }
+    // V (upper: 00 01 02 11 12 22) and gl
+    double c9[9];
+    if (act) {
+      c9[0] = w * (Jl[0] * Jl[0] + Jl[3] * Jl[3]);
+      c9[1] = w * (Jl[0] * Jl[1] + Jl[3] * Jl[4]);
+      c9[2] = w * (Jl[0] * Jl[2] + Jl[3] * Jl[5]);
+      c9[3] = w * (Jl[1] * Jl[1] + Jl[4] * Jl[4]);
+      c9[4] = w * (Jl[1] * Jl[2] + Jl[4] * Jl[5]);
+      c9[5] = w * (Jl[2] * Jl[2] + Jl[5] * Jl[5]);
+      c9[6] = w * (Jl[0] * r[0] + Jl[3] * r[1]);
+      c9[7] = w * (Jl[1] * r[0] + Jl[4] * r[1]);
+      c9[8] = w * (Jl[2] * r[0] + Jl[5] * r[1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) c9[i] = 0.0;
+    }
+    int prev = __shfl_up_sync(0xffffffffu, l, 1);
+    bool head = act && (lane == 0 || prev != l);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      double s = seg_sum(c9[i], l, lane);
+      if (head) {
+        if (i < 6) atomicAdd(&V[6 * (int64_t)l + i], s);
+        else atomicAdd(&gl[3 * (int64_t)l + (i - 6)], s);
+      }
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+
+// one warp per pose: U_pp = sum w Jp^T Jp, g_p = sum w Jp^T r over the pose's observations (recomputed)
+__global__ void __launch_bounds__(256) k_proj_pose(int P, const int64_t* __restrict__ pose_obs_ptr, const int64_t* __restrict__ pose_obs,
+                                                   const int* __restrict__ obs_point, const double* __restrict__ obs_uv,
+                                                   const double* __restrict__ obs_w, Vals vals, const double* __restrict__ calib,
+                                                   const double* __restrict__ sensor, const int* __restrict__ off_pose,
+                                                   SysView sys, double* g_r) {
+  int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= P) return;
+  int64_t b = pose_obs_ptr[wid], e = pose_obs_ptr[wid + 1];
+  if (b == e) return;
+  double X[12], K[9], S[12];
+  load_pose(vals.v[T_POSE], wid, X);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) K[i] = __ldg(calib + i);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) S[i] = __ldg(sensor + i);
+  double acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+  for (int64_t k = b + lane; k < e; k += 32) {
+    int64_t o = pose_obs[k];
+    int l = obs_point[o];
+    double p[3] = {vals.v[T_POINT][3 * (int64_t)l], vals.v[T_POINT][3 * (int64_t)l + 1], vals.v[T_POINT][3 * (int64_t)l + 2]};
+    double uv[2] = {obs_uv[2 * o], obs_uv[2 * o + 1]};
+    double w = obs_w[o], r[2], Jp[12], Jl[6];
+    projection_eval<true>(X, p, uv, K, S, r, Jp, Jl);
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) acc[q++] += w * (Jp[i] * Jp[j] + Jp[6 + i] * Jp[6 + j]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[21 + i] += w * (Jp[i] * r[0] + Jp[6 + i] * r[1]);
+  }
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+    int o = off_pose[wid], ld;
+    int64_t base = sys_find(sys, o, o, &ld);
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) atomicAdd(&sys.L[base + i + (int64_t)j * ld], acc[q++]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) atomicAdd(&g_r[o + i], acc[21 + i]);
+  }
+}
+
+// damp diagonal and write the rhs row: L[C,C] += lambda ; L[rhs, C] = -g_r[C]
+__global__ void k_damp_rhs(SysView sys, const double* __restrict__ g_r, double lambda, int add_rhs) {
+  int C = blockIdx.x * blockDim.x + threadIdx.x;
+  if (C >= sys.n_r) return;
+  int sn = sys.col2sn[C];
+  int c = C - sys.sn_col0[sn], nr = sys.sn_nrows[sn];
+  double* col = sys.L + sys.sn_valptr[sn] + (int64_t)c * nr;
+  col[c] += lambda;
+  if (add_rhs) col[nr - 1] -= g_r[C];
+}
+
+// Schur complement, generic path: one warp per landmark, atomics into the panel storage.
+//   Vinv = (V + lambda I)^-1 ; S_pq -= W_p Vinv W_q^T ; rhs_p += W_p Vinv g_l
+__global__ void __launch_bounds__(128) k_schur(int64_t L, int64_t M, const int64_t* __restrict__ lm_ptr, const int* __restrict__ obs_pose,
+                                               const double* __restrict__ W, const double* __restrict__ V,
+                                               const double* __restrict__ gl, double* __restrict__ Vinv, double lambda,
+                                               const int* __restrict__ off_pose, SysView sys) {
+  int64_t l = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (l >= L) return;
+  double A[9] = {V[6 * l] + lambda, V[6 * l + 1], V[6 * l + 2],
+                 V[6 * l + 1], V[6 * l + 3] + lambda, V[6 * l + 4],
+                 V[6 * l + 2], V[6 * l + 4], V[6 * l + 5] + lambda};
+  double Ai[9];
+  inv3(A, Ai);
+  if (lane == 0) {
+    Vinv[6 * l] = Ai[0]; Vinv[6 * l + 1] = Ai[1]; Vinv[6 * l + 2] = Ai[2];
+    Vinv[6 * l + 3] = Ai[4]; Vinv[6 * l + 4] = Ai[5]; Vinv[6 * l + 5] = Ai[8];
+  }
+  double g3[3] = {gl[3 * l], gl[3 * l + 1], gl[3 * l + 2]}, y[3];
+  m3_vec(Ai, g3, y);
+  int64_t b = lm_ptr[l];
+  int k = (int)(lm_ptr[l + 1] - b);
+  // rhs contribution: 6 entries per observation
+  for (int t = lane; t < 6 * k; t += 32) {
+    int a = t / 6, i = t % 6;
+    int64_t o = b + a;
+    double s = W[(int64_t)(3 * i) * M + o] * y[0] + W[(int64_t)(3 * i + 1) * M + o] * y[1] + W[(int64_t)(3 * i + 2) * M + o] * y[2];
+    int C = off_pose[obs_pose[o]] + i;
+    int sn = sys.col2sn[C];
+    int nr = sys.sn_nrows[sn];
+    atomicAdd(&sys.L[sys.sn_valptr[sn] + (int64_t)(C - sys.sn_col0[sn]) * nr + nr - 1], s);
+  }
+  // pairs (a >= bb)
+  int npairs = k * (k + 1) / 2;
+  for (int t = lane; t < npairs; t += 32) {
+    int a = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((a + 1) * (a + 2) / 2 <= t) ++a;
+    while (a * (a + 1) / 2 > t) --a;
+    int bb = t - a * (a + 1) / 2;
+    int64_t oa = b + a, ob = b + bb;
+    double Wa[18], Wb[18], Y[18], B[36];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) { Wa[i] = W[(int64_t)i * M + oa]; Wb[i] = W[(int64_t)i * M + ob]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Y[3 * i + c] = Wa[3 * i] * Ai[c] + Wa[3 * i + 1] * Ai[3 + c] + Wa[3 * i + 2] * Ai[6 + c];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) B[6 * i + j] = -(Y[3 * i] * Wb[3 * j] + Y[3 * i + 1] * Wb[3 * j + 1] + Y[3 * i + 2] * Wb[3 * j + 2]);
+    int offa = off_pose[obs_pose[oa]], offb = off_pose[obs_pose[ob]];
+    if (offa == offb && a != bb) {
+      // the same pose observed twice by one landmark: both orderings land on the diagonal block
+      sys_add_block(sys, offa, 6, offb, 6, B, 6);
+      double Bt[36];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Bt[6 * i + j] = B[6 * j + i];
+      sys_add_block(sys, offa, 6, offb, 6, Bt, 6);
+    } else {
+      sys_add_block(sys, offa, 6, offb, 6, B, 6);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K9/K10 back-substitution and retraction
+// t_l = sum_o W_o^T delta_p(o) by warp-segmented reduction (thread per observation)
+__global__ void __launch_bounds__(256) k_lm_backsub_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+                                                        const double* __restrict__ W, const double* __restrict__ delta,
+                                                        const int* __restrict__ off_pose, double* tl) {
+  int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int lane = threadIdx.x & 31;
+  bool act = o < M;
+  int l = act ? obs_point[o] : -1;
+  double t3[3] = {0, 0, 0};
+  if (act) {
+    const double* d = delta + off_pose[obs_pose[o]];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double di = d[i];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) t3[c] += W[(int64_t)(3 * i + c) * M + o] * di;
+    }
+  }
+  int prev = __shfl_up_sync(0xffffffffu, l, 1);
+  bool head = act && (lane == 0 || prev != l);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double s = seg_sum(t3[c], l, lane);
+    if (head) atomicAdd(&tl[3 * (int64_t)l + c], s);
+  }
+}
+
+// delta_l = -Vinv (g_l + t_l) ; p_new = p + delta_l ; accumulates g^T delta and |delta|^2
+__global__ void k_lm_update(int64_t L, const double* __restrict__ pts, const double* __restrict__ Vinv,
+                            const double* __restrict__ gl, const double* __restrict__ tl, double* pts_new, double* scal) {
+  int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double gd = 0.0, dd = 0.0;
+  if (l < L) {
+    double s[3] = {gl[3 * l] + tl[3 * l], gl[3 * l + 1] + tl[3 * l + 1], gl[3 * l + 2] + tl[3 * l + 2]};
+    const double* vi = Vinv + 6 * l;
+    double d0 = -(vi[0] * s[0] + vi[1] * s[1] + vi[2] * s[2]);
+    double d1 = -(vi[1] * s[0] + vi[3] * s[1] + vi[4] * s[2]);
+    double d2 = -(vi[2] * s[0] + vi[4] * s[1] + vi[5] * s[2]);
+    pts_new[3 * l] = pts[3 * l] + d0; pts_new[3 * l + 1] = pts[3 * l + 1] + d1; pts_new[3 * l + 2] = pts[3 * l + 2] + d2;
+    gd = gl[3 * l] * d0 + gl[3 * l + 1] * d1 + gl[3 * l + 2] * d2;
+    dd = d0 * d0 + d1 * d1 + d2 * d2;
+  }
+  gd = warp_sum(gd); dd = warp_sum(dd);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&scal[1], gd); atomicAdd(&scal[2], dd); }
+}
+
+// Values::retract for the reduced variables; accumulates g_r^T delta and |delta|^2 (once per scalar)
+template <int TYPE>
+__global__ void k_retract_reduced(int64_t n, const double* __restrict__ val, double* val_new, const int* __restrict__ off,
+                                  const double* __restrict__ delta, const double* __restrict__ g_r, double* scal, int count_scal) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double gd = 0.0, dd = 0.0;
+  if (i < n) {
+    const int D = (TYPE == T_POSE || TYPE == T_BIAS) ? 6 : 3;
+    const double* d = delta + off[i];
+    const double* g = g_r + off[i];
+    double dl[6];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { dl[k] = d[k]; gd += g[k] * dl[k]; dd += dl[k] * dl[k]; }
+    if (TYPE == T_POSE) {
+      double X[12], Y[12];
+      load_pose(val, (int)i, X);
+      pose_retract(X, X + 9, dl, Y, Y + 9);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) val_new[12 * i + k] = Y[k];
+    } else if (TYPE == T_PLANE) {
+      double out[4];
+      plane_retract(val + 4 * i, dl, out);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) val_new[4 * i + k] = out[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) val_new[D * i + k] = val[D * i + k] + dl[k];
+    }
+  }
+  if (count_scal) {
+    gd = warp_sum(gd); dd = warp_sum(dd);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&scal[1], gd); atomicAdd(&scal[2], dd); }
+  }
+}
+
+// ------------------------------------------------------------------ K3 IMU preintegration
+__global__ void k_preintegrate(int n, const int* __restrict__ offsets, const double* __restrict__ imu6, double dt,
+                               const ImuParamsDev* __restrict__ par, const double* __restrict__ bias_hat, fg_pim* out) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  double pre[9], Hba[27], Hbg[27], P[225], F[225], T[225];
+  for (int i = 0; i < 9; ++i) pre[i] = 0;
+  for (int i = 0; i < 27; ++i) { Hba[i] = 0; Hbg[i] = 0; }
+  for (int i = 0; i < 225; ++i) P[i] = 0;
+  const double* bh = bias_hat + 6 * (int64_t)f;
+  double dt22 = 0.5 * dt * dt;
+  int s0 = offsets[f], s1 = offsets[f + 1];
+  for (int s = s0; s < s1; ++s) {
+    const double* m = imu6 + 6 * (int64_t)s;
+    double acc[3] = {m[3] - bh[0], m[4] - bh[1], m[5] - bh[2]};
+    double om[3] = {m[0] - bh[3], m[1] - bh[4], m[2] - bh[5]};
+    double* th = pre;
+    double Jr[9], invH[9], wt[3], D[9], wH[9], R[9], an[3];
+    so3_jr(th, Jr);
+    inv3(Jr, invH);
+    m3_vec(invH, om, wt);
+    d_jr_c(th, wt, D);
+    m3_mul(invH, D, wH);             // w_tangent_H_theta = -invH * D
+    so3_exp(th, R);
+    m3_vec(R, acc, an);
+    // a_nav_H_theta = R * skew(-acc) * Jr
+    double Sa[9], RS[9], aH[9];
+    double nacc[3] = {-acc[0], -acc[1], -acc[2]};
+    skew3(nacc, Sa);
+    m3_mul(R, Sa, RS);
+    m3_mul(RS, Jr, aH);
+    // A (9x9): identity + blocks ; B: rows 3-5 R dt22, rows 6-8 R dt ; C: rows 0-2 invH dt
+    // Hb <- A Hb - B ; Hg <- A Hg - C     (A applied blockwise)
+    double nHba[27], nHbg[27];
+    for (int c = 0; c < 3; ++c) {
+      for (int i = 0; i < 3; ++i) {
+        // theta rows: (I - wH dt) * H[0:3]
+        double s_a = Hba[3 * i + c], s_g = Hbg[3 * i + c];
+        double p_a = Hba[3 * (3 + i) + c] + dt * Hba[3 * (6 + i) + c];
+        double p_g = Hbg[3 * (3 + i) + c] + dt * Hbg[3 * (6 + i) + c];
+        double v_a = Hba[3 * (6 + i) + c], v_g = Hbg[3 * (6 + i) + c];
+        for (int k = 0; k < 3; ++k) {
+          s_a -= dt * wH[3 * i + k] * Hba[3 * k + c];
+          s_g -= dt * wH[3 * i + k] * Hbg[3 * k + c];
+          p_a += dt22 * aH[3 * i + k] * Hba[3 * k + c];
+          p_g += dt22 * aH[3 * i + k] * Hbg[3 * k + c];
+          v_a += dt * aH[3 * i + k] * Hba[3 * k + c];
+          v_g += dt * aH[3 * i + k] * Hbg[3 * k + c];
+        }
+        nHba[3 * i + c] = s_a;                          nHbg[3 * i + c] = s_g - dt * invH[3 * i + c];
+        nHba[3 * (3 + i) + c] = p_a - dt22 * R[3 * i + c]; nHbg[3 * (3 + i) + c] = p_g;
+        nHba[3 * (6 + i) + c] = v_a - dt * R[3 * i + c];   nHbg[3 * (6 + i) + c] = v_g;
+      }
+    }
+    for (int i = 0; i < 27; ++i) { Hba[i] = nHba[i]; Hbg[i] = nHbg[i]; }
+    // F (15x15)
+    for (int i = 0; i < 225; ++i) F[i] = 0;
+    for (int i = 0; i < 15; ++i) F[16 * i] = 1.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        F[15 * i + j] -= dt * wH[3 * i + j];                  // A theta-theta
+        F[15 * (3 + i) + j] = dt22 * aH[3 * i + j];          // A p-theta
+        F[15 * (6 + i) + j] = dt * aH[3 * i + j];            // A v-theta
+        F[15 * i + 12 + j] = -dt * invH[3 * i + j];          // theta_H_biasOmega = -C[0:3]
+        F[15 * (6 + i) + 9 + j] = -dt * R[3 * i + j];        // vel_H_biasAcc = -B[6:9]
+      }
+    for (int i = 0; i < 3; ++i) F[15 * (3 + i) + 6 + i] = dt;  // A p-v
+    // P <- F P F^T + G
+    for (int i = 0; i < 15; ++i)
+      for (int j = 0; j < 15; ++j) {
+        double s_ = 0;
+        for (int k = 0; k < 15; ++k) s_ += F[15 * i + k] * P[15 * k + j];
+        T[15 * i + j] = s_;
+      }
+    for (int i = 0; i < 15; ++i)
+      for (int j = 0; j < 15; ++j) {
+        double s_ = 0;
+        for (int k = 0; k < 15; ++k) s_ += T[15 * i + k] * F[15 * j + k];
+        P[15 * i + j] = s_;
+      }
+    // G terms
+    double thH[9], vH[9];
+    for (int i = 0; i < 9; ++i) { thH[i] = -dt * invH[i]; vH[i] = -dt * R[i]; }
+    double Ca[9], Cw[9], Cx[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        Ca[3 * i + j] = par->acc_cov[3 * i + j] + par->bint[6 * i + j];
+        Cw[3 * i + j] = par->gyro_cov[3 * i + j] + par->bint[6 * (3 + i) + 3 + j];
+        Cx[3 * i + j] = par->bint[6 * (3 + i) + j];
+      }
+    double t1[9], t2[9];
+    m3_mul(vH, Ca, t1); m3_mult(t1, vH, t2);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) P[15 * (6 + i) + 6 + j] += t2[3 * i + j] / dt;
+    m3_mul(thH, Cw, t1); m3_mult(t1, thH, t2);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) P[15 * i + j] += t2[3 * i + j] / dt;
+    m3_mul(vH, Cx, t1); m3_mult(t1, thH, t2);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        P[15 * (6 + i) + j] += t2[3 * i + j];
+        P[15 * j + 6 + i] += t2[3 * i + j];
+        P[15 * (3 + i) + 3 + j] += dt * par->int_cov[3 * i + j];
+        P[15 * (9 + i) + 9 + j] += dt * par->bias_acc_cov[3 * i + j];
+        P[15 * (12 + i) + 12 + j] += dt * par->bias_gyro_cov[3 * i + j];
+      }
+    // state
+    double np_[9];
+    for (int i = 0; i < 3; ++i) {
+      np_[i] = pre[i] + wt[i] * dt;
+      np_[3 + i] = pre[3 + i] + pre[6 + i] * dt + an[i] * dt22;
+      np_[6 + i] = pre[6 + i] + an[i] * dt;
+    }
+    for (int i = 0; i < 9; ++i) pre[i] = np_[i];
+  }
+  fg_pim* o = out + f;
+  o->dt = (s1 - s0) * dt;
+  for (int i = 0; i < 9; ++i) o->preint[i] = pre[i];
+  for (int i = 0; i < 27; ++i) { o->H_ba[i] = Hba[i]; o->H_bg[i] = Hbg[i]; }
+  for (int i = 0; i < 6; ++i) o->bias_hat[i] = bh[i];
+  for (int i = 0; i < 225; ++i) o->cov[i] = P[i];
+  for (int i = 0; i < 3; ++i) o->gravity[i] = par->gravity[i];
+}
+
+void launch_preintegrate(int n, const int* d_off, const double* d_imu, double dt, const ImuParamsDev* d_par,
+                         const double* d_bias, fg_pim* d_out, cudaStream_t st) {
+  if (n <= 0) return;
+  k_preintegrate<<<cdiv(n, 64), 64, 0, st>>>(n, d_off, d_imu, dt, d_par, d_bias, d_out);
+}
+
+// ------------------------------------------------------------------ launch wrappers
+static SysView make_view(fg_ctx* c, double* Lbuf) {
+  SysView s;
+  s.L = Lbuf; s.col2sn = c->d.col2sn; s.sn_col0 = c->d.sn_col0; s.sn_ncols = c->d.sn_ncols; s.sn_nrows = c->d.sn_nrows;
+  s.sn_rowptr = c->d.sn_rowptr; s.sn_valptr = c->d.sn_valptr; s.rowidx = c->d.rowidx; s.n_r = c->sym.n_r;
+  return s;
+}
+
+template <bool JAC>
+static void run_factors(fg_ctx* c, bool trial, double* chi2) {
+  DevGraph& d = c->d;
+  cudaStream_t st = c->stream;
+  Vals v;
+  for (int t = 0; t < T_COUNT; ++t) v.v[t] = trial ? d.val_new[t] : d.val[t];
+  SysView sys = make_view(c, d.U0);
+  const bool pose_side = (c->rank == 0);     // replicated factors are counted once
+  const int T = 128;
+  if (pose_side) {
+    if (d.n_pp) k_prior_pose<JAC><<<cdiv(d.n_pp, T), T, 0, st>>>(d.n_pp, d.pp_var, d.pp_mean, d.pp_info, v, d.off[T_POSE], sys, d.g_r, chi2);
+    if (d.n_pv) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(d.n_pv, T), T, 0, st>>>(d.n_pv, d.pv_var, d.pv_mean, d.pv_info, v, d.off[T_VEC3], sys, d.g_r, chi2);
+    if (d.n_pb) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(d.n_pb, T), T, 0, st>>>(d.n_pb, d.pb_var, d.pb_mean, d.pb_info, v, d.off[T_BIAS], sys, d.g_r, chi2);
+    if (d.n_bt) k_between<JAC><<<cdiv(d.n_bt, T), T, 0, st>>>(d.n_bt, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, chi2);
+    if (d.n_imu) k_imu<JAC><<<cdiv(d.n_imu, IMU_WPB), 32 * IMU_WPB, 0, st>>>(d.n_imu, d.imu_var, d.imu_rec, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, chi2);
+    if (d.n_pl) k_plane<JAC><<<cdiv(d.n_pl, T), T, 0, st>>>(d.n_pl, d.pl_pose, d.pl_plane, d.pl_meas, d.pl_info, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, chi2);
+  }
+  int64_t L = d.n[T_POINT];
+  if (L) {
+    k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, st>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, chi2);
+    if (d.n_obs) {
+      k_proj_obs<JAC><<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, chi2);
+      if (JAC) {
+        int P = (int)d.n[T_POSE];
+        k_proj_pose<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.off[T_POSE], sys, d.g_r);
+      }
+    }
+  }
+}
+
+void launch_linearize(fg_ctx* c) {
+  DevGraph& d = c->d;
+  cudaMemsetAsync(d.U0, 0, sizeof(double) * (c->sym.nnz + 8), c->stream);
+  cudaMemsetAsync(d.g_r, 0, sizeof(double) * c->sym.n_r, c->stream);
+  cudaMemsetAsync(d.scal, 0, sizeof(double) * 8, c->stream);
+  run_factors<true>(c, false, d.scal + 0);
+}
+
+void launch_error_only(fg_ctx* c, bool trial) {
+  DevGraph& d = c->d;
+  double* target = d.scal + (trial ? 3 : 0);
+  cudaMemsetAsync(target, 0, sizeof(double), c->stream);
+  run_factors<false>(c, trial, target);
+}
+
+void launch_build_and_schur(fg_ctx* c, double lambda) {
+  DevGraph& d = c->d;
+  cudaStream_t st = c->stream;
+  cudaMemcpyAsync(d.L, d.U0, sizeof(double) * (c->sym.nnz + 8), cudaMemcpyDeviceToDevice, st);
+  SysView sys = make_view(c, d.L);
+  // damping and the pose-side gradient are replicated terms: added by rank 0 only
+  if (c->rank == 0) k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, st>>>(sys, d.g_r, lambda, 1);
+  int64_t L = d.n[T_POINT];
+  if (L) k_schur<<<cdiv(L * 32, 128), 128, 0, st>>>(L, d.n_obs, d.lm_ptr, d.obs_pose, d.W, d.V, d.gl, d.Vinv, lambda, d.off[T_POSE], sys);
+}
+
+void launch_retract_error(fg_ctx* c, double lambda) {
+  DevGraph& d = c->d;
+  cudaStream_t st = c->stream;
+  cudaMemsetAsync(d.scal + 1, 0, sizeof(double) * 3, st);
+  const int T = 128;
+  int cnt = (c->rank == 0) ? 1 : 0;
+  if (d.n[T_POSE]) k_retract_reduced<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], d.off[T_POSE], d.delta, d.g_r, d.scal, cnt);
+  if (d.n[T_VEC3]) k_retract_reduced<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], d.off[T_VEC3], d.delta, d.g_r, d.scal, cnt);
+  if (d.n[T_BIAS]) k_retract_reduced<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], d.off[T_BIAS], d.delta, d.g_r, d.scal, cnt);
+  if (d.n[T_PLANE]) k_retract_reduced<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], d.off[T_PLANE], d.delta, d.g_r, d.scal, cnt);
+  int64_t L = d.n[T_POINT];
+  if (L) {
+    cudaMemsetAsync(d.tl, 0, sizeof(double) * 3 * L, st);
+    if (d.n_obs) k_lm_backsub_obs<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_pose, d.obs_point, d.W, d.delta, d.off[T_POSE], d.tl);
+    k_lm_update<<<cdiv(L, 256), 256, 0, st>>>(L, d.val[T_POINT], d.Vinv, d.gl, d.tl, d.val_new[T_POINT], d.scal);
+  }
+  run_factors<false>(c, true, d.scal + 3);
+}
+
+}  // namespace fg

@@ -1,0 +1,126 @@
+"""The formulas the CUDA kernels execute (graph_slam_b200/csrc/fg_math.cuh, fg_factors.cuh), compiled for the
+host by the test-only shim tests/hostmath, compared with the numpy oracle on seeded inputs.  Runs without a GPU."""
+import ctypes as C
+import numpy as np
+import pytest
+from oracle import lie, factors as F, imu as oimu
+
+DP = C.POINTER(C.c_double)
+
+
+def p(a):
+    return a.ctypes.data_as(DP)
+
+
+def arr(*shape):
+    return np.zeros(shape, dtype=np.float64)
+
+
+def T12(R, t):
+    return np.concatenate([R.ravel(), t.ravel()])
+
+
+def rand_pose(rng, scale=0.7):
+    return lie.se3_exp(rng.normal(size=6) * scale)
+
+
+@pytest.fixture(scope='module')
+def rng():
+    return np.random.default_rng(123)
+
+
+def test_lie(hostmath, rng):
+    for _ in range(200):
+        w = rng.normal(size=3) * rng.choice([1e-9, 1e-3, 1.0, 2.5])
+        R = arr(9); hostmath.hm_so3_exp(p(w), p(R))
+        assert np.allclose(R.reshape(3, 3), lie.so3_exp(w), atol=1e-14)
+        w2 = arr(3); hostmath.hm_so3_log(p(R), p(w2))
+        assert np.allclose(w2, lie.so3_log(lie.so3_exp(w)), atol=1e-12)
+        J = arr(9); hostmath.hm_jr(p(w), p(J))
+        assert np.allclose(J.reshape(3, 3), lie.so3_jr(w), atol=1e-13)
+        hostmath.hm_jr_inv(p(w), p(J))
+        assert np.allclose(J.reshape(3, 3), lie.so3_jr_inv(w), atol=1e-11)
+        xi = np.concatenate([w, rng.normal(size=3)])
+        T = arr(12); hostmath.hm_se3_exp(p(xi), p(T))
+        Ro, to = lie.se3_exp(xi)
+        assert np.allclose(T, T12(Ro, to), atol=1e-13)
+        x2 = arr(6); hostmath.hm_se3_log(p(T), p(x2))
+        assert np.allclose(x2, lie.se3_log(Ro, to), atol=1e-11)
+
+
+def test_between_and_prior(hostmath, rng):
+    for _ in range(100):
+        R1, t1 = rand_pose(rng); R2, t2 = rand_pose(rng)
+        Rz, tz = lie.pose_between(R1, t1, R2, t2)
+        Rz, tz = lie.pose_retract(Rz, tz, rng.normal(size=6) * 0.05)
+        r = arr(6); J = arr(36)
+        hostmath.hm_between(p(T12(R1, t1)), p(T12(R2, t2)), p(T12(Rz, tz)), p(r), p(J))
+        ro, H1, _ = F.between_pose(R1, t1, R2, t2, Rz, tz)
+        assert np.allclose(r, ro, atol=1e-12)
+        assert np.allclose(J.reshape(6, 6), H1, atol=1e-12)
+        hostmath.hm_prior_pose(p(T12(R1, t1)), p(T12(R2, t2)), p(r))
+        assert np.allclose(r, F.prior_pose(R1, t1, R2, t2, jac=False), atol=1e-12)
+
+
+def test_projection(hostmath, rng):
+    K = np.array([250.5773, 250.5773, 0.3, 90.0, 70.0, -0.8466, 0.5370, 1e-3, -2e-3])
+    Rs = lie.rzryrx(np.pi / 2, 0, np.pi / 2); ts = np.array([0.02, -0.01, 0.03])
+    for k in range(200):
+        R, t = rand_pose(rng)
+        Rc, tc = lie.pose_compose(R, t, Rs, ts)
+        pc = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0.5, 6)])
+        if k % 10 == 0:
+            pc[2] = -abs(pc[2])          # cheirality branch
+        pw = Rc @ pc + tc
+        uv = rng.normal(size=2) * 50 + 80
+        r = arr(2); Jp = arr(12); Jl = arr(6)
+        hostmath.hm_projection(p(T12(R, t)), p(pw), p(uv), p(K), p(T12(Rs, ts)), p(r), p(Jp), p(Jl))
+        ro, Jpo, Jlo = F.projection(R, t, pw, uv, K, Rs, ts)
+        assert np.allclose(r, ro, rtol=1e-12, atol=1e-10)
+        assert np.allclose(Jp.reshape(2, 6), Jpo, rtol=1e-11, atol=1e-9)
+        assert np.allclose(Jl.reshape(2, 3), Jlo, rtol=1e-11, atol=1e-9)
+
+
+def test_plane(hostmath, rng):
+    for _ in range(200):
+        R, t = rand_pose(rng)
+        pl = F.plane_from_coeffs(np.concatenate([rng.normal(size=3), rng.uniform(0.5, 8, size=1)]))
+        z = F.plane_from_coeffs(np.concatenate([rng.normal(size=3), rng.uniform(0.5, 8, size=1)]))
+        r = arr(3); Hr = arr(18); Hp = arr(9)
+        hostmath.hm_plane(p(T12(R, t)), p(pl), p(z), p(r), p(Hr), p(Hp))
+        ro, Hro, Hpo = F.plane_factor(R, t, pl, z)
+        assert np.allclose(r, ro, atol=1e-12)
+        assert np.allclose(Hr.reshape(3, 6), Hro, atol=1e-12)
+        assert np.allclose(Hp.reshape(3, 3), Hpo, atol=1e-12)
+        v = rng.normal(size=3) * 0.3
+        out = arr(4); hostmath.hm_plane_retract(p(pl), p(v), p(out))
+        assert np.allclose(out, F.plane_retract(pl, v), atol=1e-13)
+
+
+def test_imu_factor(hostmath, rng):
+    par = oimu.vn100_params()
+    S = 20
+    for _ in range(20):
+        samples = np.concatenate([rng.normal(size=(1, S, 3)) * 0.3, rng.normal(size=(1, S, 3)) * 0.5 + np.array([0, 0, -9.7])], -1)
+        bh = rng.normal(size=(1, 6)) * 0.01
+        pim = oimu.preintegrate(samples, 0.005, par, bh)
+        Ri, ti = rand_pose(rng); vi = rng.normal(size=3); bi = bh[0] + rng.normal(size=6) * 0.01
+        Rj, tj, vj = oimu.predict({k: (v[0] if isinstance(v, np.ndarray) and v.ndim > 1 else v) for k, v in pim.items()} | {'dt': pim['dt'][0]}, Ri, ti, vi, bi)
+        Rj, tj = lie.pose_retract(Rj, tj, rng.normal(size=6) * 0.01); vj = vj + rng.normal(size=3) * 0.01
+        bj = bi + rng.normal(size=6) * 1e-3
+        pim1 = dict(dt=pim['dt'][0], preint=pim['preint'][0], Hba=pim['Hba'][0], Hbg=pim['Hbg'][0], bias_hat=pim['bias_hat'][0], gravity=pim['gravity'])
+        ro, Js = F.imu_combined(Ri, ti, vi, Rj, tj, vj, bi, bj, pim1)
+        Jo = np.concatenate(Js, -1)
+        r = arr(15); J = arr(450)
+        hostmath.hm_imu(p(T12(Ri, ti)), p(vi), p(T12(Rj, tj)), p(vj), p(bi), p(bj), C.c_double(float(pim1['dt'])),
+                        p(np.ascontiguousarray(pim1['preint'])), p(np.ascontiguousarray(pim1['Hba'])), p(np.ascontiguousarray(pim1['Hbg'])),
+                        p(np.ascontiguousarray(pim1['bias_hat'])), p(np.ascontiguousarray(pim1['gravity'])), p(r), p(J))
+        assert np.allclose(r, ro, atol=1e-12)
+        assert np.allclose(J.reshape(15, 30), Jo, atol=1e-11)
+
+
+def test_d_jr_c(hostmath, rng):
+    for _ in range(100):
+        th = rng.normal(size=3) * rng.choice([1e-7, 0.1, 1.5]); c = rng.normal(size=3)
+        D = arr(9); hostmath.hm_d_jr_c(p(th), p(c), p(D))
+        assert np.allclose(D.reshape(3, 3), oimu._d_jr_c(th, c), atol=1e-12)

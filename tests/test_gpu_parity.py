@@ -1,0 +1,152 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Tolerances (BASELINE.md section 3 / SURVEY 8d): identical accept/reject sequence; final chi2 rel <= 1e-9 (C1-C3),
+<= 1e-7 (C4-C5 shapes); poses <= 1e-8 rad / 1e-8 m (C1-C3), <= 1e-6 (C4)."""
+import numpy as np
+import pytest
+from graph_slam_b200 import abi, synth
+from oracle import build, lm, lie, imu as oimu
+
+pytestmark = pytest.mark.gpu
+
+
+def rot_angle(Ra, Rb):
+    return np.linalg.norm(lie.so3_log(np.swapaxes(Ra, -1, -2) @ Rb), axis=-1)
+
+
+def run_both(spec, solver='direct', **lm_kw):
+    ctx = abi.Context(device=0)
+    abi.load_spec(ctx, spec)
+    g0 = build.from_spec(spec)
+    e_dev, e_orc = ctx.error(), g0.error()
+    rep = ctx.optimize(**lm_kw)
+    g1, orep = lm.optimize_gtsam(g0, lm.LMParams(**lm_kw), solver=solver)
+    return ctx, rep, g0, g1, orep, e_dev, e_orc
+
+
+def check(spec, tol_chi2, tol_pose, solver='direct', **lm_kw):
+    ctx, rep, g0, g1, orep, e_dev, e_orc = run_both(spec, solver, **lm_kw)
+    assert abs(e_dev - e_orc) <= 1e-11 * e_orc, (e_dev, e_orc)
+    dt, ot = rep.trace(), orep['trace']
+    assert [t['accepted'] for t in dt] == [t['accepted'] for t in ot]
+    assert np.allclose([t['lam'] for t in dt], [t['lam'] for t in ot], rtol=1e-12)
+    assert rep.iterations == orep['iterations']
+    assert abs(rep.final_error - orep['error']) <= tol_chi2 * orep['error'], (rep.final_error, orep['error'])
+    T = ctx.get_values(abi.T_POSE)
+    R = T[:, :9].reshape(-1, 3, 3); t = T[:, 9:]
+    assert rot_angle(R, g1.R).max() <= tol_pose
+    assert np.abs(t - g1.t).max() <= tol_pose
+    if len(g1.vel):
+        assert np.abs(ctx.get_values(abi.T_VEC3) - g1.vel).max() <= 10 * tol_pose
+        assert np.abs(ctx.get_values(abi.T_BIAS) - g1.bias).max() <= 10 * tol_pose
+    if len(g1.point):
+        assert np.abs(ctx.get_values(abi.T_POINT) - g1.point).max() <= 10 * tol_pose
+    if len(g1.plane):
+        assert np.abs(ctx.get_values(abi.T_PLANE) - g1.plane).max() <= 10 * tol_pose
+    # the optimiser moved the estimate (not a no-op) and graph.error agrees with the report
+    assert rep.final_error < rep.initial_error
+    assert abs(ctx.error() - rep.final_error) <= 1e-10 * rep.final_error
+    ctx.close()
+    return rep
+
+
+def test_preintegration_matches_oracle():
+    spec = synth.make_config('C2', seed=3, scale=0.06)
+    P = spec['n_poses']; S = spec['imu_samples'].shape[1]
+    rng = np.random.default_rng(0)
+    bh = rng.normal(size=(P - 1, 6)) * 0.01
+    ctx = abi.Context(device=0)
+    pims = ctx.preintegrate(np.arange(P) * S, spec['imu_samples'].reshape(-1, 6), spec['imu_dt'], abi.vn100_imu_params(), bh)
+    ref = oimu.preintegrate(spec['imu_samples'], spec['imu_dt'], oimu.vn100_params(), bh)
+    for i in range(P - 1):
+        assert abs(pims[i].dt - ref['dt'][i]) < 1e-15
+        assert np.allclose(np.array(pims[i].preint), ref['preint'][i], rtol=1e-12, atol=1e-14)
+        assert np.allclose(np.array(pims[i].H_ba).reshape(9, 3), ref['Hba'][i], rtol=1e-11, atol=1e-14)
+        assert np.allclose(np.array(pims[i].H_bg).reshape(9, 3), ref['Hbg'][i], rtol=1e-11, atol=1e-14)
+        c = np.array(pims[i].cov).reshape(15, 15)
+        assert np.allclose(c, ref['cov'][i], rtol=1e-10, atol=1e-22)
+    ctx.close()
+
+
+def test_ragged_intervals_and_empty():
+    spec = synth.make_config('C2', seed=4, scale=0.06)
+    flat = spec['imu_samples'].reshape(-1, 6)
+    offsets = np.array([0, 0, 7, 7 + 33, 7 + 33 + 1])          # empty, 7, 33, 1 samples
+    ctx = abi.Context(device=0)
+    pims = ctx.preintegrate(offsets, flat, 0.005, abi.vn100_imu_params(), np.zeros((4, 6)))
+    assert pims[0].dt == 0.0 and np.all(np.array(pims[0].cov) == 0)
+    for k, (a, b) in enumerate(zip(offsets[:-1], offsets[1:])):
+        if b > a:
+            ref = oimu.preintegrate(flat[a:b][None], 0.005, oimu.vn100_params(), np.zeros((1, 6)))
+            assert np.allclose(np.array(pims[k].preint), ref['preint'][0], rtol=1e-12, atol=1e-15)
+            assert np.allclose(np.array(pims[k].cov).reshape(15, 15), ref['cov'][0], rtol=1e-10, atol=1e-22)
+    ctx.close()
+
+
+def test_c1_pose_graph():
+    check(synth.make_config('C1', seed=1), 1e-9, 1e-8)
+
+
+def test_c2_vio():
+    check(synth.make_config('C2', seed=1, scale=0.1), 1e-9, 1e-8)
+
+
+def test_c3_vio_planes():
+    check(synth.make_config('C3', seed=1, scale=0.1), 1e-9, 1e-8)
+
+
+def test_c4_ba_imu_schur():
+    check(synth.make_config('C4', seed=1, scale=0.03), 1e-7, 1e-6, solver='schur')
+
+
+@pytest.mark.parametrize('seed', [2, 3])
+def test_c4_other_seeds(seed):
+    check(synth.make_config('C4', seed=seed, scale=0.02), 1e-7, 1e-6, solver='schur')
+
+
+def test_rejected_steps_follow_oracle():
+    """A badly initialised pose graph makes LM reject trials; lambda must climb exactly as in the oracle."""
+    spec = synth.make_config('C1', seed=5)
+    rng = np.random.default_rng(1)
+    nz = rng.normal(size=(spec['n_poses'], 6)) * np.array([0.6] * 3 + [1.5] * 3)
+    nz[0] = 0
+    dR, dt = lie.se3_exp(nz)
+    spec['pose_init_R'], spec['pose_init_t'] = lie.pose_compose(spec['pose_init_R'], spec['pose_init_t'], dR, dt)
+    ctx, rep, g0, g1, orep, e_dev, e_orc = run_both(spec, max_iterations=15)
+    dt_, ot = rep.trace(), orep['trace']
+    assert [t['accepted'] for t in dt_] == [t['accepted'] for t in ot]
+    assert not all(t['accepted'] for t in dt_), 'test graph did not trigger a rejection'
+    assert abs(rep.final_error - orep['error']) <= 1e-7 * orep['error']
+    ctx.close()
+
+
+def test_values_api_and_errors():
+    ctx = abi.Context(device=0)
+    I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0.5, 0, 0.0])
+    k0, k1 = abi.symbol('x', 0), abi.symbol('x', 1)
+    ctx.add_pose(k0, I)
+    with pytest.raises(abi.FgError) as e:
+        ctx.add_pose(k0, I)
+    assert e.value.code == -2
+    with pytest.raises(abi.FgError) as e:
+        ctx.add_between(k0, k1, I, np.eye(6))
+    assert e.value.code == -3
+    assert ctx.exists(k0) and not ctx.exists(k1)
+    ctx.add_pose(k1, I)
+    ctx.add_prior_pose(k0, I, np.eye(6) * 1e4)
+    Z = I.copy(); Z[9:] = [1.0, 0.2, -0.1]
+    ctx.add_between(k0, k1, Z, np.eye(6) * 100)
+    rep = ctx.optimize()
+    got = ctx.get_value(k1)
+    assert np.allclose(got[9:], [1.5, 0.2, -0.1], atol=1e-6) and rep.final_error < 1e-10
+    ctx.update_value(k1, I)
+    assert abs(ctx.error() - 0.5 * 100 * (1 + 0.04 + 0.01)) < 1e-9
+    ctx.close()
+
+
+def test_single_pose_and_empty_landmark():
+    """Edge cases: a landmark with zero observations (prior only) and a pose with no projection factors."""
+    spec = synth.make_config('C4', seed=6, scale=0.02)
+    keep = spec['proj_point'] != 3
+    for k in ('proj_pose', 'proj_point', 'proj_uv'):
+        spec[k] = spec[k][keep]
+    check(spec, 1e-7, 1e-6, solver='schur')

@@ -1,0 +1,123 @@
+"""Host logic of the reduced solve, exercised without a GPU through a detached context (fg_create(-1,..)):
+the symbolic structure (ordering, supernodes, row lists, update lists) produced by fg_symbolic.cpp is used by a
+numpy emulation of the left-looking supernodal algorithm that k_chol / k_backsolve implement, and the result is
+compared with a dense solve of the oracle's reduced system."""
+import numpy as np
+import pytest
+from graph_slam_b200 import abi, synth
+from oracle import build
+
+
+def reduced_system(spec, lam):
+    """Oracle: damped reduced system (Schur complement over points) and the oracle->reduced index map."""
+    g = build.from_spec(spec)
+    H, grad, err = g.normal_equations()
+    d = g.dims
+    n_r = d['o_pt']
+    H = H.toarray() + lam * np.eye(H.shape[0])
+    U, W, V = H[:n_r, :n_r], H[:n_r, n_r:], H[n_r:, n_r:]
+    if d['L']:
+        Vi = np.linalg.inv(V)
+        S = U - W @ Vi @ W.T
+        b = -(grad[:n_r] - W @ Vi @ grad[n_r:])
+    else:
+        S, b = U, -grad[:n_r]
+    return g, S, b
+
+
+def perm_from_offsets(ctx, g):
+    d = g.dims
+    off = {k: ctx.symbolic(w) for k, w in (('pose', 11), ('vel', 12), ('bias', 13), ('plane', 14))}
+    perm = np.zeros(d['o_pt'], dtype=np.int64)       # oracle reduced index -> solver reduced index
+    for i in range(d['P']):
+        perm[6 * i:6 * i + 6] = off['pose'][i] + np.arange(6)
+    for i in range(d['Nv']):
+        perm[d['o_v'] + 3 * i: d['o_v'] + 3 * i + 3] = off['vel'][i] + np.arange(3)
+    for i in range(d['Nb']):
+        perm[d['o_b'] + 6 * i: d['o_b'] + 6 * i + 6] = off['bias'][i] + np.arange(6)
+    for i in range(d['Npl']):
+        perm[d['o_pl'] + 3 * i: d['o_pl'] + 3 * i + 3] = off['plane'][i] + np.arange(3)
+    return perm
+
+
+def emulate(sym, Sp, bp):
+    """numpy emulation of k_chol (left-looking, rhs row) + k_backsolve on the panel layout."""
+    n_r, n_sn = int(sym[0][0]), int(sym[0][1])
+    col0, ncols, nrows, rowptr, valptr, rowidx, uptr, ud, ua, ub = sym[1:11]
+    aug = np.zeros((n_r + 1, n_r + 1)); aug[:n_r, :n_r] = Sp; aug[n_r, :n_r] = bp
+    panels = []
+    for s in range(n_sn):
+        rows = rowidx[rowptr[s]:rowptr[s] + nrows[s]]
+        cols = np.arange(col0[s], col0[s] + ncols[s])
+        assert np.array_equal(rows[:ncols[s]], cols) and rows[-1] == n_r and np.all(np.diff(rows) > 0)
+        # structure check: every nonzero of the lower part of these columns lies in the row list
+        full = np.nonzero(np.abs(aug[col0[s]:, cols]).sum(1))[0] + col0[s]
+        assert set(full.tolist()) <= set(rows.tolist()), 'S has an entry outside the symbolic structure'
+        panels.append(np.tril(aug[np.ix_(rows, cols)][:ncols[s]], 0).tolist() and aug[np.ix_(rows, cols)].copy())
+        panels[s][:ncols[s]] = np.tril(panels[s][:ncols[s]])
+    for s in range(n_sn):
+        rows_s = rowidx[rowptr[s]:rowptr[s] + nrows[s]]
+        pos = {int(r): k for k, r in enumerate(rows_s)}
+        for u in range(uptr[s], uptr[s + 1]):
+            d, a, b = int(ud[u]), int(ua[u]), int(ub[u])
+            assert d < s
+            rows_d = rowidx[rowptr[d]:rowptr[d] + nrows[d]]
+            Ld = panels[d]
+            upd = Ld[a:] @ Ld[a:b].T
+            for ii, R in enumerate(rows_d[a:]):
+                assert int(R) in pos, 'descendant row missing from ancestor structure'
+                for jj in range(b - a):
+                    C = int(rows_d[a + jj])
+                    if R >= C:
+                        panels[s][pos[int(R)], C - col0[s]] -= upd[ii, jj]
+        nc = ncols[s]
+        Ldd = np.linalg.cholesky(panels[s][:nc] + np.tril(panels[s][:nc], -1).T)
+        panels[s][:nc] = Ldd
+        panels[s][nc:] = np.linalg.solve(Ldd, panels[s][nc:].T).T
+    x = np.zeros(n_r)
+    for s in range(n_sn - 1, -1, -1):
+        rows = rowidx[rowptr[s]:rowptr[s] + nrows[s]]
+        nc = ncols[s]
+        t = panels[s][-1] - panels[s][nc:-1].T @ x[rows[nc:-1]]
+        x[col0[s]:col0[s] + nc] = np.linalg.solve(panels[s][:nc].T, t)
+    return x
+
+
+@pytest.mark.parametrize('name,scale', [('C1', 1.0), ('C2', 0.08), ('C3', 0.08), ('C4', 0.03)])
+def test_symbolic_and_left_looking(fglib, name, scale):
+    spec = synth.make_config(name, seed=2, scale=scale)
+    lam = 1e-3
+    g, S, b = reduced_system(spec, lam)
+    ctx = abi.Context(device=-1)
+    # detached context cannot preintegrate on a device: hand it oracle-preintegrated records
+    pims = None
+    if 'imu' in g.f:
+        q = g.f['imu']['pim']
+        pims = (abi.Pim * len(q['dt']))()
+        for i in range(len(q['dt'])):
+            pims[i].dt = q['dt'][i]
+            pims[i].preint[:] = q['preint'][i].tolist(); pims[i].H_ba[:] = q['Hba'][i].ravel().tolist()
+            pims[i].H_bg[:] = q['Hbg'][i].ravel().tolist(); pims[i].bias_hat[:] = q['bias_hat'][i].tolist()
+            pims[i].cov[:] = q['cov'][i].ravel().tolist(); pims[i].gravity[:] = q['gravity'].tolist()
+    abi.load_spec(ctx, spec, preintegrated=pims)
+    sym = [ctx.symbolic(w) for w in range(11)]
+    perm = perm_from_offsets(ctx, g)
+    n_r = len(perm)
+    assert sym[0][0] == n_r and sorted(perm.tolist()) == list(range(n_r))
+    Sp = np.zeros_like(S); Sp[np.ix_(perm, perm)] = S
+    bp = np.zeros_like(b); bp[perm] = b
+    x = emulate(sym, Sp, bp)
+    ref = np.linalg.solve(Sp, bp)
+    assert np.allclose(x, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+    ctx.close()
+
+
+def test_detached_context_has_no_cpu_solver(fglib):
+    ctx = abi.Context(device=-1)
+    ctx.add_pose(abi.symbol('x', 0), np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]))
+    with pytest.raises(abi.FgError) as e:
+        ctx.error()
+    assert e.value.code == -4
+    with pytest.raises(abi.FgError):
+        ctx.optimize()
+    ctx.close()
