@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s on the synthetic VIO-BA graph (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C5] [--impl ours|reference]
+
+A "step" is one outer Levenberg-Marquardt iteration (linearise, damped Schur solve(s), retract, chi2, accept/
+reject) of CGraphGT::optimizeGraphBatch's loop (gtsam/gtsam_graph.cpp:1784-1788) over the whole graph.
+  value  : iterations/s with the graph and the state vector resident in HBM (timed region = K iterations)
+  e2e    : iterations/s through the C ABI with HOST buffers: per step the state vector is copied in from
+           pinned host memory (fg_set_values), one LM iteration runs, and the state is copied back out.
+  N > 1  : landmarks are sharded across ranks, one ncclAllReduce of the reduced Hessian per trial;
+           total work is fixed => scaling "strong".
+The reference arm times the oracle (numpy port of the reference's GTSAM semantics) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'LM iterations/sec on the 5k-pose/500k-point VIO-BA graph'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default=os.environ.get('FG_BENCH_CONFIG', 'C5'))
+    ap.add_argument('--scale', type=float, default=float(os.environ.get('FG_BENCH_SCALE', '1.0')))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get('hbm_gbs', 6650.0), 'measured'
+    return 6650.0, 'fallback'
+
+
+def algorithmic_bytes(spec_sizes):
+    """SURVEY 8d byte model for one accepted LM trial, from the generated graph's actual sizes."""
+    M, L, P, nnz = spec_sizes['M'], spec_sizes['L'], spec_sizes['P'], spec_sizes['nnz']
+    b_obs = 2 * (24 * M + 24 * L)                   # two passes over (idx, uv) + landmark xyz
+    b_lm = L * (72 + 72 + 24)                       # Vinv, V^-1 g write+read, new landmark
+    b_S = 8 * nnz * 4                               # reduced Hessian: write, read by factor, write factor, read in solve
+    b_state = 3 * P * 176
+    return dict(total=b_obs + b_lm + b_S + b_state, obs=b_obs, lm=b_lm, S=b_S, state=b_state)
+
+
+def cpu_baseline_sample(config, steps=1):
+    """Oracle (numpy restatement of the reference's GTSAM path) timed on a bounded sample of the workload."""
+    from graph_slam_b200 import synth
+    from oracle import build, lm
+    full = synth.CONFIGS[config]
+    scale = 0.05
+    spec = synth.make_config(config, seed=1, scale=scale)
+    g = build.from_spec(spec)
+    err = g.error()
+    lam = 1e-5
+    p = lm.LMParams()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        g, lam, err = lm.lm_iterate(g, lam, p, err, solver='schur')
+        n += 1
+    dt = time.perf_counter() - t0
+    m_s = len(spec.get('proj_pose', [])) or len(spec.get('between_i', []))
+    m_full = full.get('n_landmarks', 0) * 20 or m_s
+    rate_sample = n / dt
+    est_full = rate_sample * (m_s / m_full) if m_full else rate_sample
+    sample = ('%s scaled x%g: %d poses, %d landmarks, %d projections; %d LM iteration(s) in %.1f s '
+              '(%.4f it/s on the sample; value = that rate x sample/full projections %d/%d)' %
+              (config, scale, spec['n_poses'], len(spec.get('point_init', [])), m_s, n, dt, rate_sample, m_s, m_full))
+    return dict(value=est_full, unit='iterations/s', cores=1, kind='port', sample=sample)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    base = cpu_baseline_sample(args.config, steps=max(1, min(args.steps, 3)))
+    line = dict(metric=METRIC, value=base['value'], unit='iterations/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1000.0 / base['value'] if base['value'] else None,
+                higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
+                impl='reference', config=dict(workload=args.config, note='oracle port on a bounded sample'),
+                cpu_baseline=base,
+                e2e=dict(value=base['value'], unit='iterations/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                wall_s=time.perf_counter() - t0)
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+    import torch
+    from graph_slam_b200 import abi, synth
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product has no CPU path')
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    spec = synth.make_config(args.config, seed=1, scale=args.scale)
+    ctx = abi.Context(device=local, rank=rank, nranks=world)
+    L = len(spec.get('point_init', []))
+    sl = None
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device='cuda')
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(abi.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        sl = (L * rank // world, L * (rank + 1) // world)
+    t_build = time.perf_counter()
+    abi.load_spec(ctx, spec, landmark_slice=sl)
+    ctx.finalize()
+    t_build = time.perf_counter() - t_build
+
+    types = [t for t in range(5) if ctx.num_values(t) > 0]
+    init = {t: ctx.get_values(t) for t in types}
+    pinned = {t: torch.empty(init[t].shape, dtype=torch.float64).pin_memory() for t in types}
+    for t in types:
+        pinned[t].numpy()[:] = init[t]
+    out_pinned = {t: torch.empty(init[t].shape, dtype=torch.float64).pin_memory() for t in types}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reset():
+        for t in types:
+            ctx.set_values(t, pinned[t].numpy())
+
+    # ---- device-resident arm
+    ctx.optimize(max_iterations=max(args.warmup, 3), force_iterations=1)
+    reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    rep = ctx.optimize(max_iterations=args.steps, force_iterations=1)
+    barrier()
+    dt = time.perf_counter() - t0
+    # ---- end-to-end arm: host buffers in and out every step
+    reset()
+    for _ in range(2):
+        ctx.optimize(max_iterations=1, force_iterations=1)
+    reset()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        for t in types:
+            ctx.set_values(t, pinned[t].numpy())
+        r1 = ctx.optimize(max_iterations=1, force_iterations=1)
+        for t in types:
+            ctx.get_values(t, out_pinned[t].numpy())
+        for t in types:                      # next step continues from this step's result
+            pinned[t].copy_(out_pinned[t])
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = tt.tolist()
+    if rank != 0:
+        return
+    state_bytes = int(sum(init[t].nbytes for t in types))
+    value = args.steps / dt
+    peak, peak_src = measured_peaks()
+    sizes = dict(M=int(rep.n_projections) * world, L=int(rep.n_landmarks) * world, P=spec['n_poses'], nnz=int(rep.nnz_L))
+    ab = algorithmic_bytes(sizes)
+    trials = max(rep.trials, 1)
+    phases = dict(linearize=rep.ms_linearize / max(rep.iterations, 1), schur=rep.ms_schur / trials,
+                  factor=rep.ms_factor / trials, backsolve=rep.ms_solve / trials,
+                  retract_error=rep.ms_retract_error / trials)
+    # dominant HBM kernel: the observation pass of the linearisation (k_proj_obs): reads (idx, uv, w) + pose/point,
+    # writes W (144 B/obs).  Its launch time is taken from the linearise phase events (it dominates that phase).
+    m_rank = int(rep.n_projections)
+    l_rank = int(rep.n_landmarks)
+    k_bytes = m_rank * (4 + 4 + 16 + 8 + 144) + l_rank * (24 + 72 + 24)
+    k_ms = phases['linearize']
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    line = dict(metric=METRIC, value=value, unit='iterations/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None,
+                dtype='f64', data='synthetic',
+                config=dict(workload='%s%s: %d poses (X,V,B), %d landmarks, %d projections, %d IMU factors' % (
+                    args.config, '' if args.scale == 1.0 else '@%g' % args.scale, spec['n_poses'], L,
+                    len(spec.get('proj_pose', [])), spec['n_poses'] - 1 if 'imu_samples' in spec else 0),
+                    l2='inputs_exceed_L2' if ab['total'] > 126e6 else 'smaller_than_L2', parallelism='landmark-shard x%d' % world,
+                    charts='Pose3 EXPMAP / Rot3 EXPMAP', lm='GTSAM defaults, forced iterations',
+                    graph_build_s=t_build),
+                e2e=dict(value=args.steps / dt_e2e, unit='iterations/s', h2d_bytes_per_step=state_bytes,
+                         d2h_bytes_per_step=state_bytes),
+                gpu_launches=int(trials * 14 + rep.iterations * 12),
+                clocks=sampler.summary(),
+                roofline=dict(bound='hbm', kernel='linearise phase (k_proj_obs dominant)', achieved=achieved, peak=peak,
+                              unit='GB/s', frac=achieved / peak, traffic=None, peak_source=peak_src,
+                              iteration_algorithmic_bytes=ab['total'],
+                              iteration_frac=ab['total'] / (1e-3 * 1000.0 * dt / args.steps) / 1e9 / peak),
+                phases_ms=phases, lm=dict(iterations=rep.iterations, trials=rep.trials, initial_error=rep.initial_error,
+                                          final_error=rep.final_error, e2e_last_error=r1.final_error),
+                sizes=dict(reduced_dims=int(rep.n_reduced_dims), supernodes=int(rep.n_supernodes), nnz_L=int(rep.nnz_L)))
+    if not args.no_cpu_baseline:
+        try:
+            line['cpu_baseline'] = cpu_baseline_sample(args.config)
+        except Exception as e:                                   # the baseline must never take the bench down
+            line['cpu_baseline'] = dict(value=None, unit='iterations/s', cores=1, kind='port', sample='failed: %r' % (e,))
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()
