@@ -535,7 +535,10 @@ extern "C" int fg_finalize(fg_ctx* c) {
   if ((rc = dev_upload(c, &d.col2sn, S.col2sn)) || (rc = dev_upload(c, &d.sn_col0, S.sn_col0)) || (rc = dev_upload(c, &d.sn_ncols, S.sn_ncols)) ||
       (rc = dev_upload(c, &d.sn_nrows, S.sn_nrows)) || (rc = dev_upload(c, &d.sn_rowptr, S.sn_rowptr)) || (rc = dev_upload(c, &d.sn_valptr, S.sn_valptr)) ||
       (rc = dev_upload(c, &d.rowidx, S.rowidx)) || (rc = dev_upload(c, &d.upd_ptr, S.upd_ptr)) || (rc = dev_upload(c, &d.upd_d, S.upd_d)) ||
-      (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b))) return rc;
+      (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b)) ||
+      (rc = dev_upload(c, &d.anc_ptr, S.anc_ptr)) || (rc = dev_upload(c, &d.anc_t, S.anc_t)) || (rc = dev_upload(c, &d.anc_a, S.anc_a)) ||
+      (rc = dev_upload(c, &d.anc_b, S.anc_b)) || (rc = dev_upload(c, &d.sched, S.sched)) ||
+      (rc = dev_upload<int>(c, &d.flags2, nullptr, S.n_sn)) || (rc = dev_upload<int>(c, &d.counters, nullptr, 4))) return rc;
   CK(cudaStreamSynchronize(c->stream));
   c->epoch = 0;
   c->finalized = true;
@@ -728,7 +731,7 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
   std::vector<int64_t> v;
   auto put = [&](const std::vector<int>& a) { v.assign(a.begin(), a.end()); };
   switch (which) {
-    case 0: v = {S.n_r, S.n_sn, S.nnz, S.max_nrows, S.max_ncols, (int64_t)S.flops_factor}; break;
+    case 0: v = {S.n_r, S.n_sn, S.nnz, S.max_nrows, S.max_ncols, (int64_t)S.flops_factor, S.n_levels}; break;
     case 1: put(S.sn_col0); break;
     case 2: put(S.sn_ncols); break;
     case 3: put(S.sn_nrows); break;
@@ -743,6 +746,12 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 12: put(S.off[T_VEC3]); break;
     case 13: put(S.off[T_BIAS]); break;
     case 14: put(S.off[T_PLANE]); break;
+    case 15: put(S.sched); break;
+    case 16: put(S.level); break;
+    case 17: put(S.anc_ptr); break;
+    case 18: put(S.anc_t); break;
+    case 19: put(S.anc_a); break;
+    case 20: put(S.anc_b); break;
     default: return FG_ERR_INVALID;
   }
   if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];

@@ -7,19 +7,23 @@
 // carries the right-hand side).  Because the rhs rides as an extra matrix row, the factorisation also
 // performs the forward substitution: after k_chol the rhs row holds y = L^-1 b.
 //
-// k_chol is a persistent left-looking supernodal factorisation: CTA b owns supernodes b, b+G, ...;
-// a supernode pulls the updates of its descendants (host-precomputed list, ascending) as soon as each
-// descendant's epoch flag is published, so on the chain-like elimination trees of VIO/BA graphs the
-// updates from all but the immediate predecessor are applied while waiting.  There is no fp64 kind of
-// tcgen05.mma, so the dense tiles use DFMA on CUDA cores (SURVEY.md section 7, K7 note).
+// k_chol is a persistent left-looking supernodal factorisation.  CTAs take supernodes from a
+// level-sorted schedule (a topological order of the nested-dissection elimination tree, fg_symbolic.cpp)
+// through an atomic counter, so every independent chain of the tree is worked on at once; a supernode
+// pulls the updates of its descendants in list order as soon as their epoch flags are published (flags
+// are polled 256 at a time), i.e. everything except the immediate predecessor's update is applied while
+// waiting.  k_backsolve runs the backward substitution the same way, top-down.
+// There is no fp64 kind of tcgen05.mma, so the dense tiles use DFMA on CUDA cores.
 #include "fg_internal.h"
 
 namespace fg {
 
 #define CH_T 256
-#define CH_RCH 96      // rows per staged chunk of a descendant panel
-#define CH_KMAX 32     // max supernode width (must match kMaxSnCols)
+#define CH_KMAX 32        // max supernode width (must match kMaxSnCols)
 #define CH_DP 33
+#define CH_PS 4096        // doubles staged per chunk of a descendant panel
+#define CH_RMAX 512       // max rows per chunk
+#define CH_ROWCAP 2048    // own row list cached in shared memory up to this length
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -30,117 +34,149 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict__ upd_ptr, const int* __restrict__ upd_d,
-                                               const int* __restrict__ upd_a, const int* __restrict__ upd_b,
-                                               int* flags, int epoch, int n_sn, int* status) {
-  __shared__ double Ps[CH_KMAX * CH_RCH];   // [k][i]  chunk of descendant rows
-  __shared__ double Bs[CH_KMAX * CH_KMAX];  // [k][j]  descendant rows that fall in this supernode's columns
-  __shared__ double Ds[CH_KMAX * CH_DP];    // diagonal block
-  __shared__ int rel[CH_RCH];
-  __shared__ int colj[CH_KMAX];
-  __shared__ int rowg[CH_RCH];
+struct CholSmem {
+  double Ps[CH_PS];                 // [k][i] chunk of descendant rows
+  double Bs[CH_KMAX * CH_KMAX];     // [k][j] descendant rows that fall in this supernode's columns
+  double Ds[CH_KMAX * CH_DP];       // diagonal block
+  int rows_s[CH_ROWCAP];
+  int rel[CH_RMAX];
+  int rowg[CH_RMAX];
+  int colj[CH_KMAX];
+  int slot;
+  int first_not_ready;
+};
+
+__global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict__ sched, const int* __restrict__ upd_ptr,
+                                               const int* __restrict__ upd_d, const int* __restrict__ upd_a,
+                                               const int* __restrict__ upd_b, int* flags, int* counters, int epoch,
+                                               int n_sn, int* status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CholSmem& sm = *reinterpret_cast<CholSmem*>(smem_raw);
   const int tid = threadIdx.x;
 
-  for (int sn = blockIdx.x; sn < n_sn; sn += gridDim.x) {
+  while (true) {
+    if (tid == 0) sm.slot = atomicAdd(&counters[0], 1);
+    __syncthreads();
+    const int slot = sm.slot;
+    __syncthreads();
+    if (slot >= n_sn) break;
+    const int sn = sched[slot];
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     double* Lp = s.L + s.sn_valptr[sn];
-    const int* rows_s = s.rowidx + s.sn_rowptr[sn];
+    const int* rows_g = s.rowidx + s.sn_rowptr[sn];
+    const bool cached = nr <= CH_ROWCAP;
+    if (cached) for (int i = tid; i < nr; i += CH_T) sm.rows_s[i] = rows_g[i];
+    const int* rows_s = cached ? sm.rows_s : rows_g;
+    __syncthreads();
 
-    for (int u = upd_ptr[sn]; u < upd_ptr[sn + 1]; ++u) {
-      const int d = upd_d[u], a = upd_a[u], b = upd_b[u];
-      if (tid == 0) {
-        while (ld_acquire(&flags[d]) != epoch) __nanosleep(40);
-      }
+    int u = upd_ptr[sn];
+    const int u1 = upd_ptr[sn + 1];
+    while (u < u1) {
+      // ---- poll up to 256 pending descendants at once; process the ready prefix in list order
+      const int win = min(CH_T, u1 - u);
+      if (tid == 0) sm.first_not_ready = win;
       __syncthreads();
-      const int K = s.sn_ncols[d], nrd = s.sn_nrows[d];
-      const double* Ld = s.L + s.sn_valptr[d];
-      const int* rows_d = s.rowidx + s.sn_rowptr[d];
-      const int nb = b - a;
-      for (int i = tid; i < nb * K; i += CH_T) {
-        int j = i % nb, k = i / nb;
-        Bs[k * CH_KMAX + j] = __ldcg(&Ld[a + j + (int64_t)k * nrd]);
-      }
-      if (tid < nb) colj[tid] = rows_d[a + tid] - c0;
-      for (int r0 = a; r0 < nrd; r0 += CH_RCH) {
-        const int nrc = min(CH_RCH, nrd - r0);
-        for (int i = tid; i < nrc * K; i += CH_T) {
-          int ii = i % nrc, k = i / nrc;
-          Ps[k * CH_RCH + ii] = __ldcg(&Ld[r0 + ii + (int64_t)k * nrd]);
+      if (tid < win && ld_acquire(&flags[upd_d[u + tid]]) != epoch) atomicMin(&sm.first_not_ready, tid);
+      __syncthreads();
+      const int nready = sm.first_not_ready;
+      __syncthreads();
+      if (nready == 0) { __nanosleep(100); continue; }
+      for (int uu = u; uu < u + nready; ++uu) {
+        const int d = upd_d[uu], a = upd_a[uu], b = upd_b[uu];
+        const int K = s.sn_ncols[d], nrd = s.sn_nrows[d];
+        const double* Ld = s.L + s.sn_valptr[d];
+        const int* rows_d = s.rowidx + s.sn_rowptr[d];
+        const int nb = b - a;
+        for (int i = tid; i < nb * K; i += CH_T) {
+          int j = i % nb, k = i / nb;
+          sm.Bs[k * CH_KMAX + j] = __ldcg(&Ld[a + j + (int64_t)k * nrd]);
         }
-        for (int i = tid; i < nrc; i += CH_T) {
-          int R = rows_d[r0 + i];
-          rowg[i] = R;
-          int r;
-          if (R < c0 + nc) r = R - c0;
-          else {
-            int lo = nc, hi = nr - 1;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (rows_s[mid] < R) lo = mid + 1; else hi = mid; }
-            r = lo;
+        if (tid < nb) sm.colj[tid] = rows_d[a + tid] - c0;
+        int rch = (CH_PS / K) & ~3;
+        if (rch > CH_RMAX) rch = CH_RMAX;
+        for (int r0 = a; r0 < nrd; r0 += rch) {
+          const int nrc = min(rch, nrd - r0);
+          for (int i = tid; i < nrc * K; i += CH_T) {
+            int ii = i % nrc, k = i / nrc;
+            sm.Ps[k * rch + ii] = __ldcg(&Ld[r0 + ii + (int64_t)k * nrd]);
           }
-          rel[i] = r;
-        }
-        __syncthreads();
-        // micro tiles: 4 rows x 4 cols
-        const int ntr = (nrc + 3) >> 2, ntc = (nb + 3) >> 2;
-        for (int t = tid; t < ntr * ntc; t += CH_T) {
-          const int ti = t % ntr, tj = t / ntr;
-          const int i0 = ti << 2, j0 = tj << 2;
-          double acc[4][4];
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-          for (int k = 0; k < K; ++k) {
-            double p[4], q[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) p[x] = (i0 + x < nrc) ? Ps[k * CH_RCH + i0 + x] : 0.0;
-#pragma unroll
-            for (int y = 0; y < 4; ++y) q[y] = (j0 + y < nb) ? Bs[k * CH_KMAX + j0 + y] : 0.0;
+          for (int i = tid; i < nrc; i += CH_T) {
+            int R = rows_d[r0 + i];
+            sm.rowg[i] = R;
+            int r;
+            if (R < c0 + nc) r = R - c0;
+            else {
+              int lo = nc, hi = nr - 1;
+              while (lo < hi) { int mid = (lo + hi) >> 1; if (rows_s[mid] < R) lo = mid + 1; else hi = mid; }
+              r = lo;
+            }
+            sm.rel[i] = r;
+          }
+          __syncthreads();
+          // micro tiles: 4 rows x 4 cols
+          const int ntr = (nrc + 3) >> 2, ntc = (nb + 3) >> 2;
+          for (int t = tid; t < ntr * ntc; t += CH_T) {
+            const int ti = t % ntr, tj = t / ntr;
+            const int i0 = ti << 2, j0 = tj << 2;
+            double acc[4][4];
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
-              for (int y = 0; y < 4; ++y) acc[x][y] += p[x] * q[y];
-          }
+              for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+            for (int k = 0; k < K; ++k) {
+              double p[4], q[4];
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            if (i0 + x >= nrc) continue;
-            const int rr = rel[i0 + x];
-            const int Rg = rowg[i0 + x];
+              for (int x = 0; x < 4; ++x) p[x] = (i0 + x < nrc) ? sm.Ps[k * rch + i0 + x] : 0.0;
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
-              if (j0 + y >= nb) continue;
-              const int cj = colj[j0 + y];
-              if (Rg < c0 + cj) continue;     // strictly upper part of the diagonal block: not stored
-              Lp[rr + (int64_t)cj * nr] -= acc[x][y];
+              for (int y = 0; y < 4; ++y) q[y] = (j0 + y < nb) ? sm.Bs[k * CH_KMAX + j0 + y] : 0.0;
+#pragma unroll
+              for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] += p[x] * q[y];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              if (i0 + x >= nrc) continue;
+              const int rr = sm.rel[i0 + x];
+              const int Rg = sm.rowg[i0 + x];
+#pragma unroll
+              for (int y = 0; y < 4; ++y) {
+                if (j0 + y >= nb) continue;
+                const int cj = sm.colj[j0 + y];
+                if (Rg < c0 + cj) continue;     // strictly upper part of the diagonal block: not stored
+                Lp[rr + (int64_t)cj * nr] -= acc[x][y];
+              }
             }
           }
+          __syncthreads();
         }
-        __syncthreads();
       }
+      u += nready;
     }
 
     // ---- dense Cholesky of the diagonal block (warp 0, shared memory)
     for (int i = tid; i < nc * nc; i += CH_T) {
       int r = i % nc, c = i / nc;
-      Ds[r * CH_DP + c] = (r >= c) ? Lp[r + (int64_t)c * nr] : 0.0;
+      sm.Ds[r * CH_DP + c] = (r >= c) ? Lp[r + (int64_t)c * nr] : 0.0;
     }
     __syncthreads();
     if (tid < 32) {
       const int lane = tid;
       for (int c = 0; c < nc; ++c) {
-        double dcc = Ds[c * CH_DP + c];
+        double dcc = sm.Ds[c * CH_DP + c];
         if (!(dcc > 0.0)) {          // not positive definite (or NaN): flag and keep going with a safe pivot
           if (lane == 0) atomicExch(status, 1);
           dcc = 1.0;
         }
-        double l = sqrt(dcc), inv = 1.0 / l;
+        double inv = rsqrt(dcc);
+        double l = dcc * inv;
         __syncwarp();
-        if (lane == c) Ds[c * CH_DP + c] = l;
-        if (lane > c && lane < nc) Ds[lane * CH_DP + c] *= inv;
+        if (lane == c) sm.Ds[c * CH_DP + c] = l;
+        if (lane > c && lane < nc) sm.Ds[lane * CH_DP + c] *= inv;
         __syncwarp();
         if (lane > c && lane < nc) {
-          double li = Ds[lane * CH_DP + c];
-          for (int j = c + 1; j <= lane; ++j) Ds[lane * CH_DP + j] -= li * Ds[j * CH_DP + c];
+          double li = sm.Ds[lane * CH_DP + c];
+          for (int j = c + 1; j <= lane; ++j) sm.Ds[lane * CH_DP + j] -= li * sm.Ds[j * CH_DP + c];
         }
         __syncwarp();
       }
@@ -148,7 +184,7 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
     __syncthreads();
     for (int i = tid; i < nc * nc; i += CH_T) {
       int r = i % nc, c = i / nc;
-      if (r >= c) Lp[r + (int64_t)c * nr] = Ds[r * CH_DP + c];
+      if (r >= c) Lp[r + (int64_t)c * nr] = sm.Ds[r * CH_DP + c];
     }
     // ---- panel solve: X L_dd^T = A  (one row per thread, registers)
     for (int r = nc + tid; r < nr; r += CH_T) {
@@ -158,8 +194,8 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
         if (c < nc) {
           double v = Lp[r + (int64_t)c * nr];
 #pragma unroll
-          for (int k = 0; k < c; ++k) v -= x[k] * Ds[c * CH_DP + k];
-          x[c] = v / Ds[c * CH_DP + c];
+          for (int k = 0; k < c; ++k) v -= x[k] * sm.Ds[c * CH_DP + k];
+          x[c] = v / sm.Ds[c * CH_DP + c];
           Lp[r + (int64_t)c * nr] = x[c];
         }
       }
@@ -170,37 +206,88 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
   }
 }
 
-// Backward substitution x = L^-T y (y = rhs rows), single CTA walking the supernodes in reverse.
-__global__ void __launch_bounds__(256) k_backsolve(SysView s, int n_sn, double* x) {
-  __shared__ double tsum[CH_KMAX];
+// Backward substitution x = L^-T y (y = rhs rows).  Supernodes are taken from the schedule in reverse;
+// x_s needs the solutions of the supernodes that own its below-diagonal rows (ancestor list).
+__global__ void __launch_bounds__(CH_T) k_backsolve(SysView s, const int* __restrict__ sched, const int* __restrict__ anc_ptr,
+                                                    const int* __restrict__ anc_t, const int* __restrict__ anc_b,
+                                                    int* flags2, int* counters, int epoch, int n_sn, double* x) {
+  __shared__ double Ds[CH_KMAX * CH_DP];
+  __shared__ double part[8][CH_KMAX];
   __shared__ double xs[CH_KMAX];
+  __shared__ int s_slot, s_pending;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int sn = n_sn - 1; sn >= 0; --sn) {
+  while (true) {
+    if (tid == 0) s_slot = atomicAdd(&counters[1], 1);
+    __syncthreads();
+    const int slot = s_slot;
+    __syncthreads();
+    if (slot >= n_sn) break;
+    const int sn = sched[n_sn - 1 - slot];
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     const double* Lp = s.L + s.sn_valptr[sn];
     const int* rows = s.rowidx + s.sn_rowptr[sn];
-    // t_c = y_c - sum_{r in below rows} L[r,c] x[rows[r]]
-    for (int c = w; c < nc; c += 8) {
-      double acc = 0.0;
-      const double* col = Lp + (int64_t)c * nr;
-      for (int r = nc + lane; r < nr - 1; r += 32) acc += col[r] * x[rows[r]];
+    for (int i = tid; i < nc * nc; i += CH_T) {
+      int r = i % nc, c = i / nc;
+      Ds[r * CH_DP + c] = Lp[r + (int64_t)c * nr];
+    }
+    double acc[CH_KMAX / 8];
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-      if (lane == 0) tsum[c] = col[nr - 1] - acc;
+    for (int q = 0; q < CH_KMAX / 8; ++q) acc[q] = 0.0;
+    // phase 1: all ancestors except the nearest one; phase 2: the nearest (it finishes last)
+    const int a0 = anc_ptr[sn], a1 = anc_ptr[sn + 1];
+    for (int phase = 0; phase < 2; ++phase) {
+      int lo_e, hi_e, r_lo, r_hi;
+      if (phase == 0) { lo_e = a0 + 1; hi_e = a1; r_lo = (a1 > a0) ? anc_b[a0] : nr - 1; r_hi = nr - 1; }
+      else { lo_e = a0; hi_e = min(a0 + 1, a1); r_lo = nc; r_hi = (a1 > a0) ? anc_b[a0] : nc; }
+      // wait for every ancestor of this phase (polled in parallel)
+      while (true) {
+        if (tid == 0) s_pending = 0;
+        __syncthreads();
+        int pend = 0;
+        for (int e = lo_e + tid; e < hi_e; e += CH_T)
+          if (ld_acquire(&flags2[anc_t[e]]) != epoch) pend = 1;
+        if (pend) atomicOr(&s_pending, 1);
+        __syncthreads();
+        const int p = s_pending;
+        __syncthreads();
+        if (!p) break;
+        __nanosleep(100);
+      }
+      // warp w owns columns w, w+8, ... ; lanes stride over the rows of this phase
+#pragma unroll
+      for (int q = 0; q < CH_KMAX / 8; ++q) {
+        const int c = w + 8 * q;
+        if (c < nc) {
+          const double* col = Lp + (int64_t)c * nr;
+          double a = 0.0;
+          for (int r = r_lo + lane; r < r_hi; r += 32) a += col[r] * __ldcg(&x[rows[r]]);
+          acc[q] += a;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CH_KMAX / 8; ++q) {
+      double a = acc[q];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) a += __shfl_down_sync(0xffffffffu, a, d);
+      const int c = w + 8 * q;
+      if (lane == 0 && c < nc) part[w][q] = Lp[(nr - 1) + (int64_t)c * nr] - a;
     }
     __syncthreads();
     if (tid < 32) {
       // L_dd^T x = t : backward, lane c owns t_c
-      double t = (lane < nc) ? tsum[lane] : 0.0;
+      double t = (lane < nc) ? part[lane & 7][lane >> 3] : 0.0;
       for (int c = nc - 1; c >= 0; --c) {
-        double xc = __shfl_sync(0xffffffffu, t, c) / Lp[c + (int64_t)c * nr];
+        double xc = __shfl_sync(0xffffffffu, t, c) / Ds[c * CH_DP + c];
         if (lane == c) xs[c] = xc;
-        if (lane < c) t -= Lp[c + (int64_t)lane * nr] * xc;
+        if (lane < c) t -= Ds[c * CH_DP + lane] * xc;
       }
     }
     __syncthreads();
     if (tid < nc) x[c0 + tid] = xs[tid];
+    __threadfence();
     __syncthreads();
+    if (tid == 0) st_release(&flags2[sn], epoch);
   }
 }
 
@@ -216,20 +303,28 @@ void launch_factor(fg_ctx* c) {
   DevGraph& d = c->d;
   SysView s = chol_view(c);
   static int max_blocks_per_sm = 0;
+  const size_t smem = sizeof(CholSmem);
   if (!max_blocks_per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k_chol, CH_T, 0);
+    cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k_chol, CH_T, smem);
     if (max_blocks_per_sm < 1) max_blocks_per_sm = 1;
   }
-  int grid = c->num_sms * max_blocks_per_sm;      // all CTAs must be co-resident (flag waits)
+  int grid = c->num_sms * max_blocks_per_sm;
   if (grid > c->sym.n_sn) grid = c->sym.n_sn;
   c->epoch += 1;
   cudaMemsetAsync(d.status, 0, sizeof(int), c->stream);
-  k_chol<<<grid, CH_T, 0, c->stream>>>(s, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.flags, c->epoch, c->sym.n_sn, d.status);
+  cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, c->stream);
+  k_chol<<<grid, CH_T, smem, c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.flags, d.counters, c->epoch,
+                                          c->sym.n_sn, d.status);
 }
 
 void launch_backsolve(fg_ctx* c) {
+  DevGraph& d = c->d;
   SysView s = chol_view(c);
-  k_backsolve<<<1, 256, 0, c->stream>>>(s, c->sym.n_sn, c->d.delta);
+  int grid = c->num_sms * 2;
+  if (grid > c->sym.n_sn) grid = c->sym.n_sn;
+  k_backsolve<<<grid, CH_T, 0, c->stream>>>(s, d.sched, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch,
+                                            c->sym.n_sn, d.delta);
 }
 
 }  // namespace fg

@@ -50,6 +50,9 @@ struct Symbolic {
   std::vector<int> rowidx;           // concatenated row lists (global scalar rows; last = n_r = rhs row)
   std::vector<int> col2sn;           // scalar column -> supernode
   std::vector<int> upd_ptr, upd_d, upd_a, upd_b;   // per target supernode: (descendant, row range [a,b) in d)
+  std::vector<int> anc_ptr, anc_t, anc_a, anc_b;   // per supernode: (ancestor t, row range [a,b) of this supernode inside t's columns)
+  std::vector<int> level, sched;                   // dependency level per supernode; supernodes sorted by level
+  int n_levels = 0;
   int max_nrows = 0, max_ncols = 0;
   double flops_factor = 0;
 };
@@ -151,6 +154,10 @@ struct DevGraph {
   int *col2sn = nullptr, *sn_col0 = nullptr, *sn_ncols = nullptr, *sn_nrows = nullptr, *sn_rowptr = nullptr, *rowidx = nullptr;
   int64_t* sn_valptr = nullptr;
   int *upd_ptr = nullptr, *upd_d = nullptr, *upd_a = nullptr, *upd_b = nullptr;
+  int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
+  int *sched = nullptr;
+  int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
+  int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve)
 };
 
 }  // namespace fg

@@ -6,12 +6,16 @@
 // they are eliminated first by the Schur complement (north_star); their co-visibility only
 // contributes pose-pose couplings here.
 //
-// Ordering: frames in key-index order, [X_i V_i B_i] per frame, plane landmarks last.  For the
-// sequential VIO/BA graphs the reference produces this is a banded ordering whose fill equals the
-// covisibility band; loop closures and planes add a bordered block.  Supernodes are maximal runs of
-// consecutive variables with nested structure, capped at kMaxSnCols scalar columns.
+// Ordering: nested dissection over the frame sequence.  Frames ([X_i V_i B_i] by key index) of a
+// sequential VIO/BA graph form a band; a segment [lo,hi) is split at its middle, the separator is the
+// set of variables of the right half adjacent to the left half (for a covisibility band of w frames:
+// the w poses after the cut plus one velocity/bias pair), and the two halves recurse.  This turns the
+// 5000-step dependency chain of a banded Cholesky into ~log2 levels of short independent chains, which
+// is what lets the persistent kernel in fg_chol.cu use the whole GPU.  Plane landmarks are ordered last.
+// Supernodes are maximal runs of consecutive variables with nested structure, capped at kMaxSnCols.
 #include <algorithm>
 #include <cstdio>
+#include <functional>
 #include <numeric>
 #include "fg_internal.h"
 
@@ -23,7 +27,7 @@ int build_symbolic(fg_ctx* c) {
   HostGraph& h = c->h;
   Symbolic& S = c->sym;
   S = Symbolic();
-  // ---- reduced variables and ordering
+  // ---- reduced variables in frame-major base order
   struct RV { int type, idx; uint64_t kidx; int cls; };
   std::vector<RV> rv;
   const uint64_t mask = (1ull << 56) - 1;
@@ -37,49 +41,111 @@ int build_symbolic(fg_ctx* c) {
   });
   const int nv = (int)rv.size();
   if (nv == 0) return FG_ERR_STATE;
-  std::vector<int> pos[T_COUNT];
-  for (int t = 0; t < T_COUNT; ++t) pos[t].assign(h.keys[t].size(), -1);
-  std::vector<int> voff(nv + 1, 0), vdim(nv);
-  for (int p = 0; p < nv; ++p) {
-    pos[rv[p].type][rv[p].idx] = p;
-    vdim[p] = kDim[rv[p].type];
-    voff[p + 1] = voff[p] + vdim[p];
+  std::vector<int> base[T_COUNT];           // (type, idx) -> base index
+  for (int t = 0; t < T_COUNT; ++t) base[t].assign(h.keys[t].size(), -1);
+  std::vector<int> bdim(nv);
+  for (int p = 0; p < nv; ++p) { base[rv[p].type][rv[p].idx] = p; bdim[p] = kDim[rv[p].type]; }
+
+  // ---- symmetric adjacency on base indices
+  std::vector<std::vector<int>> adj(nv);
+  auto edge = [&](int a, int b) { if (a != b) { adj[a].push_back(b); adj[b].push_back(a); } };
+  for (size_t f = 0; f < h.bt_i.size(); ++f) edge(base[T_POSE][h.bt_i[f]], base[T_POSE][h.bt_j[f]]);
+  for (size_t f = 0; f < h.imu_rec.size(); ++f) {
+    const int* v = &h.imu_var[6 * f];
+    int p[6] = {base[T_POSE][v[0]], base[T_VEC3][v[1]], base[T_POSE][v[2]], base[T_VEC3][v[3]], base[T_BIAS][v[4]], base[T_BIAS][v[5]]};
+    for (int a = 0; a < 6; ++a) for (int b = a + 1; b < 6; ++b) edge(p[a], p[b]);
   }
+  for (size_t f = 0; f < h.pl_pose.size(); ++f) edge(base[T_POSE][h.pl_pose[f]], base[T_PLANE][h.pl_plane[f]]);
+  {
+    // landmark co-visibility: every pair of poses observing one landmark is coupled through the Schur complement
+    const int64_t L = h.count(T_POINT), M = (int64_t)h.pj_pose.size(), P = h.count(T_POSE);
+    if (L && M) {
+      std::vector<int64_t> lp(L + 1, 0), pp(P + 1, 0);
+      for (int64_t o = 0; o < M; ++o) { lp[h.pj_point[o] + 1]++; pp[h.pj_pose[o] + 1]++; }
+      for (int64_t l = 0; l < L; ++l) lp[l + 1] += lp[l];
+      for (int64_t p = 0; p < P; ++p) pp[p + 1] += pp[p];
+      std::vector<int> lm_pose(M), pose_lm(M);
+      {
+        std::vector<int64_t> c1(lp.begin(), lp.end() - 1), c2(pp.begin(), pp.end() - 1);
+        for (int64_t o = 0; o < M; ++o) { lm_pose[c1[h.pj_point[o]]++] = h.pj_pose[o]; pose_lm[c2[h.pj_pose[o]]++] = h.pj_point[o]; }
+      }
+      std::vector<int> stamp(P, -1);
+      for (int p = 0; p < (int)P; ++p) {
+        stamp[p] = p;
+        int bp = base[T_POSE][p];
+        for (int64_t k = pp[p]; k < pp[p + 1]; ++k) {
+          int l = pose_lm[k];
+          for (int64_t k2 = lp[l]; k2 < lp[l + 1]; ++k2) {
+            int q = lm_pose[k2];
+            if (stamp[q] != p) { stamp[q] = p; adj[bp].push_back(base[T_POSE][q]); }
+          }
+        }
+      }
+    }
+  }
+  for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+
+  // ---- nested dissection over frames -> elimination order
+  std::vector<int> elim; elim.reserve(nv);
+  {
+    // frames: maximal runs of class-0 variables with the same key index (base order is frame-major)
+    std::vector<std::vector<int>> frames;
+    int n0 = 0;
+    while (n0 < nv && rv[n0].cls == 0) ++n0;
+    for (int p = 0; p < n0;) {
+      int q = p;
+      std::vector<int> f;
+      while (q < n0 && rv[q].kidx == rv[p].kidx) f.push_back(q++);
+      frames.push_back(f);
+      p = q;
+    }
+    std::vector<int> region(nv, -1);
+    int next_region = 0;
+    auto dims = [&](const std::vector<std::vector<int>>& F) { int d = 0; for (auto& f : F) for (int v : f) d += bdim[v]; return d; };
+    std::function<void(std::vector<std::vector<int>>&)> nd = [&](std::vector<std::vector<int>>& F) {
+      auto emit = [&]() { for (auto& f : F) for (int v : f) elim.push_back(v); };
+      if (F.size() < 8) { emit(); return; }
+      size_t mid = F.size() / 2;
+      int ra = next_region++, rb = next_region++;
+      for (size_t i = 0; i < F.size(); ++i) for (int v : F[i]) region[v] = i < mid ? ra : rb;
+      std::vector<char> inS;
+      std::vector<std::vector<int>> A(F.begin(), F.begin() + mid), B, Sep;
+      int dS = 0, dB = 0;
+      for (size_t i = mid; i < F.size(); ++i) {
+        std::vector<int> keep, sep;
+        for (int v : F[i]) {
+          bool touch = false;
+          for (int u : adj[v]) if (region[u] == ra) { touch = true; break; }
+          if (touch) { sep.push_back(v); dS += bdim[v]; } else { keep.push_back(v); dB += bdim[v]; }
+        }
+        if (!keep.empty()) B.push_back(keep);
+        if (!sep.empty()) Sep.push_back(sep);
+      }
+      int dA = dims(A);
+      if (dS == 0 || 4 * dS > std::min(dA, dB) || B.size() < 4) { emit(); return; }
+      nd(A);
+      nd(B);
+      for (auto& f : Sep) for (int v : f) elim.push_back(v);
+    };
+    if (!frames.empty()) nd(frames);
+    for (int p = n0; p < nv; ++p) elim.push_back(p);     // plane landmarks last
+  }
+  // ---- positions / offsets in elimination order
+  std::vector<int> posb(nv);                 // base index -> position
+  for (int p = 0; p < nv; ++p) posb[elim[p]] = p;
+  std::vector<int> voff(nv + 1, 0), vdim(nv);
+  for (int p = 0; p < nv; ++p) { vdim[p] = bdim[elim[p]]; voff[p + 1] = voff[p] + vdim[p]; }
   S.n_r = voff[nv];
   for (int t : {T_POSE, T_VEC3, T_BIAS, T_PLANE}) {
     S.off[t].resize(h.keys[t].size());
-    for (size_t i = 0; i < h.keys[t].size(); ++i) S.off[t][i] = voff[pos[t][i]];
+    for (size_t i = 0; i < h.keys[t].size(); ++i) S.off[t][i] = voff[posb[base[t][i]]];
   }
-  // ---- adjacency (higher-ordered neighbours)
   std::vector<std::vector<int>> hadj(nv);
-  auto edge = [&](int a, int b) {
-    if (a == b) return;
-    if (a > b) std::swap(a, b);
-    hadj[a].push_back(b);
-  };
-  for (size_t f = 0; f < h.bt_i.size(); ++f) edge(pos[T_POSE][h.bt_i[f]], pos[T_POSE][h.bt_j[f]]);
-  for (size_t f = 0; f < h.imu_rec.size(); ++f) {
-    const int* v = &h.imu_var[6 * f];
-    int p[6] = {pos[T_POSE][v[0]], pos[T_VEC3][v[1]], pos[T_POSE][v[2]], pos[T_VEC3][v[3]], pos[T_BIAS][v[4]], pos[T_BIAS][v[5]]};
-    for (int a = 0; a < 6; ++a) for (int b = a + 1; b < 6; ++b) edge(p[a], p[b]);
-  }
-  for (size_t f = 0; f < h.pl_pose.size(); ++f) edge(pos[T_POSE][h.pl_pose[f]], pos[T_PLANE][h.pl_plane[f]]);
-  // landmarks: clique over observing poses == star from the lowest-ordered pose (same filled graph)
-  {
-    const int64_t L = h.count(T_POINT);
-    std::vector<int> lowest(L, INT32_MAX);
-    for (size_t o = 0; o < h.pj_pose.size(); ++o) {
-      int p = pos[T_POSE][h.pj_pose[o]];
-      int& lo = lowest[h.pj_point[o]];
-      if (p < lo) lo = p;
-    }
-    for (size_t o = 0; o < h.pj_pose.size(); ++o) {
-      int p = pos[T_POSE][h.pj_pose[o]];
-      int lo = lowest[h.pj_point[o]];
-      if (p != lo) hadj[lo].push_back(p);
-    }
-  }
-  for (auto& a : hadj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+  for (int b = 0; b < nv; ++b)
+    for (int u : adj[b]) if (posb[u] > posb[b]) hadj[posb[b]].push_back(posb[u]);
+  adj.clear(); adj.shrink_to_fit();
+  for (auto& a : hadj) std::sort(a.begin(), a.end());
+
   // ---- symbolic elimination (variable level)
   std::vector<std::vector<int>> st(nv);
   std::vector<int> parent(nv, -1);
@@ -91,7 +157,6 @@ int build_symbolic(fg_ctx* c) {
     for (int ch : children[v]) {
       tmp.clear();
       const std::vector<int>& cs = st[ch];
-      // merge s and cs \ {v}
       size_t i = 0, j = 0;
       while (i < s.size() || j < cs.size()) {
         int a = i < s.size() ? s[i] : INT32_MAX;
@@ -124,7 +189,6 @@ int build_symbolic(fg_ctx* c) {
   S.sn_col0.resize(S.n_sn); S.sn_ncols.resize(S.n_sn); S.sn_nrows.resize(S.n_sn);
   S.sn_rowptr.assign(S.n_sn + 1, 0); S.sn_valptr.assign(S.n_sn + 1, 0);
   S.col2sn.resize(S.n_r);
-  std::vector<int> var2sn(nv);
   for (int s = 0; s < S.n_sn; ++s) {
     int c0 = voff[sn_first[s]], nc = voff[sn_last[s] + 1] - c0;
     S.sn_col0[s] = c0; S.sn_ncols[s] = nc;
@@ -134,7 +198,6 @@ int build_symbolic(fg_ctx* c) {
     S.sn_rowptr[s + 1] = S.sn_rowptr[s] + S.sn_nrows[s];
     S.sn_valptr[s + 1] = S.sn_valptr[s] + (int64_t)S.sn_nrows[s] * nc;
     for (int k = 0; k < nc; ++k) S.col2sn[c0 + k] = s;
-    for (int v = sn_first[s]; v <= sn_last[s]; ++v) var2sn[v] = s;
     S.max_nrows = std::max(S.max_nrows, S.sn_nrows[s]);
     S.max_ncols = std::max(S.max_ncols, nc);
     double m = S.sn_nrows[s] - 1, k = nc;
@@ -149,8 +212,9 @@ int build_symbolic(fg_ctx* c) {
     for (int u : st[sn_last[s]]) for (int j = 0; j < vdim[u]; ++j) r[k++] = voff[u] + j;
     r[k++] = S.n_r;
   }
-  // ---- update lists: for descendant d, group its below-rows by target supernode
+  // ---- update lists (target <- descendants) and ancestor lists (descendant -> targets)
   std::vector<std::vector<int>> ul(S.n_sn);   // triples (d, a, b)
+  S.anc_ptr.assign(S.n_sn + 1, 0);
   for (int d = 0; d < S.n_sn; ++d) {
     const int* r = &S.rowidx[S.sn_rowptr[d]];
     int nr = S.sn_nrows[d] - 1;   // exclude rhs row
@@ -160,8 +224,10 @@ int build_symbolic(fg_ctx* c) {
       int b = a + 1;
       while (b < nr && S.col2sn[r[b]] == t) ++b;
       ul[t].push_back(d); ul[t].push_back(a); ul[t].push_back(b);
+      S.anc_t.push_back(t); S.anc_a.push_back(a); S.anc_b.push_back(b);
       a = b;
     }
+    S.anc_ptr[d + 1] = (int)S.anc_t.size();
   }
   S.upd_ptr.assign(S.n_sn + 1, 0);
   for (int s = 0; s < S.n_sn; ++s) S.upd_ptr[s + 1] = S.upd_ptr[s] + (int)ul[s].size() / 3;
@@ -172,6 +238,15 @@ int build_symbolic(fg_ctx* c) {
       S.upd_a[S.upd_ptr[s] + k] = ul[s][3 * k + 1];
       S.upd_b[S.upd_ptr[s] + k] = ul[s][3 * k + 2];
     }
+  // ---- schedule: supernodes by dependency level (longest path), a topological order that interleaves
+  //      the independent chains so that the persistent kernel works on all of them at once
+  S.level.assign(S.n_sn, 0);
+  for (int s = 0; s < S.n_sn; ++s)
+    for (int u = S.upd_ptr[s]; u < S.upd_ptr[s + 1]; ++u) S.level[s] = std::max(S.level[s], S.level[S.upd_d[u]] + 1);
+  S.sched.resize(S.n_sn);
+  std::iota(S.sched.begin(), S.sched.end(), 0);
+  std::stable_sort(S.sched.begin(), S.sched.end(), [&](int a, int b) { return S.level[a] < S.level[b]; });
+  S.n_levels = S.n_sn ? *std::max_element(S.level.begin(), S.level.end()) + 1 : 0;
   return FG_OK;
 }
 

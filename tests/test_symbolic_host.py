@@ -107,6 +107,26 @@ def test_symbolic_and_left_looking(fglib, name, scale):
     Sp = np.zeros_like(S); Sp[np.ix_(perm, perm)] = S
     bp = np.zeros_like(b); bp[perm] = b
     x = emulate(sym, Sp, bp)
+    # schedule = topological order by level; ancestor lists = transpose of the update lists
+    sched, level = ctx.symbolic(15), ctx.symbolic(16)
+    anc_ptr, anc_t, anc_a, anc_b = (ctx.symbolic(w) for w in (17, 18, 19, 20))
+    n_sn = int(sym[0][1])
+    assert sorted(sched.tolist()) == list(range(n_sn)) and np.all(np.diff(level[sched]) >= 0)
+    uptr, ud, ua, ub = sym[7:11]
+    pairs_u = set()
+    for t in range(n_sn):
+        for u in range(uptr[t], uptr[t + 1]):
+            assert level[ud[u]] < level[t]
+            pairs_u.add((int(ud[u]), t, int(ua[u]), int(ub[u])))
+    pairs_a = set()
+    for d in range(n_sn):
+        ents = [(int(anc_t[e]), int(anc_a[e]), int(anc_b[e])) for e in range(anc_ptr[d], anc_ptr[d + 1])]
+        assert [e[1] for e in ents] == sorted(e[1] for e in ents)
+        if ents:
+            assert ents[0][1] == sym[2][d] and ents[-1][2] == sym[3][d] - 1
+        for (t, a, b) in ents:
+            pairs_a.add((d, t, a, b))
+    assert pairs_u == pairs_a
     ref = np.linalg.solve(Sp, bp)
     assert np.allclose(x, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
     ctx.close()
