@@ -18,13 +18,12 @@
 
 namespace fg {
 
-#define CH_T 512
+#define CH_T 256
 #define CH_KMAX 32        // max supernode width (must match kMaxSnCols)
 #define CH_DP 33
 #define CH_PS 4096        // doubles staged per chunk of a descendant panel
 #define CH_RMAX 512       // max rows per chunk
 #define CH_ROWCAP 2048    // own row list cached in shared memory up to this length
-#define CH_PANEL 20480    // target panel kept in shared memory when nrows*ncols fits (160 KB)
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -36,7 +35,6 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 
 struct CholSmem {
-  double P[CH_PANEL];               // target panel (column-major, ld = nrows) while it is being built
   double Ps[CH_PS];                 // [k][i] chunk of descendant rows
   double Bs[CH_KMAX * CH_KMAX];     // [k][j] descendant rows that fall in this supernode's columns
   double Ds[CH_KMAX * CH_DP];       // diagonal block
@@ -54,8 +52,7 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
                                                int n_sn, int* status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CholSmem& sm = *reinterpret_cast<CholSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NW = CH_T / 32;
+  const int tid = threadIdx.x;
 
   while (true) {
     if (tid == 0) sm.slot = atomicAdd(&counters[0], 1);
@@ -68,17 +65,14 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
     double* Lp = s.L + s.sn_valptr[sn];
     const int* rows_g = s.rowidx + s.sn_rowptr[sn];
     const bool cached = nr <= CH_ROWCAP;
-    const bool in_smem = nr * nc <= CH_PANEL;
-    double* T = in_smem ? sm.P : Lp;         // generic pointer: shared or global
     if (cached) for (int i = tid; i < nr; i += CH_T) sm.rows_s[i] = rows_g[i];
-    if (in_smem) for (int i = tid; i < nr * nc; i += CH_T) sm.P[i] = Lp[i];
     const int* rows_s = cached ? sm.rows_s : rows_g;
     __syncthreads();
 
     int u = upd_ptr[sn];
     const int u1 = upd_ptr[sn + 1];
     while (u < u1) {
-      // ---- poll pending descendants (CH_T at a time); process the ready prefix in list order
+      // ---- poll up to 256 pending descendants at once; process the ready prefix in list order
       const int win = min(CH_T, u1 - u);
       if (tid == 0) sm.first_not_ready = win;
       __syncthreads();
@@ -86,22 +80,26 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
       __syncthreads();
       const int nready = sm.first_not_ready;
       __syncthreads();
-      if (nready == 0) { __nanosleep(64); continue; }
+      if (nready == 0) { __nanosleep(100); continue; }
       for (int uu = u; uu < u + nready; ++uu) {
         const int d = upd_d[uu], a = upd_a[uu], b = upd_b[uu];
         const int K = s.sn_ncols[d], nrd = s.sn_nrows[d];
         const double* Ld = s.L + s.sn_valptr[d];
         const int* rows_d = s.rowidx + s.sn_rowptr[d];
         const int nb = b - a;
-        for (int k = warp; k < K; k += NW)
-          for (int j = lane; j < nb; j += 32) sm.Bs[k * CH_KMAX + j] = __ldcg(&Ld[a + j + (int64_t)k * nrd]);
+        for (int i = tid; i < nb * K; i += CH_T) {
+          int j = i % nb, k = i / nb;
+          sm.Bs[k * CH_KMAX + j] = __ldcg(&Ld[a + j + (int64_t)k * nrd]);
+        }
         if (tid < nb) sm.colj[tid] = rows_d[a + tid] - c0;
         int rch = (CH_PS / K) & ~3;
         if (rch > CH_RMAX) rch = CH_RMAX;
         for (int r0 = a; r0 < nrd; r0 += rch) {
           const int nrc = min(rch, nrd - r0);
-          for (int k = warp; k < K; k += NW)
-            for (int ii = lane; ii < nrc; ii += 32) sm.Ps[k * rch + ii] = __ldcg(&Ld[r0 + ii + (int64_t)k * nrd]);
+          for (int i = tid; i < nrc * K; i += CH_T) {
+            int ii = i % nrc, k = i / nrc;
+            sm.Ps[k * rch + ii] = __ldcg(&Ld[r0 + ii + (int64_t)k * nrd]);
+          }
           for (int i = tid; i < nrc; i += CH_T) {
             int R = rows_d[r0 + i];
             sm.rowg[i] = R;
@@ -115,40 +113,38 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
             sm.rel[i] = r;
           }
           __syncthreads();
-          // micro tiles: 4 rows x 4 cols, tile rows fastest across threads
+          // micro tiles: 4 rows x 4 cols
           const int ntr = (nrc + 3) >> 2, ntc = (nb + 3) >> 2;
-          for (int tj = 0; tj < ntc; ++tj) {
-            const int j0 = tj << 2;
-            for (int ti = tid; ti < ntr; ti += CH_T) {
-              const int i0 = ti << 2;
-              double acc[4][4];
+          for (int t = tid; t < ntr * ntc; t += CH_T) {
+            const int ti = t % ntr, tj = t / ntr;
+            const int i0 = ti << 2, j0 = tj << 2;
+            double acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+              for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+            for (int k = 0; k < K; ++k) {
+              double p[4], q[4];
+#pragma unroll
+              for (int x = 0; x < 4; ++x) p[x] = (i0 + x < nrc) ? sm.Ps[k * rch + i0 + x] : 0.0;
+#pragma unroll
+              for (int y = 0; y < 4; ++y) q[y] = (j0 + y < nb) ? sm.Bs[k * CH_KMAX + j0 + y] : 0.0;
 #pragma unroll
               for (int x = 0; x < 4; ++x)
 #pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-              for (int k = 0; k < K; ++k) {
-                double p[4], q[4];
+                for (int y = 0; y < 4; ++y) acc[x][y] += p[x] * q[y];
+            }
 #pragma unroll
-                for (int x = 0; x < 4; ++x) p[x] = (i0 + x < nrc) ? sm.Ps[k * rch + i0 + x] : 0.0;
+            for (int x = 0; x < 4; ++x) {
+              if (i0 + x >= nrc) continue;
+              const int rr = sm.rel[i0 + x];
+              const int Rg = sm.rowg[i0 + x];
 #pragma unroll
-                for (int y = 0; y < 4; ++y) q[y] = (j0 + y < nb) ? sm.Bs[k * CH_KMAX + j0 + y] : 0.0;
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                  for (int y = 0; y < 4; ++y) acc[x][y] += p[x] * q[y];
-              }
-#pragma unroll
-              for (int x = 0; x < 4; ++x) {
-                if (i0 + x >= nrc) continue;
-                const int rr = sm.rel[i0 + x];
-                const int Rg = sm.rowg[i0 + x];
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                  if (j0 + y >= nb) continue;
-                  const int cj = sm.colj[j0 + y];
-                  if (Rg < c0 + cj) continue;     // strictly upper part of the diagonal block: not stored
-                  T[rr + cj * nr] -= acc[x][y];
-                }
+              for (int y = 0; y < 4; ++y) {
+                if (j0 + y >= nb) continue;
+                const int cj = sm.colj[j0 + y];
+                if (Rg < c0 + cj) continue;     // strictly upper part of the diagonal block: not stored
+                Lp[rr + (int64_t)cj * nr] -= acc[x][y];
               }
             }
           }
@@ -161,10 +157,11 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
     // ---- dense Cholesky of the diagonal block (warp 0, shared memory)
     for (int i = tid; i < nc * nc; i += CH_T) {
       int r = i % nc, c = i / nc;
-      sm.Ds[r * CH_DP + c] = (r >= c) ? T[r + c * nr] : 0.0;
+      sm.Ds[r * CH_DP + c] = (r >= c) ? Lp[r + (int64_t)c * nr] : 0.0;
     }
     __syncthreads();
     if (tid < 32) {
+      const int lane = tid;
       for (int c = 0; c < nc; ++c) {
         double dcc = sm.Ds[c * CH_DP + c];
         if (!(dcc > 0.0)) {          // not positive definite (or NaN): flag and keep going with a safe pivot
@@ -185,17 +182,17 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
       }
     }
     __syncthreads();
-    // diagonal block straight to global; panel rows: X L_dd^T = A (one row per thread, registers)
     for (int i = tid; i < nc * nc; i += CH_T) {
       int r = i % nc, c = i / nc;
       if (r >= c) Lp[r + (int64_t)c * nr] = sm.Ds[r * CH_DP + c];
     }
+    // ---- panel solve: X L_dd^T = A  (one row per thread, registers)
     for (int r = nc + tid; r < nr; r += CH_T) {
       double x[CH_KMAX];
 #pragma unroll
       for (int c = 0; c < CH_KMAX; ++c) {
         if (c < nc) {
-          double v = T[r + c * nr];
+          double v = Lp[r + (int64_t)c * nr];
 #pragma unroll
           for (int k = 0; k < c; ++k) v -= x[k] * sm.Ds[c * CH_DP + k];
           x[c] = v / sm.Ds[c * CH_DP + c];
@@ -211,8 +208,7 @@ __global__ void __launch_bounds__(CH_T) k_chol(SysView s, const int* __restrict_
 
 // Backward substitution x = L^-T y (y = rhs rows).  Supernodes are taken from the schedule in reverse;
 // x_s needs the solutions of the supernodes that own its below-diagonal rows (ancestor list).
-#define BS_T 256
-__global__ void __launch_bounds__(BS_T) k_backsolve(SysView s, const int* __restrict__ sched, const int* __restrict__ anc_ptr,
+__global__ void __launch_bounds__(CH_T) k_backsolve(SysView s, const int* __restrict__ sched, const int* __restrict__ anc_ptr,
                                                     const int* __restrict__ anc_t, const int* __restrict__ anc_b,
                                                     int* flags2, int* counters, int epoch, int n_sn, double* x) {
   __shared__ double Ds[CH_KMAX * CH_DP];
@@ -230,7 +226,7 @@ __global__ void __launch_bounds__(BS_T) k_backsolve(SysView s, const int* __rest
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     const double* Lp = s.L + s.sn_valptr[sn];
     const int* rows = s.rowidx + s.sn_rowptr[sn];
-    for (int i = tid; i < nc * nc; i += BS_T) {
+    for (int i = tid; i < nc * nc; i += CH_T) {
       int r = i % nc, c = i / nc;
       Ds[r * CH_DP + c] = Lp[r + (int64_t)c * nr];
     }
@@ -248,7 +244,7 @@ __global__ void __launch_bounds__(BS_T) k_backsolve(SysView s, const int* __rest
         if (tid == 0) s_pending = 0;
         __syncthreads();
         int pend = 0;
-        for (int e = lo_e + tid; e < hi_e; e += BS_T)
+        for (int e = lo_e + tid; e < hi_e; e += CH_T)
           if (ld_acquire(&flags2[anc_t[e]]) != epoch) pend = 1;
         if (pend) atomicOr(&s_pending, 1);
         __syncthreads();
@@ -327,7 +323,7 @@ void launch_backsolve(fg_ctx* c) {
   SysView s = chol_view(c);
   int grid = c->num_sms * 2;
   if (grid > c->sym.n_sn) grid = c->sym.n_sn;
-  k_backsolve<<<grid, BS_T, 0, c->stream>>>(s, d.sched, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch,
+  k_backsolve<<<grid, CH_T, 0, c->stream>>>(s, d.sched, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch,
                                             c->sym.n_sn, d.delta);
 }
 

@@ -22,7 +22,6 @@
 namespace fg {
 
 static const int kMaxSnCols = 32;
-static const int kRelaxVars = 4;      // extra structure (in variables) tolerated when merging into a supernode
 
 int build_symbolic(fg_ctx* c) {
   HostGraph& h = c->h;
@@ -178,10 +177,8 @@ int build_symbolic(fg_ctx* c) {
     int v = 0;
     while (v < nv) {
       int first = v, cols = vdim[v];
-      // relaxed amalgamation: v+1 joins the run when its structure adds at most kRelaxRows explicit-zero
-      // rows to the columns already in the run (st[v] \ {v+1} is always a subset of st[v+1])
-      while (v + 1 < nv && parent[v] == v + 1 && cols + vdim[v + 1] <= kMaxSnCols &&
-             (int)st[v + 1].size() + 1 - (int)st[v].size() <= kRelaxVars) {
+      while (v + 1 < nv && parent[v] == v + 1 && st[v].size() == st[v + 1].size() + 1 &&
+             cols + vdim[v + 1] <= kMaxSnCols) {
         ++v; cols += vdim[v];
       }
       sn_first.push_back(first); sn_last.push_back(v);
