@@ -525,6 +525,58 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<double>(c, &d.gl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Vinv, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.tl, nullptr, (size_t)3 * L))) return rc;
     if ((rc = dev_upload(c, &d.calib, h.calib.data() + 9 * cid, 9)) || (rc = dev_upload(c, &d.sensor, h.sensor.data() + 12 * sid, 12))) return rc;
+    if ((rc = dev_upload<double>(c, &d.yl, nullptr, (size_t)3 * L))) return rc;
+    // Schur blocks and pair lists.  Block (p, q): poses co-visible through a landmark with order(q) <= order(p);
+    // its pair list holds every (observation of p, observation of q) of a common landmark.
+    {
+      const std::vector<int>& offp = S.off[T_POSE];
+      std::vector<int64_t> nbr_ptr(P + 1, 0);
+      std::vector<int> nbr_q;
+      for (int64_t p = 0; p < P; ++p) {
+        size_t b0 = nbr_q.size();
+        if (!S.cov_ptr.empty())
+          for (int64_t k = S.cov_ptr[p]; k < S.cov_ptr[p + 1]; ++k) {
+            int q = S.cov_pose[k];
+            if (offp[q] <= offp[p]) nbr_q.push_back(q);
+          }
+        std::sort(nbr_q.begin() + b0, nbr_q.end());
+        nbr_ptr[p + 1] = (int64_t)nbr_q.size();
+      }
+      const int64_t nblk = (int64_t)nbr_q.size();
+      std::vector<int> blk_p(nblk);
+      for (int64_t p = 0; p < P; ++p) for (int64_t k = nbr_ptr[p]; k < nbr_ptr[p + 1]; ++k) blk_p[k] = (int)p;
+      auto find_blk = [&](int p, int q) -> int64_t {
+        const int* lo = nbr_q.data() + nbr_ptr[p];
+        const int* hi = nbr_q.data() + nbr_ptr[p + 1];
+        return std::lower_bound(lo, hi, q) - nbr_q.data();
+      };
+      std::vector<int64_t> blk_ptr(nblk + 1, 0);
+      for (int64_t l = 0; l < L; ++l)
+        for (int64_t a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
+          for (int64_t b = lm_ptr[l]; b < lm_ptr[l + 1]; ++b) {
+            int pa = s_pose[a], pb = s_pose[b];
+            if (offp[pb] < offp[pa] || pa == pb) blk_ptr[find_blk(pa, pb) + 1]++;
+          }
+      for (int64_t k = 0; k < nblk; ++k) blk_ptr[k + 1] += blk_ptr[k];
+      const int64_t npairs = blk_ptr[nblk];
+      std::vector<int> pair_a(npairs), pair_b(npairs);
+      {
+        std::vector<int64_t> cur(blk_ptr.begin(), blk_ptr.end() - 1);
+        for (int64_t l = 0; l < L; ++l)
+          for (int64_t a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
+            for (int64_t b = lm_ptr[l]; b < lm_ptr[l + 1]; ++b) {
+              int pa = s_pose[a], pb = s_pose[b];
+              if (offp[pb] < offp[pa] || pa == pb) {
+                int64_t k = cur[find_blk(pa, pb)]++;
+                pair_a[k] = (int)a; pair_b[k] = (int)b;
+              }
+            }
+      }
+      d.n_blk = nblk;
+      if ((rc = dev_upload(c, &d.blk_p, blk_p)) || (rc = dev_upload(c, &d.blk_q, nbr_q)) || (rc = dev_upload(c, &d.blk_ptr, blk_ptr)) ||
+          (rc = dev_upload(c, &d.pair_a, pair_a)) || (rc = dev_upload(c, &d.pair_b, pair_b))) return rc;
+      CK(cudaStreamSynchronize(c->stream));
+    }
     CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   }
   // reduced system

@@ -53,6 +53,7 @@ struct Symbolic {
   std::vector<int> anc_ptr, anc_t, anc_a, anc_b;   // per supernode: (ancestor t, row range [a,b) of this supernode inside t's columns)
   std::vector<int> level, sched;                   // dependency level per supernode; supernodes sorted by level
   int n_levels = 0;
+  std::vector<int64_t> cov_ptr; std::vector<int> cov_pose;   // pose co-visibility through landmarks (incl. self)
   int max_nrows = 0, max_ncols = 0;
   double flops_factor = 0;
 };
@@ -135,7 +136,11 @@ struct DevGraph {
   int* obs_point = nullptr;         // M
   double* lm_prior_mean = nullptr;  // 3L (NaN weight = no prior)
   double* lm_prior_w = nullptr;     // L
-  double* W = nullptr;              // 18 M : Jp^T Jl * w
+  double* W = nullptr;              // M x 18 (AoS): w Jp^T Jl per observation
+  double* yl = nullptr;             // 3 L : (V + lambda I)^-1 g_l
+  // Schur blocks: one (row pose, col pose) block per co-visible pair with order(col) <= order(row)
+  int64_t n_blk = 0; int* blk_p = nullptr; int* blk_q = nullptr; int64_t* blk_ptr = nullptr;
+  int* pair_a = nullptr; int* pair_b = nullptr;   // observation index pairs grouped by block
   double* V = nullptr;              // 6 L  : upper of sum Jl^T Jl w + prior
   double* gl = nullptr;             // 3 L
   double* Vinv = nullptr;           // 6 L
@@ -185,6 +190,7 @@ int build_symbolic(fg_ctx* c);
 // kernels (launch wrappers), all asynchronous on c->stream
 void launch_linearize(fg_ctx* c);                         // U0, g_r, V, gl, W, chi2 -> scal[0]
 void launch_build_and_schur(fg_ctx* c, double lambda);    // L = U0 + lambda I - W V'^-1 W^T ; rhs row = -(g_red)
+void launch_schur(fg_ctx* c, double lambda);              // fg_schur.cu: the landmark part of the line above
 void launch_factor(fg_ctx* c);                            // cholesky; the rhs row makes it the forward solve too
 void launch_backsolve(fg_ctx* c);                         // backward solve -> delta
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]

@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) k_proj_obs(int64_t M, const int* __restri
       for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          W[(int64_t)(3 * i + c) * M + o] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
+          W[o * 18 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
     }
     // V (upper: 00 01 02 11 12 22) and gl
     double c9[9];
@@ -449,8 +449,7 @@ __global__ void k_damp_rhs(SysView sys, const double* __restrict__ g_r, double l
   if (add_rhs) col[nr - 1] -= g_r[C];
 }
 
-// Schur complement, generic path: one warp per landmark, atomics into the panel storage.
-//   Vinv = (V + lambda I)^-1 ; S_pq -= W_p Vinv W_q^T ; rhs_p += W_p Vinv g_l
+#if 0   // first version of the Schur complement (one warp per landmark, fp64 atomics); superseded by fg_schur.cu
 __global__ void __launch_bounds__(128) k_schur(int64_t L, int64_t M, const int64_t* __restrict__ lm_ptr, const int* __restrict__ obs_pose,
                                                const double* __restrict__ W, const double* __restrict__ V,
                                                const double* __restrict__ gl, double* __restrict__ Vinv, double lambda,
@@ -516,6 +515,8 @@ __global__ void __launch_bounds__(128) k_schur(int64_t L, int64_t M, const int64
   }
 }
 
+#endif
+
 // ------------------------------------------------------------------ K9/K10 back-substitution and retraction
 // t_l = sum_o W_o^T delta_p(o) by warp-segmented reduction (thread per observation)
 __global__ void __launch_bounds__(256) k_lm_backsub_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(256) k_lm_backsub_obs(int64_t M, const int* __
     for (int i = 0; i < 6; ++i) {
       double di = d[i];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) t3[c] += W[(int64_t)(3 * i + c) * M + o] * di;
+      for (int c = 0; c < 3; ++c) t3[c] += W[o * 18 + 3 * i + c] * di;
     }
   }
   int prev = __shfl_up_sync(0xffffffffu, l, 1);
@@ -787,7 +788,7 @@ void launch_build_and_schur(fg_ctx* c, double lambda) {
   // damping and the pose-side gradient are replicated terms: added by rank 0 only
   if (c->rank == 0) k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, st>>>(sys, d.g_r, lambda, 1);
   int64_t L = d.n[T_POINT];
-  if (L) k_schur<<<cdiv(L * 32, 128), 128, 0, st>>>(L, d.n_obs, d.lm_ptr, d.obs_pose, d.W, d.V, d.gl, d.Vinv, lambda, d.off[T_POSE], sys);
+  if (L) launch_schur(c, lambda);
 }
 
 void launch_retract_error(fg_ctx* c, double lambda) {

@@ -70,16 +70,19 @@ int build_symbolic(fg_ctx* c) {
         for (int64_t o = 0; o < M; ++o) { lm_pose[c1[h.pj_point[o]]++] = h.pj_pose[o]; pose_lm[c2[h.pj_pose[o]]++] = h.pj_point[o]; }
       }
       std::vector<int> stamp(P, -1);
+      S.cov_ptr.assign(P + 1, 0);
       for (int p = 0; p < (int)P; ++p) {
         stamp[p] = p;
         int bp = base[T_POSE][p];
+        if (pp[p + 1] > pp[p]) S.cov_pose.push_back(p);      // self (diagonal block)
         for (int64_t k = pp[p]; k < pp[p + 1]; ++k) {
           int l = pose_lm[k];
           for (int64_t k2 = lp[l]; k2 < lp[l + 1]; ++k2) {
             int q = lm_pose[k2];
-            if (stamp[q] != p) { stamp[q] = p; adj[bp].push_back(base[T_POSE][q]); }
+            if (stamp[q] != p) { stamp[q] = p; adj[bp].push_back(base[T_POSE][q]); S.cov_pose.push_back(q); }
           }
         }
+        S.cov_ptr[p + 1] = (int64_t)S.cov_pose.size();
       }
     }
   }
