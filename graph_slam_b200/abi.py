@@ -98,6 +98,7 @@ SIGNATURES = {
     'fg_error': (C.c_int, [_vp, _dp]),
     'fg_comm_unique_id': (C.c_int, [C.c_char_p]),
     'fg_comm_init': (C.c_int, [_vp, C.c_char_p]),
+    'fg_add_structure_edges': (C.c_int, [_vp, C.c_int64, _kp, _kp]),
     'fg_debug_sizes': (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     'fg_debug_symbolic': (C.c_int64, [_vp, C.c_int, C.POINTER(C.c_int64), C.c_int64]),
 }
@@ -254,6 +255,10 @@ class Context:
 
     def comm_init(self, uid): self.call('fg_comm_init', uid)
 
+    def add_structure_edges(self, ka, kb):
+        a, pa = _k(ka); b, pb = _k(kb)
+        self.call('fg_add_structure_edges', len(a), pa, pb)
+
     def symbolic(self, which):
         n = self.l.fg_debug_symbolic(self.h, which, None, 0)
         if n < 0:
@@ -290,6 +295,23 @@ def vn100_imu_params():
     return make_imu_params(I3 * (0.14e-3 * g) ** 2, I3 * np.deg2rad(0.0035) ** 2, I3 * 1e-4,
                            I3 * ((0.04e-3 * g) * np.sqrt(fps)) ** 2,
                            I3 * ((np.deg2rad(10.0) / 3600.0) * np.sqrt(fps)) ** 2, np.eye(6) * 1e-3, [0, 0, 9.71])
+
+
+def covisibility_band(spec):
+    """Pose pairs (p, q), p < q, covering every landmark's pose span [lo, hi]: a superset of the true
+    co-visibility that every rank can compute cheaply and declare with fg_add_structure_edges."""
+    P = spec['n_poses']
+    pose, pt = spec['proj_pose'].astype(np.int64), spec['proj_point'].astype(np.int64)
+    L = int(pt.max()) + 1 if len(pt) else 0
+    lo = np.full(L, P, dtype=np.int64); hi = np.full(L, -1, dtype=np.int64)
+    np.minimum.at(lo, pt, pose); np.maximum.at(hi, pt, pose)
+    reach = np.full(P, -1, dtype=np.int64)
+    ok = hi >= 0
+    np.maximum.at(reach, lo[ok], hi[ok])
+    reach = np.maximum.accumulate(reach)
+    a = np.repeat(np.arange(P), np.maximum(reach - np.arange(P), 0))
+    b = np.concatenate([np.arange(p + 1, r + 1) for p, r in enumerate(reach) if r > p]) if len(a) else np.zeros(0, dtype=np.int64)
+    return a, b
 
 
 def load_spec(ctx, spec, landmark_slice=None, preintegrated=None):
@@ -332,6 +354,9 @@ def load_spec(ctx, spec, landmark_slice=None, preintegrated=None):
         ctx.set_sensor(0, pose12(spec['Rs'], spec['ts'])[0])
         ctx.add_points(Q, spec['point_init'][lo:hi])
         ctx.add_prior_points(Q, spec['point_init'][lo:hi], spec['point_prior_sigma'])
+        if landmark_slice is not None:
+            a, b = covisibility_band(spec)
+            ctx.add_structure_edges(X[a], X[b])
         m = (spec['proj_point'] >= lo) & (spec['proj_point'] < hi)
         ctx.add_projections(X[spec['proj_pose'][m]], symbols('q', spec['proj_point'][m]), spec['proj_uv'][m],
                             spec['proj_sigma'])

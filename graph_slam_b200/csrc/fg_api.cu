@@ -286,6 +286,15 @@ extern "C" int fg_add_between(fg_ctx* c, fg_key k1, fg_key k2, const double T[12
   c->finalized = false;
   return FG_OK;
 }
+extern "C" int fg_add_structure_edges(fg_ctx* c, int64_t n, const fg_key* ka, const fg_key* kb) {
+  if (!c || !ka || !kb || n < 0) return fail(c, FG_ERR_INVALID, "bad argument");
+  for (int64_t i = 0; i < n; ++i) {
+    int a, b; FIND(ka[i], T_POSE, &a); FIND(kb[i], T_POSE, &b);
+    c->h.se_a.push_back(a); c->h.se_b.push_back(b);
+  }
+  c->finalized = false;
+  return FG_OK;
+}
 extern "C" int fg_set_calibration(fg_ctx* c, int id, const double K[9]) {
   if (!c || !K || id < 0) return fail(c, FG_ERR_INVALID, "bad argument");
   if ((size_t)(id + 1) * 9 > c->h.calib.size()) c->h.calib.resize((size_t)(id + 1) * 9, 0.0);

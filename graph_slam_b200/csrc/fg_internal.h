@@ -35,6 +35,7 @@ struct HostGraph {
   std::vector<int> pl_pose, pl_plane; std::vector<double> pl_meas, pl_info;      // plane factor: 4, 9
   std::vector<double> calib;    // 9 per id
   std::vector<double> sensor;   // 12 per id
+  std::vector<int> se_a, se_b;  // structure-only pose couplings (other ranks' landmark co-visibility)
 
   int64_t count(int t) const { return (int64_t)keys[t].size(); }
 };

@@ -56,6 +56,7 @@ int build_symbolic(fg_ctx* c) {
     for (int a = 0; a < 6; ++a) for (int b = a + 1; b < 6; ++b) edge(p[a], p[b]);
   }
   for (size_t f = 0; f < h.pl_pose.size(); ++f) edge(base[T_POSE][h.pl_pose[f]], base[T_PLANE][h.pl_plane[f]]);
+  for (size_t f = 0; f < h.se_a.size(); ++f) edge(base[T_POSE][h.se_a[f]], base[T_POSE][h.se_b[f]]);
   {
     // landmark co-visibility: every pair of poses observing one landmark is coupled through the Schur complement
     const int64_t L = h.count(T_POINT), M = (int64_t)h.pj_pose.size(), P = h.count(T_POSE);

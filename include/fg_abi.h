@@ -182,6 +182,9 @@ int fg_error(fg_ctx* ctx, double* error);
  * variables and factors must be added identically on every rank. */
 int fg_comm_unique_id(char id[128]);
 int fg_comm_init(fg_ctx* ctx, const char id[128]);
+/* Declares pose-pose couplings that exist only through landmarks held by OTHER ranks, so that every rank builds
+ * the same reduced-system structure (no numeric effect; a superset of the true co-visibility is allowed). */
+int fg_add_structure_edges(fg_ctx* ctx, int64_t n, const fg_key* kpose_a, const fg_key* kpose_b);
 
 /* ------------------------------------------------------------------ introspection for tests/bench */
 /* Linearise at the current values and copy out chi2 (=2*error), the reduced gradient norm and sizes. */

@@ -1,0 +1,89 @@
+// vio_driver.cpp -- test program in the shape of the reference's offline VIO driver
+// (gtsam/test_vro_imu_graph.cpp:76-360, without images, planes and ROS): VRO edge log + IMU log + image time
+// log -> CGraphGT / CImuVn100 -> optimizeGraphBatch, through the host mirror in graph_slam_b200/host.
+//   usage: vio_driver <vro.log> <imu.log> <times.log> <out_poses.txt>
+#include <cstdio>
+#include <fstream>
+#include <map>
+#include "../../graph_slam_b200/host/gtsam_graph.h"
+
+using namespace gtsam;
+using symbol_shorthand::B;
+using symbol_shorthand::V;
+using symbol_shorthand::X;
+
+static bool loadImgTime(const char* f, std::map<int, double>& m) {   // `img_id timestamp` (test_vro_imu_graph.cpp:425-442)
+  std::ifstream inf(f);
+  if (!inf.is_open()) return false;
+  int id; double t;
+  while (inf >> id >> t) m[id] = t;
+  return true;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 5) { fprintf(stderr, "usage: %s vro.log imu.log times.log out.txt\n", argv[0]); return 2; }
+  try {
+    CGraphGT gt_graph;
+    gt_graph.readVRORecord(argv[1]);
+    gt_graph.setCamera2IMU(0);
+    std::map<int, double> img_times;
+    if (!loadImgTime(argv[3], img_times)) { ROS_ERROR("failed to read time file %s", argv[3]); return 1; }
+    imuBias::ConstantBias prior_bias;
+    double dt = 0.005;   // 200 Hz
+    CImuVn100* imu = new CImuVn100(dt, prior_bias);
+    if (!imu->readImuData(argv[2])) { ROS_ERROR("failed to load imu data from file %s", argv[2]); return 1; }
+    const int g_f_start = 0;
+    CCameraNode* pNewNode = new CCameraNode();
+    pNewNode->m_seq_id = g_f_start;
+    gt_graph.firstNode(pNewNode, false);
+    imu->setStartPoint(img_times[g_f_start]);
+    int cur_frame_id = g_f_start;
+    for (size_t i = 0; i < gt_graph.mv_vro_res.size(); i++) {
+      MatchingResult* pm = gt_graph.mv_vro_res[i];
+      if (pm->edge.id2 <= g_f_start) continue;
+      if (pm->edge.id2 > cur_frame_id) {           // a new frame: incremental edge + IMU factor
+        int cur_imu_id = pm->edge.id2;
+        CCameraNode* node = new CCameraNode();
+        bool valid_match = gt_graph.addNodeOffline(node, pm);
+        if (!valid_match) gt_graph.m_graph_map[node->m_id] = node;
+        NavState cur_p;
+        bool imu_available = imu->predictNextFlag(img_times[cur_imu_id], cur_p);
+        PreintegratedCombinedMeasurements* preint = dynamic_cast<PreintegratedCombinedMeasurements*>(imu->mp_combined_pre_imu);
+        if (imu_available) {
+          int cur_node_id = node->m_id;
+          CombinedImuFactor imu_factor(X(cur_node_id - 1), V(cur_node_id - 1), X(cur_node_id), V(cur_node_id),
+                                       B(cur_node_id - 1), B(cur_node_id), *preint);
+          gt_graph.mp_fac_graph->add(imu_factor);
+          gt_graph.mp_new_fac->add(imu_factor);
+          gt_graph.addToGTSAM(cur_p, cur_node_id, !valid_match);
+          // re-seed the integrator from the current estimate (test_vro_imu_graph.cpp:346-356)
+          NavState st(gt_graph.mp_node_values->at<Pose3>(X(cur_node_id)), gt_graph.mp_node_values->at<Vector3>(V(cur_node_id)));
+          imu->setState(st);
+          imu->resetPreintegrationAndBias(*gt_graph.mp_prev_bias);
+        }
+        cur_frame_id = pm->edge.id2;
+      } else {
+        gt_graph.addEdgeOffline(pm);               // look-back / loop-closure edge
+      }
+    }
+    double e0 = gt_graph.error();
+    gt_graph.optimizeGraphBatch();
+    double e1 = gt_graph.error();
+    printf("RESULT nodes %zu error_before %.17g error_after %.17g\n", gt_graph.camnodeSize(), e0, e1);
+    std::ofstream ouf(argv[4]);
+    ouf.precision(17);
+    for (auto& kv : gt_graph.m_graph_map) {
+      double T[12];
+      gt_graph.mp_node_values->at<Pose3>(X(kv.first)).toArray12(T);
+      ouf << kv.first;
+      for (int k = 0; k < 12; ++k) ouf << " " << T[k];
+      Vector3 v = gt_graph.mp_node_values->at<Vector3>(V(kv.first));
+      ouf << " " << v[0] << " " << v[1] << " " << v[2] << "\n";
+    }
+    delete imu;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "vio_driver failed: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

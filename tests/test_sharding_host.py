@@ -1,0 +1,53 @@
+"""Host side of the multi-GPU path on CPU: two gloo ranks build their landmark shards in detached contexts and
+must arrive at the SAME reduced-system structure (what makes the single allreduce of the panel buffer legal),
+and that structure must equal the unsharded one declared with the same co-visibility band."""
+import hashlib
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import hashlib, os, sys
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, %r)
+    from graph_slam_b200 import abi, synth
+    dist.init_process_group('gloo')
+    rank, world = dist.get_rank(), dist.get_world_size()
+    spec = synth.make_config('C4', seed=3, scale=0.04)
+    L = len(spec['point_init']); P = spec['n_poses']
+    pims = (abi.Pim * (P - 1))()
+    for i in range(P - 1):
+        pims[i].dt = 0.1; pims[i].cov[:] = np.eye(15).ravel().tolist()
+    def digest(sl):
+        ctx = abi.Context(device=-1, rank=rank, nranks=world)
+        abi.load_spec(ctx, spec, landmark_slice=sl, preintegrated=pims)
+        h = hashlib.sha256()
+        for w in range(0, 17):
+            h.update(ctx.symbolic(w).tobytes())
+        ctx.close()
+        return h.hexdigest()
+    mine = digest((L * rank // world, L * (rank + 1) // world))
+    full = digest((0, L))
+    out = [None] * world
+    dist.all_gather_object(out, (mine, full))
+    if rank == 0:
+        assert len(set(o[0] for o in out)) == 1, 'ranks disagree on the reduced-system structure'
+        assert out[0][0] == out[0][1], 'sharded structure differs from the unsharded one'
+        print('SHARDING_OK')
+    dist.destroy_process_group()
+''') % ROOT
+
+
+def test_two_rank_structures_agree(fglib, tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert 'SHARDING_OK' in res.stdout
