@@ -593,10 +593,9 @@ __global__ void k_retract_reduced(int64_t n, const double* __restrict__ val, dou
       for (int k = 0; k < D; ++k) val_new[D * i + k] = val[D * i + k] + dl[k];
     }
   }
-  if (count_scal) {
-    gd = warp_sum(gd); dd = warp_sum(dd);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&scal[1], gd); atomicAdd(&scal[2], dd); }
-  }
+  // g_r is this rank's share of the gradient (always counted); |delta_r|^2 is replicated (rank 0 only)
+  gd = warp_sum(gd); dd = warp_sum(dd);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&scal[1], gd); if (count_scal) atomicAdd(&scal[2], dd); }
 }
 
 // ------------------------------------------------------------------ K3 IMU preintegration
@@ -786,7 +785,8 @@ void launch_build_and_schur(fg_ctx* c, double lambda) {
   cudaMemcpyAsync(d.L, d.U0, sizeof(double) * (c->sym.nnz + 8), cudaMemcpyDeviceToDevice, st);
   SysView sys = make_view(c, d.L);
   // damping and the pose-side gradient are replicated terms: added by rank 0 only
-  if (c->rank == 0) k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, st>>>(sys, d.g_r, lambda, 1);
+  // damping is a replicated term (rank 0 only); every rank contributes its own share of the gradient
+  k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, st>>>(sys, d.g_r, c->rank == 0 ? lambda : 0.0, 1);
   int64_t L = d.n[T_POINT];
   if (L) launch_schur(c, lambda);
 }

@@ -57,7 +57,8 @@ def oracle_graph_from_logs(spec, recs):
     # the reference reads IMU samples into float variables (gtsam/imu_vn100.cpp:86-90)
     samples = spec['imu_samples'].astype(np.float32).astype(np.float64)
     par = oimu.vn100_params()
-    pim = oimu.preintegrate(samples, spec['imu_dt'], par, np.zeros((P - 1, 6)))
+    # CImuBase keeps the sample period in a float member (`float m_dt`, gtsam/imu_base.h:73)
+    pim = oimu.preintegrate(samples, float(np.float32(spec['imu_dt'])), par, np.zeros((P - 1, 6)))
     for j in range(1, P):
         R[j], t[j] = lie.pose_compose(R[j - 1], t[j - 1], *edges[j])
         one = {k: (val[j - 1] if isinstance(val, np.ndarray) and val.ndim >= 1 and len(val) == P - 1 else val) for k, val in pim.items()}
