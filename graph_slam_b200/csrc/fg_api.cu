@@ -682,7 +682,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
       launch_build_and_schur(c, lam);
       if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) break;
       CK(cudaEventRecord(ev[2], c->stream));
-      launch_factor(c);
+      if (chol_reg_supported(c)) launch_factor_reg(c); else launch_factor(c);
       CK(cudaEventRecord(ev[3], c->stream));
       launch_backsolve(c);
       CK(cudaEventRecord(ev[4], c->stream));

@@ -193,6 +193,8 @@ void launch_linearize(fg_ctx* c);                         // U0, g_r, V, gl, W, 
 void launch_build_and_schur(fg_ctx* c, double lambda);    // L = U0 + lambda I - W V'^-1 W^T ; rhs row = -(g_red)
 void launch_schur(fg_ctx* c, double lambda);              // fg_schur.cu: the landmark part of the line above
 void launch_factor(fg_ctx* c);                            // cholesky; the rhs row makes it the forward solve too
+bool chol_reg_supported(const fg_ctx* c);                 // fg_chol_reg.cu: width <= 16, height <= 1024
+void launch_factor_reg(fg_ctx* c);                        // register-tiled fast path of the same factorisation
 void launch_backsolve(fg_ctx* c);                         // backward solve -> delta
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
 void launch_error_only(fg_ctx* c, bool trial);            // chi2 of val (or val_new) -> scal[0] (or scal[3])

@@ -21,7 +21,7 @@
 
 namespace fg {
 
-static const int kMaxSnCols = 32;
+static const int kMaxSnCols = 16;     // one [X V B] frame (15) or two poses (12); fits the register-tiled k_chol_reg
 
 int build_symbolic(fg_ctx* c) {
   HostGraph& h = c->h;

@@ -28,10 +28,11 @@ def write_logs(spec, vro_path, imu_path, times_path):
     flat = spec['imu_samples'].reshape(-1, 6)
     with open(imu_path, 'w') as f:
         for k, m in enumerate(flat):
-            f.write('%r %r %r %r %r %r %r 0 0 0\n' % (k * spec['imu_dt'], m[3], m[4], m[5], m[0], m[1], m[2]))
+            f.write('%r %r %r %r %r %r %r 0 0 0\n' % (float(k * spec['imu_dt']), float(m[3]), float(m[4]), float(m[5]),
+                                                      float(m[0]), float(m[1]), float(m[2])))
     with open(times_path, 'w') as f:
         for j in range(P):
-            f.write('%d %r\n' % (j, j * S * spec['imu_dt']))
+            f.write('%d %r\n' % (j, float(j * S * spec['imu_dt'])))
     return recs
 
 
