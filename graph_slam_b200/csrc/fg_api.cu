@@ -534,7 +534,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<double>(c, &d.gl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Vinv, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.tl, nullptr, (size_t)3 * L))) return rc;
     if ((rc = dev_upload(c, &d.calib, h.calib.data() + 9 * cid, 9)) || (rc = dev_upload(c, &d.sensor, h.sensor.data() + 12 * sid, 12))) return rc;
-    if ((rc = dev_upload<double>(c, &d.yl, nullptr, (size_t)3 * L))) return rc;
+    if ((rc = dev_upload<double>(c, &d.yl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Y, nullptr, (size_t)18 * M))) return rc;
     // Schur blocks and pair lists.  Block (p, q): poses co-visible through a landmark with order(q) <= order(p);
     // its pair list holds every (observation of p, observation of q) of a common landmark.
     {

@@ -139,6 +139,7 @@ struct DevGraph {
   double* lm_prior_w = nullptr;     // L
   double* W = nullptr;              // M x 18 (AoS): w Jp^T Jl per observation
   double* yl = nullptr;             // 3 L : (V + lambda I)^-1 g_l
+  double* Y = nullptr;              // M x 18 (AoS): W_o (V_l + lambda I)^-1 per observation
   // Schur blocks: one (row pose, col pose) block per co-visible pair with order(col) <= order(row)
   int64_t n_blk = 0; int* blk_p = nullptr; int* blk_q = nullptr; int64_t* blk_ptr = nullptr;
   int* pair_a = nullptr; int* pair_b = nullptr;   // observation index pairs grouped by block

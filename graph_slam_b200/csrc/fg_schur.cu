@@ -40,12 +40,36 @@ __device__ __forceinline__ void load18(const double* __restrict__ W, int o, doub
   for (int i = 0; i < 9; ++i) { double2 v = __ldg(p + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }
 }
 
+// per observation: Y_o = W_o Vinv_l  (6x3), so that the pair loop below is two 144 B reads and 108 DFMA
+__global__ void __launch_bounds__(256) k_ymat(int64_t M, const int* __restrict__ obs_point, const double* __restrict__ W,
+                                              const double* __restrict__ Vinv, double* __restrict__ Y) {
+  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (o >= M) return;
+  const int l = obs_point[o];
+  double w[18], vi[6];
+  load18(W, (int)o, w);
+  {
+    const double2* p = reinterpret_cast<const double2*>(Vinv + (int64_t)l * 6);
+    double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+    vi[0] = v0.x; vi[1] = v0.y; vi[2] = v1.x; vi[3] = v1.y; vi[4] = v2.x; vi[5] = v2.y;
+  }
+  double2* out = reinterpret_cast<double2*>(Y + o * 18);
+  double y[18];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    y[3 * i + 0] = w[3 * i] * vi[0] + w[3 * i + 1] * vi[1] + w[3 * i + 2] * vi[2];
+    y[3 * i + 1] = w[3 * i] * vi[1] + w[3 * i + 1] * vi[3] + w[3 * i + 2] * vi[4];
+    y[3 * i + 2] = w[3 * i] * vi[2] + w[3 * i + 1] * vi[4] + w[3 * i + 2] * vi[5];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[i] = make_double2(y[2 * i], y[2 * i + 1]);
+}
+
 // one warp per block (p, q)
-__global__ void __launch_bounds__(256) k_schur_blocks(int64_t n_blk, const int* __restrict__ blk_p, const int* __restrict__ blk_q,
-                                                      const int64_t* __restrict__ blk_ptr, const int* __restrict__ pair_a,
-                                                      const int* __restrict__ pair_b, const int* __restrict__ obs_point,
-                                                      const double* __restrict__ W, const double* __restrict__ Vinv,
-                                                      const int* __restrict__ off_pose, SysView sys) {
+__global__ void __launch_bounds__(256, 2) k_schur_blocks(int64_t n_blk, const int* __restrict__ blk_p, const int* __restrict__ blk_q,
+                                                         const int64_t* __restrict__ blk_ptr, const int* __restrict__ pair_a,
+                                                         const int* __restrict__ pair_b, const double* __restrict__ Y,
+                                                         const double* __restrict__ W, const int* __restrict__ off_pose, SysView sys) {
   const int64_t blk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (blk >= n_blk) return;
@@ -53,28 +77,24 @@ __global__ void __launch_bounds__(256) k_schur_blocks(int64_t n_blk, const int* 
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
   const int64_t s = blk_ptr[blk], e = blk_ptr[blk + 1];
-  for (int64_t k = s + lane; k < e; k += 32) {
-    const int oa = __ldg(pair_a + k), ob = __ldg(pair_b + k);
-    const int l = __ldg(obs_point + oa);
-    double wa[18], wb[18], vi[6], Y[18];
-    load18(W, oa, wa);
+  int64_t k = s + lane;
+  int oa = -1, ob = -1;
+  if (k < e) { oa = __ldg(pair_a + k); ob = __ldg(pair_b + k); }
+  while (oa >= 0) {
+    double wb[18];
     load18(W, ob, wb);
-    {
-      const double2* p = reinterpret_cast<const double2*>(Vinv + (int64_t)l * 6);
-      double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-      vi[0] = v0.x; vi[1] = v0.y; vi[2] = v1.x; vi[3] = v1.y; vi[4] = v2.x; vi[5] = v2.y;
-    }
+    const double* ya = Y + (int64_t)oa * 18;
+    // prefetch the next pair's indices before the arithmetic
+    k += 32;
+    int na = -1, nb2 = -1;
+    if (k < e) { na = __ldg(pair_a + k); nb2 = __ldg(pair_b + k); }
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      Y[3 * i + 0] = wa[3 * i] * vi[0] + wa[3 * i + 1] * vi[1] + wa[3 * i + 2] * vi[2];
-      Y[3 * i + 1] = wa[3 * i] * vi[1] + wa[3 * i + 1] * vi[3] + wa[3 * i + 2] * vi[4];
-      Y[3 * i + 2] = wa[3 * i] * vi[2] + wa[3 * i + 1] * vi[4] + wa[3 * i + 2] * vi[5];
+      const double y0 = __ldg(ya + 3 * i), y1 = __ldg(ya + 3 * i + 1), y2 = __ldg(ya + 3 * i + 2);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) acc[6 * i + j] += y0 * wb[3 * j] + y1 * wb[3 * j + 1] + y2 * wb[3 * j + 2];
     }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = 0; j < 6; ++j)
-        acc[6 * i + j] += Y[3 * i] * wb[3 * j] + Y[3 * i + 1] * wb[3 * j + 1] + Y[3 * i + 2] * wb[3 * j + 2];
+    oa = na; ob = nb2;
   }
   // butterfly: every lane ends with the full sums
 #pragma unroll
@@ -139,8 +159,9 @@ void launch_schur(fg_ctx* c, double lambda) {
   sys.sn_rowptr = d.sn_rowptr; sys.sn_valptr = d.sn_valptr; sys.rowidx = d.rowidx; sys.n_r = c->sym.n_r;
   const int64_t L = d.n[T_POINT];
   k_vinv<<<cdiv(L, 256), 256, 0, st>>>(L, d.V, d.gl, lambda, d.Vinv, d.yl);
-  if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk * 32, 256), 256, 0, st>>>(d.n_blk, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.obs_point,
-                                                                        d.W, d.Vinv, d.off[T_POSE], sys);
+  if (d.n_obs) k_ymat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.W, d.Vinv, d.Y);
+  if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk * 32, 256), 256, 0, st>>>(d.n_blk, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.Y,
+                                                                        d.W, d.off[T_POSE], sys);
   const int P = (int)d.n[T_POSE];
   if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.W, d.yl, d.off[T_POSE], sys);
 }

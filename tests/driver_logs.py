@@ -30,6 +30,11 @@ def write_logs(spec, vro_path, imu_path, times_path):
         for k, m in enumerate(flat):
             f.write('%r %r %r %r %r %r %r 0 0 0\n' % (float(k * spec['imu_dt']), float(m[3]), float(m[4]), float(m[5]),
                                                       float(m[0]), float(m[1]), float(m[2])))
+        # the recordings' IMU logs run past the last image; two trailing samples let findIndexAt bracket it
+        for k in range(len(flat), len(flat) + 2):
+            m = flat[-1]
+            f.write('%r %r %r %r %r %r %r 0 0 0\n' % (float(k * spec['imu_dt']), float(m[3]), float(m[4]), float(m[5]),
+                                                      float(m[0]), float(m[1]), float(m[2])))
     with open(times_path, 'w') as f:
         for j in range(P):
             f.write('%d %r\n' % (j, float(j * S * spec['imu_dt'])))
