@@ -13,6 +13,9 @@
 // memory and written to global memory once, coalesced.
 // Limits: supernode width <= 16 columns (fg_symbolic.cpp caps it), panel height <= 1024 rows; graphs beyond that
 // use the generic kernel in fg_chol.cu.  No fp64 tcgen05 kind exists, hence DFMA.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "fg_internal.h"
 
 namespace fg {
@@ -44,7 +47,7 @@ struct CrSmem {
 __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __restrict__ sched, const int* __restrict__ upd_ptr,
                                                       const int* __restrict__ upd_d, const int* __restrict__ upd_a,
                                                       const int* __restrict__ upd_b, int* flags, int* counters, int epoch,
-                                                      int n_sn, int* status) {
+                                                      int n_sn, int* status, long long* dbg) {
   extern __shared__ __align__(16) unsigned char cr_raw[];
   CrSmem& sm = *reinterpret_cast<CrSmem*>(cr_raw);
   const int tid = threadIdx.x;
@@ -59,6 +62,7 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     double* Lp = s.L + s.sn_valptr[sn];
     const int* rows_g = s.rowidx + s.sn_rowptr[sn];
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4 * sn] = t; dbg[4 * sn + 3] = blockIdx.x; }
     for (int i = tid; i < nr; i += CR_T) sm.rows_s[i] = rows_g[i];
     for (int i = tid; i < nr * nc; i += CR_T) sm.P[i] = Lp[i];
     __syncthreads();
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
       __syncthreads();
     }
     __syncthreads();
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4 * sn + 1] = t; }
 
     // ---- diagonal block
     for (int i = tid; i < nc * nc; i += CR_T) {
@@ -194,6 +199,7 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
     __threadfence();
     __syncthreads();
     if (tid == 0) cr_st_release(&flags[sn], epoch);
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4 * sn + 2] = t; }
   }
 }
 
@@ -214,8 +220,26 @@ void launch_factor_reg(fg_ctx* c) {
   c->epoch += 1;
   cudaMemsetAsync(d.status, 0, sizeof(int), c->stream);
   cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, c->stream);
+  // FG_CHOL_TRACE=<file>: dump per-supernode (grab, updates done, published) globaltimer stamps of the 3rd factorisation
+  static int n_calls = 0;
+  long long* dbg = nullptr;
+  const char* trace = getenv("FG_CHOL_TRACE");
+  if (trace && ++n_calls == 3) cudaMalloc((void**)&dbg, sizeof(long long) * 4 * c->sym.n_sn);
   k_chol_reg<<<grid, CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.flags, d.counters,
-                                                         c->epoch, c->sym.n_sn, d.status);
+                                                         c->epoch, c->sym.n_sn, d.status, dbg);
+  if (dbg) {
+    std::vector<long long> h(4 * (size_t)c->sym.n_sn);
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    FILE* f = fopen(trace, "w");
+    if (f) {
+      for (int i = 0; i < c->sym.n_sn; ++i)
+        fprintf(f, "%d %d %d %d %d %lld %lld %lld %lld\n", i, c->sym.level[i], c->sym.sn_ncols[i], c->sym.sn_nrows[i],
+                c->sym.upd_ptr[i + 1] - c->sym.upd_ptr[i], h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      fclose(f);
+    }
+  }
 }
 
 }  // namespace fg
