@@ -117,6 +117,7 @@ extern "C" fg_ctx* fg_create(int device, int rank, int nranks) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  for (auto& e : c->kev) cudaEventCreate(&e);
   c->h.calib.assign(9, 0.0);
   c->h.sensor = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
   return c;
@@ -127,6 +128,7 @@ extern "C" void fg_destroy(fg_ctx* c) {
   cudaSetDevice(c->device);
   if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
   dev_free_all(c);
+  for (auto& e : c->kev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -581,7 +583,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
               }
             }
       }
-      d.n_blk = nblk;
+      d.n_blk = nblk; d.n_pairs = npairs;
       if ((rc = dev_upload(c, &d.blk_p, blk_p)) || (rc = dev_upload(c, &d.blk_q, nbr_q)) || (rc = dev_upload(c, &d.blk_ptr, blk_ptr)) ||
           (rc = dev_upload(c, &d.pair_a, pair_a)) || (rc = dev_upload(c, &d.pair_b, pair_b))) return rc;
       CK(cudaStreamSynchronize(c->stream));
@@ -664,6 +666,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   rep->initial_error = err;
   rep->n_reduced_dims = c->sym.n_r; rep->n_supernodes = c->sym.n_sn; rep->nnz_L = c->sym.nnz;
   rep->n_projections = d.n_obs; rep->n_landmarks = d.n[T_POINT];
+  rep->n_schur_pairs = d.n_pairs; rep->n_levels = c->sym.n_levels;
   double lam = p.lambda_initial;
   const double inf = std::numeric_limits<double>::infinity();
   int it = 0;
@@ -693,7 +696,11 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
       if ((rc = read_scalars(c, hs, &st)) != FG_OK) break;
       CK(cudaGetLastError());
       float ms;
-      if (first) { cudaEventElapsedTime(&ms, ev[0], ev[1]); rep->ms_linearize += ms; }
+      if (first) {
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); rep->ms_linearize += ms;
+        if (d.n_obs && c->kev[0] && cudaEventElapsedTime(&ms, c->kev[0], c->kev[1]) == cudaSuccess) rep->ms_proj_obs += ms;
+      }
+      if (d.n_blk && c->kev[2] && cudaEventElapsedTime(&ms, c->kev[2], c->kev[3]) == cudaSuccess) rep->ms_schur_blocks += ms;
       cudaEventElapsedTime(&ms, ev[1], ev[2]); rep->ms_schur += ms;
       cudaEventElapsedTime(&ms, ev[2], ev[3]); rep->ms_factor += ms;
       cudaEventElapsedTime(&ms, ev[3], ev[4]); rep->ms_solve += ms;

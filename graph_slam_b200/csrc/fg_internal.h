@@ -141,6 +141,7 @@ struct DevGraph {
   double* yl = nullptr;             // 3 L : (V + lambda I)^-1 g_l
   double* Y = nullptr;              // M x 18 (AoS): W_o (V_l + lambda I)^-1 per observation
   // Schur blocks: one (row pose, col pose) block per co-visible pair with order(col) <= order(row)
+  int64_t n_pairs = 0;
   int64_t n_blk = 0; int* blk_p = nullptr; int* blk_q = nullptr; int64_t* blk_ptr = nullptr;
   int* pair_a = nullptr; int* pair_b = nullptr;   // observation index pairs grouped by block
   double* V = nullptr;              // 6 L  : upper of sum Jl^T Jl w + prior
@@ -183,6 +184,7 @@ struct fg_ctx {
   int epoch = 0;
   int num_sms = 148;
   void* nccl_comm = nullptr;
+  cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // around k_proj_obs<JAC> and k_schur_blocks (roofline timing)
   std::vector<void*> allocs;
 };
 

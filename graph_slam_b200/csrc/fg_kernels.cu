@@ -755,7 +755,9 @@ static void run_factors(fg_ctx* c, bool trial, double* chi2) {
   if (L) {
     k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, st>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, chi2);
     if (d.n_obs) {
+      if (JAC && c->kev[0]) cudaEventRecord(c->kev[0], st);
       k_proj_obs<JAC><<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, chi2);
+      if (JAC && c->kev[1]) cudaEventRecord(c->kev[1], st);
       if (JAC) {
         int P = (int)d.n[T_POSE];
         k_proj_pose<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.off[T_POSE], sys, d.g_r);

@@ -160,8 +160,10 @@ void launch_schur(fg_ctx* c, double lambda) {
   const int64_t L = d.n[T_POINT];
   k_vinv<<<cdiv(L, 256), 256, 0, st>>>(L, d.V, d.gl, lambda, d.Vinv, d.yl);
   if (d.n_obs) k_ymat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.W, d.Vinv, d.Y);
+  if (c->kev[2]) cudaEventRecord(c->kev[2], st);
   if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk * 32, 256), 256, 0, st>>>(d.n_blk, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.Y,
                                                                         d.W, d.off[T_POSE], sys);
+  if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];
   if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.W, d.yl, d.off[T_POSE], sys);
 }
