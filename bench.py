@@ -123,7 +123,7 @@ def run_reference(args):
     line = dict(metric=METRIC, value=base['value'], unit='iterations/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000.0 / base['value'] if base['value'] else None,
                 higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
-                impl='reference', config=dict(workload=args.config, note='oracle port on a bounded sample'),
+                impl='reference', config=dict(workload='%s (oracle port timed on a bounded sample of it, see cpu_baseline.sample)' % args.config),
                 cpu_baseline=base,
                 e2e=dict(value=base['value'], unit='iterations/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 wall_s=time.perf_counter() - t0)
@@ -234,9 +234,15 @@ def main():
     t_cho = phases['factor']                              # k_chol_reg: one read of the assembled panels, one write of L
     b_cho = 2 * 8 * int(rep.nnz_L)
 
+    # dram__bytes_read+write per launch from the committed ncu --set full capture (single GPU, C5 only)
+    traffic = {}
+    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tp) and args.config == 'C5' and args.scale == 1.0 and world == 1:
+        traffic = json.load(open(tp)).get('dram_bytes_per_launch', {})
+
     def roof(name, nbytes, ms, note):
         a = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return dict(kernel=name, bound='hbm', achieved=a, peak=peak, unit='GB/s', frac=a / peak, traffic=None,
+        return dict(kernel=name, bound='hbm', achieved=a, peak=peak, unit='GB/s', frac=a / peak, traffic=traffic.get(name),
                     algorithmic_bytes=nbytes, ms=ms, note=note)
     roofs = [roof('k_chol_reg', b_cho, t_cho, 'dominant by time; dependency-latency bound (%d levels), not bandwidth bound' % int(rep.n_levels)),
              roof('k_schur_blocks', b_sch, t_sch, 'L2-bandwidth bound: %d pairs x 288 B mostly served by L2' % int(rep.n_schur_pairs)),

@@ -598,7 +598,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
   if ((rc = dev_upload(c, &d.col2sn, S.col2sn)) || (rc = dev_upload(c, &d.sn_col0, S.sn_col0)) || (rc = dev_upload(c, &d.sn_ncols, S.sn_ncols)) ||
       (rc = dev_upload(c, &d.sn_nrows, S.sn_nrows)) || (rc = dev_upload(c, &d.sn_rowptr, S.sn_rowptr)) || (rc = dev_upload(c, &d.sn_valptr, S.sn_valptr)) ||
       (rc = dev_upload(c, &d.rowidx, S.rowidx)) || (rc = dev_upload(c, &d.upd_ptr, S.upd_ptr)) || (rc = dev_upload(c, &d.upd_d, S.upd_d)) ||
-      (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b)) ||
+      (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b)) || (rc = dev_upload(c, &d.upd_rec, S.upd_rec)) ||
       (rc = dev_upload(c, &d.anc_ptr, S.anc_ptr)) || (rc = dev_upload(c, &d.anc_t, S.anc_t)) || (rc = dev_upload(c, &d.anc_a, S.anc_a)) ||
       (rc = dev_upload(c, &d.anc_b, S.anc_b)) || (rc = dev_upload(c, &d.sched, S.sched)) ||
       (rc = dev_upload<int>(c, &d.flags2, nullptr, S.n_sn)) || (rc = dev_upload<int>(c, &d.counters, nullptr, 4))) return rc;

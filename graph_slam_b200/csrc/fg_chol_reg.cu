@@ -46,8 +46,8 @@ struct CrSmem {
 
 __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __restrict__ sched, const int* __restrict__ upd_ptr,
                                                       const int* __restrict__ upd_d, const int* __restrict__ upd_a,
-                                                      const int* __restrict__ upd_b, int* flags, int* counters, int epoch,
-                                                      int n_sn, int* status, long long* dbg) {
+                                                      const int* __restrict__ upd_b, const UpdRec* __restrict__ upd_rec, int* flags, int* counters,
+                                                      int epoch, int n_sn, int* status, long long* dbg) {
   extern __shared__ __align__(16) unsigned char cr_raw[];
   CrSmem& sm = *reinterpret_cast<CrSmem*>(cr_raw);
   const int tid = threadIdx.x;
@@ -79,12 +79,13 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
       const int nready = sm.first_not_ready;
       __syncthreads();
       if (nready == 0) { __nanosleep(200); continue; }
+      UpdRec rec = upd_rec[u];
       for (int uu = u; uu < u + nready; ++uu, buf ^= 1) {
-        const int d = upd_d[uu], a = upd_a[uu], b = upd_b[uu];
-        const int K = s.sn_ncols[d], nrd = s.sn_nrows[d];
-        const double* Ld = s.L + s.sn_valptr[d];
-        const int* rd = s.rowidx + s.sn_rowptr[d];
-        const int nrows_u = nrd - a, nb = b - a;
+        const int K = rec.K, nrd = rec.nrd, nrows_u = rec.nrows_u, nb = rec.nb;
+        const double* Ld = s.L + rec.val_off;          // points at descendant row a
+        const int* rd = s.rowidx + rec.row_off;        // row list from row a on
+        const int a = 0;
+        if (uu + 1 < u + nready) rec = upd_rec[uu + 1];   // next record rides under this update's latency
         // ---- issue every load of this update up front (all independent)
         int R[CR_RPT];
         double x[CR_RPT][CR_NC];
@@ -225,7 +226,7 @@ void launch_factor_reg(fg_ctx* c) {
   long long* dbg = nullptr;
   const char* trace = getenv("FG_CHOL_TRACE");
   if (trace && ++n_calls == 3) cudaMalloc((void**)&dbg, sizeof(long long) * 4 * c->sym.n_sn);
-  k_chol_reg<<<grid, CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.flags, d.counters,
+  k_chol_reg<<<grid, CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.upd_rec, d.flags, d.counters,
                                                          c->epoch, c->sym.n_sn, d.status, dbg);
   if (dbg) {
     std::vector<long long> h(4 * (size_t)c->sym.n_sn);

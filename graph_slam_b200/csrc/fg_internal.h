@@ -40,6 +40,16 @@ struct HostGraph {
   int64_t count(int t) const { return (int64_t)keys[t].size(); }
 };
 
+// one descendant update, everything the factorisation kernel needs in a single 32-byte load
+struct __align__(16) UpdRec {
+  long long val_off;   // offset in L of descendant row a, column 0
+  int row_off;         // offset in rowidx of descendant row a
+  int nrd;             // descendant leading dimension (rows)
+  int nrows_u;         // descendant rows taking part (nrd - a)
+  short K, nb;         // descendant width, rows of it inside the target's columns
+  int pad[2];
+};
+
 // ------------------------------------------------------------------ symbolic structure of the reduced system
 struct Symbolic {
   int n_r = 0;                       // reduced scalar dimension (poses, vels, biases, planes)
@@ -51,6 +61,7 @@ struct Symbolic {
   std::vector<int> rowidx;           // concatenated row lists (global scalar rows; last = n_r = rhs row)
   std::vector<int> col2sn;           // scalar column -> supernode
   std::vector<int> upd_ptr, upd_d, upd_a, upd_b;   // per target supernode: (descendant, row range [a,b) in d)
+  std::vector<UpdRec> upd_rec;                     // packed per-update record (same indexing as upd_d)
   std::vector<int> anc_ptr, anc_t, anc_a, anc_b;   // per supernode: (ancestor t, row range [a,b) of this supernode inside t's columns)
   std::vector<int> level, sched;                   // dependency level per supernode; supernodes sorted by level
   int n_levels = 0;
@@ -162,6 +173,7 @@ struct DevGraph {
   int *col2sn = nullptr, *sn_col0 = nullptr, *sn_ncols = nullptr, *sn_nrows = nullptr, *sn_rowptr = nullptr, *rowidx = nullptr;
   int64_t* sn_valptr = nullptr;
   int *upd_ptr = nullptr, *upd_d = nullptr, *upd_a = nullptr, *upd_b = nullptr;
+  UpdRec* upd_rec = nullptr;
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve

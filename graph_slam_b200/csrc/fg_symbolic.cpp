@@ -242,6 +242,13 @@ int build_symbolic(fg_ctx* c) {
       S.upd_a[S.upd_ptr[s] + k] = ul[s][3 * k + 1];
       S.upd_b[S.upd_ptr[s] + k] = ul[s][3 * k + 2];
     }
+  S.upd_rec.resize(S.upd_d.size());
+  for (size_t u = 0; u < S.upd_d.size(); ++u) {
+    const int d = S.upd_d[u], a = S.upd_a[u], b = S.upd_b[u];
+    UpdRec& r = S.upd_rec[u];
+    r.val_off = S.sn_valptr[d] + a; r.row_off = S.sn_rowptr[d] + a; r.nrd = S.sn_nrows[d]; r.nrows_u = S.sn_nrows[d] - a;
+    r.K = (short)S.sn_ncols[d]; r.nb = (short)(b - a); r.pad[0] = r.pad[1] = 0;
+  }
   // ---- schedule: supernodes by dependency level (longest path), a topological order that interleaves
   //      the independent chains so that the persistent kernel works on all of them at once
   S.level.assign(S.n_sn, 0);
