@@ -5,8 +5,8 @@
 //   K1  k_between                         BetweenFactor<Pose3>        (gtsam_graph.cpp:691-692)
 //   K4  k_imu                             CombinedImuFactor           (test_vro_imu_graph.cpp:191-196)
 //   K5  k_plane                           OrientedPlane3Factor        (gtsam_graph.cpp:1265)
-//   K6  k_lm_prior / k_proj_obs / k_proj_pose / k_schur   projection factors + landmark Schur complement
-//                                                                     (gtsam_graph.cpp:370-448)
+//   K6  k_lm_prior / k_proj_obs / k_proj_pose    projection factors (gtsam_graph.cpp:370-448); the landmark
+//       Schur complement itself is in fg_schur.cu
 //   K9  k_lm_backsub_obs / k_lm_update    landmark back-substitution + retraction
 //   K10 k_retract_reduced                 SE3 / vector / plane retraction (Values::retract)
 //   K3  k_preintegrate                    PreintegratedCombinedMeasurements::integrateMeasurement loop
@@ -448,74 +448,6 @@ __global__ void k_damp_rhs(SysView sys, const double* __restrict__ g_r, double l
   col[c] += lambda;
   if (add_rhs) col[nr - 1] -= g_r[C];
 }
-
-#if 0   // first version of the Schur complement (one warp per landmark, fp64 atomics); superseded by fg_schur.cu
-__global__ void __launch_bounds__(128) k_schur(int64_t L, int64_t M, const int64_t* __restrict__ lm_ptr, const int* __restrict__ obs_pose,
-                                               const double* __restrict__ W, const double* __restrict__ V,
-                                               const double* __restrict__ gl, double* __restrict__ Vinv, double lambda,
-                                               const int* __restrict__ off_pose, SysView sys) {
-  int64_t l = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (l >= L) return;
-  double A[9] = {V[6 * l] + lambda, V[6 * l + 1], V[6 * l + 2],
-                 V[6 * l + 1], V[6 * l + 3] + lambda, V[6 * l + 4],
-                 V[6 * l + 2], V[6 * l + 4], V[6 * l + 5] + lambda};
-  double Ai[9];
-  inv3(A, Ai);
-  if (lane == 0) {
-    Vinv[6 * l] = Ai[0]; Vinv[6 * l + 1] = Ai[1]; Vinv[6 * l + 2] = Ai[2];
-    Vinv[6 * l + 3] = Ai[4]; Vinv[6 * l + 4] = Ai[5]; Vinv[6 * l + 5] = Ai[8];
-  }
-  double g3[3] = {gl[3 * l], gl[3 * l + 1], gl[3 * l + 2]}, y[3];
-  m3_vec(Ai, g3, y);
-  int64_t b = lm_ptr[l];
-  int k = (int)(lm_ptr[l + 1] - b);
-  // rhs contribution: 6 entries per observation
-  for (int t = lane; t < 6 * k; t += 32) {
-    int a = t / 6, i = t % 6;
-    int64_t o = b + a;
-    double s = W[(int64_t)(3 * i) * M + o] * y[0] + W[(int64_t)(3 * i + 1) * M + o] * y[1] + W[(int64_t)(3 * i + 2) * M + o] * y[2];
-    int C = off_pose[obs_pose[o]] + i;
-    int sn = sys.col2sn[C];
-    int nr = sys.sn_nrows[sn];
-    atomicAdd(&sys.L[sys.sn_valptr[sn] + (int64_t)(C - sys.sn_col0[sn]) * nr + nr - 1], s);
-  }
-  // pairs (a >= bb)
-  int npairs = k * (k + 1) / 2;
-  for (int t = lane; t < npairs; t += 32) {
-    int a = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((a + 1) * (a + 2) / 2 <= t) ++a;
-    while (a * (a + 1) / 2 > t) --a;
-    int bb = t - a * (a + 1) / 2;
-    int64_t oa = b + a, ob = b + bb;
-    double Wa[18], Wb[18], Y[18], B[36];
-#pragma unroll
-    for (int i = 0; i < 18; ++i) { Wa[i] = W[(int64_t)i * M + oa]; Wb[i] = W[(int64_t)i * M + ob]; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) Y[3 * i + c] = Wa[3 * i] * Ai[c] + Wa[3 * i + 1] * Ai[3 + c] + Wa[3 * i + 2] * Ai[6 + c];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = 0; j < 6; ++j) B[6 * i + j] = -(Y[3 * i] * Wb[3 * j] + Y[3 * i + 1] * Wb[3 * j + 1] + Y[3 * i + 2] * Wb[3 * j + 2]);
-    int offa = off_pose[obs_pose[oa]], offb = off_pose[obs_pose[ob]];
-    if (offa == offb && a != bb) {
-      // the same pose observed twice by one landmark: both orderings land on the diagonal block
-      sys_add_block(sys, offa, 6, offb, 6, B, 6);
-      double Bt[36];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) Bt[6 * i + j] = B[6 * j + i];
-      sys_add_block(sys, offa, 6, offb, 6, Bt, 6);
-    } else {
-      sys_add_block(sys, offa, 6, offb, 6, B, 6);
-    }
-  }
-}
-
-#endif
 
 // ------------------------------------------------------------------ K9/K10 back-substitution and retraction
 // t_l = sum_o W_o^T delta_p(o) by warp-segmented reduction (thread per observation)

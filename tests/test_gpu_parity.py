@@ -152,3 +152,15 @@ def test_single_pose_and_empty_landmark():
     for k in ('proj_pose', 'proj_point', 'proj_uv'):
         spec[k] = spec[k][keep]
     check(spec, 1e-7, 1e-6, solver='schur')
+
+
+def test_generic_cholesky_kernel_is_equivalent(monkeypatch):
+    """fg_chol.cu (generic supernodal kernel, used when a panel exceeds the on-chip fast path) must give the same
+    optimum as fg_chol_reg.cu."""
+    spec = synth.make_config('C4', seed=2, scale=0.03)
+    ctx = abi.Context(device=0); abi.load_spec(ctx, spec); fast = ctx.optimize(); Tf = ctx.get_values(abi.T_POSE); ctx.close()
+    monkeypatch.setenv('FG_CHOL_GENERIC', '1')
+    ctx = abi.Context(device=0); abi.load_spec(ctx, spec); gen = ctx.optimize(); Tg = ctx.get_values(abi.T_POSE); ctx.close()
+    assert gen.iterations == fast.iterations
+    assert abs(gen.final_error - fast.final_error) <= 1e-10 * fast.final_error
+    assert np.abs(Tg - Tf).max() < 1e-9
