@@ -31,6 +31,11 @@ __device__ __forceinline__ int cr_ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int cr_ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cr_st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -71,14 +76,24 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
     const int u1 = upd_ptr[sn + 1];
     int buf = 0;
     while (u < u1) {
-      const int win = min(CR_T, u1 - u);
-      if (tid == 0) sm.first_not_ready = win;
-      __syncthreads();
-      if (tid < win && cr_ld_acquire(&flags[upd_d[u + tid]]) != epoch) atomicMin(&sm.first_not_ready, tid);
+      // warp 0 spins on the flags of the next (up to 32) descendants with relaxed loads and publishes the length
+      // of the ready prefix; one acquire fence once something is ready, one block barrier per batch
+      if (tid < 32) {
+        const int win = min(32, u1 - u);
+        const int* fp = flags + upd_d[u + min(tid, win - 1)];
+        int n;
+        while (true) {
+          const int f = (tid < win) ? cr_ld_relaxed(fp) : epoch;
+          const unsigned notready = ~__ballot_sync(0xffffffffu, f == epoch);
+          n = notready ? (__ffs(notready) - 1) : 32;
+          if (n > win) n = win;
+          if (n > 0) break;
+        }
+        __threadfence();
+        if (tid == 0) sm.first_not_ready = n;
+      }
       __syncthreads();
       const int nready = sm.first_not_ready;
-      __syncthreads();
-      if (nready == 0) { __nanosleep(200); continue; }
       UpdRec rec = upd_rec[u];
       for (int uu = u; uu < u + nready; ++uu, buf ^= 1) {
         const int K = rec.K, nrd = rec.nrd, nrows_u = rec.nrows_u, nb = rec.nb;
@@ -149,31 +164,35 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
     __syncthreads();
     if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4 * sn + 1] = t; }
 
-    // ---- diagonal block
-    for (int i = tid; i < nc * nc; i += CR_T) {
-      const int r = i % nc, c = i / nc;
-      sm.Ds[r * CR_DP + c] = (r >= c) ? sm.P[r + c * nr] : 0.0;
-    }
-    __syncthreads();
+    // ---- diagonal block: warp 0, lane i holds row i in registers, columns broadcast by shuffles
     if (tid < 32) {
       const int lane = tid;
-      for (int c = 0; c < nc; ++c) {
-        double dcc = sm.Ds[c * CR_DP + c];
-        if (!(dcc > 0.0)) {
-          if (lane == 0) atomicExch(status, 1);
-          dcc = 1.0;
+      double a[CR_NC];
+#pragma unroll
+      for (int c = 0; c < CR_NC; ++c) a[c] = (lane < nc && c <= lane) ? sm.P[lane + c * nr] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CR_NC; ++c) {
+        if (c < nc) {
+          double dcc = __shfl_sync(0xffffffffu, a[c], c);
+          if (!(dcc > 0.0)) {          // not positive definite (or NaN): flag and keep going with a safe pivot
+            if (lane == 0) atomicExch(status, 1);
+            dcc = 1.0;
+          }
+          const double inv = rsqrt(dcc);
+          if (lane == c) a[c] = dcc * inv;
+          else if (lane > c) a[c] *= inv;
+#pragma unroll
+          for (int j = c + 1; j < CR_NC; ++j) {
+            if (j < nc) {
+              const double ljc = __shfl_sync(0xffffffffu, a[c], j);
+              if (lane >= j) a[j] -= a[c] * ljc;
+            }
+          }
         }
-        const double inv = rsqrt(dcc);
-        const double l = dcc * inv;
-        __syncwarp();
-        if (lane == c) sm.Ds[c * CR_DP + c] = l;
-        if (lane > c && lane < nc) sm.Ds[lane * CR_DP + c] *= inv;
-        __syncwarp();
-        if (lane > c && lane < nc) {
-          const double li = sm.Ds[lane * CR_DP + c];
-          for (int j = c + 1; j <= lane; ++j) sm.Ds[lane * CR_DP + j] -= li * sm.Ds[j * CR_DP + c];
-        }
-        __syncwarp();
+      }
+      if (lane < nc) {
+#pragma unroll
+        for (int c = 0; c < CR_NC; ++c) sm.Ds[lane * CR_DP + c] = (c <= lane) ? a[c] : 0.0;
       }
     }
     __syncthreads();
