@@ -40,6 +40,24 @@ __device__ __forceinline__ void cr_st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// acc[j] = sum_k x[k] * B[k][j] for j < 2*JP: straight-line (x is zero for k >= K, the tile is zero padded)
+template <int JP>
+__device__ __forceinline__ void cr_row_times_block(const double* __restrict__ x, const double* __restrict__ Bt, double* acc) {
+#pragma unroll
+  for (int j = 0; j < 2 * JP; ++j) acc[j] = 0.0;
+#pragma unroll
+  for (int k = 0; k < CR_NC; ++k) {
+    const double xk = x[k];
+    const double2* brow = reinterpret_cast<const double2*>(Bt + k * CR_NC);
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp) {
+      const double2 bb = brow[jp];
+      acc[2 * jp] += xk * bb.x;
+      acc[2 * jp + 1] += xk * bb.y;
+    }
+  }
+}
+
 struct CrSmem {
   double P[CR_ROWS * CR_NC];            // target panel, column-major, ld = nr
   double Bs[2][CR_NC * CR_NC];          // [buf][k][j] descendant block, j < nb
@@ -67,7 +85,7 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     double* Lp = s.L + s.sn_valptr[sn];
     const int* rows_g = s.rowidx + s.sn_rowptr[sn];
-    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4 * sn] = t; dbg[4 * sn + 3] = blockIdx.x; }
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn] = t; dbg[8 * sn + 7] = blockIdx.x; }
     for (int i = tid; i < nr; i += CR_T) sm.rows_s[i] = rows_g[i];
     for (int i = tid; i < nr * nc; i += CR_T) sm.P[i] = Lp[i];
     __syncthreads();
@@ -94,6 +112,7 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
       }
       __syncthreads();
       const int nready = sm.first_not_ready;
+      if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 1] = t; }
       UpdRec rec = upd_rec[u];
       for (int uu = u; uu < u + nready; ++uu, buf ^= 1) {
         const int K = rec.K, nrd = rec.nrd, nrows_u = rec.nrows_u, nb = rec.nb;
@@ -112,9 +131,9 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
 #pragma unroll
           for (int k = 0; k < CR_NC; ++k) x[m][k] = (act && k < K) ? __ldcg(&Ld[a + i + (int64_t)k * nrd]) : 0.0;
         }
-        if (tid < nb * K) {
-          const int j = tid % nb, k = tid / nb;
-          sm.Bs[buf][k * CR_NC + j] = __ldcg(&Ld[a + j + (int64_t)k * nrd]);
+        if (tid < CR_NC * CR_NC) {
+          const int j = tid % CR_NC, k = tid / CR_NC;
+          sm.Bs[buf][tid] = (j < nb && k < K) ? __ldcg(&Ld[a + j + (int64_t)k * nrd]) : 0.0;
         }
         if (tid < nb) sm.colj[buf][tid] = __ldg(rd + a + tid) - c0;
         __syncthreads();
@@ -130,29 +149,23 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
             r = lo;
           }
           double acc[CR_NC];
-#pragma unroll
-          for (int j = 0; j < CR_NC; ++j) acc[j] = 0.0;
-#pragma unroll
-          for (int k = 0; k < CR_NC; ++k) {
-            if (k < K) {
-              const double xk = x[m][k];
-              const double2* brow = reinterpret_cast<const double2*>(&sm.Bs[buf][k * CR_NC]);
-#pragma unroll
-              for (int jp = 0; jp < CR_NC / 2; ++jp) {
-                if (2 * jp < nb) {
-                  const double2 bb = brow[jp];
-                  acc[2 * jp] += xk * bb.x;
-                  acc[2 * jp + 1] += xk * bb.y;
-                }
-              }
-            }
+          const double* Bt = sm.Bs[buf];
+          switch ((nb + 1) >> 1) {
+            case 1: cr_row_times_block<1>(x[m], Bt, acc); break;
+            case 2: cr_row_times_block<2>(x[m], Bt, acc); break;
+            case 3: cr_row_times_block<3>(x[m], Bt, acc); break;
+            case 4: cr_row_times_block<4>(x[m], Bt, acc); break;
+            case 5: cr_row_times_block<5>(x[m], Bt, acc); break;
+            case 6: cr_row_times_block<6>(x[m], Bt, acc); break;
+            case 7: cr_row_times_block<7>(x[m], Bt, acc); break;
+            default: cr_row_times_block<8>(x[m], Bt, acc); break;
           }
+          for (int j = 0; j < nb; ++j) {
+            const int cj = sm.colj[buf][j];
+            double v = acc[0];
 #pragma unroll
-          for (int j = 0; j < CR_NC; ++j) {
-            if (j < nb) {
-              const int cj = sm.colj[buf][j];
-              if (R[m] >= c0 + cj) sm.P[r + cj * nr] -= acc[j];     // strictly-upper part of the diagonal block is not stored
-            }
+            for (int q = 1; q < CR_NC; ++q) v = (j == q) ? acc[q] : v;
+            if (R[m] >= c0 + cj) sm.P[r + cj * nr] -= v;     // strictly-upper part of the diagonal block is not stored
           }
         }
         // no barrier here: the next update writes the other Bs/colj buffer, and distinct descendant rows map to
@@ -162,40 +175,40 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
       __syncthreads();
     }
     __syncthreads();
-    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4 * sn + 1] = t; }
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 2] = t; }
 
     // ---- diagonal block: warp 0, lane i holds row i in registers, columns broadcast by shuffles
     if (tid < 32) {
       const int lane = tid;
       double a[CR_NC];
-#pragma unroll
-      for (int c = 0; c < CR_NC; ++c) a[c] = (lane < nc && c <= lane) ? sm.P[lane + c * nr] : 0.0;
+      const int lrow = min(lane, nc - 1);
 #pragma unroll
       for (int c = 0; c < CR_NC; ++c) {
-        if (c < nc) {
-          double dcc = __shfl_sync(0xffffffffu, a[c], c);
-          if (!(dcc > 0.0)) {          // not positive definite (or NaN): flag and keep going with a safe pivot
-            if (lane == 0) atomicExch(status, 1);
-            dcc = 1.0;
-          }
-          const double inv = rsqrt(dcc);
-          if (lane == c) a[c] = dcc * inv;
-          else if (lane > c) a[c] *= inv;
+        const double v = sm.P[lrow + min(c, nc - 1) * nr];
+        a[c] = (lane < nc && c <= lane) ? v : ((lane == c) ? 1.0 : 0.0);      // identity padding: no predicates below
+      }
+      bool bad = false;
 #pragma unroll
-          for (int j = c + 1; j < CR_NC; ++j) {
-            if (j < nc) {
-              const double ljc = __shfl_sync(0xffffffffu, a[c], j);
-              if (lane >= j) a[j] -= a[c] * ljc;
-            }
-          }
+      for (int c = 0; c < CR_NC; ++c) {
+        double dcc = __shfl_sync(0xffffffffu, a[c], c);
+        bad = bad || !(dcc > 0.0);
+        dcc = (dcc > 0.0) ? dcc : 1.0;                 // not positive definite (or NaN): safe pivot, flagged below
+        const double inv = rsqrt(dcc);
+        a[c] = (lane == c) ? dcc * inv : a[c] * inv;
+#pragma unroll
+        for (int j = c + 1; j < CR_NC; ++j) {
+          const double ljc = __shfl_sync(0xffffffffu, a[c], j);
+          a[j] -= (lane >= j) ? a[c] * ljc : 0.0;
         }
       }
+      if (bad && lane == 0) atomicExch(status, 1);
       if (lane < nc) {
 #pragma unroll
         for (int c = 0; c < CR_NC; ++c) sm.Ds[lane * CR_DP + c] = (c <= lane) ? a[c] : 0.0;
       }
     }
     __syncthreads();
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 3] = t; }
     // ---- panel solve out of shared memory, one coalesced global store per column
     for (int r = tid; r < nr; r += CR_T) {
       if (r < nc) {
@@ -216,10 +229,11 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
         }
       }
     }
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 4] = t; }
     __threadfence();
     __syncthreads();
     if (tid == 0) cr_st_release(&flags[sn], epoch);
-    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4 * sn + 2] = t; }
+    if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 5] = t; }
   }
 }
 
@@ -248,19 +262,19 @@ void launch_factor_reg(fg_ctx* c) {
   static int n_calls = 0;
   long long* dbg = nullptr;
   const char* trace = getenv("FG_CHOL_TRACE");
-  if (trace && ++n_calls == 3) cudaMalloc((void**)&dbg, sizeof(long long) * 4 * c->sym.n_sn);
+  if (trace && ++n_calls == 3) { cudaMalloc((void**)&dbg, sizeof(long long) * 8 * c->sym.n_sn); cudaMemset(dbg, 0, sizeof(long long) * 8 * c->sym.n_sn); }
   k_chol_reg<<<grid, CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.upd_rec, d.flags, d.counters,
                                                          c->epoch, c->sym.n_sn, d.status, dbg);
   if (dbg) {
-    std::vector<long long> h(4 * (size_t)c->sym.n_sn);
+    std::vector<long long> h(8 * (size_t)c->sym.n_sn);
     cudaStreamSynchronize(c->stream);
     cudaMemcpy(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
     cudaFree(dbg);
     FILE* f = fopen(trace, "w");
     if (f) {
       for (int i = 0; i < c->sym.n_sn; ++i)
-        fprintf(f, "%d %d %d %d %d %lld %lld %lld %lld\n", i, c->sym.level[i], c->sym.sn_ncols[i], c->sym.sn_nrows[i],
-                c->sym.upd_ptr[i + 1] - c->sym.upd_ptr[i], h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        fprintf(f, "%d %d %d %d %d %lld %lld %lld %lld %lld %lld %lld\n", i, c->sym.level[i], c->sym.sn_ncols[i], c->sym.sn_nrows[i],
+                c->sym.upd_ptr[i + 1] - c->sym.upd_ptr[i], h[8 * i], h[8 * i + 1], h[8 * i + 2], h[8 * i + 3], h[8 * i + 4], h[8 * i + 5], h[8 * i + 7]);
       fclose(f);
     }
   }
