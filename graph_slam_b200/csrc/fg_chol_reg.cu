@@ -58,6 +58,37 @@ __device__ __forceinline__ void cr_row_times_block(const double* __restrict__ x,
   }
 }
 
+// Warp-level Cholesky of a 16x16 (identity padded) lower-triangular block: lane i holds row i in a[0..15].
+// Template recursion pins every register index at compile time (a rolled loop would push a[] to local memory).
+template <int C, int J>
+struct CrPotrfUpd {
+  static __device__ __forceinline__ void run(double (&a)[CR_NC], int lane) {
+    const double ljc = __shfl_sync(0xffffffffu, a[C], J);
+    a[J] -= (lane >= J) ? a[C] * ljc : 0.0;
+    CrPotrfUpd<C, J + 1>::run(a, lane);
+  }
+};
+template <int C>
+struct CrPotrfUpd<C, CR_NC> {
+  static __device__ __forceinline__ void run(double (&)[CR_NC], int) {}
+};
+template <int C>
+struct CrPotrfCol {
+  static __device__ __forceinline__ void run(double (&a)[CR_NC], int lane, bool& bad) {
+    double dcc = __shfl_sync(0xffffffffu, a[C], C);
+    bad = bad || !(dcc > 0.0);
+    dcc = (dcc > 0.0) ? dcc : 1.0;                 // not positive definite (or NaN): safe pivot, flagged by the caller
+    const double inv = rsqrt(dcc);
+    a[C] = (lane == C) ? dcc * inv : a[C] * inv;
+    CrPotrfUpd<C, C + 1>::run(a, lane);
+    CrPotrfCol<C + 1>::run(a, lane, bad);
+  }
+};
+template <>
+struct CrPotrfCol<CR_NC> {
+  static __device__ __forceinline__ void run(double (&)[CR_NC], int, bool&) {}
+};
+
 struct CrSmem {
   double P[CR_ROWS * CR_NC];            // target panel, column-major, ld = nr
   double Bs[2][CR_NC * CR_NC];          // [buf][k][j] descendant block, j < nb
@@ -188,19 +219,7 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
         a[c] = (lane < nc && c <= lane) ? v : ((lane == c) ? 1.0 : 0.0);      // identity padding: no predicates below
       }
       bool bad = false;
-#pragma unroll
-      for (int c = 0; c < CR_NC; ++c) {
-        double dcc = __shfl_sync(0xffffffffu, a[c], c);
-        bad = bad || !(dcc > 0.0);
-        dcc = (dcc > 0.0) ? dcc : 1.0;                 // not positive definite (or NaN): safe pivot, flagged below
-        const double inv = rsqrt(dcc);
-        a[c] = (lane == c) ? dcc * inv : a[c] * inv;
-#pragma unroll
-        for (int j = c + 1; j < CR_NC; ++j) {
-          const double ljc = __shfl_sync(0xffffffffu, a[c], j);
-          a[j] -= (lane >= j) ? a[c] * ljc : 0.0;
-        }
-      }
+      CrPotrfCol<0>::run(a, lane, bad);
       if (bad && lane == 0) atomicExch(status, 1);
       if (lane < nc) {
 #pragma unroll
