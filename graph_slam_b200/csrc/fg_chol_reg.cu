@@ -181,22 +181,13 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
           }
           double acc[CR_NC];
           const double* Bt = sm.Bs[buf];
-          switch ((nb + 1) >> 1) {
-            case 1: cr_row_times_block<1>(x[m], Bt, acc); break;
-            case 2: cr_row_times_block<2>(x[m], Bt, acc); break;
-            case 3: cr_row_times_block<3>(x[m], Bt, acc); break;
-            case 4: cr_row_times_block<4>(x[m], Bt, acc); break;
-            case 5: cr_row_times_block<5>(x[m], Bt, acc); break;
-            case 6: cr_row_times_block<6>(x[m], Bt, acc); break;
-            case 7: cr_row_times_block<7>(x[m], Bt, acc); break;
-            default: cr_row_times_block<8>(x[m], Bt, acc); break;
-          }
-          for (int j = 0; j < nb; ++j) {
-            const int cj = sm.colj[buf][j];
-            double v = acc[0];
+          cr_row_times_block<CR_NC / 2>(x[m], Bt, acc);     // one compact variant: instruction-cache footprint matters more than DFMA count here
 #pragma unroll
-            for (int q = 1; q < CR_NC; ++q) v = (j == q) ? acc[q] : v;
-            if (R[m] >= c0 + cj) sm.P[r + cj * nr] -= v;     // strictly-upper part of the diagonal block is not stored
+          for (int j = 0; j < CR_NC; ++j) {
+            if (j < nb) {
+              const int cj = sm.colj[buf][j];
+              if (R[m] >= c0 + cj) sm.P[r + cj * nr] -= acc[j];     // strictly-upper part of the diagonal block is not stored
+            }
           }
         }
         // no barrier here: the next update writes the other Bs/colj buffer, and distinct descendant rows map to
@@ -208,45 +199,49 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
     __syncthreads();
     if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 2] = t; }
 
-    // ---- diagonal block: warp 0, lane i holds row i in registers, columns broadcast by shuffles
+    // ---- diagonal block: compact rolled loops in shared memory (warp 0); code size is what counts on this path
+    for (int i = tid; i < nc * nc; i += CR_T) {
+      const int r = i % nc, c = i / nc;
+      sm.Ds[r * CR_DP + c] = (r >= c) ? sm.P[r + c * nr] : 0.0;
+    }
+    __syncthreads();
     if (tid < 32) {
       const int lane = tid;
-      double a[CR_NC];
-      const int lrow = min(lane, nc - 1);
-#pragma unroll
-      for (int c = 0; c < CR_NC; ++c) {
-        const double v = sm.P[lrow + min(c, nc - 1) * nr];
-        a[c] = (lane < nc && c <= lane) ? v : ((lane == c) ? 1.0 : 0.0);      // identity padding: no predicates below
-      }
-      bool bad = false;
-      CrPotrfCol<0>::run(a, lane, bad);
-      if (bad && lane == 0) atomicExch(status, 1);
-      if (lane < nc) {
-#pragma unroll
-        for (int c = 0; c < CR_NC; ++c) sm.Ds[lane * CR_DP + c] = (c <= lane) ? a[c] : 0.0;
+      for (int c = 0; c < nc; ++c) {
+        double dcc = sm.Ds[c * CR_DP + c];
+        if (!(dcc > 0.0)) {          // not positive definite (or NaN): flag and keep going with a safe pivot
+          if (lane == 0) atomicExch(status, 1);
+          dcc = 1.0;
+        }
+        const double inv = rsqrt(dcc);
+        __syncwarp();
+        double li = 0.0;
+        if (lane == c) sm.Ds[c * CR_DP + c] = dcc * inv;
+        if (lane > c && lane < nc) { li = sm.Ds[lane * CR_DP + c] * inv; sm.Ds[lane * CR_DP + c] = li; }
+        __syncwarp();
+        if (lane > c && lane < nc)
+          for (int j = c + 1; j <= lane; ++j) sm.Ds[lane * CR_DP + j] -= li * sm.Ds[j * CR_DP + c];
+        __syncwarp();
       }
     }
     __syncthreads();
     if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 3] = t; }
-    // ---- panel solve out of shared memory, one coalesced global store per column
+    // ---- panel solve in place in shared memory (thread per row, rolled), then one coalesced store per column
     for (int r = tid; r < nr; r += CR_T) {
       if (r < nc) {
-#pragma unroll
-        for (int c = 0; c < CR_NC; ++c)
-          if (c <= r) Lp[r + (int64_t)c * nr] = sm.Ds[r * CR_DP + c];
+        for (int c = 0; c <= r; ++c) sm.P[r + c * nr] = sm.Ds[r * CR_DP + c];
       } else {
-        double xs[CR_NC];
-#pragma unroll
-        for (int c = 0; c < CR_NC; ++c) {
-          if (c < nc) {
-            double v = sm.P[r + c * nr];
-#pragma unroll
-            for (int k = 0; k < c; ++k) v -= xs[k] * sm.Ds[c * CR_DP + k];
-            xs[c] = v / sm.Ds[c * CR_DP + c];
-            Lp[r + (int64_t)c * nr] = xs[c];
-          }
+        for (int c = 0; c < nc; ++c) {
+          double v = sm.P[r + c * nr];
+          for (int k = 0; k < c; ++k) v -= sm.P[r + k * nr] * sm.Ds[c * CR_DP + k];
+          sm.P[r + c * nr] = v / sm.Ds[c * CR_DP + c];
         }
       }
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * nc; i += CR_T) {
+      const int r = i % nr, c = i / nr;
+      if (r >= nc || c <= r) Lp[i] = sm.P[i];
     }
     if (dbg && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[8 * sn + 4] = t; }
     __threadfence();
