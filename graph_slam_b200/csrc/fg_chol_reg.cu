@@ -9,8 +9,8 @@
 //     a chain of them; the (b-a) x K block is broadcast from a double-buffered shared tile;
 //   * the row is located in the target's sorted row list by a binary search in shared memory and the products
 //     are subtracted in place (distinct rows per thread: no conflicts, fixed order: deterministic).
-// The diagonal block is factored by one warp, the panel rows are solved against it straight out of shared
-// memory and written to global memory once, coalesced.
+// The diagonal block is factored by one warp with compact rolled loops in shared memory, the panel rows are solved
+// against it in place in shared memory and the finished panel is written to global memory once, coalesced.
 // Limits: supernode width <= 16 columns (fg_symbolic.cpp caps it), panel height <= 1024 rows; graphs beyond that
 // use the generic kernel in fg_chol.cu.  No fp64 tcgen05 kind exists, hence DFMA.
 #include <cstdio>
@@ -40,7 +40,10 @@ __device__ __forceinline__ void cr_st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// acc[j] = sum_k x[k] * B[k][j] for j < 2*JP: straight-line (x is zero for k >= K, the tile is zero padded)
+// acc[j] = sum_k x[k] * B[k][j] for j < 2*JP: straight-line (x is zero for k >= K, the tile is zero padded).
+// Only JP = 8 is instantiated: the kernel's instruction footprint decides the latency of the single-warp sections
+// (measured: ~35 cycles/instruction when the hot path did not fit the instruction cache), so one compact variant
+// with some padded DFMAs beats eight exact ones.
 template <int JP>
 __device__ __forceinline__ void cr_row_times_block(const double* __restrict__ x, const double* __restrict__ Bt, double* acc) {
 #pragma unroll
@@ -58,41 +61,12 @@ __device__ __forceinline__ void cr_row_times_block(const double* __restrict__ x,
   }
 }
 
-// Warp-level Cholesky of a 16x16 (identity padded) lower-triangular block: lane i holds row i in a[0..15].
-// Template recursion pins every register index at compile time (a rolled loop would push a[] to local memory).
-template <int C, int J>
-struct CrPotrfUpd {
-  static __device__ __forceinline__ void run(double (&a)[CR_NC], int lane) {
-    const double ljc = __shfl_sync(0xffffffffu, a[C], J);
-    a[J] -= (lane >= J) ? a[C] * ljc : 0.0;
-    CrPotrfUpd<C, J + 1>::run(a, lane);
-  }
-};
-template <int C>
-struct CrPotrfUpd<C, CR_NC> {
-  static __device__ __forceinline__ void run(double (&)[CR_NC], int) {}
-};
-template <int C>
-struct CrPotrfCol {
-  static __device__ __forceinline__ void run(double (&a)[CR_NC], int lane, bool& bad) {
-    double dcc = __shfl_sync(0xffffffffu, a[C], C);
-    bad = bad || !(dcc > 0.0);
-    dcc = (dcc > 0.0) ? dcc : 1.0;                 // not positive definite (or NaN): safe pivot, flagged by the caller
-    const double inv = rsqrt(dcc);
-    a[C] = (lane == C) ? dcc * inv : a[C] * inv;
-    CrPotrfUpd<C, C + 1>::run(a, lane);
-    CrPotrfCol<C + 1>::run(a, lane, bad);
-  }
-};
-template <>
-struct CrPotrfCol<CR_NC> {
-  static __device__ __forceinline__ void run(double (&)[CR_NC], int, bool&) {}
-};
-
 struct CrSmem {
   double P[CR_ROWS * CR_NC];            // target panel, column-major, ld = nr
   double Bs[2][CR_NC * CR_NC];          // [buf][k][j] descendant block, j < nb
   double Ds[CR_NC * CR_DP];
+  double colbuf[CR_NC];                 // current column of the diagonal factor (keeps the potrf inner loop alias-free)
+  double dinv[CR_NC];                   // 1 / L_cc
   int rows_s[CR_ROWS];
   int colj[2][CR_NC];
   int slot, first_not_ready;
@@ -216,11 +190,15 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
         const double inv = rsqrt(dcc);
         __syncwarp();
         double li = 0.0;
-        if (lane == c) sm.Ds[c * CR_DP + c] = dcc * inv;
-        if (lane > c && lane < nc) { li = sm.Ds[lane * CR_DP + c] * inv; sm.Ds[lane * CR_DP + c] = li; }
+        if (lane == c) { sm.Ds[c * CR_DP + c] = dcc * inv; sm.dinv[c] = inv; }
+        if (lane > c && lane < nc) { li = sm.Ds[lane * CR_DP + c] * inv; sm.Ds[lane * CR_DP + c] = li; sm.colbuf[lane] = li; }
         __syncwarp();
-        if (lane > c && lane < nc)
-          for (int j = c + 1; j <= lane; ++j) sm.Ds[lane * CR_DP + j] -= li * sm.Ds[j * CR_DP + c];
+        if (lane > c && lane < nc) {
+          double* row = &sm.Ds[lane * CR_DP];
+          const double* col = sm.colbuf;
+#pragma unroll 4
+          for (int j = c + 1; j <= lane; ++j) row[j] -= li * col[j];
+        }
         __syncwarp();
       }
     }
@@ -231,10 +209,25 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
       if (r < nc) {
         for (int c = 0; c <= r; ++c) sm.P[r + c * nr] = sm.Ds[r * CR_DP + c];
       } else {
-        for (int c = 0; c < nc; ++c) {
-          double v = sm.P[r + c * nr];
-          for (int k = 0; k < c; ++k) v -= sm.P[r + k * nr] * sm.Ds[c * CR_DP + k];
-          sm.P[r + c * nr] = v / sm.Ds[c * CR_DP + c];
+        // four columns at a time: the k loop carries four independent accumulators, the 4x4 triangle is solved in registers
+        for (int cc = 0; cc < nc; cc += 4) {
+          double v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = (cc + i < nc) ? sm.P[r + (cc + i) * nr] : 0.0;
+          for (int k = 0; k < cc; ++k) {
+            const double xk = sm.P[r + k * nr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] -= xk * sm.Ds[(cc + i) * CR_DP + k];     // rows >= nc of Ds are never read with cc+i >= nc: guarded below
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (cc + i < nc) {
+#pragma unroll
+              for (int q = 0; q < i; ++q) v[i] -= v[q] * sm.Ds[(cc + i) * CR_DP + cc + q];
+              v[i] *= sm.dinv[cc + i];
+              sm.P[r + (cc + i) * nr] = v[i];
+            }
+          }
         }
       }
     }
