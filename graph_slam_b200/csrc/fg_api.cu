@@ -602,6 +602,16 @@ extern "C" int fg_finalize(fg_ctx* c) {
       (rc = dev_upload(c, &d.anc_ptr, S.anc_ptr)) || (rc = dev_upload(c, &d.anc_t, S.anc_t)) || (rc = dev_upload(c, &d.anc_a, S.anc_a)) ||
       (rc = dev_upload(c, &d.anc_b, S.anc_b)) || (rc = dev_upload(c, &d.sched, S.sched)) ||
       (rc = dev_upload<int>(c, &d.flags2, nullptr, S.n_sn)) || (rc = dev_upload<int>(c, &d.counters, nullptr, 4))) return rc;
+  if (S.use_fronts) {
+    if ((rc = dev_upload(c, &d.updr_ptr, S.updr_ptr)) || (rc = dev_upload(c, &d.updr_d, S.updr_d)) || (rc = dev_upload(c, &d.updr_rec, S.updr_rec)) ||
+        (rc = dev_upload(c, &d.sched_a, S.sched_a)) || (rc = dev_upload(c, &d.sched_c, S.sched_c)) ||
+        (rc = dev_upload(c, &d.fr_rowptr, S.fr_rowptr)) || (rc = dev_upload(c, &d.fr_rows, S.fr_rows)) || (rc = dev_upload(c, &d.fr_uptr, S.fr_uptr)) ||
+        (rc = dev_upload(c, &d.pm_ptr, S.pm_ptr)) || (rc = dev_upload(c, &d.posmap, S.posmap)) || (rc = dev_upload(c, &d.pmne_ptr, S.pmne_ptr)) ||
+        (rc = dev_upload(c, &d.pm_nonempty, S.pm_nonempty)) || (rc = dev_upload(c, &d.leaf_sn_lo, S.leaf_sn_lo)) || (rc = dev_upload(c, &d.leaf_sn_hi, S.leaf_sn_hi)) ||
+        (rc = dev_upload(c, &d.tf_ptr, S.tf_ptr)) || (rc = dev_upload(c, &d.tf_leaf, S.tf_leaf)) ||
+        (rc = dev_upload(c, &d.tile_leaf, S.tile_leaf)) || (rc = dev_upload(c, &d.tile_i, S.tile_i)) || (rc = dev_upload(c, &d.tile_j, S.tile_j)) ||
+        (rc = dev_upload<double>(c, &d.U, nullptr, (size_t)S.fr_uptr[S.n_leaves]))) return rc;
+  }
   CK(cudaStreamSynchronize(c->stream));
   c->epoch = 0;
   c->finalized = true;
@@ -820,6 +830,21 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 18: put(S.anc_t); break;
     case 19: put(S.anc_a); break;
     case 20: put(S.anc_b); break;
+    case 21: put(S.sn_leaf); break;
+    case 22: put(S.updr_ptr); break;
+    case 23: put(S.updr_d); break;
+    case 24: put(S.updr_a); break;
+    case 25: put(S.updr_b); break;
+    case 26: put(S.fr_rowptr); break;
+    case 27: put(S.fr_rows); break;
+    case 28: v.clear(); for (size_t l = 0; l < S.leaf_sn_lo.size(); ++l) { v.push_back(S.leaf_sn_lo[l]); v.push_back(S.leaf_sn_hi[l]); } break;
+    case 29: put(S.tf_ptr); break;
+    case 30: put(S.tf_leaf); break;
+    case 31: v.assign(S.pm_ptr.begin(), S.pm_ptr.end()); break;
+    case 32: put(S.posmap); break;
+    case 33: v = {S.use_fronts ? 1 : 0, S.n_leaves, S.n_levels_fronts, (int64_t)S.tile_leaf.size()}; break;
+    case 34: put(S.sched_a); break;
+    case 35: put(S.sched_c); break;
     default: return FG_ERR_INVALID;
   }
   if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];

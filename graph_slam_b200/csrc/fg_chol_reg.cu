@@ -13,6 +13,7 @@
 // against it in place in shared memory and the finished panel is written to global memory once, coalesced.
 // Limits: supernode width <= 16 columns (fg_symbolic.cpp caps it), panel height <= 1024 rows; graphs beyond that
 // use the generic kernel in fg_chol.cu.  No fp64 tcgen05 kind exists, hence DFMA.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -68,6 +69,8 @@ struct CrSmem {
   double colbuf[CR_NC];                 // current column of the diagonal factor (keeps the potrf inner loop alias-free)
   double dinv[CR_NC];                   // 1 / L_cc
   int rows_s[CR_ROWS];
+  int rl[CR_ROWS];                      // front row list of the leaf being subtracted (phase C prologue)
+  int colidx[CR_NC];
   int colj[2][CR_NC];
   int slot, first_not_ready;
 };
@@ -75,7 +78,7 @@ struct CrSmem {
 __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __restrict__ sched, const int* __restrict__ upd_ptr,
                                                       const int* __restrict__ upd_d, const int* __restrict__ upd_a,
                                                       const int* __restrict__ upd_b, const UpdRec* __restrict__ upd_rec, int* flags, int* counters,
-                                                      int epoch, int n_sn, int* status, long long* dbg) {
+                                                      int epoch, int n_sn, int* status, long long* dbg, FrontView fv) {
   extern __shared__ __align__(16) unsigned char cr_raw[];
   CrSmem& sm = *reinterpret_cast<CrSmem*>(cr_raw);
   const int tid = threadIdx.x;
@@ -94,6 +97,37 @@ __global__ void __launch_bounds__(CR_T, 1) k_chol_reg(SysView s, const int* __re
     for (int i = tid; i < nr; i += CR_T) sm.rows_s[i] = rows_g[i];
     for (int i = tid; i < nr * nc; i += CR_T) sm.P[i] = Lp[i];
     __syncthreads();
+    // ---- phase C prologue: subtract the dense leaf fronts that reach this supernode (fg_front.cu)
+    if (fv.tf_ptr) {
+      for (int e = fv.tf_ptr[sn]; e < fv.tf_ptr[sn + 1]; ++e) {
+        const int l = fv.tf_leaf[e];
+        const int* Rl = fv.fr_rows + fv.fr_rowptr[l];
+        const int nR = fv.fr_rowptr[l + 1] - fv.fr_rowptr[l];
+        const double* Ul = fv.U + fv.fr_uptr[l];
+        for (int i = tid; i < nR; i += CR_T) sm.rl[i] = Rl[i];
+        __syncthreads();
+        if (tid < nc) {
+          const int g = c0 + tid;
+          int lo = 0, hi = nR - 1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rl[mid] < g) lo = mid + 1; else hi = mid; }
+          sm.colidx[tid] = (nR > 0 && sm.rl[lo] == g) ? lo : -1;
+        }
+        __syncthreads();
+        for (int r = tid; r < nr; r += CR_T) {
+          const int g = sm.rows_s[r];
+          int lo = 0, hi = nR - 1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rl[mid] < g) lo = mid + 1; else hi = mid; }
+          if (nR > 0 && sm.rl[lo] == g) {
+            const double* urow = Ul + (int64_t)lo * nR;
+            for (int c = 0; c < nc; ++c) {
+              const int jc = sm.colidx[c];
+              if (jc >= 0 && g >= c0 + c) sm.P[r + c * nr] -= urow[jc];
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
 
     int u = upd_ptr[sn];
     const int u1 = upd_ptr[sn + 1];
@@ -260,18 +294,33 @@ void launch_factor_reg(fg_ctx* c) {
     cudaFuncSetAttribute(k_chol_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CrSmem));
     attr_set = true;
   }
-  int grid = c->num_sms;
-  if (grid > c->sym.n_sn) grid = c->sym.n_sn;
   c->epoch += 1;
   cudaMemsetAsync(d.status, 0, sizeof(int), c->stream);
-  cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, c->stream);
-  // FG_CHOL_TRACE=<file>: dump per-supernode (grab, updates done, published) globaltimer stamps of the 3rd factorisation
+  // FG_CHOL_TRACE=<file>: dump per-supernode globaltimer stamps of the 3rd factorisation
   static int n_calls = 0;
   long long* dbg = nullptr;
   const char* trace = getenv("FG_CHOL_TRACE");
   if (trace && ++n_calls == 3) { cudaMalloc((void**)&dbg, sizeof(long long) * 8 * c->sym.n_sn); cudaMemset(dbg, 0, sizeof(long long) * 8 * c->sym.n_sn); }
-  k_chol_reg<<<grid, CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.upd_rec, d.flags, d.counters,
-                                                         c->epoch, c->sym.n_sn, d.status, dbg);
+  const char* nofront = getenv("FG_NO_FRONTS");
+  const bool fronts = c->sym.use_fronts && !(nofront && nofront[0] == '1');
+  FrontView none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!fronts) {
+    int grid = std::min(c->num_sms, c->sym.n_sn);
+    cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, c->stream);
+    k_chol_reg<<<grid, CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.upd_rec, d.flags, d.counters,
+                                                           c->epoch, c->sym.n_sn, d.status, dbg, none);
+  } else {
+    // phase A: the leaves (reduced update lists); phase B: one dense update matrix per leaf; phase C: the rest
+    const int na = (int)c->sym.sched_a.size(), nc = (int)c->sym.sched_c.size();
+    cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, c->stream);
+    if (na) k_chol_reg<<<std::min(c->num_sms, na), CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched_a, d.updr_ptr, d.updr_d, nullptr, nullptr, d.updr_rec,
+                                                                                    d.flags, d.counters, c->epoch, na, d.status, dbg, none);
+    launch_front_syrk(c);
+    cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, c->stream);
+    FrontView fv = {d.tf_ptr, d.tf_leaf, d.fr_rowptr, d.fr_rows, d.fr_uptr, d.U};
+    if (nc) k_chol_reg<<<std::min(c->num_sms, nc), CR_T, sizeof(CrSmem), c->stream>>>(s, d.sched_c, d.updr_ptr, d.updr_d, nullptr, nullptr, d.updr_rec,
+                                                                                    d.flags, d.counters, c->epoch, nc, d.status, dbg, fv);
+  }
   if (dbg) {
     std::vector<long long> h(8 * (size_t)c->sym.n_sn);
     cudaStreamSynchronize(c->stream);

@@ -68,6 +68,20 @@ struct Symbolic {
   std::vector<int64_t> cov_ptr; std::vector<int> cov_pose;   // pose co-visibility through landmarks (incl. self)
   int max_nrows = 0, max_ncols = 0;
   double flops_factor = 0;
+  // ---- leaf fronts (multifrontal-style path for the separators, fg_front.cu)
+  int n_leaves = 0;
+  bool use_fronts = false;
+  std::vector<int> sn_leaf;                        // nested-dissection leaf of each supernode (-1: separator / plane)
+  std::vector<int> leaf_sn_lo, leaf_sn_hi;         // member supernodes of a leaf: [lo, hi)
+  std::vector<int> fr_rowptr, fr_rows;             // per leaf: sorted global rows below the leaf (its front), incl. the rhs row
+  std::vector<int64_t> fr_uptr;                    // per leaf: offset of its dense nR x nR update matrix in the U buffer
+  std::vector<int64_t> pm_ptr; std::vector<int> posmap;   // per member supernode: position of every front row in its row list (-1)
+  std::vector<int64_t> pmne_ptr; std::vector<unsigned char> pm_nonempty;   // per member: one flag per 64-row block of the front
+  std::vector<int> updr_ptr, updr_d, updr_a, updr_b; std::vector<UpdRec> updr_rec;   // update lists without leaf -> outside entries
+  std::vector<int> tf_ptr, tf_leaf;                // per supernode: leaves whose front must be subtracted from it
+  std::vector<int> sched_a, sched_c;               // schedules: leaf members, then everything else (both level sorted)
+  std::vector<int> tile_leaf, tile_i, tile_j;      // 64 x 64 tiles of the lower triangles of all fronts
+  int n_levels_fronts = 0;
 };
 
 // ------------------------------------------------------------------ device view passed to kernels
@@ -123,6 +137,11 @@ __device__ __forceinline__ void sys_add_block(const SysView& s, int oa, int da, 
   }
 }
 
+// leaf fronts as seen by phase C of k_chol_reg (all null when the phase has nothing to subtract)
+struct FrontView {
+  const int* tf_ptr; const int* tf_leaf; const int* fr_rowptr; const int* fr_rows; const int64_t* fr_uptr; const double* U;
+};
+
 // ------------------------------------------------------------------ device graph (raw pointers owned by the ctx)
 struct DevGraph {
   // values, current and trial
@@ -174,6 +193,15 @@ struct DevGraph {
   int64_t* sn_valptr = nullptr;
   int *upd_ptr = nullptr, *upd_d = nullptr, *upd_a = nullptr, *upd_b = nullptr;
   UpdRec* upd_rec = nullptr;
+  // leaf fronts
+  int *updr_ptr = nullptr, *updr_d = nullptr; UpdRec* updr_rec = nullptr;
+  int *sched_a = nullptr, *sched_c = nullptr;
+  int *fr_rowptr = nullptr, *fr_rows = nullptr; int64_t* fr_uptr = nullptr;
+  int64_t* pm_ptr = nullptr; int* posmap = nullptr; int64_t* pmne_ptr = nullptr; unsigned char* pm_nonempty = nullptr;
+  int *leaf_sn_lo = nullptr, *leaf_sn_hi = nullptr;
+  int *tf_ptr = nullptr, *tf_leaf = nullptr;
+  int *tile_leaf = nullptr, *tile_i = nullptr, *tile_j = nullptr;
+  double* U = nullptr;              // dense update matrices of all leaves
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
@@ -210,6 +238,7 @@ void launch_schur(fg_ctx* c, double lambda);              // fg_schur.cu: the la
 void launch_factor(fg_ctx* c);                            // cholesky; the rhs row makes it the forward solve too
 bool chol_reg_supported(const fg_ctx* c);                 // fg_chol_reg.cu: width <= 16, height <= 1024
 void launch_factor_reg(fg_ctx* c);                        // register-tiled fast path of the same factorisation
+void launch_front_syrk(fg_ctx* c);                        // fg_front.cu: dense update matrix of every leaf onto its front
 void launch_backsolve(fg_ctx* c);                         // backward solve -> delta
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
 void launch_error_only(fg_ctx* c, bool trial);            // chi2 of val (or val_new) -> scal[0] (or scal[3])

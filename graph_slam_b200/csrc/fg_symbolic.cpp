@@ -91,6 +91,8 @@ int build_symbolic(fg_ctx* c) {
 
   // ---- nested dissection over frames -> elimination order
   std::vector<int> elim; elim.reserve(nv);
+  std::vector<int> leaf_of;      // base index -> nested-dissection leaf (-1: separator / plane)
+  int n_leaves = 0;
   {
     // frames: maximal runs of class-0 variables with the same key index (base order is frame-major)
     std::vector<std::vector<int>> frames;
@@ -105,9 +107,10 @@ int build_symbolic(fg_ctx* c) {
     }
     std::vector<int> region(nv, -1);
     int next_region = 0;
+    leaf_of.assign(nv, -1);
     auto dims = [&](const std::vector<std::vector<int>>& F) { int d = 0; for (auto& f : F) for (int v : f) d += bdim[v]; return d; };
     std::function<void(std::vector<std::vector<int>>&)> nd = [&](std::vector<std::vector<int>>& F) {
-      auto emit = [&]() { for (auto& f : F) for (int v : f) elim.push_back(v); };
+      auto emit = [&]() { for (auto& f : F) for (int v : f) { elim.push_back(v); leaf_of[v] = n_leaves; } ++n_leaves; };
       if (F.size() < 8) { emit(); return; }
       size_t mid = F.size() / 2;
       int ra = next_region++, rb = next_region++;
@@ -182,7 +185,7 @@ int build_symbolic(fg_ctx* c) {
     while (v < nv) {
       int first = v, cols = vdim[v];
       while (v + 1 < nv && parent[v] == v + 1 && st[v].size() == st[v + 1].size() + 1 &&
-             cols + vdim[v + 1] <= kMaxSnCols) {
+             cols + vdim[v + 1] <= kMaxSnCols && leaf_of[elim[v]] == leaf_of[elim[v + 1]]) {
         ++v; cols += vdim[v];
       }
       sn_first.push_back(first); sn_last.push_back(v);
@@ -248,6 +251,98 @@ int build_symbolic(fg_ctx* c) {
     UpdRec& r = S.upd_rec[u];
     r.val_off = S.sn_valptr[d] + a; r.row_off = S.sn_rowptr[d] + a; r.nrd = S.sn_nrows[d]; r.nrows_u = S.sn_nrows[d] - a;
     r.K = (short)S.sn_ncols[d]; r.nb = (short)(b - a); r.pad[0] = r.pad[1] = 0;
+  }
+  // ---- leaf fronts: everything a leaf contributes to the supernodes OUTSIDE it is gathered in one dense update
+  //      matrix per leaf (fg_front.cu) instead of one rank-K update per (leaf supernode, outside target) pair
+  S.n_leaves = n_leaves;
+  S.sn_leaf.assign(S.n_sn, -1);
+  for (int s = 0; s < S.n_sn; ++s) S.sn_leaf[s] = leaf_of[elim[sn_first[s]]];
+  S.use_fronts = false;
+  if (n_leaves >= 2) {
+    S.leaf_sn_lo.assign(n_leaves, S.n_sn); S.leaf_sn_hi.assign(n_leaves, 0);
+    for (int s = 0; s < S.n_sn; ++s) {
+      int l = S.sn_leaf[s];
+      if (l >= 0) { S.leaf_sn_lo[l] = std::min(S.leaf_sn_lo[l], s); S.leaf_sn_hi[l] = std::max(S.leaf_sn_hi[l], s + 1); }
+    }
+    bool contiguous = true;
+    for (int l = 0; l < n_leaves && contiguous; ++l)
+      for (int s = S.leaf_sn_lo[l]; s < S.leaf_sn_hi[l]; ++s) if (S.sn_leaf[s] != l) { contiguous = false; break; }
+    if (contiguous) {
+      S.use_fronts = true;
+      S.fr_rowptr.assign(n_leaves + 1, 0); S.fr_uptr.assign(n_leaves + 1, 0);
+      S.pm_ptr.assign(S.n_sn + 1, 0); S.pmne_ptr.assign(S.n_sn + 1, 0);
+      std::vector<std::vector<int>> tf(S.n_sn);
+      for (int l = 0; l < n_leaves; ++l) {
+        const int lo = S.leaf_sn_lo[l], hi = S.leaf_sn_hi[l];
+        const int lc1 = (hi > lo) ? S.sn_col0[hi - 1] + S.sn_ncols[hi - 1] : 0;   // first column after the leaf
+        std::vector<int> Rl;
+        for (int s = lo; s < hi; ++s) {
+          const int* r = &S.rowidx[S.sn_rowptr[s]];
+          for (int i = S.sn_ncols[s]; i < S.sn_nrows[s]; ++i) if (r[i] >= lc1) Rl.push_back(r[i]);
+        }
+        std::sort(Rl.begin(), Rl.end()); Rl.erase(std::unique(Rl.begin(), Rl.end()), Rl.end());
+        S.fr_rows.insert(S.fr_rows.end(), Rl.begin(), Rl.end());
+        S.fr_rowptr[l + 1] = (int)S.fr_rows.size();
+        const int64_t nR = (int64_t)Rl.size();
+        S.fr_uptr[l + 1] = S.fr_uptr[l] + nR * nR;
+        // targets that receive this front
+        int last_t = -1;
+        for (int g : Rl) if (g < S.n_r) { int t = S.col2sn[g]; if (t != last_t) { tf[t].push_back(l); last_t = t; } }
+        // tiles of the lower triangle
+        const int nt = (int)((nR + 63) / 64);
+        for (int ti = 0; ti < nt; ++ti) for (int tj = 0; tj <= ti; ++tj) { S.tile_leaf.push_back(l); S.tile_i.push_back(ti); S.tile_j.push_back(tj); }
+      }
+      // position maps: for every member supernode, where each front row sits in its row list
+      for (int s = 0; s < S.n_sn; ++s) {
+        const int l = S.sn_leaf[s];
+        int64_t n = 0, nb = 0;
+        if (l >= 0) {
+          const int* Rl = &S.fr_rows[S.fr_rowptr[l]];
+          const int nR = S.fr_rowptr[l + 1] - S.fr_rowptr[l];
+          const int* r = &S.rowidx[S.sn_rowptr[s]];
+          const int nr = S.sn_nrows[s];
+          n = nR; nb = (nR + 63) / 64;
+          size_t base = S.posmap.size(), nbase = S.pm_nonempty.size();
+          S.posmap.resize(base + nR, -1); S.pm_nonempty.resize(nbase + nb, 0);
+          int i = S.sn_ncols[s];
+          for (int k = 0; k < nR; ++k) {
+            while (i < nr && r[i] < Rl[k]) ++i;
+            if (i < nr && r[i] == Rl[k]) { S.posmap[base + k] = i; S.pm_nonempty[nbase + k / 64] = 1; }
+          }
+        }
+        S.pm_ptr[s + 1] = S.pm_ptr[s] + n; S.pmne_ptr[s + 1] = S.pmne_ptr[s] + nb;
+      }
+      // reduced update lists: drop (leaf member -> target outside that leaf)
+      S.updr_ptr.assign(S.n_sn + 1, 0);
+      for (int t = 0; t < S.n_sn; ++t) {
+        for (int u = S.upd_ptr[t]; u < S.upd_ptr[t + 1]; ++u) {
+          const int d = S.upd_d[u];
+          if (S.sn_leaf[d] >= 0 && S.sn_leaf[d] != S.sn_leaf[t]) continue;
+          S.updr_d.push_back(d); S.updr_a.push_back(S.upd_a[u]); S.updr_b.push_back(S.upd_b[u]); S.updr_rec.push_back(S.upd_rec[u]);
+        }
+        S.updr_ptr[t + 1] = (int)S.updr_d.size();
+      }
+      S.tf_ptr.assign(S.n_sn + 1, 0);
+      for (int t = 0; t < S.n_sn; ++t) {
+        for (int l : tf[t]) if (S.sn_leaf[t] != l) { S.tf_leaf.push_back(l); if (S.sn_leaf[t] >= 0) S.use_fronts = false; }   // a leaf never feeds another leaf
+        S.tf_ptr[t + 1] = (int)S.tf_leaf.size();
+      }
+      // levels and the two phase schedules
+      std::vector<int> lv(S.n_sn, 0);
+      for (int s = 0; s < S.n_sn; ++s) {
+        for (int u = S.updr_ptr[s]; u < S.updr_ptr[s + 1]; ++u) lv[s] = std::max(lv[s], lv[S.updr_d[u]] + 1);
+        for (int e = S.tf_ptr[s]; e < S.tf_ptr[s + 1]; ++e) {
+          const int l = S.tf_leaf[e];
+          for (int m = S.leaf_sn_lo[l]; m < S.leaf_sn_hi[l]; ++m) lv[s] = std::max(lv[s], lv[m] + 1);
+        }
+      }
+      for (int s = 0; s < S.n_sn; ++s) (S.sn_leaf[s] >= 0 ? S.sched_a : S.sched_c).push_back(s);
+      auto bylevel = [&](int a, int b) { return lv[a] < lv[b]; };
+      std::stable_sort(S.sched_a.begin(), S.sched_a.end(), bylevel);
+      std::stable_sort(S.sched_c.begin(), S.sched_c.end(), bylevel);
+      S.n_levels_fronts = S.n_sn ? *std::max_element(lv.begin(), lv.end()) + 1 : 0;
+      for (int l = 0; l < n_leaves; ++l) if (S.fr_rowptr[l + 1] - S.fr_rowptr[l] > 1024) S.use_fronts = false;   // k_chol_reg stages a front's row list in shared memory
+    }
   }
   // ---- schedule: supernodes by dependency level (longest path), a topological order that interleaves
   //      the independent chains so that the persistent kernel works on all of them at once

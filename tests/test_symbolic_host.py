@@ -83,6 +83,84 @@ def emulate(sym, Sp, bp):
     return x
 
 
+def emulate_fronts(ctx, sym, Sp, bp):
+    """numpy emulation of the leaf-front path (fg_front.cu + the phase split of k_chol_reg): leaf members use the
+    reduced update lists, every leaf's contribution to the outside is one dense matrix U = sum_d A_d A_d^T gathered
+    through the position maps, and the remaining supernodes subtract the U entries that fall in their panels."""
+    n_r, n_sn = int(sym[0][0]), int(sym[0][1])
+    col0, ncols, nrows, rowptr, valptr, rowidx = sym[1:7]
+    sn_leaf = ctx.symbolic(21)
+    uptr, ud, ua, ub = (ctx.symbolic(w) for w in (22, 23, 24, 25))
+    fr_rowptr, fr_rows, members = ctx.symbolic(26), ctx.symbolic(27), ctx.symbolic(28).reshape(-1, 2)
+    tf_ptr, tf_leaf, pm_ptr, posmap = ctx.symbolic(29), ctx.symbolic(30), ctx.symbolic(31), ctx.symbolic(32)
+    sched_a, sched_c = ctx.symbolic(34), ctx.symbolic(35)
+    assert sorted(sched_a.tolist() + sched_c.tolist()) == list(range(n_sn))
+    assert all(sn_leaf[s] >= 0 for s in sched_a) and all(sn_leaf[s] < 0 for s in sched_c)
+    aug = np.zeros((n_r + 1, n_r + 1)); aug[:n_r, :n_r] = Sp; aug[n_r, :n_r] = bp
+    rows_of = [rowidx[rowptr[s]:rowptr[s] + nrows[s]] for s in range(n_sn)]
+    panels = []
+    for s in range(n_sn):
+        cols = np.arange(col0[s], col0[s] + ncols[s])
+        P = aug[np.ix_(rows_of[s], cols)].copy(); P[:ncols[s]] = np.tril(P[:ncols[s]])
+        panels.append(P)
+    done = np.zeros(n_sn, dtype=bool)
+
+    def finish(s):
+        pos = {int(r): k for k, r in enumerate(rows_of[s])}
+        for u in range(uptr[s], uptr[s + 1]):
+            d, a, b = int(ud[u]), int(ua[u]), int(ub[u])
+            assert done[d], 'reduced update list is not topological within its phase'
+            Ld = panels[d]
+            upd = Ld[a:] @ Ld[a:b].T
+            for ii, R in enumerate(rows_of[d][a:]):
+                for jj in range(b - a):
+                    C = int(rows_of[d][a + jj])
+                    if R >= C:
+                        panels[s][pos[int(R)], C - col0[s]] -= upd[ii, jj]
+        nc = ncols[s]
+        Ldd = np.linalg.cholesky(panels[s][:nc] + np.tril(panels[s][:nc], -1).T)
+        panels[s][:nc] = Ldd
+        panels[s][nc:] = np.linalg.solve(Ldd, panels[s][nc:].T).T
+        done[s] = True
+
+    for s in sched_a:
+        finish(int(s))
+    U = []
+    for l, (lo, hi) in enumerate(members):
+        Rl = fr_rows[fr_rowptr[l]:fr_rowptr[l + 1]]
+        Ul = np.zeros((len(Rl), len(Rl)))
+        for d in range(lo, hi):
+            pm = posmap[pm_ptr[d]:pm_ptr[d + 1]]
+            assert len(pm) == len(Rl)
+            for k, pidx in enumerate(pm):
+                assert pidx < 0 or rows_of[d][pidx] == Rl[k]
+            A = np.where(pm[:, None] >= 0, panels[d][np.maximum(pm, 0)], 0.0)
+            # every row of d outside its leaf must be in the front
+            outside = set(int(r) for r in rows_of[d][ncols[d]:] if r >= col0[hi - 1] + ncols[hi - 1])
+            assert outside <= set(int(r) for r in Rl)
+            Ul += A @ A.T
+        U.append((Rl, Ul))
+    for s in sched_c:
+        s = int(s)
+        for e in range(tf_ptr[s], tf_ptr[s + 1]):
+            Rl, Ul = U[int(tf_leaf[e])]
+            idx = {int(r): k for k, r in enumerate(Rl)}
+            for rr, g in enumerate(rows_of[s]):
+                if int(g) not in idx:
+                    continue
+                for c in range(ncols[s]):
+                    gc = int(col0[s] + c)
+                    if gc in idx and g >= gc:
+                        panels[s][rr, c] -= Ul[idx[int(g)], idx[gc]]
+        finish(s)
+    x = np.zeros(n_r)
+    for s in range(n_sn - 1, -1, -1):
+        rows = rows_of[s]; nc = ncols[s]
+        t = panels[s][-1] - panels[s][nc:-1].T @ x[rows[nc:-1]]
+        x[col0[s]:col0[s] + nc] = np.linalg.solve(panels[s][:nc].T, t)
+    return x
+
+
 @pytest.mark.parametrize('name,scale', [('C1', 1.0), ('C2', 0.08), ('C3', 0.08), ('C4', 0.03)])
 def test_symbolic_and_left_looking(fglib, name, scale):
     spec = synth.make_config(name, seed=2, scale=scale)
@@ -129,6 +207,9 @@ def test_symbolic_and_left_looking(fglib, name, scale):
     assert pairs_u == pairs_a
     ref = np.linalg.solve(Sp, bp)
     assert np.allclose(x, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+    if ctx.symbolic(33)[0]:
+        xf = emulate_fronts(ctx, sym, Sp, bp)
+        assert np.allclose(xf, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
     ctx.close()
 
 
