@@ -584,6 +584,18 @@ extern "C" int fg_finalize(fg_ctx* c) {
             }
       }
       d.n_blk = nblk; d.n_pairs = npairs;
+      // 4 x 4 tiles of blocks per CTA: the 16 warps of a CTA then share 4 row poses and 4 column poses, so every
+      // Y / W record they stream is reused by 4 warps out of L1 instead of being fetched from L2 again
+      std::vector<int> blk_order(nblk);
+      for (int64_t k = 0; k < nblk; ++k) blk_order[k] = (int)k;
+      std::stable_sort(blk_order.begin(), blk_order.end(), [&](int x, int y) {
+        const int px = blk_p[x] >> 2, py = blk_p[y] >> 2, qx = nbr_q[x] >> 2, qy = nbr_q[y] >> 2;
+        if (px != py) return px < py;
+        if (qx != qy) return qx < qy;
+        if (blk_p[x] != blk_p[y]) return blk_p[x] < blk_p[y];
+        return nbr_q[x] < nbr_q[y];
+      });
+      if ((rc = dev_upload(c, &d.blk_order, blk_order))) return rc;
       if ((rc = dev_upload(c, &d.blk_p, blk_p)) || (rc = dev_upload(c, &d.blk_q, nbr_q)) || (rc = dev_upload(c, &d.blk_ptr, blk_ptr)) ||
           (rc = dev_upload(c, &d.pair_a, pair_a)) || (rc = dev_upload(c, &d.pair_b, pair_b))) return rc;
       CK(cudaStreamSynchronize(c->stream));
@@ -609,6 +621,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload(c, &d.pm_ptr, S.pm_ptr)) || (rc = dev_upload(c, &d.posmap, S.posmap)) || (rc = dev_upload(c, &d.pmne_ptr, S.pmne_ptr)) ||
         (rc = dev_upload(c, &d.pm_nonempty, S.pm_nonempty)) || (rc = dev_upload(c, &d.leaf_sn_lo, S.leaf_sn_lo)) || (rc = dev_upload(c, &d.leaf_sn_hi, S.leaf_sn_hi)) ||
         (rc = dev_upload(c, &d.tf_ptr, S.tf_ptr)) || (rc = dev_upload(c, &d.tf_leaf, S.tf_leaf)) ||
+        (rc = dev_upload(c, &d.tile_mptr, S.tile_mptr)) || (rc = dev_upload(c, &d.tile_mrec, S.tile_mrec)) ||
         (rc = dev_upload(c, &d.tile_leaf, S.tile_leaf)) || (rc = dev_upload(c, &d.tile_i, S.tile_i)) || (rc = dev_upload(c, &d.tile_j, S.tile_j)) ||
         (rc = dev_upload<double>(c, &d.U, nullptr, (size_t)S.fr_uptr[S.n_leaves]))) return rc;
   }

@@ -15,15 +15,15 @@ namespace fg {
 
 #define FT 64          // tile edge
 #define FK 16          // max supernode width
+#define FM 2           // members staged per barrier pair (2 x 2 x 16 KB of static shared memory)
 
 __global__ void __launch_bounds__(256) k_front_syrk(int n_tiles, const int* __restrict__ tile_leaf, const int* __restrict__ tile_i,
-                                                    const int* __restrict__ tile_j, const int* __restrict__ leaf_sn_lo,
-                                                    const int* __restrict__ leaf_sn_hi, const int* __restrict__ fr_rowptr,
-                                                    const int64_t* __restrict__ fr_uptr, const int64_t* __restrict__ pm_ptr,
-                                                    const int* __restrict__ posmap, const int64_t* __restrict__ pmne_ptr,
-                                                    const unsigned char* __restrict__ pm_nonempty, SysView s, double* __restrict__ U) {
-  __shared__ __align__(16) double Ai[FK][FT];
-  __shared__ __align__(16) double Aj[FK][FT];
+                                                    const int* __restrict__ tile_j, const int* __restrict__ tile_mptr,
+                                                    const FrontRec* __restrict__ tile_mrec, const int* __restrict__ fr_rowptr,
+                                                    const int64_t* __restrict__ fr_uptr, const int* __restrict__ posmap,
+                                                    const double* __restrict__ L, double* __restrict__ U) {
+  __shared__ __align__(16) double Ai[FM][FK][FT];
+  __shared__ __align__(16) double Aj[FM][FK][FT];
   const int t = blockIdx.x;
   if (t >= n_tiles) return;
   const int l = tile_leaf[t], ti = tile_i[t], tj = tile_j[t];
@@ -37,31 +37,43 @@ __global__ void __launch_bounds__(256) k_front_syrk(int n_tiles, const int* __re
 #pragma unroll
     for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
   const bool diag = (ti == tj);
-  for (int d = leaf_sn_lo[l]; d < leaf_sn_hi[l]; ++d) {
-    const unsigned char* ne = pm_nonempty + pmne_ptr[d];
-    if (!ne[ti] || !ne[tj]) continue;                   // uniform: this supernode has no row in one of the two blocks
-    const int K = s.sn_ncols[d], nrd = s.sn_nrows[d];
-    const double* Ld = s.L + s.sn_valptr[d];
-    const int* pm = posmap + pm_ptr[d];
-    const int pi = (gi < nR) ? pm[gi] : -1;
-    const int pj = (gj < nR) ? pm[gj] : -1;
-    for (int k = kq; k < FK; k += 4) {
-      Ai[k][r] = (pi >= 0 && k < K) ? __ldcg(&Ld[pi + (int64_t)k * nrd]) : 0.0;
-      if (!diag) Aj[k][r] = (pj >= 0 && k < K) ? __ldcg(&Ld[pj + (int64_t)k * nrd]) : 0.0;
+  const int m1 = tile_mptr[t + 1];
+  for (int m0 = tile_mptr[t]; m0 < m1; m0 += FM) {
+    // ---- stage up to FM members with all their loads in flight together
+#pragma unroll
+    for (int q = 0; q < FM; ++q) {
+      if (m0 + q < m1) {
+        const FrontRec rec = tile_mrec[m0 + q];
+        const double* Ld = L + rec.val_off;
+        const int* pm = posmap + rec.pm_off;
+        const int pi = (gi < nR) ? __ldg(pm + gi) : -1;
+        const int pj = (!diag && gj < nR) ? __ldg(pm + gj) : -1;
+#pragma unroll
+        for (int k = kq; k < FK; k += 4) {
+          Ai[q][k][r] = (pi >= 0 && k < rec.K) ? __ldcg(&Ld[pi + (int64_t)k * rec.nrd]) : 0.0;
+          if (!diag) Aj[q][k][r] = (pj >= 0 && k < rec.K) ? __ldcg(&Ld[pj + (int64_t)k * rec.nrd]) : 0.0;
+        }
+      }
     }
     __syncthreads();
-    const double (*Bj)[FT] = diag ? Ai : Aj;
 #pragma unroll
-    for (int k = 0; k < FK; ++k) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&Ai[k][4 * ty]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&Ai[k][4 * ty + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&Bj[k][4 * tx]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&Bj[k][4 * tx + 2]);
-      const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+    for (int q = 0; q < FM; ++q) {
+      if (m0 + q < m1) {
+        const double (*Bi)[FT] = Ai[q];
+        const double (*Bj)[FT] = diag ? Ai[q] : Aj[q];
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
+        for (int k = 0; k < FK; ++k) {
+          const double2 a01 = *reinterpret_cast<const double2*>(&Bi[k][4 * ty]);
+          const double2 a23 = *reinterpret_cast<const double2*>(&Bi[k][4 * ty + 2]);
+          const double2 b01 = *reinterpret_cast<const double2*>(&Bj[k][4 * tx]);
+          const double2 b23 = *reinterpret_cast<const double2*>(&Bj[k][4 * tx + 2]);
+          const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
+        }
+      }
     }
     __syncthreads();
   }
@@ -82,11 +94,10 @@ void launch_front_syrk(fg_ctx* c) {
   DevGraph& d = c->d;
   const int n_tiles = (int)c->sym.tile_leaf.size();
   if (!n_tiles) return;
-  SysView s;
-  s.L = d.L; s.col2sn = d.col2sn; s.sn_col0 = d.sn_col0; s.sn_ncols = d.sn_ncols; s.sn_nrows = d.sn_nrows;
-  s.sn_rowptr = d.sn_rowptr; s.sn_valptr = d.sn_valptr; s.rowidx = d.rowidx; s.n_r = c->sym.n_r;
-  k_front_syrk<<<n_tiles, 256, 0, c->stream>>>(n_tiles, d.tile_leaf, d.tile_i, d.tile_j, d.leaf_sn_lo, d.leaf_sn_hi, d.fr_rowptr,
-                                               d.fr_uptr, d.pm_ptr, d.posmap, d.pmne_ptr, d.pm_nonempty, s, d.U);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_front_syrk, cudaFuncAttributePreferredSharedMemoryCarveout, 100); attr = true; }
+  k_front_syrk<<<n_tiles, 256, 0, c->stream>>>(n_tiles, d.tile_leaf, d.tile_i, d.tile_j, d.tile_mptr, d.tile_mrec, d.fr_rowptr, d.fr_uptr,
+                                               d.posmap, d.L, d.U);
 }
 
 }  // namespace fg

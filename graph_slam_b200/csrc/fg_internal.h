@@ -40,6 +40,14 @@ struct HostGraph {
   int64_t count(int t) const { return (int64_t)keys[t].size(); }
 };
 
+// one (tile, leaf member) work item of k_front_syrk
+struct __align__(16) FrontRec {
+  long long val_off;   // offset of the member's panel in L
+  long long pm_off;    // offset of the member's position map
+  int nrd, K;          // panel leading dimension and width
+  int pad[2];
+};
+
 // one descendant update, everything the factorisation kernel needs in a single 32-byte load
 struct __align__(16) UpdRec {
   long long val_off;   // offset in L of descendant row a, column 0
@@ -81,6 +89,7 @@ struct Symbolic {
   std::vector<int> tf_ptr, tf_leaf;                // per supernode: leaves whose front must be subtracted from it
   std::vector<int> sched_a, sched_c;               // schedules: leaf members, then everything else (both level sorted)
   std::vector<int> tile_leaf, tile_i, tile_j;      // 64 x 64 tiles of the lower triangles of all fronts
+  std::vector<int> tile_mptr; std::vector<FrontRec> tile_mrec;   // per tile: the members that have rows in both of its blocks
   int n_levels_fronts = 0;
 };
 
@@ -174,6 +183,7 @@ struct DevGraph {
   int64_t n_pairs = 0;
   int64_t n_blk = 0; int* blk_p = nullptr; int* blk_q = nullptr; int64_t* blk_ptr = nullptr;
   int* pair_a = nullptr; int* pair_b = nullptr;   // observation index pairs grouped by block
+  int* blk_order = nullptr;                        // block ids grouped into 4 x 4 (row pose, col pose) tiles, one tile per CTA
   double* V = nullptr;              // 6 L  : upper of sum Jl^T Jl w + prior
   double* gl = nullptr;             // 3 L
   double* Vinv = nullptr;           // 6 L
@@ -200,7 +210,7 @@ struct DevGraph {
   int64_t* pm_ptr = nullptr; int* posmap = nullptr; int64_t* pmne_ptr = nullptr; unsigned char* pm_nonempty = nullptr;
   int *leaf_sn_lo = nullptr, *leaf_sn_hi = nullptr;
   int *tf_ptr = nullptr, *tf_leaf = nullptr;
-  int *tile_leaf = nullptr, *tile_i = nullptr, *tile_j = nullptr;
+  int *tile_leaf = nullptr, *tile_i = nullptr, *tile_j = nullptr, *tile_mptr = nullptr; FrontRec* tile_mrec = nullptr;
   double* U = nullptr;              // dense update matrices of all leaves
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;

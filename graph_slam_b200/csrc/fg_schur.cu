@@ -66,13 +66,14 @@ __global__ void __launch_bounds__(256) k_ymat(int64_t M, const int* __restrict__
 }
 
 // one warp per block (p, q)
-__global__ void __launch_bounds__(256, 2) k_schur_blocks(int64_t n_blk, const int* __restrict__ blk_p, const int* __restrict__ blk_q,
+__global__ void __launch_bounds__(512, 1) k_schur_blocks(int64_t n_blk, const int* __restrict__ blk_order, const int* __restrict__ blk_p, const int* __restrict__ blk_q,
                                                          const int64_t* __restrict__ blk_ptr, const int* __restrict__ pair_a,
                                                          const int* __restrict__ pair_b, const double* __restrict__ Y,
                                                          const double* __restrict__ W, const int* __restrict__ off_pose, SysView sys) {
-  const int64_t blk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t wg = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (blk >= n_blk) return;
+  if (wg >= n_blk) return;
+  const int64_t blk = blk_order[wg];
   double acc[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
@@ -161,7 +162,7 @@ void launch_schur(fg_ctx* c, double lambda) {
   k_vinv<<<cdiv(L, 256), 256, 0, st>>>(L, d.V, d.gl, lambda, d.Vinv, d.yl);
   if (d.n_obs) k_ymat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.W, d.Vinv, d.Y);
   if (c->kev[2]) cudaEventRecord(c->kev[2], st);
-  if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk * 32, 256), 256, 0, st>>>(d.n_blk, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.Y,
+  if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk * 32, 512), 512, 0, st>>>(d.n_blk, d.blk_order, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.Y,
                                                                         d.W, d.off[T_POSE], sys);
   if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];

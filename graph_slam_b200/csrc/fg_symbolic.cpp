@@ -312,6 +312,18 @@ int build_symbolic(fg_ctx* c) {
         }
         S.pm_ptr[s + 1] = S.pm_ptr[s] + n; S.pmne_ptr[s + 1] = S.pmne_ptr[s] + nb;
       }
+      // per-tile work lists for k_front_syrk
+      S.tile_mptr.assign(S.tile_leaf.size() + 1, 0);
+      for (size_t t = 0; t < S.tile_leaf.size(); ++t) {
+        const int l = S.tile_leaf[t], ti = S.tile_i[t], tj = S.tile_j[t];
+        for (int m = S.leaf_sn_lo[l]; m < S.leaf_sn_hi[l]; ++m) {
+          const unsigned char* ne = &S.pm_nonempty[S.pmne_ptr[m]];
+          if (!ne[ti] || !ne[tj]) continue;
+          FrontRec fr; fr.val_off = S.sn_valptr[m]; fr.pm_off = S.pm_ptr[m]; fr.nrd = S.sn_nrows[m]; fr.K = S.sn_ncols[m]; fr.pad[0] = fr.pad[1] = 0;
+          S.tile_mrec.push_back(fr);
+        }
+        S.tile_mptr[t + 1] = (int)S.tile_mrec.size();
+      }
       // reduced update lists: drop (leaf member -> target outside that leaf)
       S.updr_ptr.assign(S.n_sn + 1, 0);
       for (int t = 0; t < S.n_sn; ++t) {
