@@ -351,13 +351,16 @@ __global__ void __launch_bounds__(256) k_proj_obs(int64_t M, const int* __restri
     projection_eval<JAC>(X, p, uv, K, S, r, Jp, Jl);
     e = w * (r[0] * r[0] + r[1] * r[1]);
   }
+  // W records (144 B each) of the block's 256 consecutive observations go through shared memory so that the global
+  // store is coalesced (a thread writing its own record costs 32 cache-line wavefronts per store instruction)
+  __shared__ double wbuf[JAC ? 256 * 19 : 1];
   if (JAC) {
     if (act) {
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          W[o * 18 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
+          wbuf[threadIdx.x * 19 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
     }
     // V (upper: 00 01 02 11 12 22) and gl
     double c9[9];
@@ -385,6 +388,10 @@ __global__ void __launch_bounds__(256) k_proj_obs(int64_t M, const int* __restri
         else atomicAdd(&gl[3 * (int64_t)l + (i - 6)], s);
       }
     }
+    __syncthreads();
+    const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
+    const int n = (int)min((int64_t)blockDim.x, M - o0);
+    for (int i = threadIdx.x; i < n * 18; i += blockDim.x) W[o0 * 18 + i] = wbuf[(i / 18) * 19 + (i % 18)];
   }
   chi2_accumulate(e, chi2);
 }
@@ -454,18 +461,27 @@ __global__ void k_damp_rhs(SysView sys, const double* __restrict__ g_r, double l
 __global__ void __launch_bounds__(256) k_lm_backsub_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                         const double* __restrict__ W, const double* __restrict__ delta,
                                                         const int* __restrict__ off_pose, double* tl) {
+  __shared__ double wbuf[256 * 19];
   int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int lane = threadIdx.x & 31;
   bool act = o < M;
   int l = act ? obs_point[o] : -1;
   double t3[3] = {0, 0, 0};
+  {
+    // coalesced load of the block's 256 consecutive W records, transposed through shared memory
+    const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
+    const int n = (int)min((int64_t)blockDim.x, M - o0);
+    for (int i = threadIdx.x; i < n * 18; i += blockDim.x) wbuf[(i / 18) * 19 + (i % 18)] = __ldg(W + o0 * 18 + i);
+    __syncthreads();
+  }
   if (act) {
     const double* d = delta + off_pose[obs_pose[o]];
+    const double* wr = wbuf + threadIdx.x * 19;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       double di = d[i];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) t3[c] += W[o * 18 + 3 * i + c] * di;
+      for (int c = 0; c < 3; ++c) t3[c] += wr[3 * i + c] * di;
     }
   }
   int prev = __shfl_up_sync(0xffffffffu, l, 1);

@@ -40,62 +40,90 @@ __device__ __forceinline__ void load18(const double* __restrict__ W, int o, doub
   for (int i = 0; i < 9; ++i) { double2 v = __ldg(p + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }
 }
 
-// per observation: Y_o = W_o Vinv_l  (6x3), so that the pair loop below is two 144 B reads and 108 DFMA
+#define REC 18            // doubles per W / Y record
+#define RST 19            // padded record stride in shared memory (odd: conflict-free 8-byte lane accesses)
+
+// per observation: Y_o = W_o Vinv_l (6x3).  256 consecutive records are moved through shared memory so that the global
+// loads and stores are fully coalesced (a thread touching its own 144-byte record costs 32 cache-line wavefronts
+// per instruction).
 __global__ void __launch_bounds__(256) k_ymat(int64_t M, const int* __restrict__ obs_point, const double* __restrict__ W,
                                               const double* __restrict__ Vinv, double* __restrict__ Y) {
-  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (o >= M) return;
-  const int l = obs_point[o];
-  double w[18], vi[6];
-  load18(W, (int)o, w);
-  {
-    const double2* p = reinterpret_cast<const double2*>(Vinv + (int64_t)l * 6);
-    double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-    vi[0] = v0.x; vi[1] = v0.y; vi[2] = v1.x; vi[3] = v1.y; vi[4] = v2.x; vi[5] = v2.y;
-  }
-  double2* out = reinterpret_cast<double2*>(Y + o * 18);
-  double y[18];
+  __shared__ double buf[256 * RST];
+  const int64_t o0 = blockIdx.x * (int64_t)256;
+  const int n = (int)min((int64_t)256, M - o0);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n * REC; i += 256) buf[(i / REC) * RST + (i % REC)] = __ldg(W + o0 * REC + i);
+  __syncthreads();
+  if (tid < n) {
+    const int l = obs_point[o0 + tid];
+    double vi[6];
+    {
+      const double2* p = reinterpret_cast<const double2*>(Vinv + (int64_t)l * 6);
+      double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+      vi[0] = v0.x; vi[1] = v0.y; vi[2] = v1.x; vi[3] = v1.y; vi[4] = v2.x; vi[5] = v2.y;
+    }
+    double* w = buf + tid * RST;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    y[3 * i + 0] = w[3 * i] * vi[0] + w[3 * i + 1] * vi[1] + w[3 * i + 2] * vi[2];
-    y[3 * i + 1] = w[3 * i] * vi[1] + w[3 * i + 1] * vi[3] + w[3 * i + 2] * vi[4];
-    y[3 * i + 2] = w[3 * i] * vi[2] + w[3 * i + 1] * vi[4] + w[3 * i + 2] * vi[5];
+    for (int i = 0; i < 6; ++i) {
+      const double w0 = w[3 * i], w1 = w[3 * i + 1], w2 = w[3 * i + 2];
+      w[3 * i + 0] = w0 * vi[0] + w1 * vi[1] + w2 * vi[2];
+      w[3 * i + 1] = w0 * vi[1] + w1 * vi[3] + w2 * vi[4];
+      w[3 * i + 2] = w0 * vi[2] + w1 * vi[4] + w2 * vi[5];
+    }
   }
-#pragma unroll
-  for (int i = 0; i < 9; ++i) out[i] = make_double2(y[2 * i], y[2 * i + 1]);
+  __syncthreads();
+  for (int i = tid; i < n * REC; i += 256) Y[o0 * REC + i] = buf[(i / REC) * RST + (i % REC)];
 }
 
-// one warp per block (p, q)
-__global__ void __launch_bounds__(512, 1) k_schur_blocks(int64_t n_blk, const int* __restrict__ blk_order, const int* __restrict__ blk_p, const int* __restrict__ blk_q,
-                                                         const int64_t* __restrict__ blk_ptr, const int* __restrict__ pair_a,
-                                                         const int* __restrict__ pair_b, const double* __restrict__ Y,
-                                                         const double* __restrict__ W, const int* __restrict__ off_pose, SysView sys) {
-  const int64_t wg = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (wg >= n_blk) return;
-  const int64_t blk = blk_order[wg];
+// one warp per block (p, q).  Each iteration handles 32 pairs: the 64 records (Y of the 32 a-observations, W of the
+// 32 b-observations) are fetched cooperatively -- 9 lanes x 16 B per record, so one load instruction touches a few
+// cache lines instead of 32 -- and parked in the warp's shared-memory slab; then every lane multiplies its own pair.
+#define SB_WARPS 4
+__global__ void __launch_bounds__(32 * SB_WARPS, 4) k_schur_blocks(int64_t n_blk, const int* __restrict__ blk_p, const int* __restrict__ blk_q,
+                                                                    const int64_t* __restrict__ blk_ptr, const int* __restrict__ pair_a,
+                                                                    const int* __restrict__ pair_b, const double* __restrict__ Y,
+                                                                    const double* __restrict__ W, const int* __restrict__ off_pose, SysView sys) {
+  __shared__ double slab[SB_WARPS][2][32 * RST];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t blk = blockIdx.x * (int64_t)SB_WARPS + warp;
+  if (blk >= n_blk) return;
+  double* Ys = slab[warp][0];
+  double* Ws = slab[warp][1];
   double acc[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
   const int64_t s = blk_ptr[blk], e = blk_ptr[blk + 1];
-  int64_t k = s + lane;
-  int oa = -1, ob = -1;
-  if (k < e) { oa = __ldg(pair_a + k); ob = __ldg(pair_b + k); }
-  while (oa >= 0) {
-    double wb[18];
-    load18(W, ob, wb);
-    const double* ya = Y + (int64_t)oa * 18;
-    // prefetch the next pair's indices before the arithmetic
-    k += 32;
-    int na = -1, nb2 = -1;
-    if (k < e) { na = __ldg(pair_a + k); nb2 = __ldg(pair_b + k); }
+  for (int64_t k0 = s; k0 < e; k0 += 32) {
+    const int64_t k = k0 + lane;
+    const bool valid = k < e;
+    const int oa = valid ? __ldg(pair_a + k) : -1, ob = valid ? __ldg(pair_b + k) : -1;
+    // 32 records x 9 chunks of 16 B = 288 chunks per operand: 9 rounds of 32 lanes
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const double y0 = __ldg(ya + 3 * i), y1 = __ldg(ya + 3 * i + 1), y2 = __ldg(ya + 3 * i + 2);
-#pragma unroll
-      for (int j = 0; j < 6; ++j) acc[6 * i + j] += y0 * wb[3 * j] + y1 * wb[3 * j + 1] + y2 * wb[3 * j + 2];
+    for (int rnd = 0; rnd < 9; ++rnd) {
+      const int c = rnd * 32 + lane, j = c / 9, part = c - 9 * j;
+      const int ja = __shfl_sync(0xffffffffu, oa, j), jb = __shfl_sync(0xffffffffu, ob, j);
+      if (ja >= 0) {
+        const double2 y = __ldg(reinterpret_cast<const double2*>(Y + (int64_t)ja * REC) + part);
+        const double2 w = __ldg(reinterpret_cast<const double2*>(W + (int64_t)jb * REC) + part);
+        Ys[j * RST + 2 * part] = y.x; Ys[j * RST + 2 * part + 1] = y.y;
+        Ws[j * RST + 2 * part] = w.x; Ws[j * RST + 2 * part + 1] = w.y;
+      }
     }
-    oa = na; ob = nb2;
+    __syncwarp();
+    if (valid) {
+      const double* ya = Ys + lane * RST;
+      const double* wb = Ws + lane * RST;
+      double wbr[18];
+#pragma unroll
+      for (int i = 0; i < 18; ++i) wbr[i] = wb[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double y0 = ya[3 * i], y1 = ya[3 * i + 1], y2 = ya[3 * i + 2];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[6 * i + j] += y0 * wbr[3 * j] + y1 * wbr[3 * j + 1] + y2 * wbr[3 * j + 2];
+      }
+    }
+    __syncwarp();
   }
   // butterfly: every lane ends with the full sums
 #pragma unroll
@@ -162,7 +190,7 @@ void launch_schur(fg_ctx* c, double lambda) {
   k_vinv<<<cdiv(L, 256), 256, 0, st>>>(L, d.V, d.gl, lambda, d.Vinv, d.yl);
   if (d.n_obs) k_ymat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.W, d.Vinv, d.Y);
   if (c->kev[2]) cudaEventRecord(c->kev[2], st);
-  if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk * 32, 512), 512, 0, st>>>(d.n_blk, d.blk_order, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.Y,
+  if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk, SB_WARPS), 32 * SB_WARPS, 0, st>>>(d.n_blk, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.Y,
                                                                         d.W, d.off[T_POSE], sys);
   if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];
