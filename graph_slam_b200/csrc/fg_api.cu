@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <climits>
+#include <cstdlib>
 #include <dlfcn.h>
 #include <limits>
 #include "fg_internal.h"
@@ -536,68 +538,67 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<double>(c, &d.gl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Vinv, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.tl, nullptr, (size_t)3 * L))) return rc;
     if ((rc = dev_upload(c, &d.calib, h.calib.data() + 9 * cid, 9)) || (rc = dev_upload(c, &d.sensor, h.sensor.data() + 12 * sid, 12))) return rc;
-    if ((rc = dev_upload<double>(c, &d.yl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Y, nullptr, (size_t)18 * M))) return rc;
-    // Schur blocks and pair lists.  Block (p, q): poses co-visible through a landmark with order(q) <= order(p);
-    // its pair list holds every (observation of p, observation of q) of a common landmark.
+    if ((rc = dev_upload<double>(c, &d.ul, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Cf, nullptr, (size_t)6 * L)) ||
+        (rc = dev_upload<double>(c, &d.Zp, nullptr, (size_t)18 * M))) return rc;
+    // Schur tiles (fg_schur.cu).  pose_obs IS the pose-major order: position k holds observation pose_obs[k], and the
+    // observations of one pose are sorted by landmark.  Landmarks are cut into chunks of CH consecutive ids; per
+    // (pose, chunk) the kernel needs the first pose-major position and the bit mask of the landmarks seen.
     {
-      const std::vector<int>& offp = S.off[T_POSE];
-      std::vector<int64_t> nbr_ptr(P + 1, 0);
-      std::vector<int> nbr_q;
+      if (M >= (int64_t)1 << 31) return fail(c, FG_ERR_INVALID, "more than 2^31 projection factors on one rank");
+      const char* che = getenv("FG_SCHUR_CH");
+      const int CH = (che && atoi(che) == 32) ? 32 : 24;
+      d.schur_ch = CH;
+      std::vector<int> ppos(M), pzp(M);
+      for (int64_t k = 0; k < M; ++k) { ppos[pose_obs[k]] = (int)k; pzp[k] = s_point[pose_obs[k]]; }
+      std::vector<int> pc_lo(P, 0), pc_n(P, 0);
+      std::vector<int64_t> pc_ptr(P + 1, 0);
       for (int64_t p = 0; p < P; ++p) {
-        size_t b0 = nbr_q.size();
-        if (!S.cov_ptr.empty())
+        if (pose_ptr[p + 1] > pose_ptr[p]) {
+          pc_lo[p] = pzp[pose_ptr[p]] / CH;
+          pc_n[p] = pzp[pose_ptr[p + 1] - 1] / CH - pc_lo[p] + 1;
+        }
+        pc_ptr[p + 1] = pc_ptr[p] + pc_n[p];
+      }
+      std::vector<uint2> pc_ent(pc_ptr[P] ? pc_ptr[P] : 1, make_uint2(0u, 0u));
+      for (int64_t p = 0; p < P; ++p)
+        for (int64_t k = pose_ptr[p]; k < pose_ptr[p + 1]; ++k) {
+          const int l = pzp[k];
+          uint2& e = pc_ent[pc_ptr[p] + (l / CH - pc_lo[p])];
+          if (e.y == 0u) e.x = (unsigned)k;
+          e.y |= 1u << (l % CH);
+        }
+      // tiles: pairs of 16-pose groups that share a landmark, with the chunk range both sides cover
+      const int G = (int)((P + 15) / 16);
+      std::vector<int> g_lo(G, INT32_MAX), g_hi(G, 0);
+      for (int64_t p = 0; p < P; ++p)
+        if (pc_n[p]) { g_lo[p / 16] = std::min(g_lo[p / 16], pc_lo[p]); g_hi[p / 16] = std::max(g_hi[p / 16], pc_lo[p] + pc_n[p]); }
+      std::vector<int64_t> tkeys;
+      if (!S.cov_ptr.empty())
+        for (int64_t p = 0; p < P; ++p) {
+          int last = -1;
           for (int64_t k = S.cov_ptr[p]; k < S.cov_ptr[p + 1]; ++k) {
-            int q = S.cov_pose[k];
-            if (offp[q] <= offp[p]) nbr_q.push_back(q);
+            const int q = S.cov_pose[k];
+            if (q > p) continue;
+            const int gq = q / 16;
+            if (gq != last) { tkeys.push_back((int64_t)(p / 16) * G + gq); last = gq; }
           }
-        std::sort(nbr_q.begin() + b0, nbr_q.end());
-        nbr_ptr[p + 1] = (int64_t)nbr_q.size();
+        }
+      std::sort(tkeys.begin(), tkeys.end());
+      tkeys.erase(std::unique(tkeys.begin(), tkeys.end()), tkeys.end());
+      std::vector<int4> tiles;
+      for (int64_t key : tkeys) {
+        const int gi = (int)(key / G), gj = (int)(key % G);
+        const int cb = std::max(g_lo[gi], g_lo[gj]), ce = std::min(g_hi[gi], g_hi[gj]);
+        if (cb < ce) tiles.push_back(make_int4(gi, gj, cb, ce));
       }
-      const int64_t nblk = (int64_t)nbr_q.size();
-      std::vector<int> blk_p(nblk);
-      for (int64_t p = 0; p < P; ++p) for (int64_t k = nbr_ptr[p]; k < nbr_ptr[p + 1]; ++k) blk_p[k] = (int)p;
-      auto find_blk = [&](int p, int q) -> int64_t {
-        const int* lo = nbr_q.data() + nbr_ptr[p];
-        const int* hi = nbr_q.data() + nbr_ptr[p + 1];
-        return std::lower_bound(lo, hi, q) - nbr_q.data();
-      };
-      std::vector<int64_t> blk_ptr(nblk + 1, 0);
-      for (int64_t l = 0; l < L; ++l)
-        for (int64_t a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
-          for (int64_t b = lm_ptr[l]; b < lm_ptr[l + 1]; ++b) {
-            int pa = s_pose[a], pb = s_pose[b];
-            if (offp[pb] < offp[pa] || pa == pb) blk_ptr[find_blk(pa, pb) + 1]++;
-          }
-      for (int64_t k = 0; k < nblk; ++k) blk_ptr[k + 1] += blk_ptr[k];
-      const int64_t npairs = blk_ptr[nblk];
-      std::vector<int> pair_a(npairs), pair_b(npairs);
-      {
-        std::vector<int64_t> cur(blk_ptr.begin(), blk_ptr.end() - 1);
-        for (int64_t l = 0; l < L; ++l)
-          for (int64_t a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
-            for (int64_t b = lm_ptr[l]; b < lm_ptr[l + 1]; ++b) {
-              int pa = s_pose[a], pb = s_pose[b];
-              if (offp[pb] < offp[pa] || pa == pb) {
-                int64_t k = cur[find_blk(pa, pb)]++;
-                pair_a[k] = (int)a; pair_b[k] = (int)b;
-              }
-            }
-      }
-      d.n_blk = nblk; d.n_pairs = npairs;
-      // 4 x 4 tiles of blocks per CTA: the 16 warps of a CTA then share 4 row poses and 4 column poses, so every
-      // Y / W record they stream is reused by 4 warps out of L1 instead of being fetched from L2 again
-      std::vector<int> blk_order(nblk);
-      for (int64_t k = 0; k < nblk; ++k) blk_order[k] = (int)k;
-      std::stable_sort(blk_order.begin(), blk_order.end(), [&](int x, int y) {
-        const int px = blk_p[x] >> 2, py = blk_p[y] >> 2, qx = nbr_q[x] >> 2, qy = nbr_q[y] >> 2;
-        if (px != py) return px < py;
-        if (qx != qy) return qx < qy;
-        if (blk_p[x] != blk_p[y]) return blk_p[x] < blk_p[y];
-        return nbr_q[x] < nbr_q[y];
-      });
-      if ((rc = dev_upload(c, &d.blk_order, blk_order))) return rc;
-      if ((rc = dev_upload(c, &d.blk_p, blk_p)) || (rc = dev_upload(c, &d.blk_q, nbr_q)) || (rc = dev_upload(c, &d.blk_ptr, blk_ptr)) ||
-          (rc = dev_upload(c, &d.pair_a, pair_a)) || (rc = dev_upload(c, &d.pair_b, pair_b))) return rc;
+      std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
+      d.n_tiles = (int)tiles.size();
+      int64_t npairs = 0;
+      for (int64_t l = 0; l < L; ++l) { const int64_t k = lm_ptr[l + 1] - lm_ptr[l]; npairs += k * (k + 1) / 2; }
+      d.n_pairs = npairs;
+      if ((rc = dev_upload(c, &d.obs_ppos, ppos)) || (rc = dev_upload(c, &d.pz_point, pzp)) || (rc = dev_upload(c, &d.pc_lo, pc_lo)) ||
+          (rc = dev_upload(c, &d.pc_n, pc_n)) || (rc = dev_upload(c, &d.pc_ptr, pc_ptr)) || (rc = dev_upload(c, &d.pc_ent, pc_ent)) ||
+          (rc = dev_upload(c, &d.tile_desc, tiles))) return rc;
       CK(cudaStreamSynchronize(c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
@@ -723,7 +724,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
         cudaEventElapsedTime(&ms, ev[0], ev[1]); rep->ms_linearize += ms;
         if (d.n_obs && c->kev[0] && cudaEventElapsedTime(&ms, c->kev[0], c->kev[1]) == cudaSuccess) rep->ms_proj_obs += ms;
       }
-      if (d.n_blk && c->kev[2] && cudaEventElapsedTime(&ms, c->kev[2], c->kev[3]) == cudaSuccess) rep->ms_schur_blocks += ms;
+      if (d.n_tiles && c->kev[2] && cudaEventElapsedTime(&ms, c->kev[2], c->kev[3]) == cudaSuccess) rep->ms_schur_blocks += ms;
       cudaEventElapsedTime(&ms, ev[1], ev[2]); rep->ms_schur += ms;
       cudaEventElapsedTime(&ms, ev[2], ev[3]); rep->ms_factor += ms;
       cudaEventElapsedTime(&ms, ev[3], ev[4]); rep->ms_solve += ms;

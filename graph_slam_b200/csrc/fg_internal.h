@@ -177,13 +177,20 @@ struct DevGraph {
   double* lm_prior_mean = nullptr;  // 3L (NaN weight = no prior)
   double* lm_prior_w = nullptr;     // L
   double* W = nullptr;              // M x 18 (AoS): w Jp^T Jl per observation
-  double* yl = nullptr;             // 3 L : (V + lambda I)^-1 g_l
-  double* Y = nullptr;              // M x 18 (AoS): W_o (V_l + lambda I)^-1 per observation
-  // Schur blocks: one (row pose, col pose) block per co-visible pair with order(col) <= order(row)
-  int64_t n_pairs = 0;
-  int64_t n_blk = 0; int* blk_p = nullptr; int* blk_q = nullptr; int64_t* blk_ptr = nullptr;
-  int* pair_a = nullptr; int* pair_b = nullptr;   // observation index pairs grouped by block
-  int* blk_order = nullptr;                        // block ids grouped into 4 x 4 (row pose, col pose) tiles, one tile per CTA
+  double* ul = nullptr;             // 3 L : G^-1 g_l with V + lambda I = G G^T (so that W Vinv g = Z u)
+  double* Cf = nullptr;             // 6 L : upper-triangular C = G^-T (00 01 02 11 12 22); Vinv = C C^T
+  double* Zp = nullptr;             // M x 18 (AoS, POSE-major order): Z_o = W_o C_l, so that W Vinv W^T = Z Z^T
+  int* obs_ppos = nullptr;          // M : position of observation o in pose-major order (index into Zp / pose_obs)
+  int* pz_point = nullptr;          // M : landmark of the k-th pose-major observation
+  // Schur tiles (fg_schur.cu): 16 x 16 pose tiles of the reduced Hessian, landmarks cut into chunks of schur_ch
+  int64_t n_pairs = 0;              // observation pairs (a, b) of a common landmark with pose(b) <= pose(a): Schur work units
+  int schur_ch = 0;                 // landmarks per chunk (24 or 32)
+  int n_tiles = 0;
+  int4* tile_desc = nullptr;        // (row pose group, column pose group, first chunk, end chunk), heaviest first
+  int* pc_lo = nullptr;             // P : first chunk in which the pose has an observation
+  int* pc_n = nullptr;              // P : number of chunks from pc_lo to its last one
+  int64_t* pc_ptr = nullptr;        // P : offset of the pose's chunk entries
+  uint2* pc_ent = nullptr;          // per (pose, chunk): x = pose-major index of its first observation there, y = landmark bit mask
   double* V = nullptr;              // 6 L  : upper of sum Jl^T Jl w + prior
   double* gl = nullptr;             // 3 L
   double* Vinv = nullptr;           // 6 L

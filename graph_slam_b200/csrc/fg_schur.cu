@@ -5,50 +5,60 @@
 // for the GenericProjectionFactor / PriorFactor<Point3> part of the graph CGraphGT::addToGTSAM builds
 // (gtsam/gtsam_graph.cpp:370-448); in GTSAM this is the elimination of every Point3 before the poses.
 //
-// Output-stationary and deterministic: the host groups, once per graph, the (observation a, observation b)
-// pairs of every landmark by the reduced-Hessian block (pose of a, pose of b) they fall in (fg_api.cu,
-// fg_finalize).  One warp owns one 6x6 block: lanes stride over the block's pair list, accumulate
-// Y_a W_b^T in registers (Y_a = W_a Vinv_l), a shuffle butterfly sums the 36 values and the block is written
-// with plain stores -- no atomics, fixed summation order.  W is stored AoS (144 B per observation) so that a
-// pair costs two contiguous 144 B reads plus 48 B of Vinv.
+// Symmetric form.  With V_l + lambda I = G G^T (3x3 Cholesky) and C = G^-T,  W Vinv W^T = (W C)(W C)^T, so one array
+// Z_o = W_o C_l (6x3 per observation, 144 B) serves both sides of the product.  k_zmat writes Z in POSE-major order:
+// the observations of one pose are contiguous and sorted by landmark.
+//
+// k_schur_tiles: output-stationary, deterministic, no atomics, no pair lists.  One CTA owns a 16 x 16 tile of 6x6
+// blocks (16 consecutive row poses x 16 consecutive column poses); ONE LANE owns one block and keeps its 36 sums in
+// registers.  The landmarks are cut into chunks of CH consecutive ids.  Per chunk the CTA stages the Z records of its
+// 32 poses in shared memory, each lane intersects the landmark bit masks of its two poses and walks the set bits:
+//     S(p_i, q_j) += Z_(p_i, l) Z_(q_j, l)^T       (108 DFMA per hit, operands from shared memory).
+// Shared-memory layout [element e][record k][pose i] with an odd plane stride: the 16 lanes of a half-warp sit on a
+// wrapped diagonal of the tile (distinct i, distinct j), so every operand read is bank-conflict free whatever records
+// the lanes are at.  HBM/L2 traffic is one record per (pose, landmark, tile) instead of two per pair.
 #include "fg_internal.h"
 
 namespace fg {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// per landmark: Vinv = (V + lambda I)^-1 (6 upper), yl = Vinv g_l
+// per landmark: Vinv = (V + lambda I)^-1 (6 upper) for the back-substitution; C = G^-T and u = G^-1 g_l for the
+// symmetric Schur product
 __global__ void k_vinv(int64_t L, const double* __restrict__ V, const double* __restrict__ gl, double lambda,
-                       double* __restrict__ Vinv, double* __restrict__ yl) {
+                       double* __restrict__ Vinv, double* __restrict__ Cf, double* __restrict__ ul) {
   int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (l >= L) return;
-  double A[9] = {V[6 * l] + lambda, V[6 * l + 1], V[6 * l + 2],
-                 V[6 * l + 1], V[6 * l + 3] + lambda, V[6 * l + 4],
-                 V[6 * l + 2], V[6 * l + 4], V[6 * l + 5] + lambda};
+  const double a00 = V[6 * l] + lambda, a01 = V[6 * l + 1], a02 = V[6 * l + 2], a11 = V[6 * l + 3] + lambda, a12 = V[6 * l + 4],
+               a22 = V[6 * l + 5] + lambda;
+  double A[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
   double Ai[9];
   inv3(A, Ai);
   Vinv[6 * l] = Ai[0]; Vinv[6 * l + 1] = Ai[1]; Vinv[6 * l + 2] = Ai[2];
   Vinv[6 * l + 3] = Ai[4]; Vinv[6 * l + 4] = Ai[5]; Vinv[6 * l + 5] = Ai[8];
-  double g3[3] = {gl[3 * l], gl[3 * l + 1], gl[3 * l + 2]}, y[3];
-  m3_vec(Ai, g3, y);
-  yl[3 * l] = y[0]; yl[3 * l + 1] = y[1]; yl[3 * l + 2] = y[2];
+  // G (lower) and its inverse
+  const double g00 = sqrt(a00), i00 = 1.0 / g00;
+  const double g10 = a01 * i00, g20 = a02 * i00;
+  const double g11 = sqrt(a11 - g10 * g10), i11 = 1.0 / g11;
+  const double g21 = (a12 - g20 * g10) * i11;
+  const double g22 = sqrt(a22 - g20 * g20 - g21 * g21), i22 = 1.0 / g22;
+  const double i10 = -g10 * i00 * i11;
+  const double i21 = -g21 * i11 * i22;
+  const double i20 = -(g20 * i00 + g21 * i10) * i22;
+  Cf[6 * l] = i00; Cf[6 * l + 1] = i10; Cf[6 * l + 2] = i20; Cf[6 * l + 3] = i11; Cf[6 * l + 4] = i21; Cf[6 * l + 5] = i22;
+  const double g0 = gl[3 * l], g1 = gl[3 * l + 1], g2 = gl[3 * l + 2];
+  ul[3 * l] = i00 * g0; ul[3 * l + 1] = i10 * g0 + i11 * g1; ul[3 * l + 2] = i20 * g0 + i21 * g1 + i22 * g2;
 }
 
-__device__ __forceinline__ void load18(const double* __restrict__ W, int o, double* w) {
-  const double2* p = reinterpret_cast<const double2*>(W + (int64_t)o * 18);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) { double2 v = __ldg(p + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }
-}
-
-#define REC 18            // doubles per W / Y record
+#define REC 18            // doubles per W / Z record
 #define RST 19            // padded record stride in shared memory (odd: conflict-free 8-byte lane accesses)
 
-// per observation: Y_o = W_o Vinv_l (6x3).  256 consecutive records are moved through shared memory so that the global
-// loads and stores are fully coalesced (a thread touching its own 144-byte record costs 32 cache-line wavefronts
-// per instruction).
-__global__ void __launch_bounds__(256) k_ymat(int64_t M, const int* __restrict__ obs_point, const double* __restrict__ W,
-                                              const double* __restrict__ Vinv, double* __restrict__ Y) {
+// per observation: Z_o = W_o C_l (6x3), written at the observation's pose-major position.  256 consecutive W records
+// are moved through shared memory so that the global loads are coalesced; the stores go out as 9 x 16 B per record.
+__global__ void __launch_bounds__(256) k_zmat(int64_t M, const int* __restrict__ obs_point, const int* __restrict__ obs_ppos,
+                                              const double* __restrict__ W, const double* __restrict__ Cf, double* __restrict__ Zp) {
   __shared__ double buf[256 * RST];
+  __shared__ int ppos[256];
   const int64_t o0 = blockIdx.x * (int64_t)256;
   const int n = (int)min((int64_t)256, M - o0);
   const int tid = threadIdx.x;
@@ -56,119 +66,200 @@ __global__ void __launch_bounds__(256) k_ymat(int64_t M, const int* __restrict__
   __syncthreads();
   if (tid < n) {
     const int l = obs_point[o0 + tid];
-    double vi[6];
+    ppos[tid] = obs_ppos[o0 + tid];
+    double c[6];
     {
-      const double2* p = reinterpret_cast<const double2*>(Vinv + (int64_t)l * 6);
+      const double2* p = reinterpret_cast<const double2*>(Cf + (int64_t)l * 6);
       double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-      vi[0] = v0.x; vi[1] = v0.y; vi[2] = v1.x; vi[3] = v1.y; vi[4] = v2.x; vi[5] = v2.y;
+      c[0] = v0.x; c[1] = v0.y; c[2] = v1.x; c[3] = v1.y; c[4] = v2.x; c[5] = v2.y;
     }
     double* w = buf + tid * RST;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const double w0 = w[3 * i], w1 = w[3 * i + 1], w2 = w[3 * i + 2];
-      w[3 * i + 0] = w0 * vi[0] + w1 * vi[1] + w2 * vi[2];
-      w[3 * i + 1] = w0 * vi[1] + w1 * vi[3] + w2 * vi[4];
-      w[3 * i + 2] = w0 * vi[2] + w1 * vi[4] + w2 * vi[5];
+      w[3 * i + 0] = w0 * c[0];
+      w[3 * i + 1] = w0 * c[1] + w1 * c[3];
+      w[3 * i + 2] = w0 * c[2] + w1 * c[4] + w2 * c[5];
     }
   }
   __syncthreads();
-  for (int i = tid; i < n * REC; i += 256) Y[o0 * REC + i] = buf[(i / REC) * RST + (i % REC)];
+  for (int i = tid; i < n * 9; i += 256) {
+    const int r = i / 9, part = i - 9 * r;
+    const double* s = buf + r * RST + 2 * part;
+    reinterpret_cast<double2*>(Zp + (int64_t)ppos[r] * REC)[part] = make_double2(s[0], s[1]);
+  }
 }
 
-// one warp per block (p, q).  Each iteration handles 32 pairs: the 64 records (Y of the 32 a-observations, W of the
-// 32 b-observations) are fetched cooperatively -- 9 lanes x 16 B per record, so one load instruction touches a few
-// cache lines instead of 32 -- and parked in the warp's shared-memory slab; then every lane multiplies its own pair.
-#define SB_WARPS 4
-__global__ void __launch_bounds__(32 * SB_WARPS, 4) k_schur_blocks(int64_t n_blk, const int* __restrict__ blk_p, const int* __restrict__ blk_q,
-                                                                    const int64_t* __restrict__ blk_ptr, const int* __restrict__ pair_a,
-                                                                    const int* __restrict__ pair_b, const double* __restrict__ Y,
-                                                                    const double* __restrict__ W, const int* __restrict__ off_pose, SysView sys) {
-  __shared__ double slab[SB_WARPS][2][32 * RST];
+// ------------------------------------------------------------------ tile kernel
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+#define ST_THREADS 256
+template <int CH>
+struct SchurSmem {
+  static constexpr int PS = CH * 16 + 1;          // plane stride (doubles): odd, so bank = (e + i) mod 16
+  double rows[REC * PS];
+  double cols[REC * PS];
+  int src[ST_THREADS / 32][4 * CH];               // per warp: pose-major record index of every record it stages
+};
+
+template <int CH>
+__global__ void __launch_bounds__(ST_THREADS, CH <= 24 ? 2 : 1)
+k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_lo, const int* __restrict__ pc_n,
+              const int64_t* __restrict__ pc_ptr, const uint2* __restrict__ pc_ent, const double* __restrict__ Zp,
+              const int* __restrict__ off_pose, SysView sys) {
+  extern __shared__ __align__(16) unsigned char st_raw[];
+  SchurSmem<CH>& sm = *reinterpret_cast<SchurSmem<CH>*>(st_raw);
+  constexpr int PS = SchurSmem<CH>::PS;
+  const unsigned FULL = 0xffffffffu;
+  const int4 td = tiles[blockIdx.x];
+  const int gi = td.x, gj = td.y, cb = td.z, ce = td.w;
+  const bool diag = gi == gj;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t blk = blockIdx.x * (int64_t)SB_WARPS + warp;
-  if (blk >= n_blk) return;
-  double* Ys = slab[warp][0];
-  double* Ws = slab[warp][1];
+  // metadata role: lane s holds the chunk entry of pose s (0..15 row poses, 16..31 column poses)
+  const int mp = ((lane >> 4) ? gj : gi) * 16 + (lane & 15);
+  int m_lo = 0, m_n = 0;
+  int64_t m_ptr = 0;
+  if (mp < P) { m_lo = pc_lo[mp]; m_n = pc_n[mp]; m_ptr = pc_ptr[mp]; }
+  // compute role: half-warp h of warp w works on the wrapped diagonal d = 2 w + h of the tile
+  const int i = lane & 15, d = 2 * warp + (lane >> 4), j = (i + d) & 15;
+  bool active = (gi * 16 + i < P) && (gj * 16 + j < P);
+  if (diag) active = active && (d < 8 || (d == 8 && i < 8));   // diagonals d and 16 - d hold the same unordered pairs
   double acc[36];
 #pragma unroll
-  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-  const int64_t s = blk_ptr[blk], e = blk_ptr[blk + 1];
-  for (int64_t k0 = s; k0 < e; k0 += 32) {
-    const int64_t k = k0 + lane;
-    const bool valid = k < e;
-    const int oa = valid ? __ldg(pair_a + k) : -1, ob = valid ? __ldg(pair_b + k) : -1;
-    // 32 records x 9 chunks of 16 B = 288 chunks per operand: 9 rounds of 32 lanes
+  for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+  bool any = false;
+  const double* cbase = diag ? sm.rows : sm.cols;
+  int* srcl = sm.src[warp];
+  double* stage = sm.rows;                // rows, then cols: one staging area of 2 x REC planes
+  const int n_st = diag ? 16 : 32;        // poses to stage
+  const int spw = n_st / 8;               // poses per warp: s = warp + 8 t
+
+  uint2 ent = make_uint2(0u, 0u);
+  { const int r = cb - m_lo; if (r >= 0 && r < m_n) ent = __ldg(&pc_ent[m_ptr + r]); }
+  for (int c = cb; c < ce; ++c) {
+    const uint2 cur = ent;
+    ent = make_uint2(0u, 0u);
+    { const int r = c + 1 - m_lo; if (c + 1 < ce && r >= 0 && r < m_n) ent = __ldg(&pc_ent[m_ptr + r]); }   // next chunk's entry rides under this chunk
+    // landmarks seen from both sides of the tile; a pose stages only its records of those
+    unsigned any16 = cur.y;
 #pragma unroll
-    for (int rnd = 0; rnd < 9; ++rnd) {
-      const int c = rnd * 32 + lane, j = c / 9, part = c - 9 * j;
-      const int ja = __shfl_sync(0xffffffffu, oa, j), jb = __shfl_sync(0xffffffffu, ob, j);
-      if (ja >= 0) {
-        const double2 y = __ldg(reinterpret_cast<const double2*>(Y + (int64_t)ja * REC) + part);
-        const double2 w = __ldg(reinterpret_cast<const double2*>(W + (int64_t)jb * REC) + part);
-        Ys[j * RST + 2 * part] = y.x; Ys[j * RST + 2 * part + 1] = y.y;
-        Ws[j * RST + 2 * part] = w.x; Ws[j * RST + 2 * part + 1] = w.y;
+    for (int o = 8; o > 0; o >>= 1) any16 |= __shfl_xor_sync(FULL, any16, o);
+    const unsigned other = __shfl_xor_sync(FULL, any16, 16);
+    const unsigned f = cur.y & other;
+    if (!__any_sync(FULL, f != 0u)) continue;     // identical decision in every warp: all hold the same 32 entries
+    __syncthreads();                              // the previous chunk's products are done with the staging area
+    // ---- stage: list the records of this warp's poses, then copy them 3 records (27 lanes x 16 B) per step
+    int base_t[5];
+    base_t[0] = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int cnt = 0;
+      if (t < spw) {
+        const int s = warp + 8 * t;
+        const unsigned fm = __shfl_sync(FULL, f, s), mm = __shfl_sync(FULL, cur.y, s);
+        const int st = (int)__shfl_sync(FULL, cur.x, s);
+        cnt = __popc(fm);
+        if ((fm >> lane) & 1u) {
+          const unsigned low = (1u << lane) - 1u;
+          srcl[base_t[t] + __popc(fm & low)] = st + __popc(mm & low);
+        }
       }
+      base_t[t + 1] = base_t[t] + cnt;
     }
     __syncwarp();
-    if (valid) {
-      const double* ya = Ys + lane * RST;
-      const double* wb = Ws + lane * RST;
-      double wbr[18];
-#pragma unroll
-      for (int i = 0; i < 18; ++i) wbr[i] = wb[i];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double y0 = ya[3 * i], y1 = ya[3 * i + 1], y2 = ya[3 * i + 2];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc[6 * i + j] += y0 * wbr[3 * j] + y1 * wbr[3 * j + 1] + y2 * wbr[3 * j + 2];
-      }
+    {
+      // three records per step: lane (r, part) moves elements 2 part and 2 part + 1 of record pos0 + r with two
+      // 8-byte cp.async (global side: 144 contiguous bytes per record; shared side: the transposed layout)
+      const int total = base_t[4];
+      const int r = lane / 9, part = lane - 9 * r;
+      if (r < 3)
+        for (int pos = r; pos < total; pos += 3) {
+          const int t = (pos >= base_t[1]) + (pos >= base_t[2]) + (pos >= base_t[3]);
+          const int k = pos - (t == 0 ? 0 : (t == 1 ? base_t[1] : (t == 2 ? base_t[2] : base_t[3])));
+          const int s = warp + 8 * t;
+          const int e0 = 2 * part + (r & 1), e1 = 2 * part + 1 - (r & 1);      // neighbouring records start on different banks
+          const double* src = Zp + (int64_t)srcl[pos] * REC;
+          double* dst = stage + (s >> 4) * (REC * PS) + k * 16 + (s & 15);
+          cp_async8(dst + e0 * PS, src + e0);
+          cp_async8(dst + e1 * PS, src + e1);
+        }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
-    __syncwarp();
-  }
-  // butterfly: every lane ends with the full sums
+    __syncthreads();
+    // ---- products: walk the landmarks both poses of this lane's block see
+    const unsigned fi = __shfl_sync(FULL, f, i), fj = __shfl_sync(FULL, f, 16 + j);
+    unsigned hit = active ? (fi & fj) : 0u;
+    while (hit) {
+      const int b = __ffs(hit) - 1;
+      hit &= hit - 1u;
+      const unsigned low = (1u << b) - 1u;
+      const double* ra = sm.rows + __popc(fi & low) * 16 + i;
+      const double* cq = cbase + __popc(fj & low) * 16 + j;
+      double y[REC];
 #pragma unroll
-  for (int i = 0; i < 36; ++i) {
-    double v = acc[i];
+      for (int e = 0; e < REC; ++e) y[e] = ra[e * PS];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    acc[i] = v;
+      for (int jj = 0; jj < 6; ++jj) {
+        const double w0 = cq[(3 * jj) * PS], w1 = cq[(3 * jj + 1) * PS], w2 = cq[(3 * jj + 2) * PS];
+#pragma unroll
+        for (int ii = 0; ii < 6; ++ii) acc[6 * ii + jj] = fma(y[3 * ii + 2], w2, fma(y[3 * ii + 1], w1, fma(y[3 * ii], w0, acc[6 * ii + jj])));
+      }
+      any = true;
+    }
   }
-  const int p = blk_p[blk], q = blk_q[blk];
+  if (!active || !any) return;
+  // acc = sum Z_p Z_q^T with p = row pose of the tile, q = column pose; stored below the diagonal of the reduced system
+  const int p = gi * 16 + i, q = gj * 16 + j;
   const int op = off_pose[p], oq = off_pose[q];
   int ld;
-  const int64_t base = sys_find(sys, op, oq, &ld);      // rows of p, columns of q (order(q) <= order(p))
-  // lane handles entries lane and lane + 32
+  if (p == q) {
+    const int64_t base = sys_find(sys, op, op, &ld);
 #pragma unroll
-  for (int i = 0; i < 36; ++i) {
-    if ((i & 31) == lane && (i < 32 || lane < 4)) {
-      const int r = i / 6, cc = i % 6;
-      if (p != q || r >= cc) sys.L[base + r + (int64_t)cc * ld] -= acc[i];
-    }
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc <= r; ++cc) sys.L[base + r + (int64_t)cc * ld] -= acc[6 * r + cc];
+  } else if (op > oq) {
+    const int64_t base = sys_find(sys, op, oq, &ld);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) sys.L[base + r + (int64_t)cc * ld] -= acc[6 * r + cc];
+  } else {
+    const int64_t base = sys_find(sys, oq, op, &ld);     // rows of q, columns of p: the transpose
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) sys.L[base + r + (int64_t)cc * ld] -= acc[6 * cc + r];
   }
 }
 
-// one warp per pose: rhs_p += sum_a W_a yl(a)
-__global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restrict__ pose_obs_ptr, const int64_t* __restrict__ pose_obs,
-                                                   const int* __restrict__ obs_point, const double* __restrict__ W,
-                                                   const double* __restrict__ yl, const int* __restrict__ off_pose, SysView sys) {
+// one warp per pose: rhs_p += sum_k Z_k u_l(k) over the pose's (contiguous, pose-major) records
+__global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restrict__ pose_obs_ptr, const int* __restrict__ pz_point,
+                                                   const double* __restrict__ Zp, const double* __restrict__ ul,
+                                                   const int* __restrict__ off_pose, SysView sys) {
   const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (p >= P) return;
   const int64_t b = pose_obs_ptr[p], e = pose_obs_ptr[p + 1];
   if (b == e) return;
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int64_t k = b + lane; k < e; k += 32) {
-    const int o = (int)pose_obs[k];
-    const int l = obs_point[o];
-    double w[18];
-    load18(W, o, w);
-    const double y0 = yl[3 * (int64_t)l], y1 = yl[3 * (int64_t)l + 1], y2 = yl[3 * (int64_t)l + 2];
+    const int l = pz_point[k];
+    double w[REC];
+    const double2* zp = reinterpret_cast<const double2*>(Zp + k * REC);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) acc[i] += w[3 * i] * y0 + w[3 * i + 1] * y1 + w[3 * i + 2] * y2;
+    for (int q = 0; q < 9; ++q) { const double2 v = __ldg(zp + q); w[2 * q] = v.x; w[2 * q + 1] = v.y; }
+    const double y0 = ul[3 * (int64_t)l], y1 = ul[3 * (int64_t)l + 1], y2 = ul[3 * (int64_t)l + 2];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) acc[q] += w[3 * q] * y0 + w[3 * q + 1] * y1 + w[3 * q + 2] * y2;
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int q = 0; q < 6; ++q)
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], d);
+    for (int dd = 16; dd > 0; dd >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], dd);
   if (lane < 6) {
     const int C = off_pose[p] + lane;
     const int sn = sys.col2sn[C];
@@ -180,6 +271,18 @@ __global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restr
   }
 }
 
+template <int CH>
+static void launch_tiles(fg_ctx* c, const SysView& sys) {
+  DevGraph& d = c->d;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_schur_tiles<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchurSmem<CH>));
+    attr_set = true;
+  }
+  k_schur_tiles<CH><<<d.n_tiles, ST_THREADS, sizeof(SchurSmem<CH>), c->stream>>>(d.tile_desc, (int)d.n[T_POSE], d.pc_lo, d.pc_n, d.pc_ptr, d.pc_ent,
+                                                                                 d.Zp, d.off[T_POSE], sys);
+}
+
 void launch_schur(fg_ctx* c, double lambda) {
   DevGraph& d = c->d;
   cudaStream_t st = c->stream;
@@ -187,14 +290,16 @@ void launch_schur(fg_ctx* c, double lambda) {
   sys.L = d.L; sys.col2sn = d.col2sn; sys.sn_col0 = d.sn_col0; sys.sn_ncols = d.sn_ncols; sys.sn_nrows = d.sn_nrows;
   sys.sn_rowptr = d.sn_rowptr; sys.sn_valptr = d.sn_valptr; sys.rowidx = d.rowidx; sys.n_r = c->sym.n_r;
   const int64_t L = d.n[T_POINT];
-  k_vinv<<<cdiv(L, 256), 256, 0, st>>>(L, d.V, d.gl, lambda, d.Vinv, d.yl);
-  if (d.n_obs) k_ymat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.W, d.Vinv, d.Y);
+  k_vinv<<<cdiv(L, 256), 256, 0, st>>>(L, d.V, d.gl, lambda, d.Vinv, d.Cf, d.ul);
+  if (d.n_obs) k_zmat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.obs_ppos, d.W, d.Cf, d.Zp);
   if (c->kev[2]) cudaEventRecord(c->kev[2], st);
-  if (d.n_blk) k_schur_blocks<<<cdiv(d.n_blk, SB_WARPS), 32 * SB_WARPS, 0, st>>>(d.n_blk, d.blk_p, d.blk_q, d.blk_ptr, d.pair_a, d.pair_b, d.Y,
-                                                                        d.W, d.off[T_POSE], sys);
+  if (d.n_tiles) {
+    if (d.schur_ch == 32) launch_tiles<32>(c, sys);
+    else launch_tiles<24>(c, sys);
+  }
   if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];
-  if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.W, d.yl, d.off[T_POSE], sys);
+  if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pz_point, d.Zp, d.ul, d.off[T_POSE], sys);
 }
 
 }  // namespace fg
