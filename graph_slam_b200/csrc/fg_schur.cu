@@ -124,9 +124,14 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
   int64_t m_ptr = 0;
   if (mp < P) { m_lo = pc_lo[mp]; m_n = pc_n[mp]; m_ptr = pc_ptr[mp]; }
   // compute role: half-warp h of warp w works on the wrapped diagonal d = 2 w + h of the tile
-  const int i = lane & 15, d = 2 * warp + (lane >> 4), j = (i + d) & 15;
+  // (warp w takes diagonals w and 15 - w: pose distance, hence work, grows along d, and the pair sums to a constant).
+  // In a diagonal tile the diagonals d and 16 - d hold the same unordered pose pairs: the two lanes of a pair split its
+  // landmarks by bit parity and their sums are joined at the end; the p == q blocks are left to k_schur_rhs.
+  const int i = lane & 15, d = (lane >> 4) ? 15 - warp : warp, j = (i + d) & 15;
   bool active = (gi * 16 + i < P) && (gj * 16 + j < P);
-  if (diag) active = active && (d < 8 || (d == 8 && i < 8));   // diagonals d and 16 - d hold the same unordered pairs
+  const bool primary = !diag || d < 8 || (d == 8 && i < 8);
+  unsigned hit_sel = 0xffffffffu;
+  if (diag) { active = active && d != 0; hit_sel = primary ? 0x55555555u : 0xaaaaaaaau; }
   double acc[36];
 #pragma unroll
   for (int q = 0; q < 36; ++q) acc[q] = 0.0;
@@ -137,12 +142,15 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
   const int n_st = diag ? 16 : 32;        // poses to stage
   const int spw = n_st / 8;               // poses per warp: s = warp + 8 t
 
-  uint2 ent = make_uint2(0u, 0u);
-  { const int r = cb - m_lo; if (r >= 0 && r < m_n) ent = __ldg(&pc_ent[m_ptr + r]); }
+  auto fetch = [&](int c) -> uint2 {
+    const int r = c - m_lo;
+    return (c < ce && r >= 0 && r < m_n) ? __ldg(&pc_ent[m_ptr + r]) : make_uint2(0u, 0u);
+  };
+  uint2 ent1 = fetch(cb), ent2 = fetch(cb + 1);
   for (int c = cb; c < ce; ++c) {
-    const uint2 cur = ent;
-    ent = make_uint2(0u, 0u);
-    { const int r = c + 1 - m_lo; if (c + 1 < ce && r >= 0 && r < m_n) ent = __ldg(&pc_ent[m_ptr + r]); }   // next chunk's entry rides under this chunk
+    const uint2 cur = ent1;
+    ent1 = ent2;
+    ent2 = fetch(c + 2);                          // entries ride two chunks ahead of their use
     // landmarks seen from both sides of the tile; a pose stages only its records of those
     unsigned any16 = cur.y;
 #pragma unroll
@@ -192,7 +200,7 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
     __syncthreads();
     // ---- products: walk the landmarks both poses of this lane's block see
     const unsigned fi = __shfl_sync(FULL, f, i), fj = __shfl_sync(FULL, f, 16 + j);
-    unsigned hit = active ? (fi & fj) : 0u;
+    unsigned hit = active ? (fi & fj & hit_sel) : 0u;
     while (hit) {
       const int b = __ffs(hit) - 1;
       hit &= hit - 1u;
@@ -211,18 +219,31 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
       any = true;
     }
   }
+  if (diag) {
+    // join the two halves of every pose pair: the secondary lane (j, i) parks its sums, transposed, in the staging area
+    __syncthreads();
+    double* xch = stage + (primary ? i * 16 + j : j * 16 + i) * 37;
+    if (active && !primary) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) xch[6 * r + cc] = acc[6 * cc + r];
+      xch[36] = any ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (active && primary) {
+#pragma unroll
+      for (int q = 0; q < 36; ++q) acc[q] += xch[q];
+      any = any || xch[36] != 0.0;
+    }
+    if (!primary) return;
+  }
   if (!active || !any) return;
   // acc = sum Z_p Z_q^T with p = row pose of the tile, q = column pose; stored below the diagonal of the reduced system
   const int p = gi * 16 + i, q = gj * 16 + j;
   const int op = off_pose[p], oq = off_pose[q];
   int ld;
-  if (p == q) {
-    const int64_t base = sys_find(sys, op, op, &ld);
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int cc = 0; cc <= r; ++cc) sys.L[base + r + (int64_t)cc * ld] -= acc[6 * r + cc];
-  } else if (op > oq) {
+  if (op > oq) {
     const int64_t base = sys_find(sys, op, oq, &ld);
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -237,7 +258,8 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
   }
 }
 
-// one warp per pose: rhs_p += sum_k Z_k u_l(k) over the pose's (contiguous, pose-major) records
+// one warp per pose over its (contiguous, pose-major) records: rhs_p += sum_k Z_k u_l(k), and the diagonal block
+// S_pp -= sum_k Z_k Z_k^T (lower triangle) that k_schur_tiles leaves out
 __global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restrict__ pose_obs_ptr, const int* __restrict__ pz_point,
                                                    const double* __restrict__ Zp, const double* __restrict__ ul,
                                                    const int* __restrict__ off_pose, SysView sys) {
@@ -245,7 +267,9 @@ __global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restr
   if (p >= P) return;
   const int64_t b = pose_obs_ptr[p], e = pose_obs_ptr[p + 1];
   if (b == e) return;
-  double acc[6] = {0, 0, 0, 0, 0, 0};
+  double acc[27];
+#pragma unroll
+  for (int q = 0; q < 27; ++q) acc[q] = 0.0;
   for (int64_t k = b + lane; k < e; k += 32) {
     const int l = pz_point[k];
     double w[REC];
@@ -255,19 +279,33 @@ __global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restr
     const double y0 = ul[3 * (int64_t)l], y1 = ul[3 * (int64_t)l + 1], y2 = ul[3 * (int64_t)l + 2];
 #pragma unroll
     for (int q = 0; q < 6; ++q) acc[q] += w[3 * q] * y0 + w[3 * q + 1] * y1 + w[3 * q + 2] * y2;
+    int t = 6;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc <= r; ++cc, ++t)
+        acc[t] = fma(w[3 * r + 2], w[3 * cc + 2], fma(w[3 * r + 1], w[3 * cc + 1], fma(w[3 * r], w[3 * cc], acc[t])));
   }
 #pragma unroll
-  for (int q = 0; q < 6; ++q)
+  for (int q = 0; q < 27; ++q)
 #pragma unroll
     for (int dd = 16; dd > 0; dd >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], dd);
-  if (lane < 6) {
-    const int C = off_pose[p] + lane;
-    const int sn = sys.col2sn[C];
-    const int nr = sys.sn_nrows[sn];
-    double v = acc[0];
-    if (lane == 1) v = acc[1]; else if (lane == 2) v = acc[2]; else if (lane == 3) v = acc[3];
-    else if (lane == 4) v = acc[4]; else if (lane == 5) v = acc[5];
-    sys.L[sys.sn_valptr[sn] + (int64_t)(C - sys.sn_col0[sn]) * nr + nr - 1] += v;
+  const int C0 = off_pose[p];
+  const int sn = sys.col2sn[C0];
+  const int nr = sys.sn_nrows[sn];
+  double* col0 = sys.L + sys.sn_valptr[sn] + (int64_t)(C0 - sys.sn_col0[sn]) * nr;     // column C0 of the panel; a pose never straddles supernodes
+  const int r0 = C0 - sys.sn_col0[sn];                                               // row of the pose's first scalar inside the panel
+  if (lane < 27) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < 27; ++q) if (q == lane) v = acc[q];
+    if (lane < 6) {
+      col0[(int64_t)lane * nr + nr - 1] += v;                 // rhs row
+    } else {
+      int t = lane - 6, r = 0;
+      while (t > r) { t -= r + 1; ++r; }                      // lower-triangle index -> (r, cc = t)
+      col0[(int64_t)t * nr + r0 + r] -= v;
+    }
   }
 }
 
