@@ -229,14 +229,15 @@ def main():
     iters = max(rep.iterations, 1)
     t_obs = rep.ms_proj_obs / iters                       # k_proj_obs<JAC>: 176 B per observation (idx 8, uv 16, w 8, W 144)
     b_obs = m_rank * 176 + l_rank * (24 + 72)
-    t_sch = rep.ms_schur_blocks / trials                  # k_schur_blocks: W and Y read once (288 B/obs), 8 B per pair, panels RMW
-    b_sch = m_rank * 288 + int(rep.n_schur_pairs) * 8 + 2 * 8 * int(rep.nnz_L)
+    t_sch = rep.ms_schur_blocks / trials                  # k_schur_tiles: every Z record read once (144 B/obs), reduced blocks RMW
+    b_sch = m_rank * 144 + 2 * 8 * int(rep.nnz_L)
+    f_sch = 216.0 * int(rep.n_schur_pairs)                # 108 DFMA per (observation a, observation b) pair of a landmark
     t_cho = phases['factor']                              # k_chol_reg: one read of the assembled panels, one write of L
     b_cho = 2 * 8 * int(rep.nnz_L)
 
     # dram__bytes_read+write per launch from the committed ncu --set full capture (single GPU, C5 only)
     traffic = {}
-    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')   # refreshed with every committed ncu --set full capture
     if os.path.exists(tp) and args.config == 'C5' and args.scale == 1.0 and world == 1:
         traffic = json.load(open(tp)).get('dram_bytes_per_launch', {})
 
@@ -245,7 +246,8 @@ def main():
         return dict(kernel=name, bound='hbm', achieved=a, peak=peak, unit='GB/s', frac=a / peak, traffic=traffic.get(name),
                     algorithmic_bytes=nbytes, ms=ms, note=note)
     roofs = [roof('k_chol_reg', b_cho, t_cho, 'dominant by time; dependency-latency bound (%d levels), not bandwidth bound' % int(rep.n_levels)),
-             roof('k_schur_blocks', b_sch, t_sch, 'L2-bandwidth bound: %d pairs x 288 B mostly served by L2' % int(rep.n_schur_pairs)),
+             roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA bound: %d pairs x 216 flop = %.1f TFLOP/s achieved (B200 fp64 peak ~37 TFLOP/s, not in MEASURED_PEAKS.json)' % (
+                 int(rep.n_schur_pairs), f_sch / (t_sch * 1e-3) / 1e12 if t_sch > 0 else 0.0)),
              roof('k_proj_obs', b_obs, t_obs, 'streaming pass over the observations')]
     dominant = max(roofs, key=lambda r: r['ms'])
     line = dict(metric=METRIC, value=value, unit='iterations/s', n_gpus=world, steps=args.steps, warmup=args.warmup,

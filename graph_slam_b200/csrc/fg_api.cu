@@ -626,6 +626,10 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload(c, &d.tile_leaf, S.tile_leaf)) || (rc = dev_upload(c, &d.tile_i, S.tile_i)) || (rc = dev_upload(c, &d.tile_j, S.tile_j)) ||
         (rc = dev_upload<double>(c, &d.U, nullptr, (size_t)S.fr_uptr[S.n_leaves]))) return rc;
   }
+  if (S.rs_ok) {
+    if ((rc = dev_upload(c, &d.rs_units, S.rs_units)) || (rc = dev_upload(c, &d.rs_uoff, S.rs_uoff)) || (rc = dev_upload(c, &d.rs_sub, S.rs_sub)) ||
+        (rc = dev_upload<int>(c, &d.rs_done, nullptr, 2 * (size_t)S.n_sn))) return rc;
+  }
   CK(cudaStreamSynchronize(c->stream));
   c->epoch = 0;
   c->finalized = true;
@@ -709,7 +713,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
       launch_build_and_schur(c, lam);
       if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) break;
       CK(cudaEventRecord(ev[2], c->stream));
-      if (chol_reg_supported(c)) launch_factor_reg(c); else launch_factor(c);
+      if (chol_rs_supported(c)) launch_factor_rs(c); else if (chol_reg_supported(c)) launch_factor_reg(c); else launch_factor(c);
       CK(cudaEventRecord(ev[3], c->stream));
       launch_backsolve(c);
       CK(cudaEventRecord(ev[4], c->stream));
@@ -859,6 +863,10 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 33: v = {S.use_fronts ? 1 : 0, S.n_leaves, S.n_levels_fronts, (int64_t)S.tile_leaf.size()}; break;
     case 34: put(S.sched_a); break;
     case 35: put(S.sched_c); break;
+    case 36: v.clear(); for (const int4& u : S.rs_units) { v.push_back(u.x); v.push_back(u.y); v.push_back(u.z); v.push_back(u.w); } break;
+    case 37: v.assign(S.rs_uoff.begin(), S.rs_uoff.end()); break;
+    case 38: v.clear(); for (const int2& u : S.rs_sub) { v.push_back(u.x); v.push_back(u.y); } break;
+    case 39: v = {S.rs_ok ? 1 : 0, S.rs_units_a, (int64_t)S.rs_units.size()}; break;
     default: return FG_ERR_INVALID;
   }
   if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];

@@ -91,6 +91,13 @@ struct Symbolic {
   std::vector<int> tile_leaf, tile_i, tile_j;      // 64 x 64 tiles of the lower triangles of all fronts
   std::vector<int> tile_mptr; std::vector<FrontRec> tile_mrec;   // per tile: the members that have rows in both of its blocks
   int n_levels_fronts = 0;
+  // ---- row-split work units (fg_chol_rs.cu): (supernode, first own row, end own row, blocks of the supernode), level sorted;
+  //      the first rs_units_a units are phase A (leaf members, or everything when fronts are off)
+  bool rs_ok = false;
+  int rs_units_a = 0;
+  std::vector<int4> rs_units;
+  std::vector<int64_t> rs_uoff;                    // per unit: offset of its per-update sub-ranges
+  std::vector<int2> rs_sub;                        // per (unit, update): descendant rows (from row a) that land in the unit's own rows: (first, count)
 };
 
 // ------------------------------------------------------------------ device view passed to kernels
@@ -221,6 +228,7 @@ struct DevGraph {
   double* U = nullptr;              // dense update matrices of all leaves
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;
+  int4* rs_units = nullptr; int64_t* rs_uoff = nullptr; int2* rs_sub = nullptr; int* rs_done = nullptr;   // rs_done: n_sn done flags, then n_sn arrival counters
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
   int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve)
 };
@@ -255,6 +263,8 @@ void launch_schur(fg_ctx* c, double lambda);              // fg_schur.cu: the la
 void launch_factor(fg_ctx* c);                            // cholesky; the rhs row makes it the forward solve too
 bool chol_reg_supported(const fg_ctx* c);                 // fg_chol_reg.cu: width <= 16, height <= 1024
 void launch_factor_reg(fg_ctx* c);                        // register-tiled fast path of the same factorisation
+bool chol_rs_supported(const fg_ctx* c);                  // fg_chol_rs.cu: row-split units, width <= 16
+void launch_factor_rs(fg_ctx* c);
 void launch_front_syrk(fg_ctx* c);                        // fg_front.cu: dense update matrix of every leaf onto its front
 void launch_backsolve(fg_ctx* c);                         // backward solve -> delta
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]

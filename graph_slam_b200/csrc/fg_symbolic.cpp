@@ -356,6 +356,58 @@ int build_symbolic(fg_ctx* c) {
       for (int l = 0; l < n_leaves; ++l) if (S.fr_rowptr[l + 1] - S.fr_rowptr[l] > 1024) S.use_fronts = false;   // k_chol_reg stages a front's row list in shared memory
     }
   }
+  // ---- row-split work units for k_chol_rs: blocks of <= kRsRows below-diagonal rows per supernode
+  {
+    const int kRsRows = 240;
+    const bool fr = S.use_fronts;
+    const std::vector<int>& UP = fr ? S.updr_ptr : S.upd_ptr;
+    const std::vector<int>& UD = fr ? S.updr_d : S.upd_d;
+    const std::vector<int>& UA = fr ? S.updr_a : S.upd_a;
+    const std::vector<int>& UB = fr ? S.updr_b : S.upd_b;
+    std::vector<int> nblk(S.n_sn);
+    for (int s = 0; s < S.n_sn; ++s) nblk[s] = std::max(1, (S.sn_nrows[s] - S.sn_ncols[s] + kRsRows - 1) / kRsRows);
+    // level-sorted supernode order of each phase (levels under the update lists in use)
+    std::vector<int> lv(S.n_sn, 0);
+    for (int s = 0; s < S.n_sn; ++s) {
+      for (int u = UP[s]; u < UP[s + 1]; ++u) lv[s] = std::max(lv[s], lv[UD[u]] + 1);
+      if (fr)
+        for (int e = S.tf_ptr[s]; e < S.tf_ptr[s + 1]; ++e) {
+          const int l = S.tf_leaf[e];
+          for (int m = S.leaf_sn_lo[l]; m < S.leaf_sn_hi[l]; ++m) lv[s] = std::max(lv[s], lv[m] + 1);
+        }
+    }
+    std::vector<int> order_a, order_c;
+    for (int s = 0; s < S.n_sn; ++s) ((fr && S.sn_leaf[s] < 0) ? order_c : order_a).push_back(s);
+    auto bylevel = [&](int a, int b) { return lv[a] < lv[b]; };
+    std::stable_sort(order_a.begin(), order_a.end(), bylevel);
+    std::stable_sort(order_c.begin(), order_c.end(), bylevel);
+    auto emit = [&](const std::vector<int>& order) {
+      for (int s : order) {
+        const int nc = S.sn_ncols[s], nr = S.sn_nrows[s], nb = nblk[s];
+        const int per = (nr - nc + nb - 1) / nb;
+        const int* rows = &S.rowidx[S.sn_rowptr[s]];
+        for (int b = 0; b < nb; ++b) {
+          const int r0 = nc + b * per, r1 = std::min(nr, r0 + per);
+          S.rs_units.push_back(make_int4(s, r0, r1, nb));
+          S.rs_uoff.push_back((int64_t)S.rs_sub.size());
+          const int glo = rows[r0], ghi = rows[r1 - 1];
+          for (int u = UP[s]; u < UP[s + 1]; ++u) {
+            const int d = UD[u], a = UA[u], bb = UB[u];
+            const int* rd = &S.rowidx[S.sn_rowptr[d]];
+            const int nrd = S.sn_nrows[d];
+            const int* lo = std::lower_bound(rd + bb, rd + nrd, glo);
+            const int* hi = std::upper_bound(rd + bb, rd + nrd, ghi);
+            S.rs_sub.push_back(make_int2((int)(lo - (rd + a)), (int)(hi - lo)));
+          }
+        }
+      }
+    };
+    emit(order_a);
+    S.rs_units_a = (int)S.rs_units.size();
+    emit(order_c);
+    S.rs_ok = S.max_ncols <= 16;
+    for (const int4& un : S.rs_units) if (un.z - un.y > kRsRows || un.z <= un.y) S.rs_ok = false;
+  }
   // ---- schedule: supernodes by dependency level (longest path), a topological order that interleaves
   //      the independent chains so that the persistent kernel works on all of them at once
   S.level.assign(S.n_sn, 0);

@@ -98,6 +98,11 @@ def test_c4_ba_imu_schur():
     check(synth.make_config('C4', seed=1, scale=0.03), 1e-7, 1e-6, solver='schur')
 
 
+def test_c4_multi_block_supernodes():
+    """120 poses: panels taller than one row block of k_chol_rs (fg_chol_rs.cu), several leaf fronts."""
+    check(synth.make_config('C4', seed=1, scale=0.06), 1e-7, 1e-6, solver='schur')
+
+
 @pytest.mark.parametrize('seed', [2, 3])
 def test_c4_other_seeds(seed):
     check(synth.make_config('C4', seed=seed, scale=0.02), 1e-7, 1e-6, solver='schur')
@@ -159,8 +164,11 @@ def test_generic_cholesky_kernel_is_equivalent(monkeypatch):
     optimum as fg_chol_reg.cu."""
     spec = synth.make_config('C4', seed=2, scale=0.03)
     ctx = abi.Context(device=0); abi.load_spec(ctx, spec); fast = ctx.optimize(); Tf = ctx.get_values(abi.T_POSE); ctx.close()
-    monkeypatch.setenv('FG_CHOL_GENERIC', '1')
+    monkeypatch.setenv('FG_CHOL_RS', '0')             # whole-supernode kernel (fg_chol_reg.cu)
+    ctx = abi.Context(device=0); abi.load_spec(ctx, spec); reg = ctx.optimize(); Tr = ctx.get_values(abi.T_POSE); ctx.close()
+    monkeypatch.setenv('FG_CHOL_GENERIC', '1')        # generic kernel (fg_chol.cu)
     ctx = abi.Context(device=0); abi.load_spec(ctx, spec); gen = ctx.optimize(); Tg = ctx.get_values(abi.T_POSE); ctx.close()
-    assert gen.iterations == fast.iterations
-    assert abs(gen.final_error - fast.final_error) <= 1e-10 * fast.final_error
-    assert np.abs(Tg - Tf).max() < 1e-9
+    for other, To in ((reg, Tr), (gen, Tg)):
+        assert other.iterations == fast.iterations
+        assert abs(other.final_error - fast.final_error) <= 1e-10 * fast.final_error
+        assert np.abs(To - Tf).max() < 1e-9

@@ -161,7 +161,101 @@ def emulate_fronts(ctx, sym, Sp, bp):
     return x
 
 
-@pytest.mark.parametrize('name,scale', [('C1', 1.0), ('C2', 0.08), ('C3', 0.08), ('C4', 0.03)])
+def emulate_rowsplit(ctx, sym, Sp, bp):
+    """numpy emulation of k_chol_rs (fg_chol_rs.cu): the unit of work is a block of below-diagonal rows of a
+    supernode.  A unit reads the ASSEMBLED diagonal block and its own rows, applies every descendant update restricted
+    to the descendant rows the host listed for it (rs_sub) plus the part landing on the diagonal block, factors its own
+    copy of the diagonal block and solves its rows; the diagonal factor is stored once per supernode."""
+    n_r, n_sn = int(sym[0][0]), int(sym[0][1])
+    col0, ncols, nrows, rowptr, valptr, rowidx = sym[1:7]
+    use_fr = bool(ctx.symbolic(33)[0])
+    ok, n_a, n_units = (int(v) for v in ctx.symbolic(39))
+    assert ok
+    units = ctx.symbolic(36).reshape(-1, 4); uoff = ctx.symbolic(37); sub = ctx.symbolic(38).reshape(-1, 2)
+    assert len(units) == n_units
+    uptr, ud, ua, ub = (ctx.symbolic(w) for w in ((22, 23, 24, 25) if use_fr else (7, 8, 9, 10)))
+    aug = np.zeros((n_r + 1, n_r + 1)); aug[:n_r, :n_r] = Sp; aug[n_r, :n_r] = bp
+    rows_of = [rowidx[rowptr[s]:rowptr[s] + nrows[s]] for s in range(n_sn)]
+    A0, Lf = [], []                      # assembled panels (read-only) and factored panels
+    for s in range(n_sn):
+        cols = np.arange(col0[s], col0[s] + ncols[s])
+        P = aug[np.ix_(rows_of[s], cols)].copy(); P[:ncols[s]] = np.tril(P[:ncols[s]])
+        A0.append(P); Lf.append(np.full_like(P, np.nan))
+    arrived = np.zeros(n_sn, dtype=int)
+    covered = [np.zeros(nrows[s], dtype=int) for s in range(n_sn)]
+    U = None
+
+    def fronts():
+        fr_rowptr, fr_rows, members = ctx.symbolic(26), ctx.symbolic(27), ctx.symbolic(28).reshape(-1, 2)
+        pm_ptr, posmap = ctx.symbolic(31), ctx.symbolic(32)
+        out = []
+        for l, (lo, hi) in enumerate(members):
+            Rl = fr_rows[fr_rowptr[l]:fr_rowptr[l + 1]]
+            Ul = np.zeros((len(Rl), len(Rl)))
+            for d in range(lo, hi):
+                assert arrived[d] == -1
+                pm = posmap[pm_ptr[d]:pm_ptr[d + 1]]
+                A = np.where(pm[:, None] >= 0, Lf[d][np.maximum(pm, 0)], 0.0)
+                Ul += A @ A.T
+            out.append((Rl, Ul))
+        return out
+
+    for k, (s, r0, r1, nblk) in enumerate(units.tolist()):
+        if use_fr and k == n_a:
+            U = fronts()
+        nc = int(ncols[s])
+        assert nc <= r0 < r1 <= nrows[s] and r1 - r0 <= 240
+        loc = list(range(nc)) + list(range(r0, r1))
+        P = A0[s][loc].copy()
+        g = [int(rows_of[s][i]) for i in loc]
+        pos = {r: i for i, r in enumerate(g)}
+        if use_fr and k >= n_a:
+            tf_ptr, tf_leaf = ctx.symbolic(29), ctx.symbolic(30)
+            for e in range(tf_ptr[s], tf_ptr[s + 1]):
+                Rl, Ul = U[int(tf_leaf[e])]
+                idx = {int(r): q for q, r in enumerate(Rl)}
+                for rr, gr in enumerate(g):
+                    if gr not in idx:
+                        continue
+                    for c in range(nc):
+                        gc = int(col0[s] + c)
+                        if gc in idx and gr >= gc:
+                            P[rr, c] -= Ul[idx[gr], idx[gc]]
+        for q, u in enumerate(range(uptr[s], uptr[s + 1])):
+            d, a, b = int(ud[u]), int(ua[u]), int(ub[u])
+            assert arrived[d] == -1, 'descendant not complete when its update is pulled'
+            first, cnt = (int(v) for v in sub[uoff[k] + q])
+            Ld = Lf[d]
+            take = list(range(a, b)) + list(range(a + first, a + first + cnt))
+            assert first >= b - a and a + first + cnt <= nrows[d]
+            # the listed sub-range is exactly the set of descendant rows inside this unit's own rows
+            inside = [i for i in range(b, nrows[d]) if g[nc] <= rows_of[d][i] <= g[-1]]
+            assert inside == list(range(a + first, a + first + cnt))
+            upd = Ld[take] @ Ld[a:b].T
+            for ii, i in enumerate(take):
+                R = int(rows_of[d][i])
+                for jj in range(b - a):
+                    C = int(rows_of[d][a + jj])
+                    if R >= C:
+                        P[pos[R], C - col0[s]] -= upd[ii, jj]
+        Ldd = np.linalg.cholesky(P[:nc] + np.tril(P[:nc], -1).T)
+        Lf[s][r0:r1] = np.linalg.solve(Ldd, P[nc:].T).T
+        covered[s][r0:r1] += 1
+        arrived[s] += 1
+        if arrived[s] == nblk:
+            Lf[s][:nc] = Ldd
+            covered[s][:nc] += 1
+            arrived[s] = -1                  # done flag
+    assert all(np.all(c == 1) for c in covered) and np.all(arrived == -1)
+    x = np.zeros(n_r)
+    for s in range(n_sn - 1, -1, -1):
+        rows = rows_of[s]; nc = ncols[s]
+        t = Lf[s][-1] - Lf[s][nc:-1].T @ x[rows[nc:-1]]
+        x[col0[s]:col0[s] + nc] = np.linalg.solve(Lf[s][:nc].T, t)
+    return x
+
+
+@pytest.mark.parametrize('name,scale', [('C1', 1.0), ('C2', 0.08), ('C3', 0.08), ('C4', 0.03), ('C4', 0.06)])
 def test_symbolic_and_left_looking(fglib, name, scale):
     spec = synth.make_config(name, seed=2, scale=scale)
     lam = 1e-3
@@ -210,6 +304,9 @@ def test_symbolic_and_left_looking(fglib, name, scale):
     if ctx.symbolic(33)[0]:
         xf = emulate_fronts(ctx, sym, Sp, bp)
         assert np.allclose(xf, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+    if ctx.symbolic(39)[0]:
+        xr = emulate_rowsplit(ctx, sym, Sp, bp)
+        assert np.allclose(xr, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
     ctx.close()
 
 
