@@ -627,7 +627,8 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<double>(c, &d.U, nullptr, (size_t)S.fr_uptr[S.n_leaves]))) return rc;
   }
   if (S.rs_ok) {
-    if ((rc = dev_upload(c, &d.rs_units, S.rs_units)) || (rc = dev_upload(c, &d.rs_uoff, S.rs_uoff)) || (rc = dev_upload(c, &d.rs_sub, S.rs_sub)) ||
+    if ((rc = dev_upload(c, &d.rs_units, S.rs_units)) || (rc = dev_upload(c, &d.rs_moff, S.rs_moff)) || (rc = dev_upload(c, &d.rs_map, S.rs_map)) ||
+        (rc = dev_upload(c, &d.rs_colinv, S.rs_colinv)) ||
         (rc = dev_upload<int>(c, &d.rs_done, nullptr, 2 * (size_t)S.n_sn))) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));
@@ -864,8 +865,9 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 34: put(S.sched_a); break;
     case 35: put(S.sched_c); break;
     case 36: v.clear(); for (const int4& u : S.rs_units) { v.push_back(u.x); v.push_back(u.y); v.push_back(u.z); v.push_back(u.w); } break;
-    case 37: v.assign(S.rs_uoff.begin(), S.rs_uoff.end()); break;
-    case 38: v.clear(); for (const int2& u : S.rs_sub) { v.push_back(u.x); v.push_back(u.y); } break;
+    case 37: v.assign(S.rs_moff.begin(), S.rs_moff.end()); break;
+    case 38: v.assign(S.rs_map.begin(), S.rs_map.end()); break;
+    case 40: v.assign(S.rs_colinv.begin(), S.rs_colinv.end()); break;
     case 39: v = {S.rs_ok ? 1 : 0, S.rs_units_a, (int64_t)S.rs_units.size()}; break;
     default: return FG_ERR_INVALID;
   }

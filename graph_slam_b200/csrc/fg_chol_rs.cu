@@ -5,16 +5,19 @@
 // 32 independent leaf chains at C5 (fg_symbolic.cpp); with one CTA per supernode 32 of the 148 SMs carried three
 // quarters of the flops.  Here a supernode of nr rows x nc columns (nc <= 16) is cut into blocks of <= RS_RB
 // below-diagonal rows.  A unit (supernode, block)
-//   * keeps the diagonal block (nc x nc) and its own rows of the panel in shared memory,
-//   * pulls every descendant update restricted to those rows -- the descendant rows that land in the block form a
-//     contiguous sub-range of the descendant's sorted row list, precomputed on the host -- plus the small part that
-//     lands on the diagonal block (recomputed by every block of the supernode: 15 x 15 x K flops),
+//   * is output stationary: thread t owns local row t (the nc diagonal rows, then the block's own rows) and keeps its
+//     nc values in registers from the first load to the final store -- no shared-memory panel, no write conflicts,
+//   * pulls every descendant update restricted to those rows: a host-built map (int16 per unit, update and row) names
+//     the descendant row that lands on each local row, so an update is one coalesced index load, K coalesced value
+//     loads and K x nc DFMA per thread against the descendant's (rows in the target's columns) block, staged in shared
+//     memory already scattered to target columns; the part that lands on the diagonal block is recomputed by every
+//     block of the supernode (15 x 15 x K flops),
 //   * factors the diagonal block (every block redundantly: no intra-supernode synchronisation), solves its own rows
 //     against it and stores them,
 //   * bumps the supernode's arrival counter; the block that arrives LAST stores the factored diagonal block (the others
 //     read the assembled one when they start, so it must not be overwritten earlier) and publishes the supernode's
 //     done flag (release); consumers poll the flag (acquire).
-// One descendant row per thread, the next update's loads are issued before the current one is multiplied.
+// The next update's loads are issued before the current one is multiplied.
 // Deterministic: every panel entry is owned by one unit and updated in list order.  DFMA on CUDA cores: tcgen05 has
 // no fp64 kind.
 #include <algorithm>
@@ -38,15 +41,11 @@ __device__ __forceinline__ int rs_ld_relaxed(const int* p) {
 }
 
 struct RsSmem {
-  double P[RS_LR * RS_NC];              // column-major, ld = nloc
-  double Bs[2][RS_NC * RS_NC];          // [buf][k][j] descendant rows that fall in the target's columns
+  double Bs[2][RS_NC * RS_NC];          // [buf][k][c]: descendant rows that fall in the target's columns, scattered to TARGET columns
   double Ds[RS_NC * RS_DP];
-  double colbuf[RS_NC];
   double dinv[RS_NC];
-  int rows_s[RS_LR];                    // global row of every local row
   int rl[1024];                         // row list of the leaf front being subtracted
   int colidx[RS_NC];
-  int colj[2][RS_NC];
   int slot, first_not_ready;
 };
 
@@ -84,9 +83,9 @@ __device__ __forceinline__ void rs_potrf_warp(RsSmem& sm, int nc, int lane, int*
 }
 
 __global__ void __launch_bounds__(RS_T, 2)
-k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__ unit_uoff, const int2* __restrict__ sub,
-          const int* __restrict__ upd_ptr, const int* __restrict__ upd_d,
-          const UpdRec* __restrict__ upd_rec, int* arrived, int* done, int* counter, int n_units, int* status, FrontView fv,
+k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__ unit_moff, const short* __restrict__ rowmap,
+          const int* __restrict__ upd_ptr, const int* __restrict__ upd_d, const UpdRec* __restrict__ upd_rec,
+          const signed char* __restrict__ colinv, int* arrived, int* done, int* counter, int n_units, int* status, FrontView fv,
           long long* dbg) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
@@ -103,46 +102,45 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     const int4 un = units[slot];
     const int sn = un.x, r0 = un.y, r1 = un.z, nblk = un.w;   // own rows [r0, r1) of the panel, r0 >= nc; blocks of this supernode
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
-    const int nown = r1 - r0, nloc = nc + nown;
+    const int nloc = nc + (r1 - r0);
     double* Lp = s.L + s.sn_valptr[sn];
-    const int* rows_g = s.rowidx + s.sn_rowptr[sn];
-    const int2* usub = sub + unit_uoff[slot];
-    // local row lr: panel row (lr < nc ? lr : r0 + lr - nc)
-    for (int i = tid; i < nloc; i += RS_T) sm.rows_s[i] = rows_g[i < nc ? i : r0 + i - nc];
-    for (int i = tid; i < nloc * nc; i += RS_T) {
-      const int lr = i % nloc, c = i / nloc;
-      sm.P[i] = Lp[(lr < nc ? lr : r0 + lr - nc) + (int64_t)c * nr];
-    }
-    __syncthreads();
+    // thread tid owns local row tid of the unit: the diagonal rows first, then the own rows; its nc values live in registers
+    const bool has_row = tid < nloc;
+    const int prow = tid < nc ? tid : r0 + tid - nc;
+    const short* umap = rowmap + unit_moff[slot] + tid;
+    double acc[RS_NC];
+#pragma unroll
+    for (int c = 0; c < RS_NC; ++c) acc[c] = (has_row && c < nc) ? Lp[prow + (int64_t)c * nr] : 0.0;
     // ---- subtract the dense leaf fronts that reach this supernode (fg_front.cu)
     if (fv.tf_ptr) {
+      const int g = has_row ? s.rowidx[s.sn_rowptr[sn] + prow] : -1;
       for (int e = fv.tf_ptr[sn]; e < fv.tf_ptr[sn + 1]; ++e) {
         const int l = fv.tf_leaf[e];
         const int* Rl = fv.fr_rows + fv.fr_rowptr[l];
         const int nR = fv.fr_rowptr[l + 1] - fv.fr_rowptr[l];
         const double* Ul = fv.U + fv.fr_uptr[l];
+        __syncthreads();
         for (int i = tid; i < nR; i += RS_T) sm.rl[i] = Rl[i];
         __syncthreads();
-        if (tid < nc) {
-          const int g = c0 + tid;
+        if (tid < RS_NC) {
+          const int gc = c0 + tid;
           int lo = 0, hi = nR - 1;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rl[mid] < g) lo = mid + 1; else hi = mid; }
-          sm.colidx[tid] = (nR > 0 && sm.rl[lo] == g) ? lo : -1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rl[mid] < gc) lo = mid + 1; else hi = mid; }
+          sm.colidx[tid] = (tid < nc && nR > 0 && sm.rl[lo] == gc) ? lo : -1;
         }
         __syncthreads();
-        for (int r = tid; r < nloc; r += RS_T) {
-          const int g = sm.rows_s[r];
+        if (has_row) {
           int lo = 0, hi = nR - 1;
           while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rl[mid] < g) lo = mid + 1; else hi = mid; }
           if (nR > 0 && sm.rl[lo] == g) {
             const double* urow = Ul + (int64_t)lo * nR;
-            for (int c = 0; c < nc; ++c) {
+#pragma unroll
+            for (int c = 0; c < RS_NC; ++c) {
               const int jc = sm.colidx[c];
-              if (jc >= 0 && g >= c0 + c) sm.P[r + c * nloc] -= urow[jc];
+              if (jc >= 0 && jc <= lo) acc[c] -= urow[jc];      // lower triangle of U only (above it: the unused upper part of the diagonal block)
             }
           }
         }
-        __syncthreads();
       }
     }
 
@@ -151,7 +149,7 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     const int u1 = upd_ptr[sn + 1];
     int buf = 0;
     while (u < u1) {
-      // warp 0 spins on the completion counters of the next (up to 32) descendants and publishes the ready prefix
+      // warp 0 spins on the done flags of the next (up to 32) descendants and publishes the ready prefix
       if (tid < 32) {
         const int win = min(32, u1 - u);
         const int ui = u + min(tid, win - 1);
@@ -171,117 +169,88 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
       const int nready = sm.first_not_ready;
       RS_STAMP(1)                                          // last time a batch of descendants was seen ready
       // ---- software pipeline over the ready updates: loads of update uu + 1 are in flight while uu is multiplied
-      int Rn = -1, cjn = 0;
+      int min_ = -1, halfn = 0;
       double xn[RS_NC], bn = 0.0;
-      int nbn = 0;
       auto issue = [&](int uu) {
         const UpdRec rec = upd_rec[uu];
-        const int2 sr = usub[uu - ubase];                 // own-row part: descendant rows [sr.x, sr.x + sr.y) counted from row a
         const double* Ld = s.L + rec.val_off;
-        const int* rd = s.rowidx + rec.row_off;
-        const int K = rec.K, nrd = rec.nrd, nb = rec.nb;
-        int i = -1;
-        if (tid < nb) i = tid;                            // rows that land on the diagonal block
-        else if (tid >= RS_NC && tid - RS_NC < sr.y) i = sr.x + tid - RS_NC;
-        Rn = (i >= 0) ? __ldg(rd + i) : -1;
+        const int K = rec.K, nrd = rec.nrd;
+        min_ = has_row ? (int)__ldg(umap + (int64_t)(uu - ubase) * nloc) : -1;     // descendant row (from row a) that lands on this thread's row
 #pragma unroll
-        for (int k = 0; k < RS_NC; ++k) xn[k] = (i >= 0 && k < K) ? __ldcg(&Ld[i + (int64_t)k * nrd]) : 0.0;
+        for (int k = 0; k < RS_NC; ++k) xn[k] = (min_ >= 0 && k < K) ? __ldcg(&Ld[min_ + (int64_t)k * nrd]) : 0.0;
         {
-          const int j = tid % RS_NC, k = tid / RS_NC;     // RS_T == RS_NC * RS_NC
-          bn = (j < nb && k < K) ? __ldcg(&Ld[j + (int64_t)k * nrd]) : 0.0;
+          const int c = tid % RS_NC, k = tid / RS_NC;     // RS_T == RS_NC * RS_NC
+          const int j = colinv[(int64_t)uu * RS_NC + c];  // descendant row (from a) holding target column c, or -1
+          bn = (j >= 0 && k < K) ? __ldcg(&Ld[j + (int64_t)k * nrd]) : 0.0;
         }
-        cjn = (tid < nb) ? __ldg(rd + tid) - c0 : 0;
-        nbn = nb;
+        halfn = rec.pad[0];                               // 1: only target columns < 8 are touched
       };
-      if (nready > 0) issue(u);
+      issue(u);
       for (int uu = u; uu < u + nready; ++uu, buf ^= 1) {
-        const int R = Rn, nb = nbn;
+        const int mi = min_, half = halfn;
         double x[RS_NC];
 #pragma unroll
         for (int k = 0; k < RS_NC; ++k) x[k] = xn[k];
         sm.Bs[buf][tid] = bn;                             // last read two updates ago: every thread is past that barrier
-        if (tid < nb) sm.colj[buf][tid] = cjn;
-        __syncthreads();                                  // Bs[buf] / colj[buf] of this update are in place; the previous product is done
+        __syncthreads();
         if (uu + 1 < u + nready) issue(uu + 1);
-        if (R >= 0) {
-          int r;
-          if (R < c0 + nc) r = R - c0;
-          else {
-            int lo = nc, hi = nloc - 1;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rows_s[mid] < R) lo = mid + 1; else hi = mid; }
-            r = lo;
-          }
+        if (mi >= 0) {
           const double* Bt = sm.Bs[buf];
-          double acc[RS_NC];
+          if (half) {
 #pragma unroll
-          for (int j = 0; j < RS_NC; ++j) acc[j] = 0.0;
+            for (int k = 0; k < RS_NC; ++k) {
+              const double xk = -x[k];
+              const double2* brow = reinterpret_cast<const double2*>(Bt + k * RS_NC);
 #pragma unroll
-          for (int k = 0; k < RS_NC; ++k) {
-            const double xk = x[k];
-            const double2* brow = reinterpret_cast<const double2*>(Bt + k * RS_NC);
-#pragma unroll
-            for (int jp = 0; jp < RS_NC / 2; ++jp) {
-              const double2 bb = brow[jp];
-              acc[2 * jp] = fma(xk, bb.x, acc[2 * jp]);
-              acc[2 * jp + 1] = fma(xk, bb.y, acc[2 * jp + 1]);
+              for (int jp = 0; jp < RS_NC / 4; ++jp) {
+                const double2 bb = brow[jp];
+                acc[2 * jp] = fma(xk, bb.x, acc[2 * jp]);
+                acc[2 * jp + 1] = fma(xk, bb.y, acc[2 * jp + 1]);
+              }
             }
-          }
+          } else {
 #pragma unroll
-          for (int j = 0; j < RS_NC; ++j) {
-            if (j < nb) {
-              const int cj = sm.colj[buf][j];
-              if (R >= c0 + cj) sm.P[r + cj * nloc] -= acc[j];     // the strictly-upper part of the diagonal block is not stored
+            for (int k = 0; k < RS_NC; ++k) {
+              const double xk = -x[k];
+              const double2* brow = reinterpret_cast<const double2*>(Bt + k * RS_NC);
+#pragma unroll
+              for (int jp = 0; jp < RS_NC / 2; ++jp) {
+                const double2 bb = brow[jp];
+                acc[2 * jp] = fma(xk, bb.x, acc[2 * jp]);
+                acc[2 * jp + 1] = fma(xk, bb.y, acc[2 * jp + 1]);
+              }
             }
           }
         }
       }
       u += nready;
-      __syncthreads();
     }
     __syncthreads();
     RS_STAMP(2)
 
     // ---- diagonal block (every block of the supernode factors its own copy)
-    for (int i = tid; i < nc * nc; i += RS_T) {
-      const int r = i % nc, c = i / nc;
-      sm.Ds[r * RS_DP + c] = (r >= c) ? sm.P[r + c * nloc] : 0.0;
+    if (tid < nc) {
+#pragma unroll
+      for (int c = 0; c < RS_NC; ++c) if (c <= tid) sm.Ds[tid * RS_DP + c] = acc[c];
     }
     __syncthreads();
     if (tid < 32) rs_potrf_warp(sm, nc, tid, status);
     __syncthreads();
     RS_STAMP(3)
-    // ---- panel solve of the own rows in place, then the store
-    for (int r = tid; r < nloc; r += RS_T) {
-      if (r < nc) {
-        for (int c = 0; c <= r; ++c) sm.P[r + c * nloc] = sm.Ds[r * RS_DP + c];
-      } else {
-        for (int cc = 0; cc < nc; cc += 4) {
-          double v[4];
+    // ---- solve the own row against the diagonal factor in registers and store it (coalesced per column)
+    if (has_row && tid >= nc) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = (cc + i < nc) ? sm.P[r + (cc + i) * nloc] : 0.0;
-          for (int k = 0; k < cc; ++k) {
-            const double xk = sm.P[r + k * nloc];
+      for (int c = 0; c < RS_NC; ++c) {
+        if (c < nc) {
+          double v = acc[c];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] -= xk * sm.Ds[(cc + i) * RS_DP + k];
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (cc + i < nc) {
-#pragma unroll
-              for (int q = 0; q < i; ++q) v[i] -= v[q] * sm.Ds[(cc + i) * RS_DP + cc + q];
-              v[i] *= sm.dinv[cc + i];
-              sm.P[r + (cc + i) * nloc] = v[i];
-            }
-          }
+          for (int k = 0; k < c; ++k) v = fma(-acc[k], sm.Ds[c * RS_DP + k], v);
+          acc[c] = v * sm.dinv[c];
+          Lp[prow + (int64_t)c * nr] = acc[c];
         }
       }
     }
-    __syncthreads();
     RS_STAMP(4)
-    for (int i = tid; i < nown * nc; i += RS_T) {
-      const int lr = nc + i % nown, c = i / nown;
-      Lp[(r0 + lr - nc) + (int64_t)c * nr] = sm.P[lr + c * nloc];
-    }
     __threadfence();
     __syncthreads();
     if (tid == 0) sm.slot = atomicAdd(&arrived[sn], 1);
@@ -293,7 +262,7 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
       // every block of this supernode has read the assembled diagonal block and stored its rows
       for (int i = tid; i < nc * nc; i += RS_T) {
         const int r = i % nc, c = i / nc;
-        if (c <= r) Lp[r + (int64_t)c * nr] = sm.P[r + c * nloc];
+        if (c <= r) Lp[r + (int64_t)c * nr] = sm.Ds[r * RS_DP + c];
       }
       __threadfence();
       __syncthreads();
@@ -357,17 +326,17 @@ void launch_factor_rs(fg_ctx* c) {
   FrontView none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const int cap = c->num_sms * per_sm;
   if (!S.use_fronts) {
-    k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_uoff, d.rs_sub, d.upd_ptr, d.upd_d, d.upd_rec,
+    k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.upd_ptr, d.upd_d, d.upd_rec, d.rs_colinv,
                                                                 d.rs_done + S.n_sn, d.rs_done, d.counters, na, d.status, none, dbg);
     return;
   }
   // phase A: the leaves; phase B: one dense update matrix per leaf; phase C: the separators
-  if (na) k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_uoff, d.rs_sub, d.updr_ptr, d.updr_d, d.updr_rec,
+  if (na) k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.updr_ptr, d.updr_d, d.updr_rec, d.rs_colinv,
                                                                       d.rs_done + S.n_sn, d.rs_done, d.counters, na, d.status, none, dbg);
   launch_front_syrk(c);
   FrontView fv = {d.tf_ptr, d.tf_leaf, d.fr_rowptr, d.fr_rows, d.fr_uptr, d.U};
-  if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units + na, d.rs_uoff + na, d.rs_sub, d.updr_ptr, d.updr_d,
-                                                                      d.updr_rec, d.rs_done + S.n_sn, d.rs_done, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr);
+  if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.updr_ptr, d.updr_d,
+                                                                      d.updr_rec, d.rs_colinv, d.rs_done + S.n_sn, d.rs_done, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr);
 }
 
 }  // namespace fg

@@ -96,8 +96,9 @@ struct Symbolic {
   bool rs_ok = false;
   int rs_units_a = 0;
   std::vector<int4> rs_units;
-  std::vector<int64_t> rs_uoff;                    // per unit: offset of its per-update sub-ranges
-  std::vector<int2> rs_sub;                        // per (unit, update): descendant rows (from row a) that land in the unit's own rows: (first, count)
+  std::vector<int64_t> rs_moff;                    // per unit: offset of its row maps
+  std::vector<short> rs_map;                       // per (unit, update, local row): descendant row (from row a) landing on that row, or -1
+  std::vector<signed char> rs_colinv;              // per update of the list in use, 16 entries: descendant row (from a) holding target column c, or -1
 };
 
 // ------------------------------------------------------------------ device view passed to kernels
@@ -228,7 +229,7 @@ struct DevGraph {
   double* U = nullptr;              // dense update matrices of all leaves
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;
-  int4* rs_units = nullptr; int64_t* rs_uoff = nullptr; int2* rs_sub = nullptr; int* rs_done = nullptr;   // rs_done: n_sn done flags, then n_sn arrival counters
+  int4* rs_units = nullptr; int64_t* rs_moff = nullptr; short* rs_map = nullptr; signed char* rs_colinv = nullptr; int* rs_done = nullptr;   // rs_done: n_sn done flags, then n_sn arrival counters
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
   int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve)
 };

@@ -389,19 +389,38 @@ int build_symbolic(fg_ctx* c) {
         for (int b = 0; b < nb; ++b) {
           const int r0 = nc + b * per, r1 = std::min(nr, r0 + per);
           S.rs_units.push_back(make_int4(s, r0, r1, nb));
-          S.rs_uoff.push_back((int64_t)S.rs_sub.size());
-          const int glo = rows[r0], ghi = rows[r1 - 1];
+          S.rs_moff.push_back((int64_t)S.rs_map.size());
+          const int nloc = nc + (r1 - r0);
           for (int u = UP[s]; u < UP[s + 1]; ++u) {
             const int d = UD[u], a = UA[u], bb = UB[u];
             const int* rd = &S.rowidx[S.sn_rowptr[d]];
             const int nrd = S.sn_nrows[d];
-            const int* lo = std::lower_bound(rd + bb, rd + nrd, glo);
-            const int* hi = std::upper_bound(rd + bb, rd + nrd, ghi);
-            S.rs_sub.push_back(make_int2((int)(lo - (rd + a)), (int)(hi - lo)));
+            const size_t base = S.rs_map.size();
+            S.rs_map.resize(base + nloc, (short)-1);
+            for (int i = a; i < bb; ++i) S.rs_map[base + (rd[i] - S.sn_col0[s])] = (short)(i - a);      // rows landing on the diagonal block
+            // own rows: both lists are sorted, the descendant's rows inside the block are a subset of the block's rows
+            int i = (int)(std::lower_bound(rd + bb, rd + nrd, rows[r0]) - rd);
+            for (int lr = nc; lr < nloc && i < nrd; ++lr) {
+              const int g = rows[r0 + lr - nc];
+              while (i < nrd && rd[i] < g) { ++i; }
+              if (i < nrd && rd[i] == g) { S.rs_map[base + lr] = (short)(i - a); ++i; }
+            }
           }
         }
       }
     };
+    // per update of the list in use: which descendant row (from row a) holds each target column; "half" when only target
+    // columns < 8 are touched (a non-adjacent frame couples to the 6 pose columns only)
+    std::vector<UpdRec>& UR = fr ? S.updr_rec : S.upd_rec;
+    S.rs_colinv.assign(UD.size() * 16, (signed char)-1);
+    for (int s = 0; s < S.n_sn; ++s)
+      for (int u = UP[s]; u < UP[s + 1]; ++u) {
+        const int d = UD[u], a = UA[u], bb = UB[u];
+        const int* rd = &S.rowidx[S.sn_rowptr[d]];
+        int maxc = -1;
+        for (int i = a; i < bb; ++i) { const int c = rd[i] - S.sn_col0[s]; if (c >= 0 && c < 16) { S.rs_colinv[(size_t)u * 16 + c] = (signed char)(i - a); maxc = std::max(maxc, c); } }
+        UR[u].pad[0] = (maxc < 8) ? 1 : 0;
+      }
     emit(order_a);
     S.rs_units_a = (int)S.rs_units.size();
     emit(order_c);

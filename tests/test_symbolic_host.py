@@ -164,14 +164,15 @@ def emulate_fronts(ctx, sym, Sp, bp):
 def emulate_rowsplit(ctx, sym, Sp, bp):
     """numpy emulation of k_chol_rs (fg_chol_rs.cu): the unit of work is a block of below-diagonal rows of a
     supernode.  A unit reads the ASSEMBLED diagonal block and its own rows, applies every descendant update restricted
-    to the descendant rows the host listed for it (rs_sub) plus the part landing on the diagonal block, factors its own
+    to the descendant rows the host mapped onto its rows (rs_map / rs_colinv), the diagonal block included, factors its own
     copy of the diagonal block and solves its rows; the diagonal factor is stored once per supernode."""
     n_r, n_sn = int(sym[0][0]), int(sym[0][1])
     col0, ncols, nrows, rowptr, valptr, rowidx = sym[1:7]
     use_fr = bool(ctx.symbolic(33)[0])
     ok, n_a, n_units = (int(v) for v in ctx.symbolic(39))
     assert ok
-    units = ctx.symbolic(36).reshape(-1, 4); uoff = ctx.symbolic(37); sub = ctx.symbolic(38).reshape(-1, 2)
+    units = ctx.symbolic(36).reshape(-1, 4); moff = ctx.symbolic(37); rmap = ctx.symbolic(38)
+    colinv = ctx.symbolic(40).reshape(-1, 16)
     assert len(units) == n_units
     uptr, ud, ua, ub = (ctx.symbolic(w) for w in ((22, 23, 24, 25) if use_fr else (7, 8, 9, 10)))
     aug = np.zeros((n_r + 1, n_r + 1)); aug[:n_r, :n_r] = Sp; aug[n_r, :n_r] = bp
@@ -224,20 +225,24 @@ def emulate_rowsplit(ctx, sym, Sp, bp):
         for q, u in enumerate(range(uptr[s], uptr[s + 1])):
             d, a, b = int(ud[u]), int(ua[u]), int(ub[u])
             assert arrived[d] == -1, 'descendant not complete when its update is pulled'
-            first, cnt = (int(v) for v in sub[uoff[k] + q])
             Ld = Lf[d]
-            take = list(range(a, b)) + list(range(a + first, a + first + cnt))
-            assert first >= b - a and a + first + cnt <= nrows[d]
-            # the listed sub-range is exactly the set of descendant rows inside this unit's own rows
-            inside = [i for i in range(b, nrows[d]) if g[nc] <= rows_of[d][i] <= g[-1]]
-            assert inside == list(range(a + first, a + first + cnt))
-            upd = Ld[take] @ Ld[a:b].T
-            for ii, i in enumerate(take):
-                R = int(rows_of[d][i])
-                for jj in range(b - a):
-                    C = int(rows_of[d][a + jj])
-                    if R >= C:
-                        P[pos[R], C - col0[s]] -= upd[ii, jj]
+            nloc = len(loc)
+            mp = rmap[moff[k] + q * nloc: moff[k] + (q + 1) * nloc]
+            where = {int(r): i for i, r in enumerate(rows_of[d]) if i >= a}
+            assert mp.tolist() == [where.get(gr, a - 1) - a for gr in g], 'row map does not name the descendant rows'
+            ci = colinv[u]
+            assert ci.tolist() == [where.get(int(col0[s] + c), a - 1) - a if c < nc else -1 for c in range(16)]
+            assert all(0 <= v < b - a for v in ci if v >= 0) and sum(v >= 0 for v in ci) == b - a
+            Bfull = np.zeros((Ld.shape[1], 16))
+            for c in range(16):
+                if ci[c] >= 0:
+                    Bfull[:, c] = Ld[a + ci[c]]
+            for lr in range(nloc):
+                if mp[lr] >= 0:
+                    upd = Ld[a + mp[lr]] @ Bfull
+                    for c in range(nc):
+                        if lr >= nc or c <= lr:
+                            P[lr, c] -= upd[c]
         Ldd = np.linalg.cholesky(P[:nc] + np.tril(P[:nc], -1).T)
         Lf[s][r0:r1] = np.linalg.solve(Ldd, P[nc:].T).T
         covered[s][r0:r1] += 1
