@@ -168,32 +168,40 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
       __syncthreads();
       const int nready = sm.first_not_ready;
       RS_STAMP(1)                                          // last time a batch of descendants was seen ready
-      // ---- software pipeline over the ready updates: loads of update uu + 1 are in flight while uu is multiplied
+      // ---- software pipeline over the ready updates, two stages deep: the record / row-map / column-map loads of
+      //      update uu + 2 (static data) and the value loads of update uu + 1 are in flight while uu is multiplied.
+      //      (Measured alternatives: parking the values in shared memory to prefetch two updates deep costs more
+      //      shared-memory bandwidth than the latency it hides; cp.async is not usable because its 8-byte form allocates
+      //      in L1, which may hold lines of panels that were not final when they were cached.)
+      const int uend = u + nready;
+      const double* Ld1 = nullptr; int K1 = 0, nrd1 = 0, half1 = 0, mi1 = -1, j1 = -1;      // stage A results (indices) of the next update
       int min_ = -1, halfn = 0;
       double xn[RS_NC], bn = 0.0;
-      auto issue = [&](int uu) {
+      auto stage_a = [&](int uu) {
         const UpdRec rec = upd_rec[uu];
-        const double* Ld = s.L + rec.val_off;
-        const int K = rec.K, nrd = rec.nrd;
-        min_ = has_row ? (int)__ldg(umap + (int64_t)(uu - ubase) * nloc) : -1;     // descendant row (from row a) that lands on this thread's row
-#pragma unroll
-        for (int k = 0; k < RS_NC; ++k) xn[k] = (min_ >= 0 && k < K) ? __ldcg(&Ld[min_ + (int64_t)k * nrd]) : 0.0;
-        {
-          const int c = tid % RS_NC, k = tid / RS_NC;     // RS_T == RS_NC * RS_NC
-          const int j = colinv[(int64_t)uu * RS_NC + c];  // descendant row (from a) holding target column c, or -1
-          bn = (j >= 0 && k < K) ? __ldcg(&Ld[j + (int64_t)k * nrd]) : 0.0;
-        }
-        halfn = rec.pad[0];                               // 1: only target columns < 8 are touched
+        Ld1 = s.L + rec.val_off; K1 = rec.K; nrd1 = rec.nrd; half1 = rec.pad[0];               // half: only target columns < 8 are touched
+        mi1 = has_row ? (int)__ldg(umap + (int64_t)(uu - ubase) * nloc) : -1;                 // descendant row (from row a) landing on this thread's row
+        j1 = colinv[(int64_t)uu * RS_NC + (tid % RS_NC)];                                     // descendant row (from a) holding target column tid % 16, or -1
       };
-      issue(u);
-      for (int uu = u; uu < u + nready; ++uu, buf ^= 1) {
+      auto stage_b = [&]() {
+        const int k = tid / RS_NC;                        // RS_T == RS_NC * RS_NC
+#pragma unroll
+        for (int q = 0; q < RS_NC; ++q) xn[q] = (mi1 >= 0 && q < K1) ? __ldcg(&Ld1[mi1 + (int64_t)q * nrd1]) : 0.0;
+        bn = (j1 >= 0 && k < K1) ? __ldcg(&Ld1[j1 + (int64_t)k * nrd1]) : 0.0;
+        min_ = mi1; halfn = half1;
+      };
+      stage_a(u);
+      stage_b();
+      if (u + 1 < uend) stage_a(u + 1);
+      for (int uu = u; uu < uend; ++uu, buf ^= 1) {
         const int mi = min_, half = halfn;
         double x[RS_NC];
 #pragma unroll
         for (int k = 0; k < RS_NC; ++k) x[k] = xn[k];
         sm.Bs[buf][tid] = bn;                             // last read two updates ago: every thread is past that barrier
         __syncthreads();
-        if (uu + 1 < u + nready) issue(uu + 1);
+        if (uu + 1 < uend) stage_b();
+        if (uu + 2 < uend) stage_a(uu + 2);
         if (mi >= 0) {
           const double* Bt = sm.Bs[buf];
           if (half) {
