@@ -212,6 +212,9 @@ def main():
         tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dt_e2e = tt.tolist()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     state_bytes = int(sum(init[t].nbytes for t in types))
