@@ -97,6 +97,7 @@ SIGNATURES = {
     'fg_finalize': (C.c_int, [_vp]),
     'fg_optimize_lm': (C.c_int, [_vp, C.POINTER(LMParams), C.POINTER(LMReport)]),
     'fg_error': (C.c_int, [_vp, _dp]),
+    'fg_marginal_cov': (C.c_int, [_vp, C.c_uint64, _dp, C.POINTER(C.c_int)]),
     'fg_comm_unique_id': (C.c_int, [C.c_char_p]),
     'fg_comm_init': (C.c_int, [_vp, C.c_char_p]),
     'fg_add_structure_edges': (C.c_int, [_vp, C.c_int64, _kp, _kp]),
@@ -253,6 +254,13 @@ class Context:
         rep = LMReport()
         self.call('fg_optimize_lm', C.byref(p), C.byref(rep))
         return rep
+
+    def marginal_covariance(self, key):
+        """Marginals(graph, values).marginalCovariance(key) (gtsam_graph.cpp:598-601) for a pose / velocity / bias / plane key."""
+        out = np.zeros(36)
+        n = C.c_int(0)
+        self.call('fg_marginal_cov', int(key), out.ctypes.data_as(_dp), C.byref(n))
+        return out[:n.value * n.value].reshape(n.value, n.value).copy()
 
     def comm_init(self, uid): self.call('fg_comm_init', uid)
 

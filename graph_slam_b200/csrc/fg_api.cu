@@ -797,6 +797,40 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   return rc;
 }
 
+// ------------------------------------------------------------------ marginal covariance
+extern "C" int fg_marginal_cov(fg_ctx* c, fg_key key, double* cov, int* dim) {
+  if (!c || !cov) return fail(c, FG_ERR_INVALID, "null argument");
+  auto it = c->h.index.find(key);
+  if (it == c->h.index.end()) return fail(c, FG_ERR_UNKNOWN_KEY, "key does not exist in Values");
+  const int type = it->second.type;
+  if (type == T_POINT) return fail(c, FG_ERR_INVALID, "marginal covariance of a Point3 landmark is not supported (eliminated by the Schur complement)");
+  int rc = fg_finalize(c);
+  if (rc != FG_OK) return rc;
+  CK(cudaSetDevice(c->device));
+  DevGraph& d = c->d;
+  const int col0 = c->sym.off[type][it->second.idx], dm = kDim[type];
+  launch_linearize(c);
+  launch_build_and_schur(c, 0.0);
+  if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) return rc;
+  if (chol_rs_supported(c)) launch_factor_rs(c); else if (chol_reg_supported(c)) launch_factor_reg(c); else launch_factor(c);
+  double* work = nullptr;
+  CK(cudaMalloc((void**)&work, sizeof(double) * (6 * ((size_t)c->sym.n_r + 1) + 36)));
+  double* out36 = work + 6 * ((size_t)c->sym.n_r + 1);
+  launch_marginal(c, col0, dm, work, out36);
+  double h36[36];
+  int st = 0;
+  cudaError_t e = cudaMemcpyAsync(h36, out36, sizeof h36, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&st, d.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(work);
+  if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return FG_ERR_CUDA; }
+  CK(cudaGetLastError());
+  if (st != 0) return fail(c, FG_ERR_INDETERMINATE, "the undamped system is not positive definite (IndeterminantLinearSystemException in GTSAM)");
+  for (int a = 0; a < dm; ++a) for (int b = 0; b < dm; ++b) cov[a * dm + b] = h36[a * 6 + b];
+  if (dim) *dim = dm;
+  return FG_OK;
+}
+
 // ------------------------------------------------------------------ multi-GPU
 extern "C" int fg_comm_unique_id(char id[128]) {
   if (!id) return FG_ERR_INVALID;

@@ -291,6 +291,59 @@ __global__ void __launch_bounds__(CH_T) k_backsolve(SysView s, const int* __rest
   }
 }
 
+// Marginal covariance block of one reduced variable: Sigma_jj = E_j^T (L L^T)^-1 E_j = Z^T Z with L Z = E_j.
+// Z is non-zero only on the path from the variable's supernode to the root of the elimination tree, so one CTA walks
+// that path: solve the diagonal block for the (<= 6) right-hand sides, add t^T t to Sigma, push L_below t to the
+// ancestors' rows of the work vector (n_r x 6, zeroed by the launcher), move to the parent.
+__global__ void __launch_bounds__(256) k_marginal(SysView s, int col0, int dim, double* work, double* out36) {
+  __shared__ double t[CH_KMAX][6];
+  __shared__ double sig[36];
+  const int tid = threadIdx.x;
+  const int ldw = s.n_r + 1;
+  if (tid < 36) sig[tid] = 0.0;
+  if (tid < dim) work[col0 + tid + (int64_t)tid * ldw] = 1.0;
+  __threadfence_block();
+  __syncthreads();
+  int sn = s.col2sn[col0];
+  while (true) {
+    const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
+    const double* Lp = s.L + s.sn_valptr[sn];
+    const int* rows = s.rowidx + s.sn_rowptr[sn];
+    // forward substitution on the diagonal block, one right-hand side per thread
+    if (tid < dim) {
+      double v[CH_KMAX];
+      for (int c = 0; c < nc; ++c) {
+        double a = work[c0 + c + (int64_t)tid * ldw];
+        for (int k = 0; k < c; ++k) a -= Lp[c + (int64_t)k * nr] * v[k];
+        v[c] = a / Lp[c + (int64_t)c * nr];
+        t[c][tid] = v[c];
+      }
+    }
+    __syncthreads();
+    if (tid < dim * dim) {
+      const int a = tid / dim, b = tid % dim;
+      double acc = 0.0;
+      for (int c = 0; c < nc; ++c) acc += t[c][a] * t[c][b];
+      sig[a * 6 + b] += acc;
+    }
+    // below rows (the right-hand-side row nr - 1 is not part of the matrix)
+    const int nbelow = nr - 1 - nc;
+    for (int i = tid; i < nbelow * dim; i += blockDim.x) {
+      const int r = nc + i % nbelow, k = i / nbelow;
+      double a = 0.0;
+      for (int c = 0; c < nc; ++c) a += Lp[r + (int64_t)c * nr] * t[c][k];
+      work[rows[r] + (int64_t)k * ldw] -= a;
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (nbelow <= 0) break;
+    sn = s.col2sn[rows[nc]];          // parent in the elimination tree
+  }
+  if (tid < 36) out36[tid] = sig[tid];
+}
+
+void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);
+
 static SysView chol_view(fg_ctx* c) {
   DevGraph& d = c->d;
   SysView s;
@@ -316,6 +369,12 @@ void launch_factor(fg_ctx* c) {
   cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, c->stream);
   k_chol<<<grid, CH_T, smem, c->stream>>>(s, d.sched, d.upd_ptr, d.upd_d, d.upd_a, d.upd_b, d.flags, d.counters, c->epoch,
                                           c->sym.n_sn, d.status);
+}
+
+void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36) {
+  SysView s = chol_view(c);
+  cudaMemsetAsync(work, 0, sizeof(double) * 6 * ((size_t)c->sym.n_r + 1), c->stream);
+  k_marginal<<<1, 256, 0, c->stream>>>(s, col0, dim, work, out36);
 }
 
 void launch_backsolve(fg_ctx* c) {

@@ -267,7 +267,8 @@ void launch_factor_reg(fg_ctx* c);                        // register-tiled fast
 bool chol_rs_supported(const fg_ctx* c);                  // fg_chol_rs.cu: row-split units, width <= 16
 void launch_factor_rs(fg_ctx* c);
 void launch_front_syrk(fg_ctx* c);                        // fg_front.cu: dense update matrix of every leaf onto its front
-void launch_backsolve(fg_ctx* c);                         // backward solve -> delta
+void launch_backsolve(fg_ctx* c);
+void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);   // fg_chol.cu: [S^-1] block of one variable from the factor in d.L                         // backward solve -> delta
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
 void launch_error_only(fg_ctx* c, bool trial);            // chi2 of val (or val_new) -> scal[0] (or scal[3])
 void launch_preintegrate(int n, const int* d_off, const double* d_imu, double dt, const ImuParamsDev* d_par,

@@ -467,6 +467,26 @@ class LevenbergMarquardtOptimizer {
   int iterations() const { return report.iterations; }
 };
 
+// Marginals(graph, values, Marginals::CHOLESKY).marginalCovariance(key)   gtsam/gtsam_graph.cpp:598-601, :1357
+// (SURVEY 8 f2).  One undamped device factorisation per call of marginalCovariance; dimension 6 / 3 / 6 / 3 for a
+// pose / velocity / bias / plane key, returned row-major.
+class Marginals {
+ public:
+  enum Factorization { CHOLESKY, QR };
+  const NonlinearFactorGraph& g; const Values& v;
+  Marginals(const NonlinearFactorGraph& graph, const Values& solution, Factorization = CHOLESKY) : g(graph), v(solution) {}
+  std::vector<double> marginalCovariance(Key key, int* dim = nullptr) const {
+    fg_ctx* c = detail::build(g, v);
+    double cov[36]; int d = 0;
+    int rc = fg_marginal_cov(c, key, cov, &d);
+    std::string m = rc ? fg_last_error(c) : "";
+    fg_destroy(c);
+    if (rc) throw std::runtime_error("fg_marginal_cov: " + m);
+    if (dim) *dim = d;
+    return std::vector<double>(cov, cov + d * d);
+  }
+};
+
 // ISAM2 stand-in ("next"): update() appends the new factors/values to the accumulated graph and
 // calculateEstimate() runs the batch LM from the current estimate.  The converged estimate equals the batch
 // optimum; the incremental Bayes-tree bookkeeping (relinearizeThreshold/relinearizeSkip) is not reproduced.

@@ -179,6 +179,14 @@ int fg_optimize_lm(fg_ctx* ctx, const fg_lm_params* params, fg_lm_report* report
 /* graph.error(values) = 1/2 sum |r|^2_Sigma     CGraphGT::error  gtsam_graph.cpp:173-176 */
 int fg_error(fg_ctx* ctx, double* error);
 
+/* Marginals(graph, values, Marginals::CHOLESKY).marginalCovariance(key)
+ *   CGraphGT::bundleAdjust gtsam_graph.cpp:598-601 (edge information = inverse of pose 1's marginal covariance),
+ *   planeNodeAssociation :1357, gtsam/test/convert_vo2ba.cpp:413-416.
+ * Linearises at the current values, factors the UNDAMPED reduced system on the device and returns the d x d
+ * (row-major) covariance of one pose (d = 6), velocity (3), bias (6) or plane (3) variable.  Point3 keys are
+ * eliminated by the Schur complement and are not supported (FG_ERR_INVALID).  */
+int fg_marginal_cov(fg_ctx* ctx, fg_key key, double* cov, int* dim);
+
 /* ------------------------------------------------------------------ multi-GPU */
 /* Rank 0 fills a 128-byte NCCL unique id; the host launcher ships it to the other ranks (any transport);
  * every rank then calls fg_comm_init.  Landmarks added on a rank are that rank's shard; pose-side

@@ -172,3 +172,70 @@ def test_generic_cholesky_kernel_is_equivalent(monkeypatch):
         assert other.iterations == fast.iterations
         assert abs(other.final_error - fast.final_error) <= 1e-10 * fast.final_error
         assert np.abs(To - Tf).max() < 1e-9
+
+
+def oracle_marginal(g, kind, idx):
+    """Dense oracle: block of the inverse of the full (undamped) normal equations, landmarks included."""
+    H, grad, err = g.normal_equations()
+    d = g.dims
+    o, n = {'pose': (6 * idx, 6), 'vel': (d['o_v'] + 3 * idx, 3), 'bias': (d['o_b'] + 6 * idx, 6), 'plane': (d['o_pl'] + 3 * idx, 3)}[kind]
+    E = np.zeros((H.shape[0], n)); E[o + np.arange(n), np.arange(n)] = 1.0
+    import scipy.sparse.linalg as spla
+    X = spla.splu(H.tocsc()).solve(E)
+    return X[o:o + n]
+
+
+def test_marginal_covariance_matches_oracle():
+    """Marginals(...).marginalCovariance(key): SURVEY 8f-2 (gtsam_graph.cpp:598-601, :1357)."""
+    spec = synth.make_config('C4', seed=4, scale=0.03)
+    ctx = abi.Context(device=0)
+    abi.load_spec(ctx, spec)
+    ctx.optimize()
+    g = build.from_spec(spec)
+    g.R = ctx.get_values(abi.T_POSE)[:, :9].reshape(-1, 3, 3); g.t = ctx.get_values(abi.T_POSE)[:, 9:]
+    g.vel = ctx.get_values(abi.T_VEC3); g.bias = ctx.get_values(abi.T_BIAS); g.point = ctx.get_values(abi.T_POINT)
+    P = spec['n_poses']
+    for kind, ch, idx in (('pose', 'x', 0), ('pose', 'x', P // 2), ('pose', 'x', P - 1), ('vel', 'v', 3), ('bias', 'b', P - 2)):
+        got = ctx.marginal_covariance(abi.symbol(ch, idx))
+        ref = oracle_marginal(g, kind, idx)
+        assert got.shape == ref.shape
+        assert np.allclose(got, got.T, rtol=1e-9, atol=1e-30)
+        assert np.abs(got - ref).max() <= 1e-6 * np.abs(ref).max(), (kind, idx, np.abs(got - ref).max(), np.abs(ref).max())
+    with pytest.raises(abi.FgError) as e:
+        ctx.marginal_covariance(abi.symbol('q', 0))
+    assert e.value.code == -1
+    # the state is untouched and the optimiser still works afterwards
+    assert ctx.optimize().iterations <= 2
+    ctx.close()
+
+
+def test_two_view_bundle_adjust_edge_information():
+    """CGraphGT::bundleAdjust (gtsam_graph.cpp:500-610): prior on pose 0 (sigma 1e-7), PriorFactor<Point3> (0.014) and two
+    GenericProjectionFactor per match (1 px), LM, then Marginals -> the VRO edge information = inverse of pose 1's
+    marginal covariance."""
+    rng = np.random.default_rng(11)
+    full = synth.make_config('C4', seed=7, scale=0.02)
+    K, Rs, ts = full['K'], full['Rs'], full['ts']
+    n = 150
+    T1 = lie.se3_exp(np.array([[0.02, -0.03, 0.05, 0.08, -0.02, 0.03]]))
+    R = np.stack([np.eye(3), T1[0][0]]); t = np.stack([np.zeros(3), T1[1][0]])
+    Rc, tc = lie.pose_compose(R, t, np.broadcast_to(Rs, (2, 3, 3)), np.broadcast_to(ts, (2, 3)))
+    pc = np.column_stack([rng.uniform(-0.6, 0.6, n), rng.uniform(-0.5, 0.5, n), rng.uniform(1.5, 4.0, n)])
+    pts = pc @ Rc[0].T + tc[0]
+    from oracle import factors as ofac
+    uv = np.concatenate([ofac.projection(R[k], t[k], pts, np.zeros((n, 2)), K, Rs, ts, jac=False) for k in range(2)])
+    uv = uv + rng.normal(size=(2 * n, 2))
+    spec = dict(name='two_view', seed=0, n_poses=2, K=K, Rs=Rs, ts=ts,
+                pose_init_R=np.stack([np.eye(3), np.eye(3)]), pose_init_t=np.zeros((2, 3)),
+                prior_pose_R=np.eye(3), prior_pose_t=np.zeros(3),
+                point_init=pts + rng.normal(size=pts.shape) * 0.014, point_prior_sigma=0.014,
+                proj_pose=np.repeat(np.arange(2), n).astype(np.int32), proj_point=np.tile(np.arange(n), 2).astype(np.int32),
+                proj_uv=uv, proj_sigma=1.0)
+    ctx, rep, g0, g1, orep, e_dev, e_orc = run_both(spec, solver='schur')
+    assert rep.iterations == orep['iterations'] and abs(rep.final_error - orep['error']) <= 1e-7 * orep['error']
+    cov = ctx.marginal_covariance(abi.symbol('x', 1))
+    ref = oracle_marginal(g1, 'pose', 1)
+    assert np.abs(cov - ref).max() <= 1e-6 * np.abs(ref).max()
+    info = np.linalg.inv(cov)                      # what bundleAdjust hands back as the edge information (:601)
+    assert np.all(np.linalg.eigvalsh(0.5 * (info + info.T)) > 0)
+    ctx.close()
