@@ -202,8 +202,7 @@ def main():
         r1 = ctx.optimize(max_iterations=1, force_iterations=1)
         for t in types:
             ctx.get_values(t, out_pinned[t].numpy())
-        for t in types:                      # next step continues from this step's result
-            pinned[t].copy_(out_pinned[t])
+        pinned, out_pinned = out_pinned, pinned   # next step continues from this step's result
     barrier()
     dt_e2e = time.perf_counter() - t1
     sampler.stop_flag = True

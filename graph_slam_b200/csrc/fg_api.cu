@@ -212,15 +212,19 @@ extern "C" int fg_get_values(fg_ctx* c, int type, double* out) {
 }
 extern "C" int fg_set_values(fg_ctx* c, int type, const double* in) {
   if (!c || !in || type < 0 || type >= T_COUNT) return fail(c, FG_ERR_INVALID, "bad argument");
-  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
-  size_t nb = sizeof(double) * c->h.val[type].size();
-  std::memcpy(c->h.val[type].data(), in, nb);
+  const size_t nb = sizeof(double) * c->h.val[type].size();
   if (c->finalized && c->d.n[type] && !c->values_dirty) {
-    // fast path: straight host -> device copy of this one array (the caller's buffer may be pinned)
+    // fast path: one host -> device copy of this array straight from the caller's buffer (which may be pinned); the
+    // device copy becomes the authoritative one, the host mirror is refreshed lazily by pull_values
+    CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(c->d.val[type], in, nb, cudaMemcpyHostToDevice, c->stream));
-  } else {
-    c->values_dirty = true;
+    CK(cudaStreamSynchronize(c->stream));        // the caller owns `in` again on return
+    c->device_newer = true;
+    return FG_OK;
   }
+  if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  std::memcpy(c->h.val[type].data(), in, nb);
+  c->values_dirty = true;
   return FG_OK;
 }
 
@@ -690,9 +694,9 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   for (auto& e : ev) CK(cudaEventCreate(&e));
   auto cleanup = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
 
-  double err;
-  if ((rc = fg_error(c, &err)) != FG_OK) { cleanup(); rep->status = rc; return rc; }
-  rep->initial_error = err;
+  // graph.error(values) of the starting point comes out of the first linearisation (scal[0]): no separate error pass
+  double err = std::numeric_limits<double>::quiet_NaN();
+  bool have_err = false;
   rep->n_reduced_dims = c->sym.n_r; rep->n_supernodes = c->sym.n_sn; rep->nnz_L = c->sym.nnz;
   rep->n_projections = d.n_obs; rep->n_landmarks = d.n[T_POINT];
   rep->n_schur_pairs = d.n_pairs; rep->n_levels = c->sym.n_levels;
@@ -703,7 +707,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   CK(cudaEventCreate(&ev_begin)); CK(cudaEventCreate(&ev_end));
   CK(cudaEventRecord(ev_begin, c->stream));
   while (true) {
-    const double cur = err;
+    double cur = err;
     // ---- LevenbergMarquardtOptimizer::iterate()
     CK(cudaEventRecord(ev[0], c->stream));
     launch_linearize(c);
@@ -719,11 +723,13 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
       launch_backsolve(c);
       CK(cudaEventRecord(ev[4], c->stream));
       launch_retract_error(c, lam);
-      if ((rc = allreduce(c, d.scal + 1, 3)) != FG_OK) break;
+      // [0] chi2 at the linearisation point (fresh only on the first trial of an iteration), [1] g^T delta, [2] |delta|^2, [3] new chi2
+      if ((rc = first ? allreduce(c, d.scal, 4) : allreduce(c, d.scal + 1, 3)) != FG_OK) break;
       CK(cudaEventRecord(ev[5], c->stream));
       double hs[4]; int st = 0;
       if ((rc = read_scalars(c, hs, &st)) != FG_OK) break;
       CK(cudaGetLastError());
+      if (!have_err) { err = 0.5 * hs[0]; cur = err; rep->initial_error = err; have_err = true; }
       float ms;
       if (first) {
         cudaEventElapsedTime(&ms, ev[0], ev[1]); rep->ms_linearize += ms;
