@@ -8,34 +8,43 @@
 // is formed as a dense SYRK, one CTA per 64 x 64 tile of the lower triangle, and the supernodes outside the leaf
 // subtract the entries of U_leaf that fall into their panels (prologue of phase C of k_chol_reg).
 // This is the multifrontal "update matrix" of the leaf; GTSAM's multifrontal elimination forms the same quantity
-// (SURVEY.md section 3A).  DFMA on CUDA cores: tcgen05 has no fp64 kind.
+// (SURVEY.md section 3A).  The tiles are a true dense contraction and run on the fp64 tensor-core path (DMMA,
+// mma.sync.m8n8k4.f64); tcgen05 has no fp64 kind.
 #include "fg_internal.h"
 
 namespace fg {
 
 #define FT 64          // tile edge
 #define FK 16          // max supernode width
-#define FM 2           // members staged per barrier pair (2 x 2 x 16 KB of static shared memory)
+#define FM 2           // members staged per barrier pair
+#define FS 68          // shared-memory row stride (doubles): 4 (mod 16), so the 8 x 4 MMA fragment loads are conflict free
+
+// D (8x8) += A (8x4, row major) * B (4x8, column major) in fp64 on the tensor cores (DMMA).  Fragments: lane = 4 g + t
+// holds A[g][t], B[t][g] and D[g][2t], D[g][2t + 1].  Measured on this B200: 37.1 TFLOP/s against 36.2 TFLOP/s for DFMA
+// (profiles/tools/fp64_peak.cu) -- the same arithmetic peak, but one instruction carries 256 FMAs and its operands
+// come from registers, which is what a shared-memory-bound DFMA tile kernel lacks.  (tcgen05 has no fp64 kind.)
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
 
 __global__ void __launch_bounds__(256) k_front_syrk(int n_tiles, const int* __restrict__ tile_leaf, const int* __restrict__ tile_i,
                                                     const int* __restrict__ tile_j, const int* __restrict__ tile_mptr,
                                                     const FrontRec* __restrict__ tile_mrec, const int* __restrict__ fr_rowptr,
                                                     const int64_t* __restrict__ fr_uptr, const int* __restrict__ posmap,
                                                     const double* __restrict__ L, double* __restrict__ U) {
-  __shared__ __align__(16) double Ai[FM][FK][FT];
-  __shared__ __align__(16) double Aj[FM][FK][FT];
+  __shared__ __align__(16) double Ai[FM][FK][FS];
+  __shared__ __align__(16) double Aj[FM][FK][FS];
   const int t = blockIdx.x;
   if (t >= n_tiles) return;
   const int l = tile_leaf[t], ti = tile_i[t], tj = tile_j[t];
   const int nR = fr_rowptr[l + 1] - fr_rowptr[l];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x;
+  const int w = tid >> 5, g = (tid & 31) >> 2, tq = tid & 3;     // warp w owns rows [8w, 8w + 8) of the tile; MMA lane coordinates
   const int r = tid & 63, kq = tid >> 6;               // staging: this thread always loads front row r of the tile
   const int gi = ti * FT + r, gj = tj * FT + r;
-  double acc[4][4];
+  double acc[8][2];
 #pragma unroll
-  for (int x = 0; x < 4; ++x)
-#pragma unroll
-    for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+  for (int x = 0; x < 8; ++x) { acc[x][0] = 0.0; acc[x][1] = 0.0; }
   const bool diag = (ti == tj);
   const int m1 = tile_mptr[t + 1];
   for (int m0 = tile_mptr[t]; m0 < m1; m0 += FM) {
@@ -59,34 +68,31 @@ __global__ void __launch_bounds__(256) k_front_syrk(int n_tiles, const int* __re
 #pragma unroll
     for (int q = 0; q < FM; ++q) {
       if (m0 + q < m1) {
-        const double (*Bi)[FT] = Ai[q];
-        const double (*Bj)[FT] = diag ? Ai[q] : Aj[q];
+        const double (*Bi)[FS] = Ai[q];
+        const double (*Bj)[FS] = diag ? Ai[q] : Aj[q];
 #pragma unroll
-        for (int k = 0; k < FK; ++k) {
-          const double2 a01 = *reinterpret_cast<const double2*>(&Bi[k][4 * ty]);
-          const double2 a23 = *reinterpret_cast<const double2*>(&Bi[k][4 * ty + 2]);
-          const double2 b01 = *reinterpret_cast<const double2*>(&Bj[k][4 * tx]);
-          const double2 b23 = *reinterpret_cast<const double2*>(&Bj[k][4 * tx + 2]);
-          const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int ks = 0; ks < FK / 4; ++ks) {
+          const double a = Bi[4 * ks + tq][8 * w + g];
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
+          for (int nt = 0; nt < 8; ++nt) {
+            if (diag && nt > w) continue;               // blocks above the diagonal of a diagonal tile are never stored
+            dmma884(acc[nt], a, Bj[4 * ks + tq][8 * nt + g]);
+          }
         }
       }
     }
     __syncthreads();
   }
   double* Ul = U + fr_uptr[l];
+  const int i = ti * FT + 8 * w + g;
+  if (i < nR) {
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int i = ti * FT + 4 * ty + x;
-    if (i >= nR) continue;
+    for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const int j = tj * FT + 4 * tx + y;
-      if (j < nR && j <= i) Ul[(int64_t)i * nR + j] = acc[x][y];
-    }
+      for (int e = 0; e < 2; ++e) {
+        const int j = tj * FT + 8 * nt + 2 * tq + e;
+        if (j < nR && j <= i) Ul[(int64_t)i * nR + j] = acc[nt][e];
+      }
   }
 }
 
