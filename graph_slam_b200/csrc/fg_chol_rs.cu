@@ -5,21 +5,22 @@
 // 32 independent leaf chains at C5 (fg_symbolic.cpp); with one CTA per supernode 32 of the 148 SMs carried three
 // quarters of the flops.  Here a supernode of nr rows x nc columns (nc <= 16) is cut into blocks of <= RS_RB
 // below-diagonal rows.  A unit (supernode, block)
-//   * is output stationary: thread t owns local row t (the nc diagonal rows, then the block's own rows) and keeps its
-//     nc values in registers from the first load to the final store -- no shared-memory panel, no write conflicts,
+//   * is output stationary: the unit's (<= 256 rows) x (<= 16 columns) values live in registers from the first load
+//     to the final store -- no shared-memory panel, no write conflicts,
 //   * pulls every descendant update restricted to those rows: a host-built map (int16 per unit, update and row) names
-//     the descendant row that lands on each local row, so an update is one coalesced index load, K coalesced value
-//     loads and K x nc DFMA per thread against the descendant's (rows in the target's columns) block, staged in shared
-//     memory already scattered to target columns; the part that lands on the diagonal block is recomputed by every
-//     block of the supernode (15 x 15 x K flops),
+//     the descendant row that lands on each local row; the rank-K update  P -= X B^T  (X: gathered descendant rows,
+//     B: the descendant's rows in the target's columns, scattered to target columns) is a dense contraction and runs
+//     on the fp64 tensor cores (DMMA m8n8k4: 16 or 32 instructions per warp and update instead of 128-256 DFMA and as
+//     many shared-memory operand loads); X and B arrive by cp.async through a 3-stage shared-memory ring, two updates
+//     ahead of the multiplication; the part that lands on the diagonal block is recomputed by every block of the
+//     supernode (15 x 15 x K flops),
 //   * factors the diagonal block (every block redundantly: no intra-supernode synchronisation), solves its own rows
 //     against it and stores them,
 //   * bumps the supernode's arrival counter; the block that arrives LAST stores the factored diagonal block (the others
 //     read the assembled one when they start, so it must not be overwritten earlier) and publishes the supernode's
 //     done flag (release); consumers poll the flag (acquire).
-// The next update's loads are issued before the current one is multiplied.
-// Deterministic: every panel entry is owned by one unit and updated in list order.  DFMA on CUDA cores: tcgen05 has
-// no fp64 kind.
+// Deterministic: every panel entry is owned by one unit and updated in list order.  tcgen05 has no fp64 kind; DMMA
+// measured at the DFMA peak on this part (profiles/tools/fp64_peak.cu): its gain is instruction and operand traffic.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -40,14 +41,33 @@ __device__ __forceinline__ int rs_ld_relaxed(const int* p) {
   return v;
 }
 
+#define RS_ST 3                         // cp.async stages of the update pipeline
+#define RS_XLD 260                      // leading dimension of a stage's [k][row] tile (doubles): 4 (mod 16), conflict-free MMA fragment loads
+#define RS_BS 20                        // same for the [k][c] tile of the descendant's rows in the target's columns
 struct RsSmem {
-  double Bs[2][RS_NC * RS_NC];          // [buf][k][c]: descendant rows that fall in the target's columns, scattered to TARGET columns
+  double Xs[RS_ST][RS_NC * RS_XLD];     // [stage][k][row]: the descendant row that lands on each local row (gathered by the host row map)
+  double Bs[RS_ST][RS_NC * RS_BS];      // [stage][k][c]: descendant rows that fall in the target's columns, scattered to TARGET columns
   double Ds[RS_NC * RS_DP];
   double dinv[RS_NC];
-  int rl[1024];                         // row list of the leaf front being subtracted
   int colidx[RS_NC];
   int slot, first_not_ready;
 };
+// aliases inside Xs, used outside the update pipeline: the row list of a leaf front (prologue) and the per-warp slabs
+// (32 rows x 17) that convert between the thread-per-row layout and the MMA fragment layout
+static_assert(sizeof(double) * RS_ST * RS_NC * RS_XLD >= sizeof(int) * 1024 + sizeof(double) * RS_T * RS_DP, "aliases must fit");
+
+// D (8x8) += A (8x4, row major) * B (4x8, column major), fp64 tensor-core path (see fg_front.cu: dmma884)
+__device__ __forceinline__ void rs_dmma(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+// 8-byte asynchronous global -> shared copy.  The 8-byte form exists only as .ca (allocates in L1), and L1 is not coherent:
+// it is safe here because (i) panels start on 128-byte lines (fg_symbolic.cpp pads sn_valptr), so a line never mixes two
+// supernodes, (ii) a supernode's lines are only ever read through L1 after its done flag, when they are final, and
+// (iii) the one earlier read -- a unit loading its own assembled rows -- bypasses L1 (ld.cg).
+__device__ __forceinline__ void rs_cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 
 // Cholesky of the nc x nc (nc <= 16) diagonal block by one warp, the matrix in registers: lane r holds row r, the pivot
 // and the scaled column travel by shuffles, every index is static (fully unrolled: ~600 instructions, ~120 cycles per
@@ -90,6 +110,8 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
   const int tid = threadIdx.x;
+  int* const rl_s = reinterpret_cast<int*>(&sm.Xs[0][0]);                          // alias (prologue only)
+  double* const slab_s = reinterpret_cast<double*>(rl_s + 1024);                  // alias (layout conversion only)
 
   while (true) {
     if (tid == 0) sm.slot = atomicAdd(counter, 1);
@@ -107,10 +129,9 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     // thread tid owns local row tid of the unit: the diagonal rows first, then the own rows; its nc values live in registers
     const bool has_row = tid < nloc;
     const int prow = tid < nc ? tid : r0 + tid - nc;
-    const short* umap = rowmap + unit_moff[slot] + tid;
     double acc[RS_NC];
 #pragma unroll
-    for (int c = 0; c < RS_NC; ++c) acc[c] = (has_row && c < nc) ? Lp[prow + (int64_t)c * nr] : 0.0;
+    for (int c = 0; c < RS_NC; ++c) acc[c] = (has_row && c < nc) ? __ldcg(&Lp[prow + (int64_t)c * nr]) : 0.0;
     // ---- subtract the dense leaf fronts that reach this supernode (fg_front.cu)
     if (fv.tf_ptr) {
       const int g = has_row ? s.rowidx[s.sn_rowptr[sn] + prow] : -1;
@@ -120,19 +141,19 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
         const int nR = fv.fr_rowptr[l + 1] - fv.fr_rowptr[l];
         const double* Ul = fv.U + fv.fr_uptr[l];
         __syncthreads();
-        for (int i = tid; i < nR; i += RS_T) sm.rl[i] = Rl[i];
+        for (int i = tid; i < nR; i += RS_T) rl_s[i] = Rl[i];
         __syncthreads();
         if (tid < RS_NC) {
           const int gc = c0 + tid;
           int lo = 0, hi = nR - 1;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rl[mid] < gc) lo = mid + 1; else hi = mid; }
-          sm.colidx[tid] = (tid < nc && nR > 0 && sm.rl[lo] == gc) ? lo : -1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl_s[mid] < gc) lo = mid + 1; else hi = mid; }
+          sm.colidx[tid] = (tid < nc && nR > 0 && rl_s[lo] == gc) ? lo : -1;
         }
         __syncthreads();
         if (has_row) {
           int lo = 0, hi = nR - 1;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.rl[mid] < g) lo = mid + 1; else hi = mid; }
-          if (nR > 0 && sm.rl[lo] == g) {
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl_s[mid] < g) lo = mid + 1; else hi = mid; }
+          if (nR > 0 && rl_s[lo] == g) {
             const double* urow = Ul + (int64_t)lo * nR;
 #pragma unroll
             for (int c = 0; c < RS_NC; ++c) {
@@ -144,10 +165,29 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
       }
     }
 
+    // ---- the update phase runs on the fp64 tensor cores (DMMA m8n8k4): warp w owns local rows [32 w, 32 w + 32) as four
+    //      8-row tiles and the 16 target columns as two 8-column tiles; lane = 4 g + t holds the sums
+    //      (8 m + g, 8 n + 2 t + {0, 1}).  The thread-per-row registers are converted through the warp's slab.
+    const unsigned FULL = 0xffffffffu;
+    const int lane = tid & 31, wrp = tid >> 5, fgi = lane >> 2, fti = lane & 3;
+    double* slab = slab_s + wrp * 32 * RS_DP;
+    double fr[4][2][2];
+    __syncthreads();                                      // the front prologue is done with its alias
+#pragma unroll
+    for (int c = 0; c < RS_NC; ++c) slab[lane * RS_DP + c] = acc[c];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) fr[m][n][e] = slab[(8 * m + fgi) * RS_DP + 8 * n + 2 * fti + e];
+    const short* umap = rowmap + unit_moff[slot] + tid;
+    const int bk = tid / RS_NC, bc = tid % RS_NC;          // this thread's element of the B tile (RS_T == RS_NC * RS_NC)
+
     int u = upd_ptr[sn];
     const int ubase = u;
     const int u1 = upd_ptr[sn + 1];
-    int buf = 0;
     while (u < u1) {
       // warp 0 spins on the done flags of the next (up to 32) descendants and publishes the ready prefix
       if (tid < 32) {
@@ -165,74 +205,88 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
         __threadfence();
         if (tid == 0) sm.first_not_ready = n;
       }
-      __syncthreads();
+      __syncthreads();                                     // also: every product of the previous batch is done with the stages
       const int nready = sm.first_not_ready;
       RS_STAMP(1)                                          // last time a batch of descendants was seen ready
-      // ---- software pipeline over the ready updates, two stages deep: the record / row-map / column-map loads of
-      //      update uu + 2 (static data) and the value loads of update uu + 1 are in flight while uu is multiplied.
-      //      (Measured alternatives: parking the values in shared memory to prefetch two updates deep costs more
-      //      shared-memory bandwidth than the latency it hides; cp.async is not usable because its 8-byte form allocates
-      //      in L1, which may hold lines of panels that were not final when they were cached.)
+      // ---- pipeline over the ready updates: the descendant values of update uu + 2 travel by cp.async into a ring of
+      //      RS_ST shared-memory stages while uu is multiplied (the leaf panels touched by one level exceed L2, so a load
+      //      is a DRAM round trip); the record / row-map / column-map loads (static data) run one step further ahead.
       const int uend = u + nready;
-      const double* Ld1 = nullptr; int K1 = 0, nrd1 = 0, half1 = 0, mi1 = -1, j1 = -1;      // stage A results (indices) of the next update
-      int min_ = -1, halfn = 0;
-      double xn[RS_NC], bn = 0.0;
+      const double* Ld1 = nullptr; int K1 = 0, nrd1 = 0, half1 = 0, mi1 = -1, j1 = -1;      // indices of the next update to be issued
       auto stage_a = [&](int uu) {
         const UpdRec rec = upd_rec[uu];
         Ld1 = s.L + rec.val_off; K1 = rec.K; nrd1 = rec.nrd; half1 = rec.pad[0];               // half: only target columns < 8 are touched
         mi1 = has_row ? (int)__ldg(umap + (int64_t)(uu - ubase) * nloc) : -1;                 // descendant row (from row a) landing on this thread's row
-        j1 = colinv[(int64_t)uu * RS_NC + (tid % RS_NC)];                                     // descendant row (from a) holding target column tid % 16, or -1
+        j1 = colinv[(int64_t)uu * RS_NC + bc];                                                // descendant row (from a) holding target column bc, or -1
       };
-      auto stage_b = [&]() {
-        const int k = tid / RS_NC;                        // RS_T == RS_NC * RS_NC
+      // issue the copies of the update described by stage_a into stage st; returns (any row of this warp touched) | half << 1
+      auto stage_b = [&](int st) -> int {
+        const int any = __any_sync(FULL, mi1 >= 0) ? 1 : 0;
+        if (any) {
+          double* xs = sm.Xs[st] + tid;
 #pragma unroll
-        for (int q = 0; q < RS_NC; ++q) xn[q] = (mi1 >= 0 && q < K1) ? __ldcg(&Ld1[mi1 + (int64_t)q * nrd1]) : 0.0;
-        bn = (j1 >= 0 && k < K1) ? __ldcg(&Ld1[j1 + (int64_t)k * nrd1]) : 0.0;
-        min_ = mi1; halfn = half1;
+          for (int q = 0; q < RS_NC; ++q) {
+            if (mi1 >= 0 && q < K1) rs_cp_async8(xs + q * RS_XLD, &Ld1[mi1 + (int64_t)q * nrd1]);
+            else xs[q * RS_XLD] = 0.0;
+          }
+        }
+        if (j1 >= 0 && bk < K1) rs_cp_async8(&sm.Bs[st][bk * RS_BS + bc], &Ld1[j1 + (int64_t)bk * nrd1]);
+        else sm.Bs[st][bk * RS_BS + bc] = 0.0;
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        return any | (half1 << 1);
       };
+      int meta[RS_ST] = {0, 0, 0};                         // per stage: stage_b's return value
       stage_a(u);
-      stage_b();
-      if (u + 1 < uend) stage_a(u + 1);
-      for (int uu = u; uu < uend; ++uu, buf ^= 1) {
-        const int mi = min_, half = halfn;
-        double x[RS_NC];
+      meta[0] = stage_b(0);
+      if (u + 1 < uend) { stage_a(u + 1); meta[1] = stage_b(1); } else asm volatile("cp.async.commit_group;\n" ::: "memory");
+      if (u + 2 < uend) stage_a(u + 2);
+      int st = 0;
+      for (int uu = u; uu < uend; ++uu) {
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");       // this thread's copies of update uu have landed (uu + 1 may be pending)
+        __syncthreads();                                               // ... and everybody's; stage st + 2 (read by the previous product) is free
+        const int st2 = (st + 2 >= RS_ST) ? st + 2 - RS_ST : st + 2;
+        const int mt = (st == 0) ? meta[0] : (st == 1 ? meta[1] : meta[2]);
+        if (uu + 2 < uend) {
+          const int r = stage_b(st2);
+          if (st2 == 0) meta[0] = r; else if (st2 == 1) meta[1] = r; else meta[2] = r;
+          if (uu + 3 < uend) stage_a(uu + 3);
+        } else {
+          asm volatile("cp.async.commit_group;\n" ::: "memory");     // keeps the group count in step
+        }
+        if (mt & 1) {
+          const double* Xt = sm.Xs[st] + 32 * wrp + fgi;
+          const double* Bt = sm.Bs[st] + fgi;
 #pragma unroll
-        for (int k = 0; k < RS_NC; ++k) x[k] = xn[k];
-        sm.Bs[buf][tid] = bn;                             // last read two updates ago: every thread is past that barrier
-        __syncthreads();
-        if (uu + 1 < uend) stage_b();
-        if (uu + 2 < uend) stage_a(uu + 2);
-        if (mi >= 0) {
-          const double* Bt = sm.Bs[buf];
-          if (half) {
+          for (int ks = 0; ks < 4; ++ks) {
+            const int kk = 4 * ks + fti;
+            double a[4];
 #pragma unroll
-            for (int k = 0; k < RS_NC; ++k) {
-              const double xk = -x[k];
-              const double2* brow = reinterpret_cast<const double2*>(Bt + k * RS_NC);
+            for (int m = 0; m < 4; ++m) a[m] = Xt[kk * RS_XLD + 8 * m];
+            const double b0 = -Bt[kk * RS_BS];
 #pragma unroll
-              for (int jp = 0; jp < RS_NC / 4; ++jp) {
-                const double2 bb = brow[jp];
-                acc[2 * jp] = fma(xk, bb.x, acc[2 * jp]);
-                acc[2 * jp + 1] = fma(xk, bb.y, acc[2 * jp + 1]);
-              }
-            }
-          } else {
+            for (int m = 0; m < 4; ++m) rs_dmma(fr[m][0], a[m], b0);
+            if (!(mt & 2)) {
+              const double b1 = -Bt[kk * RS_BS + 8];
 #pragma unroll
-            for (int k = 0; k < RS_NC; ++k) {
-              const double xk = -x[k];
-              const double2* brow = reinterpret_cast<const double2*>(Bt + k * RS_NC);
-#pragma unroll
-              for (int jp = 0; jp < RS_NC / 2; ++jp) {
-                const double2 bb = brow[jp];
-                acc[2 * jp] = fma(xk, bb.x, acc[2 * jp]);
-                acc[2 * jp + 1] = fma(xk, bb.y, acc[2 * jp + 1]);
-              }
+              for (int m = 0; m < 4; ++m) rs_dmma(fr[m][1], a[m], b1);
             }
           }
         }
+        st = (st + 1 == RS_ST) ? 0 : st + 1;
       }
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       u += nready;
     }
+    __syncthreads();                                      // the stages are free: back to thread-per-row registers through the slabs
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) slab[(8 * m + fgi) * RS_DP + 8 * n + 2 * fti + e] = fr[m][n][e];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < RS_NC; ++c) acc[c] = slab[lane * RS_DP + c];
     __syncthreads();
     RS_STAMP(2)
 

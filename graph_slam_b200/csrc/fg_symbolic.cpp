@@ -203,7 +203,9 @@ int build_symbolic(fg_ctx* c) {
     for (int u : st[sn_last[s]]) below += vdim[u];
     S.sn_nrows[s] = nc + below + 1;
     S.sn_rowptr[s + 1] = S.sn_rowptr[s] + S.sn_nrows[s];
-    S.sn_valptr[s + 1] = S.sn_valptr[s] + (int64_t)S.sn_nrows[s] * nc;
+    // panels start on 128-byte lines: a cache line never holds values of two supernodes (k_chol_rs reads finished panels
+    // through the non-coherent L1)
+    S.sn_valptr[s + 1] = (S.sn_valptr[s] + (int64_t)S.sn_nrows[s] * nc + 15) / 16 * 16;
     for (int k = 0; k < nc; ++k) S.col2sn[c0 + k] = s;
     S.max_nrows = std::max(S.max_nrows, S.sn_nrows[s]);
     S.max_ncols = std::max(S.max_ncols, nc);
