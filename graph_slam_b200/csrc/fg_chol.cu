@@ -14,6 +14,7 @@
 // are polled 256 at a time), i.e. everything except the immediate predecessor's update is applied while
 // waiting.  k_backsolve runs the backward substitution the same way, top-down.
 // There is no fp64 kind of tcgen05.mma, so the dense tiles use DFMA on CUDA cores.
+#include <cstdlib>
 #include "fg_internal.h"
 
 namespace fg {
@@ -344,6 +345,92 @@ __global__ void __launch_bounds__(256) k_marginal(SysView s, int col0, int dim, 
 
 void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);
 
+// Warp-per-supernode variant of the backward substitution (default).  The solve is a dependency chain of ~n_levels
+// steps, so what counts is the time from "nearest ancestor published" to "own solution published": one warp does the
+// whole supernode without block barriers -- far ancestors' rows are folded in while the nearest ancestor is still
+// pending, the 16 partial sums are reduced by shuffles, the diagonal block (one column per lane, loaded up front)
+// is back-substituted with static register indices.
+#define BW_WARPS 4
+__device__ __forceinline__ int bw_ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(32 * BW_WARPS, 4) k_backsolve_w(SysView s, const int* __restrict__ sched, const int* __restrict__ anc_ptr,
+                                                              const int* __restrict__ anc_t, const int* __restrict__ anc_b,
+                                                              int* flags2, int* counters, int epoch, int n_sn, double* x) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  while (true) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&counters[1], 1);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (slot >= n_sn) break;
+    const int sn = sched[n_sn - 1 - slot];
+    const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
+    const double* Lp = s.L + s.sn_valptr[sn];
+    const int* rows = s.rowidx + s.sn_rowptr[sn];
+    const int a0 = anc_ptr[sn], a1 = anc_ptr[sn + 1];
+    // lane k keeps column k of the diagonal block (rows >= k), its reciprocal pivot and the right-hand side y_k
+    double Lcol[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) Lcol[c] = (lane < nc && c < nc && c >= lane) ? Lp[c + (int64_t)lane * nr] : 0.0;
+    const double rdg = (lane < nc) ? 1.0 / Lp[lane + (int64_t)lane * nr] : 0.0;
+    const double yk = (lane < nc) ? Lp[(nr - 1) + (int64_t)lane * nr] : 0.0;
+    double acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.0;
+    // ancestors finish from the far end of the row list towards the nearest one: fold in the rows of every ready suffix
+    // of the ancestor list as soon as it is ready, so that only the nearest ancestor's rows are left on the critical path
+    int hi = a1;                                           // entries [hi, a1) are folded in
+    while (hi > a0) {
+      int lo;
+      while (true) {
+        int nr_max = a0 - 1;                               // highest entry that is not ready
+        for (int base = a0; base < hi; base += 32) {
+          const int e = base + lane;
+          const bool notready = (e < hi) && bw_ld_relaxed(&flags2[anc_t[e]]) != epoch;
+          const unsigned m = __ballot_sync(FULL, notready);
+          if (m) nr_max = base + 31 - __clz(m);
+        }
+        lo = nr_max + 1;
+        if (lo < hi) break;
+      }
+      __threadfence();
+      const int r_lo = (lo == a0) ? nc : anc_b[lo - 1], r_hi = anc_b[hi - 1];
+      for (int r = r_lo + lane; r < r_hi; r += 32) {
+        const double xr = __ldcg(&x[rows[r]]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) if (c < nc) acc[c] = fma(Lp[r + (int64_t)c * nr], xr, acc[c]);
+      }
+      hi = lo;
+    }
+    // sums over the lanes; lane k ends with t_k = y_k - sum_k
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      double v = acc[c];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+      if (lane == c) t = yk - v;
+    }
+    // L_dd^T x = t, backwards
+    double xk = 0.0;
+#pragma unroll
+    for (int c = 15; c >= 0; --c) {
+      if (c < nc) {                                        // warp uniform
+        const double xc = __shfl_sync(FULL, t * rdg, c);
+        if (lane == c) xk = xc;
+        t = fma(-Lcol[c], xc, t);                          // lanes k < c: t_k -= L[c][k] x_c (Lcol[c] is 0 for k > c; lane c is done)
+      }
+    }
+    if (lane < nc) x[c0 + lane] = xk;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(&flags2[sn], epoch);
+  }
+}
+
 static SysView chol_view(fg_ctx* c) {
   DevGraph& d = c->d;
   SysView s;
@@ -380,6 +467,14 @@ void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36) 
 void launch_backsolve(fg_ctx* c) {
   DevGraph& d = c->d;
   SysView s = chol_view(c);
+  const char* cta = getenv("FG_BACKSOLVE_CTA");          // tests keep the CTA-per-supernode kernel covered
+  if (c->sym.max_ncols <= 16 && !(cta && cta[0] == '1')) {
+    int gridw = c->num_sms * 2;
+    if (gridw * BW_WARPS > c->sym.n_sn) gridw = (c->sym.n_sn + BW_WARPS - 1) / BW_WARPS;
+    k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, c->stream>>>(s, d.sched, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch,
+                                                         c->sym.n_sn, d.delta);
+    return;
+  }
   int grid = c->num_sms * 2;
   if (grid > c->sym.n_sn) grid = c->sym.n_sn;
   k_backsolve<<<grid, CH_T, 0, c->stream>>>(s, d.sched, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch,
