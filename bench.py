@@ -234,7 +234,7 @@ def main():
     t_sch = rep.ms_schur_blocks / trials                  # k_schur_tiles: every Z record read once (144 B/obs), reduced blocks RMW
     b_sch = m_rank * 144 + 2 * 8 * int(rep.nnz_L)
     f_sch = 216.0 * int(rep.n_schur_pairs)                # 108 DFMA per (observation a, observation b) pair of a landmark
-    t_cho = phases['factor']                              # k_chol_reg: one read of the assembled panels, one write of L
+    t_cho = phases['factor']                              # k_chol_rs (two launches) + k_front_syrk: one read of the assembled panels, one write of L
     b_cho = 2 * 8 * int(rep.nnz_L)
 
     # dram__bytes_read+write per launch from the committed ncu --set full capture (single GPU, C5 only)
@@ -247,10 +247,10 @@ def main():
         a = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         return dict(kernel=name, bound='hbm', achieved=a, peak=peak, unit='GB/s', frac=a / peak, traffic=traffic.get(name),
                     algorithmic_bytes=nbytes, ms=ms, note=note)
-    roofs = [roof('k_chol_reg', b_cho, t_cho, 'dominant by time; dependency-latency bound (%d levels), not bandwidth bound' % int(rep.n_levels)),
-             roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA bound: %d pairs x 216 flop = %.1f TFLOP/s achieved (B200 fp64 peak ~37 TFLOP/s, not in MEASURED_PEAKS.json)' % (
+    roofs = [roof('k_chol_rs', b_cho, t_cho, 'factorisation phase (k_chol_rs x2 + k_front_syrk): dependency chain of %d levels; the leaf phase streams ~12 GB of descendant panels through L2 per factorisation (profiles/r1_ncu_full_summary.md), fp64 on DMMA' % int(rep.n_levels)),
+             roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA bound: %d pairs x 216 flop = %.1f TFLOP/s achieved (fp64 peak measured on this B200: 36.2 TFLOP/s DFMA, profiles/r1_fp64_peak.txt; not in MEASURED_PEAKS.json)' % (
                  int(rep.n_schur_pairs), f_sch / (t_sch * 1e-3) / 1e12 if t_sch > 0 else 0.0)),
-             roof('k_proj_obs', b_obs, t_obs, 'streaming pass over the observations')]
+             roof('k_proj_obs<1>', b_obs, t_obs, 'streaming pass over the observations')]
     dominant = max(roofs, key=lambda r: r['ms'])
     line = dict(metric=METRIC, value=value, unit='iterations/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None,
@@ -263,7 +263,10 @@ def main():
                     graph_build_s=t_build),
                 e2e=dict(value=args.steps / dt_e2e, unit='iterations/s', h2d_bytes_per_step=state_bytes,
                          d2h_bytes_per_step=state_bytes),
-                gpu_launches=int(trials * 16 + rep.iterations * 12 + 10),
+                # kernels per outer iteration (linearise) and per lambda trial (build, Schur, factor x3, solve, retract, error pass),
+                # counted on the ncu launch list (profiles/r1_launch_summary.md: 27 per one-trial iteration at C5)
+                gpu_launches=int(rep.iterations * (7 + ('between_i' in spec) + ('plane_init' in spec)) +
+                                 trials * (20 + ('between_i' in spec) + 2 * ('plane_init' in spec))),
                 clocks=sampler.summary(),
                 roofline=dict(dominant, peak_source=peak_src, iteration_algorithmic_bytes=ab['total'],
                               iteration_frac=ab['total'] / (dt / args.steps) / 1e9 / peak),

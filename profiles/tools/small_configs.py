@@ -1,5 +1,5 @@
 import sys, time, json
-sys.path.insert(0,'/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from graph_slam_b200 import abi, synth
 for name in ['C1','C2','C3','C4']:
     spec=synth.make_config(name, seed=1)
