@@ -28,10 +28,19 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
   return v;
 }
-// every thread of the block must call; one atomic per warp
+// every thread of the block must call; one atomic per BLOCK (all warps of all blocks adding to one address made the
+// chi2-only pass atomic bound: 312 k serialised fp64 atomics per pass at C5)
 __device__ __forceinline__ void chi2_accumulate(double e, double* target) {
+  __shared__ double chi2_part[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   e = warp_sum(e);
-  if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(target, e);
+  if (lane == 0) chi2_part[w] = e;
+  __syncthreads();
+  if (w == 0) {
+    double v = lane < nw ? chi2_part[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0 && v != 0.0) atomicAdd(target, v);
+  }
 }
 
 // 128-bit loads of a pose record (12 doubles, 96 B, 16 B aligned)
@@ -327,7 +336,7 @@ __device__ __forceinline__ double seg_sum(double v, int key, int lane) {
 // one thread per observation (observations sorted by landmark): residual, Jp, Jl; W = w Jp^T Jl stored SoA;
 // V_l, g_l by warp-segmented reduction.
 template <bool JAC>
-__global__ void __launch_bounds__(256) k_proj_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+__global__ void __launch_bounds__(256, 3) k_proj_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
                                                   Vals vals, const double* __restrict__ calib, const double* __restrict__ sensor,
                                                   double* __restrict__ W, double* V, double* gl, double* chi2) {
