@@ -595,7 +595,9 @@ extern "C" int fg_finalize(fg_ctx* c) {
         const int cb = std::max(g_lo[gi], g_lo[gj]), ce = std::min(g_hi[gi], g_hi[gj]);
         if (cb < ce) tiles.push_back(make_int4(gi, gj, cb, ce));
       }
-      std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });   // heaviest first
+      // heaviest first.  (Measured: issuing the tiles in bands of neighbouring row groups, so that the CTAs in flight share
+      // Z records in L2, is 15 % slower -- the long diagonal tiles must all start early.)
+      std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
       d.n_tiles = (int)tiles.size();
       int64_t npairs = 0;
       for (int64_t l = 0; l < L; ++l) { const int64_t k = lm_ptr[l + 1] - lm_ptr[l]; npairs += k * (k + 1) / 2; }

@@ -476,6 +476,13 @@ __global__ void __launch_bounds__(256) k_lm_backsub_obs(int64_t M, const int* __
   bool act = o < M;
   int l = act ? obs_point[o] : -1;
   double t3[3] = {0, 0, 0};
+  // the dependent gather obs_pose -> off_pose -> delta is issued first so that it overlaps the streaming W loads
+  double dl[6];
+  {
+    const double* d = delta + (act ? off_pose[obs_pose[o]] : 0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dl[i] = act ? d[i] : 0.0;
+  }
   {
     // coalesced load of the block's 256 consecutive W records, transposed through shared memory
     const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
@@ -484,13 +491,11 @@ __global__ void __launch_bounds__(256) k_lm_backsub_obs(int64_t M, const int* __
     __syncthreads();
   }
   if (act) {
-    const double* d = delta + off_pose[obs_pose[o]];
     const double* wr = wbuf + threadIdx.x * 19;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      double di = d[i];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) t3[c] += wr[3 * i + c] * di;
+      for (int c = 0; c < 3; ++c) t3[c] += wr[3 * i + c] * dl[i];
     }
   }
   int prev = __shfl_up_sync(0xffffffffu, l, 1);

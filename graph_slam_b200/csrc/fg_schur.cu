@@ -62,17 +62,18 @@ __global__ void __launch_bounds__(256) k_zmat(int64_t M, const int* __restrict__
   const int64_t o0 = blockIdx.x * (int64_t)256;
   const int n = (int)min((int64_t)256, M - o0);
   const int tid = threadIdx.x;
-  for (int i = tid; i < n * REC; i += 256) buf[(i / REC) * RST + (i % REC)] = __ldg(W + o0 * REC + i);
-  __syncthreads();
+  // the dependent gather obs_point -> Cf (and the scatter position) is issued first so that it overlaps the streaming W loads
+  double c[6] = {0, 0, 0, 0, 0, 0};
   if (tid < n) {
     const int l = obs_point[o0 + tid];
     ppos[tid] = obs_ppos[o0 + tid];
-    double c[6];
-    {
-      const double2* p = reinterpret_cast<const double2*>(Cf + (int64_t)l * 6);
-      double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-      c[0] = v0.x; c[1] = v0.y; c[2] = v1.x; c[3] = v1.y; c[4] = v2.x; c[5] = v2.y;
-    }
+    const double2* p = reinterpret_cast<const double2*>(Cf + (int64_t)l * 6);
+    double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+    c[0] = v0.x; c[1] = v0.y; c[2] = v1.x; c[3] = v1.y; c[4] = v2.x; c[5] = v2.y;
+  }
+  for (int i = tid; i < n * REC; i += 256) buf[(i / REC) * RST + (i % REC)] = __ldg(W + o0 * REC + i);
+  __syncthreads();
+  if (tid < n) {
     double* w = buf + tid * RST;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
