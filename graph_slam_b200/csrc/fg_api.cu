@@ -550,7 +550,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
     {
       if (M >= (int64_t)1 << 31) return fail(c, FG_ERR_INVALID, "more than 2^31 projection factors on one rank");
       const char* che = getenv("FG_SCHUR_CH");
-      const int CH = (che && atoi(che) == 32) ? 32 : 24;
+      const int CH = (che && atoi(che) == 24) ? 24 : 32;     // 32 landmarks per chunk, 24 record slots per pose (fg_schur.cu)
       d.schur_ch = CH;
       std::vector<int> ppos(M), pzp(M);
       for (int64_t k = 0; k < M; ++k) { ppos[pose_obs[k]] = (int)k; pzp[k] = s_point[pose_obs[k]]; }

@@ -98,22 +98,25 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 
 #define ST_THREADS 256
-template <int CH>
+template <int CH, int KMAX>
 struct SchurSmem {
-  static constexpr int PS = CH * 16 + 1;          // plane stride (doubles): odd, so bank = (e + i) mod 16
+  static constexpr int PS = KMAX * 16 + 1;        // plane stride (doubles): odd, so bank = (e + i) mod 16
   double rows[REC * PS];
   double cols[REC * PS];
   int src[ST_THREADS / 32][4 * CH];               // per warp: pose-major record index of every record it stages
 };
 
-template <int CH>
-__global__ void __launch_bounds__(ST_THREADS, CH <= 24 ? 2 : 1)
+// CH landmarks per chunk, room for KMAX records per pose and chunk.  KMAX < CH (32 / 24) bets that no pose sees more than
+// KMAX of a chunk's landmarks together with the other side of the tile; a chunk that loses the bet is done as two
+// half-chunks of 16 landmarks (<= 16 records per pose).
+template <int CH, int KMAX>
+__global__ void __launch_bounds__(ST_THREADS, 2)
 k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_lo, const int* __restrict__ pc_n,
               const int64_t* __restrict__ pc_ptr, const uint2* __restrict__ pc_ent, const double* __restrict__ Zp,
               const int* __restrict__ off_pose, SysView sys) {
   extern __shared__ __align__(16) unsigned char st_raw[];
-  SchurSmem<CH>& sm = *reinterpret_cast<SchurSmem<CH>*>(st_raw);
-  constexpr int PS = SchurSmem<CH>::PS;
+  SchurSmem<CH, KMAX>& sm = *reinterpret_cast<SchurSmem<CH, KMAX>*>(st_raw);
+  constexpr int PS = SchurSmem<CH, KMAX>::PS;
   const unsigned FULL = 0xffffffffu;
   const int4 td = tiles[blockIdx.x];
   const int gi = td.x, gj = td.y, cb = td.z, ce = td.w;
@@ -157,8 +160,13 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) any16 |= __shfl_xor_sync(FULL, any16, o);
     const unsigned other = __shfl_xor_sync(FULL, any16, 16);
-    const unsigned f = cur.y & other;
-    if (!__any_sync(FULL, f != 0u)) continue;     // identical decision in every warp: all hold the same 32 entries
+    const unsigned fall = cur.y & other;
+    if (!__any_sync(FULL, fall != 0u)) continue;  // identical decision in every warp: all hold the same 32 entries
+    int nparts = 1;
+    if (KMAX < CH && __any_sync(FULL, __popc(fall) > KMAX)) nparts = 2;
+    for (int part_i = 0; part_i < nparts; ++part_i) {
+    const unsigned f = nparts == 1 ? fall : (part_i == 0 ? (fall & 0x0000ffffu) : (fall & 0xffff0000u));
+    if (nparts == 2 && !__any_sync(FULL, f != 0u)) continue;
     __syncthreads();                              // the previous chunk's products are done with the staging area
     // ---- stage: list the records of this warp's poses, then copy them 3 records (27 lanes x 16 B) per step
     int base_t[5];
@@ -218,6 +226,7 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
         for (int ii = 0; ii < 6; ++ii) acc[6 * ii + jj] = fma(y[3 * ii + 2], w2, fma(y[3 * ii + 1], w1, fma(y[3 * ii], w0, acc[6 * ii + jj])));
       }
       any = true;
+    }
     }
   }
   if (diag) {
@@ -310,15 +319,15 @@ __global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restr
   }
 }
 
-template <int CH>
+template <int CH, int KMAX>
 static void launch_tiles(fg_ctx* c, const SysView& sys) {
   DevGraph& d = c->d;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_schur_tiles<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchurSmem<CH>));
+    cudaFuncSetAttribute(k_schur_tiles<CH, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchurSmem<CH, KMAX>));
     attr_set = true;
   }
-  k_schur_tiles<CH><<<d.n_tiles, ST_THREADS, sizeof(SchurSmem<CH>), c->stream>>>(d.tile_desc, (int)d.n[T_POSE], d.pc_lo, d.pc_n, d.pc_ptr, d.pc_ent,
+  k_schur_tiles<CH, KMAX><<<d.n_tiles, ST_THREADS, sizeof(SchurSmem<CH, KMAX>), c->stream>>>(d.tile_desc, (int)d.n[T_POSE], d.pc_lo, d.pc_n, d.pc_ptr, d.pc_ent,
                                                                                  d.Zp, d.off[T_POSE], sys);
 }
 
@@ -333,8 +342,8 @@ void launch_schur(fg_ctx* c, double lambda) {
   if (d.n_obs) k_zmat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.obs_ppos, d.W, d.Cf, d.Zp);
   if (c->kev[2]) cudaEventRecord(c->kev[2], st);
   if (d.n_tiles) {
-    if (d.schur_ch == 32) launch_tiles<32>(c, sys);
-    else launch_tiles<24>(c, sys);
+    if (d.schur_ch == 32) launch_tiles<32, 24>(c, sys);
+    else launch_tiles<24, 24>(c, sys);
   }
   if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];

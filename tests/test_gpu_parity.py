@@ -239,3 +239,29 @@ def test_two_view_bundle_adjust_edge_information():
     info = np.linalg.inv(cov)                      # what bundleAdjust hands back as the edge information (:601)
     assert np.all(np.linalg.eigvalsh(0.5 * (info + info.T)) > 0)
     ctx.close()
+
+
+def test_dense_visibility_splits_schur_chunks():
+    """Every pose sees every landmark: a pose then holds 32 records in a 32-landmark chunk, more than the 24 slots
+    k_schur_tiles keeps per pose, so every chunk takes the two-half-chunk path (fg_schur.cu)."""
+    rng = np.random.default_rng(21)
+    full = synth.make_config('C4', seed=7, scale=0.02)
+    K, Rs, ts = full['K'], full['Rs'], full['ts']
+    n, P = 100, 5
+    xi = np.zeros((P, 6)); xi[:, 3] = 0.06 * np.arange(P); xi[:, 1] = 0.01 * np.arange(P)
+    R, t = lie.se3_exp(xi)
+    Rc, tc = lie.pose_compose(R, t, np.broadcast_to(Rs, (P, 3, 3)), np.broadcast_to(ts, (P, 3)))
+    pc = np.column_stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.4, 0.4, n), rng.uniform(1.5, 4.0, n)])
+    pts = pc @ Rc[0].T + tc[0]
+    from oracle import factors as ofac
+    uv = np.concatenate([ofac.projection(R[k], t[k], pts, np.zeros((n, 2)), K, Rs, ts, jac=False) for k in range(P)])
+    uv = uv + rng.normal(size=uv.shape)
+    nz = rng.normal(size=(P, 6)) * 0.01; nz[0] = 0
+    dR, dt = lie.se3_exp(nz)
+    Ri, ti = lie.pose_compose(R, t, dR, dt)
+    spec = dict(name='dense', seed=0, n_poses=P, K=K, Rs=Rs, ts=ts, pose_init_R=Ri, pose_init_t=ti,
+                prior_pose_R=np.eye(3), prior_pose_t=np.zeros(3),
+                point_init=pts + rng.normal(size=pts.shape) * 0.014, point_prior_sigma=0.014,
+                proj_pose=np.repeat(np.arange(P), n).astype(np.int32), proj_point=np.tile(np.arange(n), P).astype(np.int32),
+                proj_uv=uv, proj_sigma=1.0)
+    check(spec, 1e-7, 1e-6, solver='schur')
