@@ -259,6 +259,60 @@ bool CGraphGT::writeTrajectory(std::string f) {
   return true;
 }
 
+namespace CG {
+unsigned char g_color[][3] = {{255, 0, 0}, {0, 255, 0}, {0, 0, 255}, {255, 0, 255}, {255, 255, 255}, {255, 255, 0}, {0, 0, 0}};
+}
+
+static void quat_of(const Matrix3& R, double q[4]) {         // (x, y, z, w), w >= 0
+  q[3] = 0.5 * std::sqrt(std::max(0.0, 1 + R(0, 0) + R(1, 1) + R(2, 2)));
+  q[0] = 0.5 * std::sqrt(std::max(0.0, 1 + R(0, 0) - R(1, 1) - R(2, 2))); if (R(2, 1) - R(1, 2) < 0) q[0] = -q[0];
+  q[1] = 0.5 * std::sqrt(std::max(0.0, 1 - R(0, 0) + R(1, 1) - R(2, 2))); if (R(0, 2) - R(2, 0) < 0) q[1] = -q[1];
+  q[2] = 0.5 * std::sqrt(std::max(0.0, 1 - R(0, 0) - R(1, 1) + R(2, 2))); if (R(1, 0) - R(0, 1) < 0) q[2] = -q[2];
+}
+
+void CGraphGT::headerPLY(std::ofstream& ouf, int vertex_number) {
+  ouf << "ply" << std::endl << "format ascii 1.0" << std::endl << "element vertex " << vertex_number << std::endl
+      << "property float x" << std::endl << "property float y" << std::endl << "property float z" << std::endl
+      << "property uchar red" << std::endl << "property uchar green" << std::endl << "property uchar blue" << std::endl
+      << "end_header" << std::endl;
+}
+
+bool CGraphGT::trajectoryPLY(std::string f, CG::COLOR c) {
+  std::ofstream ouf(f.c_str());
+  if (!ouf.is_open()) { printf("%s %d failed to open f: %s to write trajectory!\n", __FILE__, __LINE__, f.c_str()); return false; }
+  headerPLY(ouf, (int)m_graph_map.size());
+  for (auto it = m_graph_map.begin(); it != m_graph_map.end(); ++it) {
+    Pose3 p = (*mp_w2o) * mp_node_values->at<Pose3>(X(it->first));
+    ouf << p.x() << " " << p.y() << " " << p.z() << " " << (int)CG::g_color[c][0] << " " << (int)CG::g_color[c][1] << " " << (int)CG::g_color[c][2] << std::endl;
+  }
+  return true;
+}
+
+// gtsam::writeG2o semantics [ext]: one VERTEX_SE3:QUAT per Pose3 value (key index, t, quaternion xyzw), one
+// EDGE_SE3:QUAT per BetweenFactor<Pose3> with the information matrix re-ordered from GTSAM's [rot, trans] tangent to
+// g2o's [trans, rot] and written as its 21 upper-triangular entries.
+void CGraphGT::writeG2O(std::string f) {
+  std::ofstream ouf(f.c_str());
+  if (!ouf.is_open()) { printf("%s failed to open f: %s to write g2o!\n", __FILE__, f.c_str()); return; }
+  ouf.precision(17);
+  const unsigned long long mask = (1ull << 56) - 1;
+  for (auto& kv : mp_node_values->m) {
+    if (kv.second.type != FG_T_POSE) continue;
+    Pose3 p = mp_node_values->at<Pose3>(kv.first);
+    double q[4]; quat_of(p.rotation().matrix(), q);
+    ouf << "VERTEX_SE3:QUAT " << (kv.first & mask) << " " << p.x() << " " << p.y() << " " << p.z() << " " << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << std::endl;
+  }
+  for (auto& fac : mp_fac_graph->f) {
+    auto* b = dynamic_cast<BetweenFactor<Pose3>*>(fac.get());
+    if (!b) continue;
+    double q[4]; quat_of(b->z.rotation().matrix(), q);
+    ouf << "EDGE_SE3:QUAT " << (b->k1 & mask) << " " << (b->k2 & mask) << " " << b->z.x() << " " << b->z.y() << " " << b->z.z() << " " << q[0] << " " << q[1] << " " << q[2] << " " << q[3];
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) ouf << " " << b->nm->info[((i + 3) % 6) * 6 + (j + 3) % 6];     // swap the rot / trans blocks
+    ouf << std::endl;
+  }
+}
+
 // ------------------------------------------------------------------ CImuBase
 CImuBase::CImuBase(double delta_t, imuBias::ConstantBias prior_bias)
     : m_curr_i(0), m_syn_start_id(0), m_prior_imu_bias(prior_bias), m_dt((float)delta_t), mp_combined_pre_imu(0) {

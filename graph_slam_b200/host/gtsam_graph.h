@@ -45,6 +45,11 @@ class CCameraNode {
 
 typedef enum { SUCC_KF, FAIL_NOT_KF, FAIL_KF } ADD_RET;   // gtsam/gtsam_graph.h:43
 
+namespace CG {                                             // gtsam/color.h
+typedef enum { RED = 0, GREEN, BLUE, PURPLE, WHITE, YELLOW, DARK } COLOR;
+extern unsigned char g_color[][3];
+}
+
 class CGraphGT {
  public:
   CGraphGT();
@@ -95,6 +100,9 @@ class CGraphGT {
   int m_plane_landmark_id = 0;
   int m_sift_landmark_id = 0;
   bool writeTrajectory(std::string ouf);                         // :1819-1840
+  bool trajectoryPLY(std::string ouf, CG::COLOR c);              // :1842-1864
+  void headerPLY(std::ofstream&, int vertex_number);             // :1927-1939
+  void writeG2O(std::string ouf);                                // :1941-1945 (gtsam::writeG2o: Pose3 vertices, BetweenFactor<Pose3> edges)
 };
 
 // ---- IMU
