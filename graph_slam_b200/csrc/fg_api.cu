@@ -635,7 +635,8 @@ extern "C" int fg_finalize(fg_ctx* c) {
   if (S.rs_ok) {
     if ((rc = dev_upload(c, &d.rs_units, S.rs_units)) || (rc = dev_upload(c, &d.rs_moff, S.rs_moff)) || (rc = dev_upload(c, &d.rs_map, S.rs_map)) ||
         (rc = dev_upload(c, &d.rs_colinv, S.rs_colinv)) ||
-        (rc = dev_upload<int>(c, &d.rs_done, nullptr, 2 * (size_t)S.n_sn))) return rc;
+        (rc = dev_upload<int>(c, &d.rs_done, nullptr, S.rs_units.size())) || (rc = dev_upload(c, &d.rs_sn_units, S.rs_sn_units)) ||
+        (rc = dev_upload<double>(c, &d.rs_dfac, nullptr, 256 * (size_t)S.n_sn))) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));
   c->epoch = 0;

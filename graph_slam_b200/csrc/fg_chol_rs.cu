@@ -16,9 +16,9 @@
 //     supernode (15 x 15 x K flops),
 //   * factors the diagonal block (every block redundantly: no intra-supernode synchronisation), solves its own rows
 //     against it and stores them,
-//   * bumps the supernode's arrival counter; the block that arrives LAST stores the factored diagonal block (the others
-//     read the assembled one when they start, so it must not be overwritten earlier) and publishes the supernode's
-//     done flag (release); consumers poll the flag (acquire).
+//   * publishes its own done flag (release); a consumer polls the flags of all blocks of a descendant (acquire).  The
+//     first block parks the diagonal factor in a side buffer (the sibling blocks read the ASSEMBLED diagonal block when
+//     they start, so it must not be overwritten while the factorisation runs); a small kernel moves it into L at the end.
 // Deterministic: every panel entry is owned by one unit and updated in list order.  tcgen05 has no fp64 kind; DMMA
 // measured at the DFMA peak on this part (profiles/tools/fp64_peak.cu): its gain is instruction and operand traffic.
 #include <algorithm>
@@ -105,8 +105,8 @@ __device__ __forceinline__ void rs_potrf_warp(RsSmem& sm, int nc, int lane, int*
 __global__ void __launch_bounds__(RS_T, 2)
 k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__ unit_moff, const short* __restrict__ rowmap,
           const int* __restrict__ upd_ptr, const int* __restrict__ upd_d, const UpdRec* __restrict__ upd_rec,
-          const signed char* __restrict__ colinv, int* arrived, int* done, int* counter, int n_units, int* status, FrontView fv,
-          long long* dbg) {
+          const signed char* __restrict__ colinv, const int2* __restrict__ sn_units, int* done, int unit_base, double* __restrict__ Dfac,
+          int* counter, int n_units, int* status, FrontView fv, long long* dbg) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
   const int tid = threadIdx.x;
@@ -122,7 +122,7 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
 #define RS_STAMP(k) if (dbg && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[8 * slot + (k)] = t_; }
     RS_STAMP(0)
     const int4 un = units[slot];
-    const int sn = un.x, r0 = un.y, r1 = un.z, nblk = un.w;   // own rows [r0, r1) of the panel, r0 >= nc; blocks of this supernode
+    const int sn = un.x, r0 = un.y, r1 = un.z;               // own rows [r0, r1) of the panel, r0 >= nc (r0 == nc: first block)
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     const int nloc = nc + (r1 - r0);
     double* Lp = s.L + s.sn_valptr[sn];
@@ -188,15 +188,25 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     int u = upd_ptr[sn];
     const int ubase = u;
     const int u1 = upd_ptr[sn + 1];
+    const double* Ld1 = nullptr; int K1 = 0, nrd1 = 0, half1 = 0, mi1 = -1, j1 = -1;        // indices of the next update to be issued
+    auto stage_a = [&](int uu) {
+      const UpdRec rec = upd_rec[uu];
+      Ld1 = s.L + rec.val_off; K1 = rec.K; nrd1 = rec.nrd; half1 = rec.pad[0];                 // half: only target columns < 8 are touched
+      mi1 = has_row ? (int)__ldg(umap + (int64_t)(uu - ubase) * nloc) : -1;                   // descendant row (from row a) landing on this thread's row
+      j1 = colinv[(int64_t)uu * RS_NC + bc];                                                  // descendant row (from a) holding target column bc, or -1
+    };
     while (u < u1) {
+      stage_a(u);                                          // static data: its latency hides behind the wait for the descendant
       // warp 0 spins on the done flags of the next (up to 32) descendants and publishes the ready prefix
       if (tid < 32) {
         const int win = min(32, u1 - u);
         const int ui = u + min(tid, win - 1);
-        const int* fp = done + upd_d[ui];
+        const int2 du = sn_units[upd_d[ui]];               // (first unit, number of units) of the descendant
+        const int* fp = done + du.x;
         int n;
         while (true) {
-          const int f = (tid < win) ? rs_ld_relaxed(fp) : 1;
+          int f = 1;
+          if (tid < win) for (int b = 0; b < du.y; ++b) f &= rs_ld_relaxed(fp + b);     // every row block of the descendant is stored
           const unsigned notready = ~__ballot_sync(0xffffffffu, f != 0);
           n = notready ? (__ffs(notready) - 1) : 32;
           if (n > win) n = win;
@@ -212,13 +222,6 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
       //      RS_ST shared-memory stages while uu is multiplied (the leaf panels touched by one level exceed L2, so a load
       //      is a DRAM round trip); the record / row-map / column-map loads (static data) run one step further ahead.
       const int uend = u + nready;
-      const double* Ld1 = nullptr; int K1 = 0, nrd1 = 0, half1 = 0, mi1 = -1, j1 = -1;      // indices of the next update to be issued
-      auto stage_a = [&](int uu) {
-        const UpdRec rec = upd_rec[uu];
-        Ld1 = s.L + rec.val_off; K1 = rec.K; nrd1 = rec.nrd; half1 = rec.pad[0];               // half: only target columns < 8 are touched
-        mi1 = has_row ? (int)__ldg(umap + (int64_t)(uu - ubase) * nloc) : -1;                 // descendant row (from row a) landing on this thread's row
-        j1 = colinv[(int64_t)uu * RS_NC + bc];                                                // descendant row (from a) holding target column bc, or -1
-      };
       // issue the copies of the update described by stage_a into stage st; returns (any row of this warp touched) | half << 1
       auto stage_b = [&](int st) -> int {
         const int any = __any_sync(FULL, mi1 >= 0) ? 1 : 0;
@@ -236,7 +239,6 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
         return any | (half1 << 1);
       };
       int meta[RS_ST] = {0, 0, 0};                         // per stage: stage_b's return value
-      stage_a(u);
       meta[0] = stage_b(0);
       if (u + 1 < uend) { stage_a(u + 1); meta[1] = stage_b(1); } else asm volatile("cp.async.commit_group;\n" ::: "memory");
       if (u + 2 < uend) stage_a(u + 2);
@@ -312,25 +314,33 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
         }
       }
     }
+    // the first block of the supernode parks the diagonal factor in Dfac: the assembled diagonal block in L stays intact
+    // for the sibling blocks that have not started yet (k_rs_copy_diag moves the factors into L at the end)
+    if (r0 == nc) {
+      double* Df = Dfac + (int64_t)sn * (RS_NC * RS_NC);
+      for (int i = tid; i < nc * nc; i += RS_T) {
+        const int r = i % nc, c = i / nc;
+        if (c <= r) Df[r + c * RS_NC] = sm.Ds[r * RS_DP + c];
+      }
+    }
     RS_STAMP(4)
     __threadfence();
     __syncthreads();
-    if (tid == 0) sm.slot = atomicAdd(&arrived[sn], 1);
-    __syncthreads();
-    const bool last = sm.slot == nblk - 1;
-    __syncthreads();
-    RS_STAMP(5)
-    if (last) {
-      // every block of this supernode has read the assembled diagonal block and stored its rows
-      for (int i = tid; i < nc * nc; i += RS_T) {
-        const int r = i % nc, c = i / nc;
-        if (c <= r) Lp[r + (int64_t)c * nr] = sm.Ds[r * RS_DP + c];
-      }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + sn), "r"(1) : "memory");
-      RS_STAMP(6)
-    }
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + unit_base + slot), "r"(1) : "memory");
+    RS_STAMP(6)
+  }
+}
+
+// diagonal factors: Dfac -> the diagonal blocks of the panels (after both phases)
+__global__ void k_rs_copy_diag(SysView s, int n_sn, const double* __restrict__ Dfac) {
+  const int sn = blockIdx.x;
+  if (sn >= n_sn) return;
+  const int nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
+  double* Lp = s.L + s.sn_valptr[sn];
+  const double* Df = Dfac + (int64_t)sn * (RS_NC * RS_NC);
+  for (int i = threadIdx.x; i < nc * nc; i += blockDim.x) {
+    const int r = i % nc, c = i / nc;
+    if (c <= r) Lp[r + (int64_t)c * nr] = Df[r + c * RS_NC];
   }
 }
 
@@ -357,7 +367,7 @@ void launch_factor_rs(fg_ctx* c) {
   cudaStream_t st = c->stream;
   c->epoch += 1;                                   // k_backsolve's flags are epoch stamped
   cudaMemsetAsync(d.status, 0, sizeof(int), st);
-  cudaMemsetAsync(d.rs_done, 0, sizeof(int) * 2 * S.n_sn, st);     // done flags, then arrival counters
+  cudaMemsetAsync(d.rs_done, 0, sizeof(int) * S.rs_units.size(), st);     // one done flag per unit
   cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, st);
   const int na = S.rs_units_a, nc = (int)S.rs_units.size() - S.rs_units_a;
   // FG_CHOL_TRACE=<file>: per-unit %globaltimer stamps of the 3rd factorisation (dev tool, profiles/tools/chol_trace.py)
@@ -389,16 +399,18 @@ void launch_factor_rs(fg_ctx* c) {
   const int cap = c->num_sms * per_sm;
   if (!S.use_fronts) {
     k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.upd_ptr, d.upd_d, d.upd_rec, d.rs_colinv,
-                                                                d.rs_done + S.n_sn, d.rs_done, d.counters, na, d.status, none, dbg);
+                                                                d.rs_sn_units, d.rs_done, 0, d.rs_dfac, d.counters, na, d.status, none, dbg);
+    k_rs_copy_diag<<<S.n_sn, 64, 0, st>>>(s, S.n_sn, d.rs_dfac);
     return;
   }
   // phase A: the leaves; phase B: one dense update matrix per leaf; phase C: the separators
   if (na) k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.updr_ptr, d.updr_d, d.updr_rec, d.rs_colinv,
-                                                                      d.rs_done + S.n_sn, d.rs_done, d.counters, na, d.status, none, dbg);
+                                                                      d.rs_sn_units, d.rs_done, 0, d.rs_dfac, d.counters, na, d.status, none, dbg);
   launch_front_syrk(c);
   FrontView fv = {d.tf_ptr, d.tf_leaf, d.fr_rowptr, d.fr_rows, d.fr_uptr, d.U};
   if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.updr_ptr, d.updr_d,
-                                                                      d.updr_rec, d.rs_colinv, d.rs_done + S.n_sn, d.rs_done, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr);
+                                                                      d.updr_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.rs_dfac, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr);
+  k_rs_copy_diag<<<S.n_sn, 64, 0, st>>>(s, S.n_sn, d.rs_dfac);
 }
 
 }  // namespace fg

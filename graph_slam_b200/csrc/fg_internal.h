@@ -96,6 +96,7 @@ struct Symbolic {
   bool rs_ok = false;
   int rs_units_a = 0;
   std::vector<int4> rs_units;
+  std::vector<int2> rs_sn_units;                   // per supernode: (global index of its first unit, number of units)
   std::vector<int64_t> rs_moff;                    // per unit: offset of its row maps
   std::vector<short> rs_map;                       // per (unit, update, local row): descendant row (from row a) landing on that row, or -1
   std::vector<signed char> rs_colinv;              // per update of the list in use, 16 entries: descendant row (from a) holding target column c, or -1
@@ -229,7 +230,8 @@ struct DevGraph {
   double* U = nullptr;              // dense update matrices of all leaves
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;
-  int4* rs_units = nullptr; int64_t* rs_moff = nullptr; short* rs_map = nullptr; signed char* rs_colinv = nullptr; int* rs_done = nullptr;   // rs_done: n_sn done flags, then n_sn arrival counters
+  int4* rs_units = nullptr; int64_t* rs_moff = nullptr; short* rs_map = nullptr; signed char* rs_colinv = nullptr; int* rs_done = nullptr;   // rs_done: one done flag per unit
+  int2* rs_sn_units = nullptr; double* rs_dfac = nullptr;   // per supernode: (first unit, number of units); 16 x 16 diagonal factors
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
   int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve)
 };
