@@ -8,6 +8,7 @@
 using namespace gtsam;
 using symbol_shorthand::B;
 using symbol_shorthand::L;
+using symbol_shorthand::Q;
 using symbol_shorthand::V;
 using symbol_shorthand::X;
 
@@ -122,6 +123,102 @@ bool CGraphGT::addToGTSAM(MatchingResult& mr, bool set_estimate) {
   noiseModel::Gaussian::shared_ptr visual_odometry_noise = noiseModel::Gaussian::Information(tmp);
   mp_fac_graph->add(BetweenFactor<Pose3>(X(mr.edge.id1), X(mr.edge.id2), inc_pose, visual_odometry_noise));
   mp_new_fac->add(BetweenFactor<Pose3>(X(mr.edge.id1), X(mr.edge.id2), inc_pose, visual_odometry_noise));
+  return true;
+}
+
+// Multi-frame BA builder (gtsam_graph.cpp:370-448): a match between two features without a landmark creates one
+// (camera point -> IMU frame -> world through X_i) with PriorFactor<Point3>(sigma 0.014) and two projection factors
+// (sigma 1 px, Cal3DS2 from the camera model, body_P_sensor = u2c); a match to an existing landmark adds one factor.
+bool CGraphGT::addToGTSAM(CCameraNodeBA* ni, CCameraNodeBA* nj, std::map<int, int>& matches, CamModel* pcam) {
+  std::shared_ptr<Cal3DS2> K(new Cal3DS2(pcam->fx, pcam->fy, 0, pcam->cx, pcam->cy, pcam->k1, pcam->k2));
+  Pose3 Pi = mp_node_values->at<Pose3>(X(ni->m_id));
+  noiseModel::Isotropic::shared_ptr pointNoise = noiseModel::Isotropic::Sigma(3, 0.014);
+  noiseModel::Isotropic::shared_ptr measNoise = noiseModel::Isotropic::Sigma(2, 1.);
+  auto meas = [](CCameraNodeBA* n, int k) { Point2 m; m[0] = n->m_feature_loc_2d[k].pt.x; m[1] = n->m_feature_loc_2d[k].pt.y; return m; };
+  auto proj = [&](CCameraNodeBA* n, int k, int qid) {
+    GenericProjectionFactor f(meas(n, k), measNoise, X(n->m_id), Q(qid), K, 0, 0, *mp_u2c);
+    mp_fac_graph->push_back(f); mp_new_fac->push_back(f);
+  };
+  for (auto it = matches.begin(); it != matches.end(); ++it) {
+    int& qi = ni->mv_feature_qid[it->first];
+    int& qj = nj->mv_feature_qid[it->second];
+    if (qi == -1 && qj == -1) {
+      const std::array<float, 4>& pt = ni->m_feature_loc_3d[it->first];
+      Point3 q = Pi.transform_from(mp_u2c->transform_from(vec3(pt[0], pt[1], pt[2])));
+      mp_node_values->insertPoint(Q(m_sift_landmark_id), q);
+      mp_new_node->insertPoint(Q(m_sift_landmark_id), q);
+      mp_fac_graph->push_back(PriorFactor<Point3>(Q(m_sift_landmark_id), q, pointNoise, true));
+      mp_new_fac->push_back(PriorFactor<Point3>(Q(m_sift_landmark_id), q, pointNoise, true));
+      proj(ni, it->first, m_sift_landmark_id);
+      proj(nj, it->second, m_sift_landmark_id);
+      qi = qj = m_sift_landmark_id++;
+    } else if (qi == -1) {
+      proj(ni, it->first, qj); qi = qj;
+    } else if (qj == -1) {
+      proj(nj, it->second, qi); qj = qi;
+    } else if (qi != qj) {
+      ROS_ERROR("%s what? Line %d different landmark at the same position", __FILE__, __LINE__);
+    }
+  }
+  return true;
+}
+
+// Two-view BA (gtsam_graph.cpp:500-610): refines the transform of a VRO edge and replaces its information matrix by the
+// inverse of pose 1's marginal covariance.  Private two-pose graph: prior on s0 (1e-7), PriorFactor<Point3> (0.014) and two
+// projection factors per match (1 px, SR4000 Cal3DS2, no body_P_sensor), LM, Marginals.
+bool CGraphGT::bundleAdjust(MatchingResult* pm, CCameraNode* pNewNode, CamModel* pcam) {
+  int pre_id1 = pm->edge.id1, pre_id2 = pm->edge.id2;
+  correctMatchingID(pm);
+  CCameraNodeBA* ni = dynamic_cast<CCameraNodeBA*>(m_graph_map[pm->edge.id1]);
+  CCameraNodeBA* nj = dynamic_cast<CCameraNodeBA*>(pNewNode);
+  Matrix4 Tji = Pose3(pm->final_trafo).inverse().matrix();
+  std::map<int, int> matches = (ni && nj) ? nj->matchNodePairBA(ni, Tji, pcam) : std::map<int, int>();
+  if (matches.size() <= 4) {
+    if (pm->edge.informationMatrix(0, 0) == 10000) ROS_ERROR("Nothing changed for edge from %d to %d", pre_id1, pre_id2);
+    pm->edge.id1 = pre_id1; pm->edge.id2 = pre_id2;
+    return false;
+  }
+  NonlinearFactorGraph g;
+  Vector6 s; for (int i = 0; i < 6; ++i) s[i] = 1e-7;
+  noiseModel::Diagonal::shared_ptr priorNoise = noiseModel::Diagonal::Sigmas(s);
+  noiseModel::Isotropic::shared_ptr measNoise = noiseModel::Isotropic::Sigma(2, 1.);
+  noiseModel::Isotropic::shared_ptr pointNoise = noiseModel::Isotropic::Sigma(3, 0.014);
+  std::shared_ptr<Cal3DS2> K(new Cal3DS2(250.5773, 250.5773, 0, 90, 70, -0.8466, 0.5370));
+  Pose3 Pi, Pj;
+  g.push_back(PriorFactor<Pose3>(Symbol('s', 0), Pi, priorNoise));
+  Values initialEstimate;
+  initialEstimate.insert<Pose3>(Symbol('s', 0), Pi);
+  initialEstimate.insert<Pose3>(Symbol('s', 1), Pj);
+  int j = 0;
+  for (auto it = matches.begin(); it != matches.end(); ++it, ++j) {
+    const std::array<float, 4>& pt = ni->m_feature_loc_3d[it->first];
+    Point3 q = vec3(pt[0], pt[1], pt[2]);
+    initialEstimate.insertPoint(Symbol('u', j), q);
+    Point2 mi, mj;
+    mi[0] = ni->m_feature_loc_2d[it->first].pt.x; mi[1] = ni->m_feature_loc_2d[it->first].pt.y;
+    mj[0] = nj->m_feature_loc_2d[it->second].pt.x; mj[1] = nj->m_feature_loc_2d[it->second].pt.y;
+    g.push_back(PriorFactor<Point3>(Symbol('u', j), q, pointNoise, true));
+    g.push_back(GenericProjectionFactor(mi, measNoise, Symbol('s', 0), Symbol('u', j), K, 0, 0, Pose3()));
+    g.push_back(GenericProjectionFactor(mj, measNoise, Symbol('s', 1), Symbol('u', j), K, 0, 0, Pose3()));
+  }
+  LevenbergMarquardtOptimizer optimizer(g, initialEstimate);
+  Values curEstimate = optimizer.optimize();
+  Pj = curEstimate.at<Pose3>(Symbol('s', 1));
+  pm->final_trafo = Pj.matrix();
+  Marginals marginals(g, curEstimate, Marginals::CHOLESKY);
+  int dim = 0;
+  std::vector<double> S_pose = marginals.marginalCovariance(Symbol('s', 1), &dim);
+  // information = inverse of the 6 x 6 marginal covariance (symmetric positive definite): Gauss-Jordan on the host
+  double A[6][12];
+  for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { A[r][c] = S_pose[r * 6 + c]; A[r][6 + c] = r == c ? 1.0 : 0.0; }
+  for (int c = 0; c < 6; ++c) {
+    int piv = c; for (int r = c + 1; r < 6; ++r) if (std::fabs(A[r][c]) > std::fabs(A[piv][c])) piv = r;
+    if (piv != c) for (int k = 0; k < 12; ++k) std::swap(A[c][k], A[piv][k]);
+    double d = A[c][c]; for (int k = 0; k < 12; ++k) A[c][k] /= d;
+    for (int r = 0; r < 6; ++r) if (r != c) { double f = A[r][c]; if (f != 0.0) for (int k = 0; k < 12; ++k) A[r][k] -= f * A[c][k]; }
+  }
+  for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) pm->edge.informationMatrix(r, c) = A[r][6 + c];
+  pm->edge.id1 = pre_id1; pm->edge.id2 = pre_id2;
   return true;
 }
 

@@ -9,6 +9,7 @@
 // Only the members on the solver path are mirrored; front-end members (feature matching, plane segmentation,
 // PLY/trajectory writers) are out of scope.
 #pragma once
+#include <array>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -43,6 +44,23 @@ class CCameraNode {
   virtual ~CCameraNode() {}
 };
 
+// BA node / camera model: the members the BA builders touch (camera_node_ba.h, cam_model.h in the sibling packages).
+// Feature matching itself (matchNodePairBA) is front end and out of scope: the base returns no matches, a caller that
+// has correspondences overrides it.
+struct KeyPoint2f { struct { float x = 0, y = 0; } pt; };
+class CamModel {
+ public:
+  CamModel(double fx_, double fy_, double cx_, double cy_, double k1_ = 0, double k2_ = 0) : fx(fx_), fy(fy_), cx(cx_), cy(cy_), k1(k1_), k2(k2_) {}
+  double fx, fy, cx, cy, k1, k2;
+};
+class CCameraNodeBA : public CCameraNode {
+ public:
+  std::vector<std::array<float, 4>> m_feature_loc_3d;    // camera-frame (x, y, z, 1)
+  std::vector<KeyPoint2f> m_feature_loc_2d;              // pixel measurements
+  std::vector<int> mv_feature_qid;                       // landmark id of every feature, -1 = none yet
+  virtual std::map<int, int> matchNodePairBA(CCameraNodeBA* /*older*/, const gtsam::Matrix4& /*Tji*/, CamModel*) { return std::map<int, int>(); }
+};
+
 typedef enum { SUCC_KF, FAIL_NOT_KF, FAIL_KF } ADD_RET;   // gtsam/gtsam_graph.h:43
 
 namespace CG {                                             // gtsam/color.h
@@ -62,6 +80,8 @@ class CGraphGT {
   void optimizeGraphIncremental();                               // :1768-1776
   bool addToGTSAM(MatchingResult&, bool set_estimate);           // :630-695
   bool addToGTSAM(gtsam::NavState&, int vid, bool add_pose);     // :613-628
+  bool addToGTSAM(CCameraNodeBA* ni, CCameraNodeBA* nj, std::map<int, int>& matches, CamModel* pcam);   // :370-448 (multi-frame BA)
+  bool bundleAdjust(MatchingResult* pm, CCameraNode* pNewNode, CamModel* pcam);                         // :500-610 (two-view BA -> edge)
   // :1118-1298 with the CPlane argument replaced by what the factor needs: plane (nx,ny,nz,d) in the IMU frame
   // and its 3x3 covariance in the OrientedPlane3 tangent (S_upj after the reference's conditioning)
   bool addPlaneFactor(const gtsam::Vector4& plane_imu, const gtsam::Matrix3& S_upj, int pose_id, int landmark);

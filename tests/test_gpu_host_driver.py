@@ -47,3 +47,90 @@ def test_vio_driver_matches_oracle(fglib, tmp_path):
     R = got[:, 1:10].reshape(-1, 3, 3); t = got[:, 10:13]; v = got[:, 13:16]
     assert np.linalg.norm(lie.so3_log(np.swapaxes(R, -1, -2) @ g1.R), axis=-1).max() <= 1e-8
     assert np.abs(t - g1.t).max() <= 1e-8 and np.abs(v - g1.vel).max() <= 1e-7
+
+
+def build_exe(fglib, name):
+    out_dir = os.path.join(ROOT, 'tests', 'hostmath', '_build')
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, name)
+    srcs = [os.path.join(ROOT, 'tests', 'cpp', name + '.cpp'), os.path.join(ROOT, 'graph_slam_b200', 'host', 'gtsam_graph.cpp')]
+    libdir = os.path.join(ROOT, 'graph_slam_b200')
+    subprocess.check_call(['g++', '-std=c++17', '-O2', '-I' + os.path.join(ROOT, 'include')] + srcs +
+                          ['-L' + libdir, '-lfg_b200', '-Wl,-rpath,' + libdir, '-o', exe])
+    return exe
+
+
+def test_ba_driver_compiles(fglib):
+    assert os.path.exists(build_exe(fglib, 'ba_driver'))
+
+
+@pytest.mark.gpu
+def test_ba_builder_and_bundle_adjust_match_oracle(fglib, tmp_path):
+    """CGraphGT::addToGTSAM(CCameraNodeBA*, ...) (gtsam_graph.cpp:370-448) + optimizeGraphBatch, and
+    CGraphGT::bundleAdjust (:500-610), through the C++ mirror, against the oracle on the graphs they define."""
+    from oracle import build, factors as ofac
+    from oracle.graph import Graph
+    exe = build_exe(fglib, 'ba_driver')
+    rng = np.random.default_rng(31)
+    P, n = 6, 60
+    K = np.array([250.5773, 250.5773, 0, 90, 70, -0.8466, 0.5370, 0, 0])
+    I3, z3 = np.eye(3), np.zeros(3)
+    r_true = np.tile(np.array([0.01, -0.015, 0.02, 0.07, -0.01, 0.02]), (P - 1, 1)) * (1 + 0.1 * rng.normal(size=(P - 1, 1)))
+    Rt, tt = [np.eye(3)], [np.zeros(3)]
+    for k in range(P - 1):
+        dR, dt = lie.se3_exp(r_true[k:k + 1])
+        R, t = lie.pose_compose(Rt[-1], tt[-1], dR[0], dt[0]); Rt.append(R); tt.append(t)
+    Rt, tt = np.array(Rt), np.array(tt)
+    pts = np.column_stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.4, 0.4, n), rng.uniform(1.5, 4.0, n)])      # world = camera 0
+    pc = np.einsum('pji,pnj->pni', Rt, pts[None] - tt[:, None])                                                  # camera-frame points
+    pc32 = (pc + rng.normal(size=pc.shape) * 0.01).astype(np.float32)
+    uv = np.stack([ofac.projection(Rt[p], tt[p], pts, np.zeros((n, 2)), K, I3, z3, jac=False) for p in range(P)])
+    uv32 = (uv + rng.normal(size=uv.shape)).astype(np.float32)
+    with open(tmp_path / 'features.txt', 'w') as f:
+        f.write('%d %d %r %r %r %r %r %r\n' % (P, n, *[float(v) for v in K[[0, 1, 3, 4, 5, 6]]]))
+        for p in range(P):
+            for k in range(n):
+                f.write('%r %r %r %r %r\n' % (float(pc32[p, k, 0]), float(pc32[p, k, 1]), float(pc32[p, k, 2]), float(uv32[p, k, 0]), float(uv32[p, k, 1])))
+    r_meas = r_true + rng.normal(size=r_true.shape) * np.array([0.005] * 3 + [0.01] * 3)
+    info = np.diag([400.0, 400, 400, 100, 100, 100])
+    with open(tmp_path / 'vro.log', 'w') as f:
+        for k in range(P - 1):
+            f.write('%d %d %s %s\n' % (k + 1, k, ' '.join(repr(float(x)) for x in r_meas[k]),
+                                      ' '.join(repr(float(info[i, j])) for i in range(6) for j in range(i, 6))))
+    res = subprocess.run([exe, str(tmp_path / 'features.txt'), str(tmp_path / 'vro.log'), str(tmp_path / 'out.txt')],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith('RESULT')][0].split()
+    assert int(line[2]) == P and int(line[6]) == n and int(line[12]) == 1
+    e0, e1 = float(line[8]), float(line[10])
+    out = np.loadtxt(tmp_path / 'out.txt')
+    # ---- oracle of the multi-frame graph: dead-reckoned poses, landmarks from frame 0, priors and projections
+    Rm, tm = lie.se3_exp(r_meas)
+    Ri, ti = [np.eye(3)], [np.zeros(3)]
+    for k in range(P - 1):
+        R, t = lie.pose_compose(Ri[-1], ti[-1], Rm[k], tm[k]); Ri.append(R); ti.append(t)
+    spec = dict(name='ba_driver', seed=0, n_poses=P, K=K, Rs=I3, ts=z3, pose_init_R=np.array(Ri), pose_init_t=np.array(ti),
+                prior_pose_R=I3, prior_pose_t=z3, between_i=np.arange(P - 1), between_j=np.arange(1, P), between_R=Rm, between_t=tm,
+                between_info=np.broadcast_to(info, (P - 1, 6, 6)).copy(),
+                point_init=pc32[0].astype(np.float64), point_prior_sigma=0.014,
+                proj_pose=np.repeat(np.arange(P), n).astype(np.int32), proj_point=np.tile(np.arange(n), P).astype(np.int32),
+                proj_uv=uv32.reshape(-1, 2).astype(np.float64), proj_sigma=1.0)
+    g0 = build.from_spec(spec)
+    assert abs(e0 - g0.error()) <= 1e-9 * g0.error()
+    g1, rep = lm.optimize_gtsam(g0, solver='schur')
+    assert abs(e1 - rep['error']) <= 1e-7 * rep['error']
+    R = out[:P, :9].reshape(-1, 3, 3); t = out[:P, 9:12]
+    assert np.linalg.norm(lie.so3_log(np.swapaxes(R, -1, -2) @ g1.R), axis=-1).max() <= 1e-6 and np.abs(t - g1.t).max() <= 1e-6
+    # ---- oracle of bundleAdjust on the first edge: two poses, no body_P_sensor, SR4000 calibration
+    spec2 = dict(name='two_view', seed=0, n_poses=2, K=K, Rs=I3, ts=z3, pose_init_R=np.stack([I3, I3]), pose_init_t=np.zeros((2, 3)),
+                 prior_pose_R=I3, prior_pose_t=z3, point_init=pc32[0].astype(np.float64), point_prior_sigma=0.014,
+                 proj_pose=np.repeat(np.arange(2), n).astype(np.int32), proj_point=np.tile(np.arange(n), 2).astype(np.int32),
+                 proj_uv=uv32[:2].reshape(-1, 2).astype(np.float64), proj_sigma=1.0)
+    h1, rep2 = lm.optimize_gtsam(build.from_spec(spec2), solver='schur')
+    Tj = out[P]
+    assert np.abs(Tj[9:12] - h1.t[1]).max() <= 1e-6 and np.abs(Tj[:9].reshape(3, 3) - h1.R[1]).max() <= 1e-6
+    H, grad, err = h1.normal_equations()
+    cov = np.linalg.inv(H.toarray())[6:12, 6:12]
+    info_ref = np.linalg.inv(cov)
+    info_got = out[P + 1:P + 7, :6]
+    assert np.abs(info_got - info_ref).max() <= 1e-5 * np.abs(info_ref).max()
