@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256, 3) k_proj_obs(int64_t M, const int* __res
 }
 
 // one warp per pose: U_pp = sum w Jp^T Jp, g_p = sum w Jp^T r over the pose's observations (recomputed)
-__global__ void __launch_bounds__(256) k_proj_pose(int P, const int64_t* __restrict__ pose_obs_ptr, const int64_t* __restrict__ pose_obs,
+__global__ void __launch_bounds__(256, 2) k_proj_pose(int P, const int64_t* __restrict__ pose_obs_ptr, const int64_t* __restrict__ pose_obs,
                                                    const int* __restrict__ obs_point, const double* __restrict__ obs_uv,
                                                    const double* __restrict__ obs_w, Vals vals, const double* __restrict__ calib,
                                                    const double* __restrict__ sensor, const int* __restrict__ off_pose,
