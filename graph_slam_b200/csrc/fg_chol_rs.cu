@@ -78,7 +78,7 @@ __device__ __forceinline__ void rs_potrf_warp(RsSmem& sm, int nc, int lane, int*
   const int r = lane & 15;
   double a[RS_NC];
 #pragma unroll
-  for (int c = 0; c < RS_NC; ++c) a[c] = (r < nc && c < nc) ? sm.Ds[r * RS_DP + c] : (r == c ? 1.0 : 0.0);
+  for (int c = 0; c < RS_NC; ++c) a[c] = (lane < nc && c < nc) ? sm.Ds[r * RS_DP + c] : (r == c ? 1.0 : 0.0);   // lanes >= 16 only ride along
   bool bad = false;
 #pragma unroll
   for (int c = 0; c < RS_NC; ++c) {
