@@ -54,7 +54,7 @@ for vals in rows[2:]:
     mult = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
     rd = float(d['dram__bytes_read.sum']) * mult.get(u['dram__bytes_read.sum'], 1.0)
     wr = float(d['dram__bytes_write.sum']) * mult.get(u['dram__bytes_write.sum'], 1.0)
-    traffic.setdefault(k.replace('void ', '').replace('k_schur_tiles<24>', 'k_schur_tiles'), []).append(rd + wr)
+    traffic.setdefault(('k_schur_tiles' if 'k_schur_tiles' in k else k.replace('void ', '')), []).append(rd + wr)
 with open(os.path.join(P, 'r1_ncu_full_summary.md'), 'w') as f:
     f.write('# ncu --set full summary, round 1 final kernels (C5, 1xB200)\n\n')
     f.write("`ncu --set full --clock-control none --import-source on -k 'regex:k_chol_rs|k_schur_tiles|k_backsolve_w|k_front_syrk|k_proj_obs|k_zmat|k_proj_pose|k_lm_backsub_obs|k_schur_rhs' -s 30 -c 14 python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (profiles/tools/profile_round.sh)\n\n")
