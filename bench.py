@@ -243,13 +243,22 @@ def main():
     if os.path.exists(tp) and args.config == 'C5' and args.scale == 1.0 and world == 1:
         traffic = json.load(open(tp)).get('dram_bytes_per_launch', {})
 
-    def roof(name, nbytes, ms, note):
+    # fp64 arithmetic peak measured on this pool's B200 with profiles/tools/fp64_peak.cu (MEASURED_PEAKS.json has bf16 only)
+    fp64_peak = dict(dfma=36.17, dmma=37.14, source='profiles/r1_fp64_peak.txt')
+    f_cho = float(ctx.debug_sizes()[5])                   # flops of one factorisation (fg_symbolic.cpp)
+
+    def roof(name, nbytes, ms, note, flops=None, pipe='dfma'):
         a = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return dict(kernel=name, bound='hbm', achieved=a, peak=peak, unit='GB/s', frac=a / peak, traffic=traffic.get(name),
-                    algorithmic_bytes=nbytes, ms=ms, note=note)
-    roofs = [roof('k_chol_rs', b_cho, t_cho, 'factorisation phase (k_chol_rs x2 + k_front_syrk): dependency chain of %d levels; the leaf phase streams ~12 GB of descendant panels through L2 per factorisation (profiles/r1_ncu_full_summary.md), fp64 on DMMA' % int(rep.n_levels)),
+        r = dict(kernel=name, bound='hbm', achieved=a, peak=peak, unit='GB/s', frac=a / peak, traffic=traffic.get(name),
+                 algorithmic_bytes=nbytes, ms=ms, note=note)
+        if flops:
+            tf = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            r['fp64'] = dict(achieved=tf, peak=fp64_peak[pipe], unit='TFLOP/s', frac=tf / fp64_peak[pipe], pipe=pipe.upper(),
+                             flops=flops, peak_source=fp64_peak['source'])
+        return r
+    roofs = [roof('k_chol_rs', b_cho, t_cho, 'factorisation phase (k_chol_rs x2 + k_front_syrk): dependency chain of %d levels; the leaf phase streams ~12 GB of descendant panels through L2 per factorisation (profiles/r1_ncu_full_summary.md), fp64 on DMMA' % int(rep.n_levels), flops=f_cho, pipe='dmma'),
              roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA bound: %d pairs x 216 flop = %.1f TFLOP/s achieved (fp64 peak measured on this B200: 36.2 TFLOP/s DFMA, profiles/r1_fp64_peak.txt; not in MEASURED_PEAKS.json)' % (
-                 int(rep.n_schur_pairs), f_sch / (t_sch * 1e-3) / 1e12 if t_sch > 0 else 0.0)),
+                 int(rep.n_schur_pairs), f_sch / (t_sch * 1e-3) / 1e12 if t_sch > 0 else 0.0), flops=f_sch, pipe='dfma'),
              roof('k_proj_obs<1>', b_obs, t_obs, 'streaming pass over the observations')]
     dominant = max(roofs, key=lambda r: r['ms'])
     line = dict(metric=METRIC, value=value, unit='iterations/s', n_gpus=world, steps=args.steps, warmup=args.warmup,

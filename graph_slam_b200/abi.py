@@ -262,6 +262,12 @@ class Context:
         self.call('fg_marginal_cov', int(key), out.ctypes.data_as(_dp), C.byref(n))
         return out[:n.value * n.value].reshape(n.value, n.value).copy()
 
+    def debug_sizes(self):
+        """[n_r, n_supernodes, nnz_L, max_nrows, max_ncols, flops of one factorisation, n_projections, n_landmarks]"""
+        out = (C.c_int64 * 8)()
+        self.call('fg_debug_sizes', out)
+        return [int(v) for v in out]
+
     def comm_init(self, uid): self.call('fg_comm_init', uid)
 
     def add_structure_edges(self, ka, kb):
