@@ -469,7 +469,8 @@ void launch_backsolve(fg_ctx* c) {
   SysView s = chol_view(c);
   const char* cta = getenv("FG_BACKSOLVE_CTA");          // tests keep the CTA-per-supernode kernel covered
   if (c->sym.max_ncols <= 16 && !(cta && cta[0] == '1')) {
-    int gridw = c->num_sms * 2;
+    const char* gm = getenv("FG_BW_GRID");
+    int gridw = c->num_sms * (gm ? atoi(gm) : 1);      // measured: 1.19 / 1.26 / 1.32 ms at 1 / 2 / 4 CTAs per SM (fewer pollers)
     if (gridw * BW_WARPS > c->sym.n_sn) gridw = (c->sym.n_sn + BW_WARPS - 1) / BW_WARPS;
     k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, c->stream>>>(s, d.sched, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch,
                                                          c->sym.n_sn, d.delta);
