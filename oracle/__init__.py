@@ -18,6 +18,10 @@ Pinning status:
     PARITY UNPINNED -- the reference holds no golden vectors for them; they are
     validated by central-difference Jacobian checks and closed-form minimisers.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this package.  The product (graph_slam_b200) never does.
+oracle/cpu_lm.cpp (+ cpu_baseline.py) is a TIMING baseline: an OpenMP C++ port of one LM
+iteration of the BA + IMU graph, checked against this numpy oracle in tests/test_cpu_baseline.py.
+It is not the parity checker (it shares the per-factor math headers with the product).
+
+Only tests/, __graft_entry__ (build of the checker, smoke()) and bench.py's cpu_baseline /
+--impl reference legs may import this package.  The product (graph_slam_b200) never does.
 """
