@@ -569,6 +569,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
           const int l = pzp[k];
           uint2& e = pc_ent[pc_ptr[p] + (l / CH - pc_lo[p])];
           if (e.y == 0u) e.x = (unsigned)k;
+          if (e.y & (1u << (l % CH))) return fail(c, FG_ERR_INVALID, "two projection factors on the same (pose, landmark) pair are not supported by the Schur tables");
           e.y |= 1u << (l % CH);
         }
       // tiles: pairs of 16-pose groups that share a landmark, with the chunk range both sides cover
