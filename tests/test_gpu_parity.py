@@ -265,3 +265,17 @@ def test_dense_visibility_splits_schur_chunks():
                 proj_pose=np.repeat(np.arange(P), n).astype(np.int32), proj_point=np.tile(np.arange(n), P).astype(np.int32),
                 proj_uv=uv, proj_sigma=1.0)
     check(spec, 1e-7, 1e-6, solver='schur')
+
+
+def test_duplicate_projection_factor_is_rejected():
+    """Two GenericProjectionFactor on one (pose, landmark) pair would break the landmark bit masks of k_schur_tiles: the
+    library must say so instead of solving something else."""
+    spec = synth.make_config('C4', seed=6, scale=0.02)
+    for k in ('proj_pose', 'proj_point', 'proj_uv'):
+        spec[k] = np.concatenate([spec[k], spec[k][:1]])
+    ctx = abi.Context(device=0)
+    abi.load_spec(ctx, spec)
+    with pytest.raises(abi.FgError) as e:
+        ctx.optimize()
+    assert e.value.code == -1
+    ctx.close()
