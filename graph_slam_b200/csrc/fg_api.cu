@@ -470,6 +470,73 @@ extern "C" int fg_pim_predict(const fg_pim* pim, const double Xi[12], const doub
   return FG_OK;
 }
 
+// ------------------------------------------------------------------ Schur tile tables (host; fg_schur.cu consumes them)
+// pose_obs IS the pose-major order: position k holds observation pose_obs[k], and the observations of one pose are sorted
+// by landmark.  Landmarks are cut into chunks of CH consecutive ids; per (pose, chunk) the kernel needs the first
+// pose-major position and the bit mask of the landmarks seen; tiles are pairs of 16-pose groups that share a landmark.
+namespace fg {
+int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::vector<int64_t>& lm_ptr, const std::vector<int64_t>& pose_ptr,
+                   const std::vector<int64_t>& pose_obs, const std::vector<int>& s_point, SchurTables& T) {
+  const Symbolic& S = c->sym;
+  std::vector<int>& ppos = T.ppos; std::vector<int>& pzp = T.pzp; std::vector<int>& pc_lo = T.pc_lo; std::vector<int>& pc_n = T.pc_n;
+  std::vector<int64_t>& pc_ptr = T.pc_ptr; std::vector<uint2>& pc_ent = T.pc_ent; std::vector<int4>& tiles = T.tiles;
+  if (M >= (int64_t)1 << 31) return fail(c, FG_ERR_INVALID, "more than 2^31 projection factors on one rank");
+  const char* che = getenv("FG_SCHUR_CH");
+  const int CH = (che && atoi(che) == 24) ? 24 : 32;     // 32 landmarks per chunk, 24 record slots per pose (fg_schur.cu)
+  ppos.assign(M, 0); pzp.assign(M, 0);
+  for (int64_t k = 0; k < M; ++k) { ppos[pose_obs[k]] = (int)k; pzp[k] = s_point[pose_obs[k]]; }
+  pc_lo.assign(P, 0); pc_n.assign(P, 0);
+  pc_ptr.assign(P + 1, 0);
+  for (int64_t p = 0; p < P; ++p) {
+    if (pose_ptr[p + 1] > pose_ptr[p]) {
+      pc_lo[p] = pzp[pose_ptr[p]] / CH;
+      pc_n[p] = pzp[pose_ptr[p + 1] - 1] / CH - pc_lo[p] + 1;
+    }
+    pc_ptr[p + 1] = pc_ptr[p] + pc_n[p];
+  }
+  pc_ent.assign(pc_ptr[P] ? pc_ptr[P] : 1, make_uint2(0u, 0u));
+  for (int64_t p = 0; p < P; ++p)
+    for (int64_t k = pose_ptr[p]; k < pose_ptr[p + 1]; ++k) {
+      const int l = pzp[k];
+      uint2& e = pc_ent[pc_ptr[p] + (l / CH - pc_lo[p])];
+      if (e.y == 0u) e.x = (unsigned)k;
+      if (e.y & (1u << (l % CH))) return fail(c, FG_ERR_INVALID, "two projection factors on the same (pose, landmark) pair are not supported by the Schur tables");
+      e.y |= 1u << (l % CH);
+    }
+  // tiles: pairs of 16-pose groups that share a landmark, with the chunk range both sides cover
+  const int G = (int)((P + 15) / 16);
+  std::vector<int> g_lo(G, INT32_MAX), g_hi(G, 0);
+  for (int64_t p = 0; p < P; ++p)
+    if (pc_n[p]) { g_lo[p / 16] = std::min(g_lo[p / 16], pc_lo[p]); g_hi[p / 16] = std::max(g_hi[p / 16], pc_lo[p] + pc_n[p]); }
+  std::vector<int64_t> tkeys;
+  if (!S.cov_ptr.empty())
+    for (int64_t p = 0; p < P; ++p) {
+      int last = -1;
+      for (int64_t k = S.cov_ptr[p]; k < S.cov_ptr[p + 1]; ++k) {
+        const int q = S.cov_pose[k];
+        if (q > p) continue;
+        const int gq = q / 16;
+        if (gq != last) { tkeys.push_back((int64_t)(p / 16) * G + gq); last = gq; }
+      }
+    }
+  std::sort(tkeys.begin(), tkeys.end());
+  tkeys.erase(std::unique(tkeys.begin(), tkeys.end()), tkeys.end());
+  tiles.clear();
+  for (int64_t key : tkeys) {
+    const int gi = (int)(key / G), gj = (int)(key % G);
+    const int cb = std::max(g_lo[gi], g_lo[gj]), ce = std::min(g_hi[gi], g_hi[gj]);
+    if (cb < ce) tiles.push_back(make_int4(gi, gj, cb, ce));
+  }
+  // heaviest first.  (Measured: issuing the tiles in bands of neighbouring row groups, so that the CTAs in flight share
+  // Z records in L2, is 15 % slower -- the long diagonal tiles must all start early.)
+  std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
+  T.ch = CH;
+  T.npairs = 0;
+  for (int64_t l = 0; l < L; ++l) { const int64_t k = lm_ptr[l + 1] - lm_ptr[l]; T.npairs += k * (k + 1) / 2; }
+  return FG_OK;
+}
+}  // namespace fg
+
 // ------------------------------------------------------------------ finalize: symbolic + upload
 extern "C" int fg_finalize(fg_ctx* c) {
   if (!c) return FG_ERR_INVALID;
@@ -544,68 +611,13 @@ extern "C" int fg_finalize(fg_ctx* c) {
     if ((rc = dev_upload(c, &d.calib, h.calib.data() + 9 * cid, 9)) || (rc = dev_upload(c, &d.sensor, h.sensor.data() + 12 * sid, 12))) return rc;
     if ((rc = dev_upload<double>(c, &d.ul, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Cf, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.Zp, nullptr, (size_t)18 * M))) return rc;
-    // Schur tiles (fg_schur.cu).  pose_obs IS the pose-major order: position k holds observation pose_obs[k], and the
-    // observations of one pose are sorted by landmark.  Landmarks are cut into chunks of CH consecutive ids; per
-    // (pose, chunk) the kernel needs the first pose-major position and the bit mask of the landmarks seen.
     {
-      if (M >= (int64_t)1 << 31) return fail(c, FG_ERR_INVALID, "more than 2^31 projection factors on one rank");
-      const char* che = getenv("FG_SCHUR_CH");
-      const int CH = (che && atoi(che) == 24) ? 24 : 32;     // 32 landmarks per chunk, 24 record slots per pose (fg_schur.cu)
-      d.schur_ch = CH;
-      std::vector<int> ppos(M), pzp(M);
-      for (int64_t k = 0; k < M; ++k) { ppos[pose_obs[k]] = (int)k; pzp[k] = s_point[pose_obs[k]]; }
-      std::vector<int> pc_lo(P, 0), pc_n(P, 0);
-      std::vector<int64_t> pc_ptr(P + 1, 0);
-      for (int64_t p = 0; p < P; ++p) {
-        if (pose_ptr[p + 1] > pose_ptr[p]) {
-          pc_lo[p] = pzp[pose_ptr[p]] / CH;
-          pc_n[p] = pzp[pose_ptr[p + 1] - 1] / CH - pc_lo[p] + 1;
-        }
-        pc_ptr[p + 1] = pc_ptr[p] + pc_n[p];
-      }
-      std::vector<uint2> pc_ent(pc_ptr[P] ? pc_ptr[P] : 1, make_uint2(0u, 0u));
-      for (int64_t p = 0; p < P; ++p)
-        for (int64_t k = pose_ptr[p]; k < pose_ptr[p + 1]; ++k) {
-          const int l = pzp[k];
-          uint2& e = pc_ent[pc_ptr[p] + (l / CH - pc_lo[p])];
-          if (e.y == 0u) e.x = (unsigned)k;
-          if (e.y & (1u << (l % CH))) return fail(c, FG_ERR_INVALID, "two projection factors on the same (pose, landmark) pair are not supported by the Schur tables");
-          e.y |= 1u << (l % CH);
-        }
-      // tiles: pairs of 16-pose groups that share a landmark, with the chunk range both sides cover
-      const int G = (int)((P + 15) / 16);
-      std::vector<int> g_lo(G, INT32_MAX), g_hi(G, 0);
-      for (int64_t p = 0; p < P; ++p)
-        if (pc_n[p]) { g_lo[p / 16] = std::min(g_lo[p / 16], pc_lo[p]); g_hi[p / 16] = std::max(g_hi[p / 16], pc_lo[p] + pc_n[p]); }
-      std::vector<int64_t> tkeys;
-      if (!S.cov_ptr.empty())
-        for (int64_t p = 0; p < P; ++p) {
-          int last = -1;
-          for (int64_t k = S.cov_ptr[p]; k < S.cov_ptr[p + 1]; ++k) {
-            const int q = S.cov_pose[k];
-            if (q > p) continue;
-            const int gq = q / 16;
-            if (gq != last) { tkeys.push_back((int64_t)(p / 16) * G + gq); last = gq; }
-          }
-        }
-      std::sort(tkeys.begin(), tkeys.end());
-      tkeys.erase(std::unique(tkeys.begin(), tkeys.end()), tkeys.end());
-      std::vector<int4> tiles;
-      for (int64_t key : tkeys) {
-        const int gi = (int)(key / G), gj = (int)(key % G);
-        const int cb = std::max(g_lo[gi], g_lo[gj]), ce = std::min(g_hi[gi], g_hi[gj]);
-        if (cb < ce) tiles.push_back(make_int4(gi, gj, cb, ce));
-      }
-      // heaviest first.  (Measured: issuing the tiles in bands of neighbouring row groups, so that the CTAs in flight share
-      // Z records in L2, is 15 % slower -- the long diagonal tiles must all start early.)
-      std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
-      d.n_tiles = (int)tiles.size();
-      int64_t npairs = 0;
-      for (int64_t l = 0; l < L; ++l) { const int64_t k = lm_ptr[l + 1] - lm_ptr[l]; npairs += k * (k + 1) / 2; }
-      d.n_pairs = npairs;
-      if ((rc = dev_upload(c, &d.obs_ppos, ppos)) || (rc = dev_upload(c, &d.pz_point, pzp)) || (rc = dev_upload(c, &d.pc_lo, pc_lo)) ||
-          (rc = dev_upload(c, &d.pc_n, pc_n)) || (rc = dev_upload(c, &d.pc_ptr, pc_ptr)) || (rc = dev_upload(c, &d.pc_ent, pc_ent)) ||
-          (rc = dev_upload(c, &d.tile_desc, tiles))) return rc;
+      SchurTables T;
+      if ((rc = build_schur_tables(c, L, M, P, lm_ptr, pose_ptr, pose_obs, s_point, T)) != FG_OK) return rc;
+      d.schur_ch = T.ch; d.n_tiles = (int)T.tiles.size(); d.n_pairs = T.npairs;
+      if ((rc = dev_upload(c, &d.obs_ppos, T.ppos)) || (rc = dev_upload(c, &d.pz_point, T.pzp)) || (rc = dev_upload(c, &d.pc_lo, T.pc_lo)) ||
+          (rc = dev_upload(c, &d.pc_n, T.pc_n)) || (rc = dev_upload(c, &d.pc_ptr, T.pc_ptr)) || (rc = dev_upload(c, &d.pc_ent, T.pc_ent)) ||
+          (rc = dev_upload(c, &d.tile_desc, T.tiles))) return rc;
       CK(cudaStreamSynchronize(c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
@@ -913,6 +925,30 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 38: v.assign(S.rs_map.begin(), S.rs_map.end()); break;
     case 40: v.assign(S.rs_colinv.begin(), S.rs_colinv.end()); break;
     case 39: v = {S.rs_ok ? 1 : 0, S.rs_units_a, (int64_t)S.rs_units.size()}; break;
+    case 41: case 42: case 43: case 44: case 45: case 46: {
+      // Schur tile tables of the projection factors held by this context (host only): 41 header [CH, n_tiles, n_pairs],
+      // 42 tiles (4 ints each), 43 pc_lo, 44 pc_n, 45 pc_ptr, 46 pc_ent (start, mask pairs)
+      const HostGraph& h = c->h;
+      const int64_t L = h.count(T_POINT), M = (int64_t)h.pj_pose.size(), P = h.count(T_POSE);
+      std::vector<int64_t> lm_ptr(L + 1, 0), pose_ptr(P + 1, 0);
+      for (int64_t o = 0; o < M; ++o) { lm_ptr[h.pj_point[o] + 1]++; pose_ptr[h.pj_pose[o] + 1]++; }
+      for (int64_t l = 0; l < L; ++l) lm_ptr[l + 1] += lm_ptr[l];
+      for (int64_t p = 0; p < P; ++p) pose_ptr[p + 1] += pose_ptr[p];
+      std::vector<int> s_pose(M), s_point(M);
+      { std::vector<int64_t> cur(lm_ptr.begin(), lm_ptr.end() - 1); for (int64_t o = 0; o < M; ++o) { int64_t k = cur[h.pj_point[o]]++; s_pose[k] = h.pj_pose[o]; s_point[k] = h.pj_point[o]; } }
+      std::vector<int64_t> pose_obs(M);
+      { std::vector<int64_t> cur(pose_ptr.begin(), pose_ptr.end() - 1); for (int64_t k = 0; k < M; ++k) pose_obs[cur[s_pose[k]]++] = k; }
+      SchurTables T;
+      int rc = build_schur_tables(c, L, M, P, lm_ptr, pose_ptr, pose_obs, s_point, T);
+      if (rc != FG_OK) return rc;
+      if (which == 41) v = {T.ch, (int64_t)T.tiles.size(), T.npairs};
+      else if (which == 42) { for (const int4& t : T.tiles) { v.push_back(t.x); v.push_back(t.y); v.push_back(t.z); v.push_back(t.w); } }
+      else if (which == 43) put(T.pc_lo);
+      else if (which == 44) put(T.pc_n);
+      else if (which == 45) v.assign(T.pc_ptr.begin(), T.pc_ptr.end());
+      else { for (const uint2& e : T.pc_ent) { v.push_back(e.x); v.push_back(e.y); } }
+      break;
+    }
     default: return FG_ERR_INVALID;
   }
   if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];

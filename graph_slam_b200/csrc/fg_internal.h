@@ -257,6 +257,13 @@ struct fg_ctx {
 };
 
 namespace fg {
+// host side of the Schur tile kernel (fg_api.cu: build_schur_tables)
+struct SchurTables {
+  int ch = 32; int64_t npairs = 0;
+  std::vector<int> ppos, pzp, pc_lo, pc_n; std::vector<int64_t> pc_ptr; std::vector<uint2> pc_ent; std::vector<int4> tiles;
+};
+int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::vector<int64_t>& lm_ptr, const std::vector<int64_t>& pose_ptr,
+                       const std::vector<int64_t>& pose_obs, const std::vector<int>& s_point, SchurTables& T);
 // host.cpp
 int build_symbolic(fg_ctx* c);
 // kernels (launch wrappers), all asynchronous on c->stream

@@ -1,0 +1,80 @@
+"""Host side of the landmark Schur complement (fg_api.cu: build_schur_tables, consumed by k_schur_tiles in fg_schur.cu),
+exercised without a GPU through a detached context: a numpy emulation of what the kernel does with the tables -- per tile
+and chunk, AND the landmark masks of a row pose and a column pose and count the hits -- must visit every pair of
+observations of a common landmark exactly once, and the (start, mask) entries must address the right pose-major records."""
+import numpy as np
+import pytest
+from graph_slam_b200 import abi, synth
+
+
+def tables(spec, landmark_slice=None):
+    ctx = abi.Context(device=-1)
+    P = spec['n_poses']
+    pims = (abi.Pim * (P - 1))()
+    for i in range(P - 1):
+        pims[i].dt = 0.1; pims[i].cov[:] = np.eye(15).ravel().tolist()
+    abi.load_spec(ctx, spec, preintegrated=pims, landmark_slice=landmark_slice)
+    ctx.symbolic(0)
+    hdr = ctx.symbolic(41)
+    t = dict(ch=int(hdr[0]), n_pairs=int(hdr[2]), tiles=ctx.symbolic(42).reshape(-1, 4), pc_lo=ctx.symbolic(43), pc_n=ctx.symbolic(44),
+             pc_ptr=ctx.symbolic(45), pc_ent=ctx.symbolic(46).reshape(-1, 2))
+    assert len(t['tiles']) == hdr[1]
+    ctx.close()
+    return t
+
+
+@pytest.mark.parametrize('scale,sl', [(0.03, None), (0.05, None), (0.05, (0.3, 0.8))])
+def test_tiles_visit_every_observation_pair_once(fglib, scale, sl):
+    spec = synth.make_config('C4', seed=5, scale=scale)
+    L = len(spec['point_init']); P = spec['n_poses']
+    lo, hi = (0, L) if sl is None else (int(sl[0] * L), int(sl[1] * L))
+    t = tables(spec, None if sl is None else (lo, hi))
+    CH = t['ch']
+    m = (spec['proj_point'] >= lo) & (spec['proj_point'] < hi)
+    pose = spec['proj_pose'][m].astype(np.int64); pt = spec['proj_point'][m].astype(np.int64) - lo      # local landmark ids
+    # expected: common landmarks of every pose pair, and the pose-major order (by pose, then by landmark)
+    vis = np.zeros((P, hi - lo), dtype=bool); vis[pose, pt] = True
+    common = vis.astype(np.int64) @ vis.T.astype(np.int64)
+    assert t['n_pairs'] == int(sum(k * (k + 1) // 2 for k in vis.sum(0)))
+    order = np.lexsort((pt, pose))
+    pm_pose, pm_pt = pose[order], pt[order]
+    # entries: for every pose and chunk, mask == landmarks seen in the chunk, start == first pose-major position
+    for p in range(P):
+        seen = np.nonzero(vis[p])[0]
+        if len(seen) == 0:
+            assert t['pc_n'][p] == 0
+            continue
+        assert t['pc_lo'][p] == seen[0] // CH and t['pc_n'][p] == seen[-1] // CH - seen[0] // CH + 1
+        for r in range(t['pc_n'][p]):
+            c = t['pc_lo'][p] + r
+            start, mask = (int(v) for v in t['pc_ent'][t['pc_ptr'][p] + r])
+            bits = [b for b in range(CH) if mask >> b & 1]
+            assert bits == [int(l - c * CH) for l in seen if l // CH == c]
+            for n, b in enumerate(bits):
+                assert pm_pose[start + n] == p and pm_pt[start + n] == c * CH + b
+    # tiles: accumulate hits the way the kernel does
+    got = np.zeros((P, P), dtype=np.int64)
+    seen_tiles = set()
+    for gi, gj, cb, ce in t['tiles'].tolist():
+        assert gj <= gi and (gi, gj) not in seen_tiles
+        seen_tiles.add((gi, gj))
+        for c in range(cb, ce):
+            def mask_of(p):
+                if p >= P:
+                    return 0
+                r = c - t['pc_lo'][p]
+                return int(t['pc_ent'][t['pc_ptr'][p] + r][1]) if 0 <= r < t['pc_n'][p] else 0
+            rows = [mask_of(gi * 16 + i) for i in range(16)]
+            cols = [mask_of(gj * 16 + j) for j in range(16)]
+            for i in range(16):
+                for j in range(16):
+                    if gi == gj and j >= i:
+                        continue                      # a diagonal tile holds each unordered pair once; p == q is k_schur_rhs's
+                    h = bin(rows[i] & cols[j]).count('1')
+                    if h:
+                        got[gi * 16 + i, gj * 16 + j] += h
+    expect = np.tril(common, -1)
+    assert np.array_equal(got, expect)
+    # heaviest tiles first
+    w = t['tiles'][:, 3] - t['tiles'][:, 2]
+    assert np.all(np.diff(w) <= 0)
