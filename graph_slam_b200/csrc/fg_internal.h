@@ -252,7 +252,7 @@ struct fg_ctx {
   int epoch = 0;
   int num_sms = 148;
   void* nccl_comm = nullptr;
-  cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // around k_proj_obs<JAC> and k_schur_blocks (roofline timing)
+  cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // around k_proj_obs<JAC> and k_schur_tiles (roofline timing)
   std::vector<void*> allocs;
 };
 

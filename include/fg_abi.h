@@ -166,7 +166,7 @@ typedef struct {
   double ms_linearize, ms_schur, ms_factor, ms_solve, ms_retract_error, ms_total;
   /* workload description used for the roofline */
   int64_t n_reduced_dims, n_supernodes, nnz_L, n_projections, n_landmarks;
-  /* single-kernel device times (ms, summed): the observation pass of the linearisation and the Schur pair kernel */
+  /* single-kernel device times (ms, summed): the observation pass of the linearisation and the Schur tile kernel */
   double ms_proj_obs, ms_schur_blocks;
   int64_t n_schur_pairs, n_levels;
 } fg_lm_report;

@@ -3,7 +3,7 @@ properties, because the numpy oracle cannot finish this size in seconds:
   * LM accepted steps decrease graph.error monotonically and the report agrees with fg_error;
   * idempotence: optimising the converged state again changes nothing beyond the LM tolerances;
   * relabelling invariance: inserting the landmarks in a shuffled order (different internal numbering, different
-    Schur pair lists) gives the same optimum;
+    Schur tile tables) gives the same optimum;
   * the optimum is closer to the generator's ground truth than the initial guess."""
 import numpy as np
 import pytest
