@@ -311,7 +311,7 @@ def main():
                 phases_ms=phases, lm=dict(iterations=rep.iterations, trials=rep.trials, initial_error=rep.initial_error,
                                           final_error=rep.final_error, e2e_last_error=r1.final_error),
                 sizes=dict(reduced_dims=int(rep.n_reduced_dims), supernodes=int(rep.n_supernodes), nnz_L=int(rep.nnz_L)))
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:                      # the CPU baseline is reported at N = 1 only
         try:
             line['cpu_baseline'] = cpu_baseline_sample(args.config, steps=2, spec=spec, scale=args.scale)
         except Exception as e:                                   # the baseline must never take the bench down
