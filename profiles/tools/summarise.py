@@ -35,7 +35,7 @@ with open(os.path.join(P, 'r1_launch_summary.md'), 'w') as f:
 out = subprocess.run(['ncu', '-i', os.path.join(G, 'r1_full.ncu-rep'), '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
-keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_sectors.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
@@ -58,7 +58,7 @@ for vals in rows[2:]:
 with open(os.path.join(P, 'r1_ncu_full_summary.md'), 'w') as f:
     f.write('# ncu --set full summary, round 1 final kernels (C5, 1xB200)\n\n')
     f.write("`ncu --set full --clock-control none --import-source on -k 'regex:k_chol_rs|k_schur_tiles|k_backsolve_w|k_front_syrk|k_proj_obs|k_zmat|k_proj_pose|k_lm_backsub_obs|k_schur_rhs' -s 30 -c 14 python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (profiles/tools/profile_round.sh)\n\n")
-    f.write('One launch per kernel (values per launch; cold-cache, serialised).  Reading: the two `k_chol_rs` launches (leaf phase, grid 296 first; separator phase second) keep fp64 and DRAM mostly idle -- the leaf phase streams its descendant panels through L2 (`lts__t_bytes`) along a 155-level dependency chain; `k_schur_tiles` runs the fp64 pipe at ~40 % with a third of the lanes active per instruction; the streaming kernels move about their algorithmic bytes.\n\n')
+    f.write('One launch per kernel (values per launch; cold-cache, serialised).  Reading: the two `k_chol_rs` launches (leaf phase, grid 296 first; separator phase second) keep fp64 and DRAM mostly idle -- the leaf phase streams its descendant panels through L2 (`lts__t_sectors` x 32 B = 11.9 GB in 3.2 ms) along a 155-level dependency chain; `k_schur_tiles` runs the fp64 pipe at ~40 % with a third of the lanes active per instruction; the streaming kernels move about their algorithmic bytes.\n\n')
     for tag, (d, u, st) in seen.items():
         f.write('## %s\n' % tag)
         for k in keys:
