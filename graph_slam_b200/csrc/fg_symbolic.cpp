@@ -428,7 +428,7 @@ int build_symbolic(fg_ctx* c) {
     emit(order_c);
     S.rs_sn_units.assign(S.n_sn, make_int2(0, 0));
     for (int k = (int)S.rs_units.size() - 1; k >= 0; --k) { int2& e = S.rs_sn_units[S.rs_units[k].x]; e.x = k; e.y += 1; }
-    S.rs_ok = S.max_ncols <= 16;
+    S.rs_ok = S.max_ncols <= 16 && S.max_nrows <= 32767;      // row maps are int16
     for (const int4& un : S.rs_units) if (un.z - un.y > kRsRows || un.z <= un.y) S.rs_ok = false;
   }
   // ---- schedule: supernodes by dependency level (longest path), a topological order that interleaves
