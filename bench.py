@@ -292,7 +292,8 @@ def main():
              roof('k_proj_obs<1>', b_obs, t_obs, 'streaming pass over the observations')]
     dominant = max(roofs, key=lambda r: r['ms'])
     line = dict(metric=METRIC, value=value, unit='iterations/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None,
+                ms_per_step=1000.0 * dt / args.steps, ms_per_step_cuda_events=float(rep.ms_total) / max(rep.iterations, 1),
+                higher_is_better=True, scaling='strong', vs_baseline=None,
                 dtype='f64', data='synthetic',
                 config=dict(workload=workload_name(args.config, args.scale), projections=len(spec.get('proj_pose', [])),
                     l2='inputs_exceed_L2' if ab['total'] > 126e6 else 'smaller_than_L2', parallelism='landmark-shard x%d' % world,
