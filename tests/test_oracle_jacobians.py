@@ -135,3 +135,37 @@ def test_single_landmark_triangulation_minimiser():
                proj=dict(i=np.array([0, 1]), l=np.array([0, 0]), uv=uv, sigma=1.0))
     g1, rep = lm.optimize_gtsam(g)
     assert np.abs(g1.point[0] - truth).max() < 1e-5 and rep['error'] < 1e-6
+
+
+def test_preintegration_closed_forms():
+    """Constant specific force without rotation, and constant rotation rate without force (SURVEY 8c ii): the preintegrated
+    deltas, their bias Jacobians (checked by re-integrating with a shifted bias) and predict() have closed forms."""
+    par = oimu.vn100_params()
+    S, dt = 20, 0.005
+    T = S * dt
+    a = np.array([0.3, -0.2, 9.6])
+    smp = np.zeros((1, S, 6)); smp[0, :, 3:6] = a
+    pim = oimu.preintegrate(smp, dt, par, np.zeros((1, 6)))
+    assert np.allclose(pim['preint'][0, 0:3], 0, atol=1e-15)
+    assert np.allclose(pim['preint'][0, 3:6], 0.5 * a * T * T, atol=1e-13) and np.allclose(pim['preint'][0, 6:9], a * T, atol=1e-13)
+    assert np.allclose(pim['Hba'][0, 3:6], -0.5 * T * T * np.eye(3), atol=1e-13) and np.allclose(pim['Hba'][0, 6:9], -T * np.eye(3), atol=1e-13)
+    # predict from rest with gravity n_gravity = (0, 0, +g): p = 1/2 (a + g) T^2, v = (a + g) T
+    Rj, tj, vj = oimu.predict({k: (v[0] if k != 'gravity' else v) for k, v in pim.items()}, np.eye(3), np.zeros(3), np.zeros(3), np.zeros(6))
+    assert np.allclose(tj, 0.5 * (a + par['gravity']) * T * T, atol=1e-13) and np.allclose(vj, (a + par['gravity']) * T, atol=1e-13)
+    # constant yaw rate, no force
+    w = np.array([0.0, 0.0, 0.7])
+    smp = np.zeros((1, S, 6)); smp[0, :, 0:3] = w
+    pim = oimu.preintegrate(smp, dt, par, np.zeros((1, 6)))
+    assert np.allclose(pim['preint'][0, 0:3], w * T, atol=1e-12) and np.allclose(pim['preint'][0, 3:9], 0, atol=1e-15)
+    # first-order bias correction: preint(b) ~= preint(0) + Hba b_a + Hbg b_g  (error second order in the bias)
+    rng = np.random.default_rng(6)
+    smp = rng.normal(size=(1, S, 6)) * np.array([0.3, 0.3, 0.3, 2, 2, 2]) + np.array([0, 0, 0, 0, 0, 9.7])
+    p0 = oimu.preintegrate(smp, dt, par, np.zeros((1, 6)))
+    for scale in (1e-3, 1e-4):
+        b = rng.normal(size=6) * scale
+        p1 = oimu.preintegrate(smp, dt, par, b[None])
+        lin = p0['preint'][0] + p0['Hba'][0] @ b[:3] + p0['Hbg'][0] @ b[3:]
+        assert np.abs(p1['preint'][0] - lin).max() <= 5.0 * scale ** 2
+    # the covariance is symmetric positive definite
+    C = p0['cov'][0]
+    assert np.allclose(C, C.T, atol=1e-18) and np.linalg.eigvalsh(C).min() > 0
