@@ -95,7 +95,7 @@ def workload_name(config, scale):
     return '%s%s: %d poses (X,V,B), %d landmarks, ~%d projections, %d IMU factors' % (config, '' if scale == 1.0 else '@%g' % scale, P, L, 20 * L, P - 1)
 
 
-def cpu_baseline_sample(config, steps=1, spec=None, scale=1.0, warmup=0):
+def cpu_baseline_sample(config, steps=1, spec=None, scale=1.0, warmup=0, one_thread=False):
     """The reference's CPU path restated (the reference itself cannot be built here), timed on the host cores.
     BA + IMU graphs (C4, C5): oracle/cpu_lm.cpp, an OpenMP C++ port of one LM iteration, on the FULL workload with every
     host thread.  Other graphs: the numpy oracle (one core) on a bounded sample."""
@@ -124,7 +124,12 @@ def cpu_baseline_sample(config, steps=1, spec=None, scale=1.0, warmup=0):
         sample = ('full %s%s (%d poses, %d landmarks, %d projections): %d LM iteration(s) in %.1f s with %d OpenMP threads '
                   '(oracle/cpu_lm.cpp: linearise, Schur, block-banded Cholesky, back-substitution, retract, error)' %
                   (config, '' if scale == 1.0 else '@%g' % scale, spec['n_poses'], len(spec['point_init']), len(spec['proj_pose']), n, dt, threads))
-        return dict(value=n / dt, unit='iterations/s', cores=threads, kind='port', sample=sample)
+        out = dict(value=n / dt, unit='iterations/s', cores=threads, kind='port', sample=sample)
+        if one_thread:                                              # also the single-thread figure (one iteration)
+            t0 = time.perf_counter()
+            st.iterate(lam, 1)
+            out['one_thread'] = dict(value=1.0 / (time.perf_counter() - t0), unit='iterations/s', cores=1)
+        return out
     from oracle import build, lm
     sc = 0.05
     spec = synth.make_config(config, seed=1, scale=sc)
@@ -314,7 +319,7 @@ def main():
                 sizes=dict(reduced_dims=int(rep.n_reduced_dims), supernodes=int(rep.n_supernodes), nnz_L=int(rep.nnz_L)))
     if not args.no_cpu_baseline and world == 1:                      # the CPU baseline is reported at N = 1 only
         try:
-            line['cpu_baseline'] = cpu_baseline_sample(args.config, steps=2, spec=spec, scale=args.scale)
+            line['cpu_baseline'] = cpu_baseline_sample(args.config, steps=2, spec=spec, scale=args.scale, one_thread=True)
         except Exception as e:                                   # the baseline must never take the bench down
             line['cpu_baseline'] = dict(value=None, unit='iterations/s', cores=1, kind='port', sample='failed: %r' % (e,))
     print(json.dumps(line))
