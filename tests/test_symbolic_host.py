@@ -323,4 +323,10 @@ def test_detached_context_has_no_cpu_solver(fglib):
     assert e.value.code == -4
     with pytest.raises(abi.FgError):
         ctx.optimize()
+    with pytest.raises(abi.FgError) as e:
+        ctx.marginal_covariance(abi.symbol('x', 0))
+    assert e.value.code == -4
+    with pytest.raises(abi.FgError) as e:
+        ctx.marginal_covariance(abi.symbol('x', 7))            # unknown key: ValuesKeyDoesNotExist
+    assert e.value.code == -3
     ctx.close()
