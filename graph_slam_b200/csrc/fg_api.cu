@@ -630,12 +630,12 @@ extern "C" int fg_finalize(fg_ctx* c) {
   if ((rc = dev_upload(c, &d.col2sn, S.col2sn)) || (rc = dev_upload(c, &d.sn_col0, S.sn_col0)) || (rc = dev_upload(c, &d.sn_ncols, S.sn_ncols)) ||
       (rc = dev_upload(c, &d.sn_nrows, S.sn_nrows)) || (rc = dev_upload(c, &d.sn_rowptr, S.sn_rowptr)) || (rc = dev_upload(c, &d.sn_valptr, S.sn_valptr)) ||
       (rc = dev_upload(c, &d.rowidx, S.rowidx)) || (rc = dev_upload(c, &d.upd_ptr, S.upd_ptr)) || (rc = dev_upload(c, &d.upd_d, S.upd_d)) ||
-      (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b)) || (rc = dev_upload(c, &d.upd_rec, S.upd_rec)) ||
+      (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b)) ||
       (rc = dev_upload(c, &d.anc_ptr, S.anc_ptr)) || (rc = dev_upload(c, &d.anc_t, S.anc_t)) || (rc = dev_upload(c, &d.anc_a, S.anc_a)) ||
       (rc = dev_upload(c, &d.anc_b, S.anc_b)) || (rc = dev_upload(c, &d.sched, S.sched)) ||
       (rc = dev_upload<int>(c, &d.flags2, nullptr, S.n_sn)) || (rc = dev_upload<int>(c, &d.counters, nullptr, 4))) return rc;
   if (S.use_fronts) {
-    if ((rc = dev_upload(c, &d.updr_ptr, S.updr_ptr)) || (rc = dev_upload(c, &d.updr_d, S.updr_d)) || (rc = dev_upload(c, &d.updr_rec, S.updr_rec)) ||
+    if ((rc = dev_upload(c, &d.updr_ptr, S.updr_ptr)) || (rc = dev_upload(c, &d.updr_d, S.updr_d)) ||
         (rc = dev_upload(c, &d.sched_a, S.sched_a)) || (rc = dev_upload(c, &d.sched_c, S.sched_c)) ||
         (rc = dev_upload(c, &d.fr_rowptr, S.fr_rowptr)) || (rc = dev_upload(c, &d.fr_rows, S.fr_rows)) || (rc = dev_upload(c, &d.fr_uptr, S.fr_uptr)) ||
         (rc = dev_upload(c, &d.pm_ptr, S.pm_ptr)) || (rc = dev_upload(c, &d.posmap, S.posmap)) || (rc = dev_upload(c, &d.pmne_ptr, S.pmne_ptr)) ||
@@ -645,11 +645,13 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload(c, &d.tile_leaf, S.tile_leaf)) || (rc = dev_upload(c, &d.tile_i, S.tile_i)) || (rc = dev_upload(c, &d.tile_j, S.tile_j)) ||
         (rc = dev_upload<double>(c, &d.U, nullptr, (size_t)S.fr_uptr[S.n_leaves]))) return rc;
   }
-  if (S.rs_ok) {
-    if ((rc = dev_upload(c, &d.rs_units, S.rs_units)) || (rc = dev_upload(c, &d.rs_moff, S.rs_moff)) || (rc = dev_upload(c, &d.rs_map, S.rs_map)) ||
+  if (!S.rs_ok)
+    return fail(c, FG_ERR_INVALID, "reduced system outside the limits of the factorisation kernel (a supernode with more than 32767 rows)");
+  {
+    if ((rc = dev_upload(c, &d.rsu_ptr, S.rsu_ptr)) || (rc = dev_upload(c, &d.rsu_d, S.rsu_d)) || (rc = dev_upload(c, &d.rsu_rec, S.rsu_rec)) ||
+        (rc = dev_upload(c, &d.rs_units, S.rs_units)) || (rc = dev_upload(c, &d.rs_moff, S.rs_moff)) || (rc = dev_upload(c, &d.rs_map, S.rs_map)) ||
         (rc = dev_upload(c, &d.rs_colinv, S.rs_colinv)) ||
-        (rc = dev_upload<int>(c, &d.rs_done, nullptr, S.rs_units.size())) || (rc = dev_upload(c, &d.rs_sn_units, S.rs_sn_units)) ||
-        (rc = dev_upload<double>(c, &d.rs_dfac, nullptr, 256 * (size_t)S.n_sn))) return rc;
+        (rc = dev_upload<int>(c, &d.rs_done, nullptr, S.rs_units.size())) || (rc = dev_upload(c, &d.rs_sn_units, S.rs_sn_units))) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));
   c->epoch = 0;
@@ -734,7 +736,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
       launch_build_and_schur(c, lam);
       if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) break;
       CK(cudaEventRecord(ev[2], c->stream));
-      if (chol_rs_supported(c)) launch_factor_rs(c); else if (chol_reg_supported(c)) launch_factor_reg(c); else launch_factor(c);
+      launch_factor_rs(c);
       CK(cudaEventRecord(ev[3], c->stream));
       launch_backsolve(c);
       CK(cudaEventRecord(ev[4], c->stream));
@@ -834,7 +836,7 @@ extern "C" int fg_marginal_cov(fg_ctx* c, fg_key key, double* cov, int* dim) {
   launch_linearize(c);
   launch_build_and_schur(c, 0.0);
   if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) return rc;
-  if (chol_rs_supported(c)) launch_factor_rs(c); else if (chol_reg_supported(c)) launch_factor_reg(c); else launch_factor(c);
+  launch_factor_rs(c);
   double* work = nullptr;
   CK(cudaMalloc((void**)&work, sizeof(double) * (6 * ((size_t)c->sym.n_r + 1) + 36)));
   double* out36 = work + 6 * ((size_t)c->sym.n_r + 1);
@@ -924,7 +926,9 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 37: v.assign(S.rs_moff.begin(), S.rs_moff.end()); break;
     case 38: v.assign(S.rs_map.begin(), S.rs_map.end()); break;
     case 40: v.assign(S.rs_colinv.begin(), S.rs_colinv.end()); break;
-    case 39: v = {S.rs_ok ? 1 : 0, S.rs_units_a, (int64_t)S.rs_units.size()}; break;
+    case 39: v = {S.rs_ok ? 1 : 0, S.rs_units_a, (int64_t)S.rs_units.size(), S.n_levels_rs}; break;
+    case 47: put(S.rsu_ptr); break;
+    case 48: v.clear(); for (size_t q = 0; q < S.rsu_d.size(); ++q) { const UpdRec& r = S.rsu_rec[q]; v.push_back(S.rsu_d[q]); v.push_back(S.rsu_src[q]); v.push_back(r.pad[1]); v.push_back(r.K); v.push_back(r.pad[0]); } break;
     case 41: case 42: case 43: case 44: case 45: case 46: {
       // Schur tile tables of the projection factors held by this context (host only): 41 header [CH, n_tiles, n_pairs],
       // 42 tiles (4 ints each), 43 pc_lo, 44 pc_n, 45 pc_ptr, 46 pc_ent (start, mask pairs)

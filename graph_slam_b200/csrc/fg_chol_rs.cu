@@ -1,24 +1,22 @@
 // fg_chol_rs.cu -- K7, row-split supernodal Cholesky (fp64): the default factorisation kernel.
 //
-// Same algorithm, panel layout and schedule idea as k_chol_reg (fg_chol_reg.cu), but the unit of work is a ROW BLOCK
-// of a supernode instead of a whole supernode.  A nested-dissection ordering of a 50-frame covisibility band only has
-// 32 independent leaf chains at C5 (fg_symbolic.cpp); with one CTA per supernode 32 of the 148 SMs carried three
-// quarters of the flops.  Here a supernode of nr rows x nc columns (nc <= 16) is cut into blocks of <= RS_RB
-// below-diagonal rows.  A unit (supernode, block)
-//   * is output stationary: the unit's (<= 256 rows) x (<= 16 columns) values live in registers from the first load
+// Persistent left-looking supernodal Cholesky whose unit of work is a ROW BLOCK of a supernode.  A nested-dissection
+// ordering of a 50-frame covisibility band only has 32 independent leaf chains at C5 (fg_symbolic.cpp); with one CTA
+// per supernode 32 of the 148 SMs carried three quarters of the flops.  Here a supernode of nr rows x nc columns
+// (nc <= 32: two [X V B] frames or five poses) is cut into blocks of <= RS_RB below-diagonal rows.  A unit (supernode, block)
+//   * is output stationary: the unit's (<= 256 rows) x (<= 32 columns) values live in registers from the first load
 //     to the final store -- no shared-memory panel, no write conflicts,
 //   * pulls every descendant update restricted to those rows: a host-built map (int16 per unit, update and row) names
 //     the descendant row that lands on each local row; the rank-K update  P -= X B^T  (X: gathered descendant rows,
 //     B: the descendant's rows in the target's columns, scattered to target columns) is a dense contraction and runs
-//     on the fp64 tensor cores (DMMA m8n8k4: 16 or 32 instructions per warp and update instead of 128-256 DFMA and as
-//     many shared-memory operand loads); X and B arrive by cp.async through a 3-stage shared-memory ring, two updates
-//     ahead of the multiplication; the part that lands on the diagonal block is recomputed by every block of the
-//     supernode (15 x 15 x K flops),
-//   * factors the diagonal block (every block redundantly: no intra-supernode synchronisation), solves its own rows
-//     against it and stores them,
-//   * publishes its own done flag (release); a consumer polls the flags of all blocks of a descendant (acquire).  The
-//     first block parks the diagonal factor in a side buffer (the sibling blocks read the ASSEMBLED diagonal block when
-//     they start, so it must not be overwritten while the factorisation runs); a small kernel moves it into L at the end.
+//     on the fp64 tensor cores (DMMA m8n8k4); a descendant wider than 16 columns arrives as two column slices (the host
+//     lists them as two updates, fg_symbolic.cpp); X and B arrive by cp.async through a 3-stage shared-memory ring, two
+//     updates ahead of the multiplication; the part that lands on the diagonal block is recomputed by every block of the
+//     supernode (nc x nc x K flops); 8-column groups of the target that the descendant does not reach are skipped,
+//   * the first unit of a supernode owns the diagonal block: it factors it (one warp, matrix in registers) and stores it;
+//     the units of below-diagonal rows finish their updates, wait for that unit's flag, solve their rows against the
+//     factor and store them,
+//   * publishes its own done flag (release); a consumer polls the flags of all units of a descendant (acquire).
 // Deterministic: every panel entry is owned by one unit and updated in list order.  tcgen05 has no fp64 kind; DMMA
 // measured at the DFMA peak on this part (profiles/tools/fp64_peak.cu): its gain is instruction and operand traffic.
 #include <algorithm>
@@ -29,11 +27,12 @@
 
 namespace fg {
 
-#define RS_T 256
-#define RS_NC 16
-#define RS_DP 17
-#define RS_RB 240                      // below-diagonal rows per block; 16 + RS_RB <= RS_T: one descendant row per thread
-#define RS_LR (RS_NC + RS_RB)          // local rows held by a unit: diagonal rows, then own rows
+#define RS_T 128                       // threads per unit: one panel row each
+#define RS_NC 32                       // columns of a target supernode (fg_symbolic.cpp: kMaxSnCols)
+#define RS_KC 16                       // columns of one update step (fg_symbolic.cpp: kUpdK)
+#define RS_NT (RS_NC / 8)              // 8-column MMA tiles of the target
+#define RS_DP 34                       // row stride of the diagonal block in shared memory (even: 16-byte row starts)
+#define RS_SP 33                       // row stride of the layout-conversion slabs
 
 __device__ __forceinline__ int rs_ld_relaxed(const int* p) {
   int v;
@@ -42,19 +41,19 @@ __device__ __forceinline__ int rs_ld_relaxed(const int* p) {
 }
 
 #define RS_ST 3                         // cp.async stages of the update pipeline
-#define RS_XLD 260                      // leading dimension of a stage's [k][row] tile (doubles): 4 (mod 16), conflict-free MMA fragment loads
-#define RS_BS 20                        // same for the [k][c] tile of the descendant's rows in the target's columns
+#define RS_XLD (RS_T + 4)               // leading dimension of a stage's [k][row] tile (doubles): 4 (mod 16), conflict-free MMA fragment loads
+#define RS_BS 36                        // same for the [k][c] tile of the descendant's rows in the target's columns
 struct RsSmem {
-  double Xs[RS_ST][RS_NC * RS_XLD];     // [stage][k][row]: the descendant row that lands on each local row (gathered by the host row map)
-  double Bs[RS_ST][RS_NC * RS_BS];      // [stage][k][c]: descendant rows that fall in the target's columns, scattered to TARGET columns
+  double Xs[RS_ST][RS_KC * RS_XLD];     // [stage][k][row]: the descendant row that lands on each local row (gathered by the host row map)
+  double Bs[RS_ST][RS_KC * RS_BS];      // [stage][k][c]: descendant rows that fall in the target's columns, scattered to TARGET columns
   double Ds[RS_NC * RS_DP];
   double dinv[RS_NC];
   int colidx[RS_NC];
   int slot, first_not_ready;
 };
 // aliases inside Xs, used outside the update pipeline: the row list of a leaf front (prologue) and the per-warp slabs
-// (32 rows x 17) that convert between the thread-per-row layout and the MMA fragment layout
-static_assert(sizeof(double) * RS_ST * RS_NC * RS_XLD >= sizeof(int) * 1024 + sizeof(double) * RS_T * RS_DP, "aliases must fit");
+// (32 rows x 33) that convert between the thread-per-row layout and the MMA fragment layout
+static_assert(sizeof(double) * RS_ST * RS_KC * RS_XLD >= sizeof(int) * 1024 + sizeof(double) * RS_T * RS_SP, "aliases must fit");
 
 // D (8x8) += A (8x4, row major) * B (4x8, column major), fp64 tensor-core path (see fg_front.cu: dmma884)
 __device__ __forceinline__ void rs_dmma(double (&d)[2], double a, double b) {
@@ -62,32 +61,29 @@ __device__ __forceinline__ void rs_dmma(double (&d)[2], double a, double b) {
 }
 // 8-byte asynchronous global -> shared copy.  The 8-byte form exists only as .ca (allocates in L1), and L1 is not coherent:
 // it is safe here because (i) panels start on 128-byte lines (fg_symbolic.cpp pads sn_valptr), so a line never mixes two
-// supernodes, (ii) a supernode's lines are only ever read through L1 after its done flag, when they are final, and
-// (iii) the one earlier read -- a unit loading its own assembled rows -- bypasses L1 (ld.cg).
+// supernodes, (ii) a supernode's lines are only ever read through L1 after its done flags, when they are final, and
+// (iii) the earlier reads -- a unit loading its own assembled rows, the diagonal factor of its own supernode -- bypass L1 (ld.cg).
 __device__ __forceinline__ void rs_cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-// Cholesky of the nc x nc (nc <= 16) diagonal block by one warp, the matrix in registers: lane r holds row r, the pivot
-// and the scaled column travel by shuffles, every index is static (fully unrolled: ~600 instructions, ~120 cycles per
-// column).  Rows / columns beyond nc are padded with the identity.  Entries above the diagonal hold garbage that never
-// feeds a used value.
+// Cholesky of the nc x nc (nc <= 32) diagonal block by one warp, the matrix in registers: lane r holds row r, the pivot
+// and the scaled column travel by shuffles, every index is static (fully unrolled).  Rows / columns beyond nc are padded
+// with the identity.  Entries above the diagonal hold garbage that never feeds a used value.
 __device__ __forceinline__ void rs_potrf_warp(RsSmem& sm, int nc, int lane, int* status) {
   const unsigned FULL = 0xffffffffu;
-  const int r = lane & 15;
   double a[RS_NC];
 #pragma unroll
-  for (int c = 0; c < RS_NC; ++c) a[c] = (lane < nc && c < nc) ? sm.Ds[r * RS_DP + c] : (r == c ? 1.0 : 0.0);   // lanes >= 16 only ride along
+  for (int c = 0; c < RS_NC; ++c) a[c] = (lane < nc && c < nc) ? sm.Ds[lane * RS_DP + c] : (lane == c ? 1.0 : 0.0);
   bool bad = false;
 #pragma unroll
   for (int c = 0; c < RS_NC; ++c) {
     double d = __shfl_sync(FULL, a[c], c);
     if (!(d > 0.0)) { bad = true; d = 1.0; }       // not positive definite (or NaN): flag and keep going with a safe pivot
     const double inv = rsqrt(d);
-    const double l = (r == c) ? d * inv : a[c] * inv;
+    const double l = (lane == c) ? d * inv : a[c] * inv;
     a[c] = l;
-    if (lane == c) sm.dinv[c] = inv;
 #pragma unroll
     for (int j = c + 1; j < RS_NC; ++j) {
       const double lj = __shfl_sync(FULL, l, j);
@@ -102,10 +98,10 @@ __device__ __forceinline__ void rs_potrf_warp(RsSmem& sm, int nc, int lane, int*
   }
 }
 
-__global__ void __launch_bounds__(RS_T, 2)
+__global__ void __launch_bounds__(RS_T, 3)
 k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__ unit_moff, const short* __restrict__ rowmap,
           const int* __restrict__ upd_ptr, const int* __restrict__ upd_d, const UpdRec* __restrict__ upd_rec,
-          const signed char* __restrict__ colinv, const int2* __restrict__ sn_units, int* done, int unit_base, double* __restrict__ Dfac,
+          const signed char* __restrict__ colinv, const int2* __restrict__ sn_units, int* done, int unit_base,
           int* counter, int n_units, int* status, FrontView fv, long long* dbg) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
@@ -122,13 +118,14 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
 #define RS_STAMP(k) if (dbg && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[8 * slot + (k)] = t_; }
     RS_STAMP(0)
     const int4 un = units[slot];
-    const int sn = un.x, r0 = un.y, r1 = un.z;               // own rows [r0, r1) of the panel, r0 >= nc (r0 == nc: first block)
+    const int sn = un.x, r0 = un.y, r1 = un.z;               // rows [r0, r1) of the panel; r0 == 0: the diagonal block [0, nc)
+    const bool is_diag = (r0 == 0);
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
-    const int nloc = nc + (r1 - r0);
+    const int nloc = r1 - r0;
     double* Lp = s.L + s.sn_valptr[sn];
-    // thread tid owns local row tid of the unit: the diagonal rows first, then the own rows; its nc values live in registers
+    // thread tid owns panel row r0 + tid; its nc values live in registers from here to the final store
     const bool has_row = tid < nloc;
-    const int prow = tid < nc ? tid : r0 + tid - nc;
+    const int prow = r0 + tid;
     double acc[RS_NC];
 #pragma unroll
     for (int c = 0; c < RS_NC; ++c) acc[c] = (has_row && c < nc) ? __ldcg(&Lp[prow + (int64_t)c * nr]) : 0.0;
@@ -166,32 +163,32 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     }
 
     // ---- the update phase runs on the fp64 tensor cores (DMMA m8n8k4): warp w owns local rows [32 w, 32 w + 32) as four
-    //      8-row tiles and the 16 target columns as two 8-column tiles; lane = 4 g + t holds the sums
+    //      8-row tiles and the 32 target columns as four 8-column tiles; lane = 4 g + t holds the sums
     //      (8 m + g, 8 n + 2 t + {0, 1}).  The thread-per-row registers are converted through the warp's slab.
     const unsigned FULL = 0xffffffffu;
     const int lane = tid & 31, wrp = tid >> 5, fgi = lane >> 2, fti = lane & 3;
-    double* slab = slab_s + wrp * 32 * RS_DP;
-    double fr[4][2][2];
+    double* slab = slab_s + wrp * 32 * RS_SP;
+    double fr[4][RS_NT][2];
     __syncthreads();                                      // the front prologue is done with its alias
 #pragma unroll
-    for (int c = 0; c < RS_NC; ++c) slab[lane * RS_DP + c] = acc[c];
+    for (int c = 0; c < RS_NC; ++c) slab[lane * RS_SP + c] = acc[c];
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int n = 0; n < 2; ++n)
+      for (int n = 0; n < RS_NT; ++n)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) fr[m][n][e] = slab[(8 * m + fgi) * RS_DP + 8 * n + 2 * fti + e];
+        for (int e = 0; e < 2; ++e) fr[m][n][e] = slab[(8 * m + fgi) * RS_SP + 8 * n + 2 * fti + e];
     const short* umap = rowmap + unit_moff[slot] + tid;
-    const int bk = tid / RS_NC, bc = tid % RS_NC;          // this thread's element of the B tile (RS_T == RS_NC * RS_NC)
+    const int bk = tid / RS_NC, bc = tid % RS_NC;          // this thread's elements of the B tile: (bk + 4 h, bc), h = 0..3
 
     int u = upd_ptr[sn];
     const int ubase = u;
     const int u1 = upd_ptr[sn + 1];
-    const double* Ld1 = nullptr; int K1 = 0, nrd1 = 0, half1 = 0, mi1 = -1, j1 = -1;        // indices of the next update to be issued
+    const double* Ld1 = nullptr; int K1 = 0, nrd1 = 0, mask1 = 0, mi1 = -1, j1 = -1;        // indices of the next update to be issued
     auto stage_a = [&](int uu) {
       const UpdRec rec = upd_rec[uu];
-      Ld1 = s.L + rec.val_off; K1 = rec.K; nrd1 = rec.nrd; half1 = rec.pad[0];                 // half: only target columns < 8 are touched
+      Ld1 = s.L + rec.val_off; K1 = rec.K; nrd1 = rec.nrd; mask1 = rec.pad[0];                 // mask: 8-column groups of the target that are touched
       mi1 = has_row ? (int)__ldg(umap + (int64_t)(uu - ubase) * nloc) : -1;                   // descendant row (from row a) landing on this thread's row
       j1 = colinv[(int64_t)uu * RS_NC + bc];                                                  // descendant row (from a) holding target column bc, or -1
     };
@@ -206,7 +203,7 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
         int n;
         while (true) {
           int f = 1;
-          if (tid < win) for (int b = 0; b < du.y; ++b) f &= rs_ld_relaxed(fp + b);     // every row block of the descendant is stored
+          if (tid < win) for (int b = 0; b < du.y; ++b) f &= rs_ld_relaxed(fp + b);     // every unit of the descendant is stored
           const unsigned notready = ~__ballot_sync(0xffffffffu, f != 0);
           n = notready ? (__ffs(notready) - 1) : 32;
           if (n > win) n = win;
@@ -219,24 +216,28 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
       const int nready = sm.first_not_ready;
       RS_STAMP(1)                                          // last time a batch of descendants was seen ready
       // ---- pipeline over the ready updates: the descendant values of update uu + 2 travel by cp.async into a ring of
-      //      RS_ST shared-memory stages while uu is multiplied (the leaf panels touched by one level exceed L2, so a load
-      //      is a DRAM round trip); the record / row-map / column-map loads (static data) run one step further ahead.
+      //      RS_ST shared-memory stages while uu is multiplied; the record / row-map / column-map loads (static data) run
+      //      one step further ahead.
       const int uend = u + nready;
-      // issue the copies of the update described by stage_a into stage st; returns (any row of this warp touched) | half << 1
+      // issue the copies of the update described by stage_a into stage st; returns (any row of this warp touched) | mask << 1
       auto stage_b = [&](int st) -> int {
         const int any = __any_sync(FULL, mi1 >= 0) ? 1 : 0;
         if (any) {
           double* xs = sm.Xs[st] + tid;
 #pragma unroll
-          for (int q = 0; q < RS_NC; ++q) {
+          for (int q = 0; q < RS_KC; ++q) {
             if (mi1 >= 0 && q < K1) rs_cp_async8(xs + q * RS_XLD, &Ld1[mi1 + (int64_t)q * nrd1]);
             else xs[q * RS_XLD] = 0.0;
           }
         }
-        if (j1 >= 0 && bk < K1) rs_cp_async8(&sm.Bs[st][bk * RS_BS + bc], &Ld1[j1 + (int64_t)bk * nrd1]);
-        else sm.Bs[st][bk * RS_BS + bc] = 0.0;
+#pragma unroll
+        for (int h = 0; h < RS_KC * RS_NC / RS_T; ++h) {
+          const int k = bk + (RS_T / RS_NC) * h;
+          if (j1 >= 0 && k < K1) rs_cp_async8(&sm.Bs[st][k * RS_BS + bc], &Ld1[j1 + (int64_t)k * nrd1]);
+          else sm.Bs[st][k * RS_BS + bc] = 0.0;
+        }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        return any | (half1 << 1);
+        return any | (mask1 << 1);
       };
       int meta[RS_ST] = {0, 0, 0};                         // per stage: stage_b's return value
       meta[0] = stage_b(0);
@@ -259,18 +260,18 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
           const double* Xt = sm.Xs[st] + 32 * wrp + fgi;
           const double* Bt = sm.Bs[st] + fgi;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
+          for (int ks = 0; ks < RS_KC / 4; ++ks) {
             const int kk = 4 * ks + fti;
             double a[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) a[m] = Xt[kk * RS_XLD + 8 * m];
-            const double b0 = -Bt[kk * RS_BS];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) rs_dmma(fr[m][0], a[m], b0);
-            if (!(mt & 2)) {
-              const double b1 = -Bt[kk * RS_BS + 8];
+            for (int n = 0; n < RS_NT; ++n) {
+              if (mt & (2 << n)) {                        // warp uniform
+                const double bn = -Bt[kk * RS_BS + 8 * n];
 #pragma unroll
-              for (int m = 0; m < 4; ++m) rs_dmma(fr[m][1], a[m], b1);
+                for (int m = 0; m < 4; ++m) rs_dmma(fr[m][n], a[m], bn);
+              }
             }
           }
         }
@@ -283,73 +284,73 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int n = 0; n < 2; ++n)
+      for (int n = 0; n < RS_NT; ++n)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) slab[(8 * m + fgi) * RS_DP + 8 * n + 2 * fti + e] = fr[m][n][e];
+        for (int e = 0; e < 2; ++e) slab[(8 * m + fgi) * RS_SP + 8 * n + 2 * fti + e] = fr[m][n][e];
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < RS_NC; ++c) acc[c] = slab[lane * RS_DP + c];
+    for (int c = 0; c < RS_NC; ++c) acc[c] = slab[lane * RS_SP + c];
     __syncthreads();
     RS_STAMP(2)
 
-    // ---- diagonal block (every block of the supernode factors its own copy)
-    if (tid < nc) {
+    if (is_diag) {
+      // ---- the diagonal block: factor it (one warp, registers) and store it into the panel; the blocks of below-diagonal
+      //      rows of this supernode wait for this unit's flag
+      if (tid < nc) {
 #pragma unroll
-      for (int c = 0; c < RS_NC; ++c) if (c <= tid) sm.Ds[tid * RS_DP + c] = acc[c];
-    }
-    __syncthreads();
-    if (tid < 32) rs_potrf_warp(sm, nc, tid, status);
-    __syncthreads();
-    RS_STAMP(3)
-    // ---- solve the own row against the diagonal factor in registers and store it (coalesced per column)
-    if (has_row && tid >= nc) {
-#pragma unroll
-      for (int c = 0; c < RS_NC; ++c) {
-        if (c < nc) {
-          double v = acc[c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) v = fma(-acc[k], sm.Ds[c * RS_DP + k], v);
-          acc[c] = v * sm.dinv[c];
-          Lp[prow + (int64_t)c * nr] = acc[c];
-        }
+        for (int c = 0; c < RS_NC; ++c) if (c <= tid) sm.Ds[tid * RS_DP + c] = acc[c];
       }
-    }
-    // the first block of the supernode parks the diagonal factor in Dfac: the assembled diagonal block in L stays intact
-    // for the sibling blocks that have not started yet (k_rs_copy_diag moves the factors into L at the end)
-    if (r0 == nc) {
-      double* Df = Dfac + (int64_t)sn * (RS_NC * RS_NC);
+      __syncthreads();
+      if (tid < 32) rs_potrf_warp(sm, nc, tid, status);
+      __syncthreads();
+      RS_STAMP(3)
       for (int i = tid; i < nc * nc; i += RS_T) {
         const int r = i % nc, c = i / nc;
-        if (c <= r) Df[r + c * RS_NC] = sm.Ds[r * RS_DP + c];
+        if (c <= r) Lp[r + (int64_t)c * nr] = sm.Ds[r * RS_DP + c];
       }
+      RS_STAMP(4)
+    } else {
+      // ---- below-diagonal rows: wait for the diagonal factor of this supernode, solve the own row against it in
+      //      registers and store it (coalesced per column)
+      if (tid == 0) {
+        const int* fp = done + sn_units[sn].x;
+        while (rs_ld_relaxed(fp) == 0) { }
+        __threadfence();
+      }
+      __syncthreads();
+      for (int i = tid; i < nc * nc; i += RS_T) {
+        const int r = i % nc, c = i / nc;
+        if (c <= r) sm.Ds[r * RS_DP + c] = __ldcg(&Lp[r + (int64_t)c * nr]);
+      }
+      __syncthreads();
+      if (tid < nc) sm.dinv[tid] = 1.0 / sm.Ds[tid * RS_DP + tid];
+      __syncthreads();
+      RS_STAMP(3)
+      if (has_row) {
+#pragma unroll
+        for (int c = 0; c < RS_NC; ++c) {
+          if (c < nc) {
+            double v = acc[c];
+            const double2* dr = reinterpret_cast<const double2*>(&sm.Ds[c * RS_DP]);
+#pragma unroll
+            for (int k2 = 0; k2 < c / 2; ++k2) {
+              const double2 dd = dr[k2];
+              v = fma(-acc[2 * k2], dd.x, v);
+              v = fma(-acc[2 * k2 + 1], dd.y, v);
+            }
+            if (c & 1) v = fma(-acc[c - 1], sm.Ds[c * RS_DP + c - 1], v);
+            acc[c] = v * sm.dinv[c];
+            Lp[prow + (int64_t)c * nr] = acc[c];
+          }
+        }
+      }
+      RS_STAMP(4)
     }
-    RS_STAMP(4)
     __threadfence();
     __syncthreads();
     if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + unit_base + slot), "r"(1) : "memory");
     RS_STAMP(6)
   }
-}
-
-// diagonal factors: Dfac -> the diagonal blocks of the panels (after both phases)
-__global__ void k_rs_copy_diag(SysView s, int n_sn, const double* __restrict__ Dfac) {
-  const int sn = blockIdx.x;
-  if (sn >= n_sn) return;
-  const int nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
-  double* Lp = s.L + s.sn_valptr[sn];
-  const double* Df = Dfac + (int64_t)sn * (RS_NC * RS_NC);
-  for (int i = threadIdx.x; i < nc * nc; i += blockDim.x) {
-    const int r = i % nc, c = i / nc;
-    if (c <= r) Lp[r + (int64_t)c * nr] = Df[r + c * RS_NC];
-  }
-}
-
-bool chol_rs_supported(const fg_ctx* c) {
-  const char* off = getenv("FG_CHOL_RS");
-  if (off && off[0] == '0') return false;
-  const char* gen = getenv("FG_CHOL_GENERIC");
-  if (gen && gen[0] == '1') return false;
-  return c->sym.rs_ok;
 }
 
 void launch_factor_rs(fg_ctx* c) {
@@ -398,19 +399,17 @@ void launch_factor_rs(fg_ctx* c) {
   FrontView none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const int cap = c->num_sms * per_sm;
   if (!S.use_fronts) {
-    k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.upd_ptr, d.upd_d, d.upd_rec, d.rs_colinv,
-                                                                d.rs_sn_units, d.rs_done, 0, d.rs_dfac, d.counters, na, d.status, none, dbg);
-    k_rs_copy_diag<<<S.n_sn, 64, 0, st>>>(s, S.n_sn, d.rs_dfac);
+    k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
+                                                                d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg);
     return;
   }
   // phase A: the leaves; phase B: one dense update matrix per leaf; phase C: the separators
-  if (na) k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.updr_ptr, d.updr_d, d.updr_rec, d.rs_colinv,
-                                                                      d.rs_sn_units, d.rs_done, 0, d.rs_dfac, d.counters, na, d.status, none, dbg);
+  if (na) k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
+                                                                      d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg);
   launch_front_syrk(c);
   FrontView fv = {d.tf_ptr, d.tf_leaf, d.fr_rowptr, d.fr_rows, d.fr_uptr, d.U};
-  if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.updr_ptr, d.updr_d,
-                                                                      d.updr_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.rs_dfac, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr);
-  k_rs_copy_diag<<<S.n_sn, 64, 0, st>>>(s, S.n_sn, d.rs_dfac);
+  if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.rsu_ptr, d.rsu_d,
+                                                                      d.rsu_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr);
 }
 
 }  // namespace fg

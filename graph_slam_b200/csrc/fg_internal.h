@@ -69,7 +69,6 @@ struct Symbolic {
   std::vector<int> rowidx;           // concatenated row lists (global scalar rows; last = n_r = rhs row)
   std::vector<int> col2sn;           // scalar column -> supernode
   std::vector<int> upd_ptr, upd_d, upd_a, upd_b;   // per target supernode: (descendant, row range [a,b) in d)
-  std::vector<UpdRec> upd_rec;                     // packed per-update record (same indexing as upd_d)
   std::vector<int> anc_ptr, anc_t, anc_a, anc_b;   // per supernode: (ancestor t, row range [a,b) of this supernode inside t's columns)
   std::vector<int> level, sched;                   // dependency level per supernode; supernodes sorted by level
   int n_levels = 0;
@@ -85,7 +84,7 @@ struct Symbolic {
   std::vector<int64_t> fr_uptr;                    // per leaf: offset of its dense nR x nR update matrix in the U buffer
   std::vector<int64_t> pm_ptr; std::vector<int> posmap;   // per member supernode: position of every front row in its row list (-1)
   std::vector<int64_t> pmne_ptr; std::vector<unsigned char> pm_nonempty;   // per member: one flag per 64-row block of the front
-  std::vector<int> updr_ptr, updr_d, updr_a, updr_b; std::vector<UpdRec> updr_rec;   // update lists without leaf -> outside entries
+  std::vector<int> updr_ptr, updr_d, updr_a, updr_b;   // update lists without leaf -> outside entries
   std::vector<int> tf_ptr, tf_leaf;                // per supernode: leaves whose front must be subtracted from it
   std::vector<int> sched_a, sched_c;               // schedules: leaf members, then everything else (both level sorted)
   std::vector<int> tile_leaf, tile_i, tile_j;      // 64 x 64 tiles of the lower triangles of all fronts
@@ -99,7 +98,11 @@ struct Symbolic {
   std::vector<int2> rs_sn_units;                   // per supernode: (global index of its first unit, number of units)
   std::vector<int64_t> rs_moff;                    // per unit: offset of its row maps
   std::vector<short> rs_map;                       // per (unit, update, local row): descendant row (from row a) landing on that row, or -1
-  std::vector<signed char> rs_colinv;              // per update of the list in use, 16 entries: descendant row (from a) holding target column c, or -1
+  std::vector<signed char> rs_colinv;              // per rsu entry, 32 entries: descendant row (from a) holding target column c, or -1
+  // the update list k_chol_rs walks: the list in use (upd_* or updr_*) with descendants wider than 16 columns cut into
+  // column slices (UpdRec.val_off points at the slice, pad[0] = 8-column groups of the target it reaches, pad[1] = k0)
+  std::vector<int> rsu_ptr, rsu_d, rsu_src; std::vector<UpdRec> rsu_rec;
+  int n_levels_rs = 0;                             // dependency levels of the factorisation as run (fronts included)
 };
 
 // ------------------------------------------------------------------ device view passed to kernels
@@ -218,9 +221,9 @@ struct DevGraph {
   int *col2sn = nullptr, *sn_col0 = nullptr, *sn_ncols = nullptr, *sn_nrows = nullptr, *sn_rowptr = nullptr, *rowidx = nullptr;
   int64_t* sn_valptr = nullptr;
   int *upd_ptr = nullptr, *upd_d = nullptr, *upd_a = nullptr, *upd_b = nullptr;
-  UpdRec* upd_rec = nullptr;
   // leaf fronts
-  int *updr_ptr = nullptr, *updr_d = nullptr; UpdRec* updr_rec = nullptr;
+  int *updr_ptr = nullptr, *updr_d = nullptr;
+  int *rsu_ptr = nullptr, *rsu_d = nullptr; UpdRec* rsu_rec = nullptr;
   int *sched_a = nullptr, *sched_c = nullptr;
   int *fr_rowptr = nullptr, *fr_rows = nullptr; int64_t* fr_uptr = nullptr;
   int64_t* pm_ptr = nullptr; int* posmap = nullptr; int64_t* pmne_ptr = nullptr; unsigned char* pm_nonempty = nullptr;
@@ -231,7 +234,7 @@ struct DevGraph {
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;
   int4* rs_units = nullptr; int64_t* rs_moff = nullptr; short* rs_map = nullptr; signed char* rs_colinv = nullptr; int* rs_done = nullptr;   // rs_done: one done flag per unit
-  int2* rs_sn_units = nullptr; double* rs_dfac = nullptr;   // per supernode: (first unit, number of units); 16 x 16 diagonal factors
+  int2* rs_sn_units = nullptr;   // per supernode: (first unit, number of units)
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
   int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve)
 };
@@ -270,11 +273,7 @@ int build_symbolic(fg_ctx* c);
 void launch_linearize(fg_ctx* c);                         // U0, g_r, V, gl, W, chi2 -> scal[0]
 void launch_build_and_schur(fg_ctx* c, double lambda);    // L = U0 + lambda I - W V'^-1 W^T ; rhs row = -(g_red)
 void launch_schur(fg_ctx* c, double lambda);              // fg_schur.cu: the landmark part of the line above
-void launch_factor(fg_ctx* c);                            // cholesky; the rhs row makes it the forward solve too
-bool chol_reg_supported(const fg_ctx* c);                 // fg_chol_reg.cu: width <= 16, height <= 1024
-void launch_factor_reg(fg_ctx* c);                        // register-tiled fast path of the same factorisation
-bool chol_rs_supported(const fg_ctx* c);                  // fg_chol_rs.cu: row-split units, width <= 16
-void launch_factor_rs(fg_ctx* c);
+void launch_factor_rs(fg_ctx* c);                         // fg_chol_rs.cu: cholesky (row-split units, width <= 32); the rhs row makes it the forward solve too
 void launch_front_syrk(fg_ctx* c);                        // fg_front.cu: dense update matrix of every leaf onto its front
 void launch_backsolve(fg_ctx* c);
 void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);   // fg_chol.cu: [S^-1] block of one variable from the factor in d.L                         // backward solve -> delta

@@ -12,7 +12,10 @@
 // the w poses after the cut plus one velocity/bias pair), and the two halves recurse.  This turns the
 // 5000-step dependency chain of a banded Cholesky into ~log2 levels of short independent chains, which
 // is what lets the persistent kernel in fg_chol.cu use the whole GPU.  Plane landmarks are ordered last.
-// Supernodes are maximal runs of consecutive variables with nested structure, capped at kMaxSnCols.
+// Supernodes are runs of consecutive variables along one elimination-tree chain, capped at kMaxSnCols columns.  The
+// amalgamation is relaxed: a child is merged with its parent when the parent brings few new rows (one more frame of a
+// banded VIO/BA graph adds 15 rows to ~600), at the price of explicit zeros in the child's columns -- half as many
+// dependency levels and half as many passes over the descendant panels in the left-looking factorisation.
 #include <algorithm>
 #include <cstdio>
 #include <functional>
@@ -21,7 +24,8 @@
 
 namespace fg {
 
-static const int kMaxSnCols = 16;     // one [X V B] frame (15) or two poses (12); fits the register-tiled k_chol_reg
+static const int kMaxSnCols = 32;     // two [X V B] frames (30) or five poses (30): the target width of k_chol_rs (RS_NC)
+static const int kUpdK = 16;          // a descendant wider than this is applied as two rank-<=16 updates (one pipeline stage each)
 
 int build_symbolic(fg_ctx* c) {
   HostGraph& h = c->h;
@@ -181,11 +185,16 @@ int build_symbolic(fg_ctx* c) {
   // ---- supernodes
   std::vector<int> sn_first, sn_last;
   {
+    std::vector<int> sdim(nv, 0);            // scalar rows below variable v
+    for (int v = 0; v < nv; ++v) for (int u : st[v]) sdim[v] += vdim[u];
     int v = 0;
     while (v < nv) {
       int first = v, cols = vdim[v];
-      while (v + 1 < nv && parent[v] == v + 1 && st[v].size() == st[v + 1].size() + 1 &&
-             cols + vdim[v + 1] <= kMaxSnCols && leaf_of[elim[v]] == leaf_of[elim[v + 1]]) {
+      while (v + 1 < nv && parent[v] == v + 1 && cols + vdim[v + 1] <= kMaxSnCols && leaf_of[elim[v]] == leaf_of[elim[v + 1]]) {
+        // struct(v) \ {v+1} is a subset of struct(v+1): the merged panel's rows are struct(v+1); `extra` of them are
+        // explicit zeros in the columns gathered so far
+        const int extra = sdim[v + 1] + vdim[v + 1] - sdim[v];
+        if (extra > std::max(16, sdim[v] / 16)) break;
         ++v; cols += vdim[v];
       }
       sn_first.push_back(first); sn_last.push_back(v);
@@ -247,13 +256,6 @@ int build_symbolic(fg_ctx* c) {
       S.upd_a[S.upd_ptr[s] + k] = ul[s][3 * k + 1];
       S.upd_b[S.upd_ptr[s] + k] = ul[s][3 * k + 2];
     }
-  S.upd_rec.resize(S.upd_d.size());
-  for (size_t u = 0; u < S.upd_d.size(); ++u) {
-    const int d = S.upd_d[u], a = S.upd_a[u], b = S.upd_b[u];
-    UpdRec& r = S.upd_rec[u];
-    r.val_off = S.sn_valptr[d] + a; r.row_off = S.sn_rowptr[d] + a; r.nrd = S.sn_nrows[d]; r.nrows_u = S.sn_nrows[d] - a;
-    r.K = (short)S.sn_ncols[d]; r.nb = (short)(b - a); r.pad[0] = r.pad[1] = 0;
-  }
   // ---- leaf fronts: everything a leaf contributes to the supernodes OUTSIDE it is gathered in one dense update
   //      matrix per leaf (fg_front.cu) instead of one rank-K update per (leaf supernode, outside target) pair
   S.n_leaves = n_leaves;
@@ -321,8 +323,11 @@ int build_symbolic(fg_ctx* c) {
         for (int m = S.leaf_sn_lo[l]; m < S.leaf_sn_hi[l]; ++m) {
           const unsigned char* ne = &S.pm_nonempty[S.pmne_ptr[m]];
           if (!ne[ti] || !ne[tj]) continue;
-          FrontRec fr; fr.val_off = S.sn_valptr[m]; fr.pm_off = S.pm_ptr[m]; fr.nrd = S.sn_nrows[m]; fr.K = S.sn_ncols[m]; fr.pad[0] = fr.pad[1] = 0;
-          S.tile_mrec.push_back(fr);
+          for (int k0 = 0; k0 < S.sn_ncols[m]; k0 += kUpdK) {      // k_front_syrk stages <= 16 columns of a member per step
+            FrontRec fr; fr.val_off = S.sn_valptr[m] + (int64_t)k0 * S.sn_nrows[m]; fr.pm_off = S.pm_ptr[m]; fr.nrd = S.sn_nrows[m];
+            fr.K = std::min(kUpdK, S.sn_ncols[m] - k0); fr.pad[0] = fr.pad[1] = 0;
+            S.tile_mrec.push_back(fr);
+          }
         }
         S.tile_mptr[t + 1] = (int)S.tile_mrec.size();
       }
@@ -332,7 +337,7 @@ int build_symbolic(fg_ctx* c) {
         for (int u = S.upd_ptr[t]; u < S.upd_ptr[t + 1]; ++u) {
           const int d = S.upd_d[u];
           if (S.sn_leaf[d] >= 0 && S.sn_leaf[d] != S.sn_leaf[t]) continue;
-          S.updr_d.push_back(d); S.updr_a.push_back(S.upd_a[u]); S.updr_b.push_back(S.upd_b[u]); S.updr_rec.push_back(S.upd_rec[u]);
+          S.updr_d.push_back(d); S.updr_a.push_back(S.upd_a[u]); S.updr_b.push_back(S.upd_b[u]);
         }
         S.updr_ptr[t + 1] = (int)S.updr_d.size();
       }
@@ -360,12 +365,34 @@ int build_symbolic(fg_ctx* c) {
   }
   // ---- row-split work units for k_chol_rs: blocks of <= kRsRows below-diagonal rows per supernode
   {
-    const int kRsRows = 240;
+    const int kRsRows = 128;                  // RS_T: one panel row per thread
     const bool fr = S.use_fronts;
     const std::vector<int>& UP = fr ? S.updr_ptr : S.upd_ptr;
     const std::vector<int>& UD = fr ? S.updr_d : S.upd_d;
     const std::vector<int>& UA = fr ? S.updr_a : S.upd_a;
     const std::vector<int>& UB = fr ? S.updr_b : S.upd_b;
+    // the kernel's update list: the list in use with every descendant wider than kUpdK cut into column slices
+    S.rsu_ptr.assign(S.n_sn + 1, 0);
+    for (int s = 0; s < S.n_sn; ++s) {
+      for (int u = UP[s]; u < UP[s + 1]; ++u) {
+        const int d = UD[u], a = UA[u], b = UB[u];
+        const int* rd = &S.rowidx[S.sn_rowptr[d]];
+        // which 8-column groups of the target the descendant's rows [a, b) reach, and where each target column comes from
+        signed char inv[kMaxSnCols];
+        for (int c = 0; c < kMaxSnCols; ++c) inv[c] = -1;
+        int mask = 0;
+        for (int i = a; i < b; ++i) { const int c = rd[i] - S.sn_col0[s]; inv[c] = (signed char)(i - a); mask |= 1 << (c >> 3); }
+        for (int k0 = 0; k0 < S.sn_ncols[d]; k0 += kUpdK) {
+          UpdRec r;
+          r.val_off = S.sn_valptr[d] + a + (int64_t)k0 * S.sn_nrows[d]; r.row_off = S.sn_rowptr[d] + a; r.nrd = S.sn_nrows[d];
+          r.nrows_u = S.sn_nrows[d] - a; r.K = (short)std::min(kUpdK, S.sn_ncols[d] - k0); r.nb = (short)(b - a);
+          r.pad[0] = mask; r.pad[1] = k0;
+          S.rsu_rec.push_back(r); S.rsu_d.push_back(d); S.rsu_src.push_back(u);
+          S.rs_colinv.insert(S.rs_colinv.end(), inv, inv + kMaxSnCols);
+        }
+      }
+      S.rsu_ptr[s + 1] = (int)S.rsu_d.size();
+    }
     std::vector<int> nblk(S.n_sn);
     for (int s = 0; s < S.n_sn; ++s) nblk[s] = std::max(1, (S.sn_nrows[s] - S.sn_ncols[s] + kRsRows - 1) / kRsRows);
     // level-sorted supernode order of each phase (levels under the update lists in use)
@@ -378,58 +405,59 @@ int build_symbolic(fg_ctx* c) {
           for (int m = S.leaf_sn_lo[l]; m < S.leaf_sn_hi[l]; ++m) lv[s] = std::max(lv[s], lv[m] + 1);
         }
     }
+    S.n_levels_rs = S.n_sn ? *std::max_element(lv.begin(), lv.end()) + 1 : 0;
     std::vector<int> order_a, order_c;
     for (int s = 0; s < S.n_sn; ++s) ((fr && S.sn_leaf[s] < 0) ? order_c : order_a).push_back(s);
     auto bylevel = [&](int a, int b) { return lv[a] < lv[b]; };
     std::stable_sort(order_a.begin(), order_a.end(), bylevel);
     std::stable_sort(order_c.begin(), order_c.end(), bylevel);
+    std::vector<short> one;
+    // units of a supernode: the diagonal block [0, nc) first (it factors the block and publishes it), then the blocks of
+    // below-diagonal rows (they wait for the diagonal factor before their triangular solve)
     auto emit = [&](const std::vector<int>& order) {
       for (int s : order) {
         const int nc = S.sn_ncols[s], nr = S.sn_nrows[s], nb = nblk[s];
         const int per = (nr - nc + nb - 1) / nb;
         const int* rows = &S.rowidx[S.sn_rowptr[s]];
-        for (int b = 0; b < nb; ++b) {
-          const int r0 = nc + b * per, r1 = std::min(nr, r0 + per);
-          S.rs_units.push_back(make_int4(s, r0, r1, nb));
+        for (int b = -1; b < nb; ++b) {
+          const int r0 = b < 0 ? 0 : nc + b * per, r1 = b < 0 ? nc : std::min(nr, r0 + per);
+          S.rs_units.push_back(make_int4(s, r0, r1, nb + 1));
           S.rs_moff.push_back((int64_t)S.rs_map.size());
-          const int nloc = nc + (r1 - r0);
-          for (int u = UP[s]; u < UP[s + 1]; ++u) {
-            const int d = UD[u], a = UA[u], bb = UB[u];
-            const int* rd = &S.rowidx[S.sn_rowptr[d]];
-            const int nrd = S.sn_nrows[d];
-            const size_t base = S.rs_map.size();
-            S.rs_map.resize(base + nloc, (short)-1);
-            for (int i = a; i < bb; ++i) S.rs_map[base + (rd[i] - S.sn_col0[s])] = (short)(i - a);      // rows landing on the diagonal block
-            // own rows: both lists are sorted, the descendant's rows inside the block are a subset of the block's rows
-            int i = (int)(std::lower_bound(rd + bb, rd + nrd, rows[r0]) - rd);
-            for (int lr = nc; lr < nloc && i < nrd; ++lr) {
-              const int g = rows[r0 + lr - nc];
-              while (i < nrd && rd[i] < g) { ++i; }
-              if (i < nrd && rd[i] == g) { S.rs_map[base + lr] = (short)(i - a); ++i; }
+          const int nloc = r1 - r0;
+          int last_src = -1;
+          for (int q = S.rsu_ptr[s]; q < S.rsu_ptr[s + 1]; ++q) {
+            const int u = S.rsu_src[q];
+            if (u != last_src) {
+              last_src = u;
+              const int d = UD[u], a = UA[u], bb = UB[u];
+              const int* rd = &S.rowidx[S.sn_rowptr[d]];
+              const int nrd = S.sn_nrows[d];
+              one.assign(nloc, (short)-1);
+              if (b < 0) {
+                for (int i = a; i < bb; ++i) one[rd[i] - S.sn_col0[s]] = (short)(i - a);      // rows landing on the diagonal block
+              } else {
+                // both lists are sorted, the descendant's rows inside the block are a subset of the block's rows
+                int i = (int)(std::lower_bound(rd + bb, rd + nrd, rows[r0]) - rd);
+                for (int lr = 0; lr < nloc && i < nrd; ++lr) {
+                  const int g = rows[r0 + lr];
+                  while (i < nrd && rd[i] < g) { ++i; }
+                  if (i < nrd && rd[i] == g) { one[lr] = (short)(i - a); ++i; }
+                }
+              }
             }
+            S.rs_map.insert(S.rs_map.end(), one.begin(), one.end());      // a column slice of the same descendant: same rows
           }
         }
       }
     };
-    // per update of the list in use: which descendant row (from row a) holds each target column; "half" when only target
-    // columns < 8 are touched (a non-adjacent frame couples to the 6 pose columns only)
-    std::vector<UpdRec>& UR = fr ? S.updr_rec : S.upd_rec;
-    S.rs_colinv.assign(UD.size() * 16, (signed char)-1);
-    for (int s = 0; s < S.n_sn; ++s)
-      for (int u = UP[s]; u < UP[s + 1]; ++u) {
-        const int d = UD[u], a = UA[u], bb = UB[u];
-        const int* rd = &S.rowidx[S.sn_rowptr[d]];
-        int maxc = -1;
-        for (int i = a; i < bb; ++i) { const int c = rd[i] - S.sn_col0[s]; if (c >= 0 && c < 16) { S.rs_colinv[(size_t)u * 16 + c] = (signed char)(i - a); maxc = std::max(maxc, c); } }
-        UR[u].pad[0] = (maxc < 8) ? 1 : 0;
-      }
     emit(order_a);
     S.rs_units_a = (int)S.rs_units.size();
     emit(order_c);
     S.rs_sn_units.assign(S.n_sn, make_int2(0, 0));
     for (int k = (int)S.rs_units.size() - 1; k >= 0; --k) { int2& e = S.rs_sn_units[S.rs_units[k].x]; e.x = k; e.y += 1; }
-    S.rs_ok = S.max_ncols <= 16 && S.max_nrows <= 32767;      // row maps are int16
+    S.rs_ok = S.max_ncols <= kMaxSnCols && S.max_nrows <= 32767;      // row maps are int16
     for (const int4& un : S.rs_units) if (un.z - un.y > kRsRows || un.z <= un.y) S.rs_ok = false;
+    static_assert(kMaxSnCols <= 128, "the diagonal unit holds one diagonal row per thread");
   }
   // ---- schedule: supernodes by dependency level (longest path), a topological order that interleaves
   //      the independent chains so that the persistent kernel works on all of them at once

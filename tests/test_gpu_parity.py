@@ -159,21 +159,6 @@ def test_single_pose_and_empty_landmark():
     check(spec, 1e-7, 1e-6, solver='schur')
 
 
-def test_generic_cholesky_kernel_is_equivalent(monkeypatch):
-    """fg_chol.cu (generic supernodal kernel, used when a panel exceeds the on-chip fast path) must give the same
-    optimum as fg_chol_reg.cu."""
-    spec = synth.make_config('C4', seed=2, scale=0.03)
-    ctx = abi.Context(device=0); abi.load_spec(ctx, spec); fast = ctx.optimize(); Tf = ctx.get_values(abi.T_POSE); ctx.close()
-    monkeypatch.setenv('FG_CHOL_RS', '0')             # whole-supernode kernel (fg_chol_reg.cu)
-    ctx = abi.Context(device=0); abi.load_spec(ctx, spec); reg = ctx.optimize(); Tr = ctx.get_values(abi.T_POSE); ctx.close()
-    monkeypatch.setenv('FG_CHOL_GENERIC', '1')        # generic kernel (fg_chol.cu)
-    ctx = abi.Context(device=0); abi.load_spec(ctx, spec); gen = ctx.optimize(); Tg = ctx.get_values(abi.T_POSE); ctx.close()
-    for other, To in ((reg, Tr), (gen, Tg)):
-        assert other.iterations == fast.iterations
-        assert abs(other.final_error - fast.final_error) <= 1e-10 * fast.final_error
-        assert np.abs(To - Tf).max() < 1e-9
-
-
 def oracle_marginal(g, kind, idx):
     """Dense oracle: block of the inverse of the full (undamped) normal equations, landmarks included."""
     H, grad, err = g.normal_equations()

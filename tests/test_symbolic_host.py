@@ -84,7 +84,7 @@ def emulate(sym, Sp, bp):
 
 
 def emulate_fronts(ctx, sym, Sp, bp):
-    """numpy emulation of the leaf-front path (fg_front.cu + the phase split of k_chol_reg): leaf members use the
+    """numpy emulation of the leaf-front path (fg_front.cu + the phase split of k_chol_rs): leaf members use the
     reduced update lists, every leaf's contribution to the outside is one dense matrix U = sum_d A_d A_d^T gathered
     through the position maps, and the remaining supernodes subtract the U entries that fall in their panels."""
     n_r, n_sn = int(sym[0][0]), int(sym[0][1])
@@ -169,12 +169,18 @@ def emulate_rowsplit(ctx, sym, Sp, bp):
     n_r, n_sn = int(sym[0][0]), int(sym[0][1])
     col0, ncols, nrows, rowptr, valptr, rowidx = sym[1:7]
     use_fr = bool(ctx.symbolic(33)[0])
-    ok, n_a, n_units = (int(v) for v in ctx.symbolic(39))
+    ok, n_a, n_units = (int(v) for v in ctx.symbolic(39)[:3])
     assert ok
     units = ctx.symbolic(36).reshape(-1, 4); moff = ctx.symbolic(37); rmap = ctx.symbolic(38)
-    colinv = ctx.symbolic(40).reshape(-1, 16)
+    colinv = ctx.symbolic(40).reshape(-1, 32)
     assert len(units) == n_units
     uptr, ud, ua, ub = (ctx.symbolic(w) for w in ((22, 23, 24, 25) if use_fr else (7, 8, 9, 10)))
+    # the kernel's own list: every update of the list in use, cut into column slices of <= 16
+    qptr = ctx.symbolic(47); qrec = ctx.symbolic(48).reshape(-1, 5)       # (d, source update, k0, K, 8-column group mask)
+    assert len(colinv) == len(qrec) and np.all(ncols <= 32)
+    for s in range(n_sn):
+        want = [(int(ud[u]), u, k0, min(16, int(ncols[ud[u]]) - k0)) for u in range(uptr[s], uptr[s + 1]) for k0 in range(0, int(ncols[ud[u]]), 16)]
+        assert [tuple(r[:4]) for r in qrec[qptr[s]:qptr[s + 1]].tolist()] == want
     aug = np.zeros((n_r + 1, n_r + 1)); aug[:n_r, :n_r] = Sp; aug[n_r, :n_r] = bp
     rows_of = [rowidx[rowptr[s]:rowptr[s] + nrows[s]] for s in range(n_sn)]
     A0, Lf = [], []                      # assembled panels (read-only) and factored panels
@@ -205,11 +211,11 @@ def emulate_rowsplit(ctx, sym, Sp, bp):
         if use_fr and k == n_a:
             U = fronts()
         nc = int(ncols[s])
-        assert nc <= r0 < r1 <= nrows[s] and r1 - r0 <= 240
-        loc = list(range(nc)) + list(range(r0, r1))
+        diag = r0 == 0
+        assert (r1 == nc if diag else nc <= r0 < r1 <= nrows[s]) and r1 - r0 <= 128
+        loc = list(range(r0, r1))
         P = A0[s][loc].copy()
         g = [int(rows_of[s][i]) for i in loc]
-        pos = {r: i for i, r in enumerate(g)}
         if use_fr and k >= n_a:
             tf_ptr, tf_leaf = ctx.symbolic(29), ctx.symbolic(30)
             for e in range(tf_ptr[s], tf_ptr[s + 1]):
@@ -222,35 +228,39 @@ def emulate_rowsplit(ctx, sym, Sp, bp):
                         gc = int(col0[s] + c)
                         if gc in idx and gr >= gc:
                             P[rr, c] -= Ul[idx[gr], idx[gc]]
-        for q, u in enumerate(range(uptr[s], uptr[s + 1])):
-            d, a, b = int(ud[u]), int(ua[u]), int(ub[u])
+        for q, qq in enumerate(range(qptr[s], qptr[s + 1])):
+            d, u, k0, K, mask = (int(v) for v in qrec[qq])
+            a, b = int(ua[u]), int(ub[u])
             assert arrived[d] == -1, 'descendant not complete when its update is pulled'
-            Ld = Lf[d]
+            Ld = Lf[d][:, k0:k0 + K]
             nloc = len(loc)
             mp = rmap[moff[k] + q * nloc: moff[k] + (q + 1) * nloc]
             where = {int(r): i for i, r in enumerate(rows_of[d]) if i >= a}
             assert mp.tolist() == [where.get(gr, a - 1) - a for gr in g], 'row map does not name the descendant rows'
-            ci = colinv[u]
-            assert ci.tolist() == [where.get(int(col0[s] + c), a - 1) - a if c < nc else -1 for c in range(16)]
+            ci = colinv[qq]
+            assert ci.tolist() == [where.get(int(col0[s] + c), a - 1) - a if c < nc else -1 for c in range(32)]
             assert all(0 <= v < b - a for v in ci if v >= 0) and sum(v >= 0 for v in ci) == b - a
-            Bfull = np.zeros((Ld.shape[1], 16))
-            for c in range(16):
-                if ci[c] >= 0:
+            assert mask == sum(1 << n for n in range(4) if any(ci[8 * n + e] >= 0 for e in range(8)))
+            Bfull = np.zeros((Ld.shape[1], 32))
+            for c in range(32):
+                if ci[c] >= 0 and (mask >> (c // 8)) & 1:
                     Bfull[:, c] = Ld[a + ci[c]]
             for lr in range(nloc):
                 if mp[lr] >= 0:
                     upd = Ld[a + mp[lr]] @ Bfull
                     for c in range(nc):
-                        if lr >= nc or c <= lr:
+                        if not diag or c <= lr:
                             P[lr, c] -= upd[c]
-        Ldd = np.linalg.cholesky(P[:nc] + np.tril(P[:nc], -1).T)
-        Lf[s][r0:r1] = np.linalg.solve(Ldd, P[nc:].T).T
+        if diag:
+            assert arrived[s] == 0, 'the diagonal unit comes first'
+            Lf[s][:nc] = np.linalg.cholesky(P + np.tril(P, -1).T)
+        else:
+            assert arrived[s] >= 1, 'the diagonal factor is not there yet'
+            Lf[s][r0:r1] = np.linalg.solve(Lf[s][:nc], P.T).T
         covered[s][r0:r1] += 1
         arrived[s] += 1
         if arrived[s] == nblk:
-            Lf[s][:nc] = Ldd
-            covered[s][:nc] += 1
-            arrived[s] = -1                  # done flag
+            arrived[s] = -1                  # every unit's done flag is up
     assert all(np.all(c == 1) for c in covered) and np.all(arrived == -1)
     x = np.zeros(n_r)
     for s in range(n_sn - 1, -1, -1):
