@@ -108,12 +108,14 @@ def cpu_baseline_sample(config, steps=1, spec=None, scale=1.0, warmup=0, one_thr
         threads = os.cpu_count() or 1
         st = cpu_baseline.State(spec)
         lam, n, dt = 1e-5, 0, 0.0
+        ph = np.zeros(5)
         for k in range(warmup + max(steps, 1)):
             keep = [a.copy() for a in (st.pose, st.vel, st.bias, st.pts)]
-            t0 = time.perf_counter()
             rc, e0, e1, secs, band = st.iterate(lam, threads)
             if k >= warmup:                                         # the first `warmup` iterations are untimed
-                dt += time.perf_counter() - t0
+                # the five phase timers of cpu_lm_iteration: linearise, Schur, factor, solve + retract, error.  Its index
+                # build and buffer allocation (a one-time cost in a real solver) are outside them and not counted.
+                dt += float(secs.sum()); ph += secs
                 n += 1
             if rc == 0 and e1 < e0:
                 lam = lam / 10.0
@@ -124,11 +126,11 @@ def cpu_baseline_sample(config, steps=1, spec=None, scale=1.0, warmup=0, one_thr
         sample = ('full %s%s (%d poses, %d landmarks, %d projections): %d LM iteration(s) in %.1f s with %d OpenMP threads '
                   '(oracle/cpu_lm.cpp: linearise, Schur, block-banded Cholesky, back-substitution, retract, error)' %
                   (config, '' if scale == 1.0 else '@%g' % scale, spec['n_poses'], len(spec['point_init']), len(spec['proj_pose']), n, dt, threads))
-        out = dict(value=n / dt, unit='iterations/s', cores=threads, kind='port', sample=sample)
+        out = dict(value=n / dt, unit='iterations/s', cores=threads, kind='port', sample=sample, steps_run=n, warmup_run=warmup,
+                   phases_s=dict(zip(('linearize', 'schur', 'factor', 'solve_retract', 'error'), (ph / n).tolist())))
         if one_thread:                                              # also the single-thread figure (one iteration)
-            t0 = time.perf_counter()
-            st.iterate(lam, 1)
-            out['one_thread'] = dict(value=1.0 / (time.perf_counter() - t0), unit='iterations/s', cores=1)
+            secs1 = st.iterate(lam, 1)[3]
+            out['one_thread'] = dict(value=1.0 / float(secs1.sum()), unit='iterations/s', cores=1)
         return out
     from oracle import build, lm
     sc = 0.05
@@ -146,7 +148,7 @@ def cpu_baseline_sample(config, steps=1, spec=None, scale=1.0, warmup=0, one_thr
     m_s = len(spec.get('between_i', []))
     sample = ('%s scaled x%g (numpy oracle, one core): %d poses, %d relative-pose edges; %d LM iteration(s) in %.1f s; value = sample rate x %g' %
               (config, sc, spec['n_poses'], m_s, n, dt, sc))
-    return dict(value=(n / dt) * sc, unit='iterations/s', cores=1, kind='port', sample=sample)
+    return dict(value=(n / dt) * sc, unit='iterations/s', cores=1, kind='port', sample=sample, steps_run=n, warmup_run=0)
 
 
 def run_reference(args):
@@ -154,11 +156,16 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    base = cpu_baseline_sample(args.config, steps=max(1, min(args.steps, 5)), scale=args.scale, warmup=min(args.warmup, 2))
-    line = dict(metric=METRIC, value=base['value'], unit='iterations/s', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1000.0 / base['value'] if base['value'] else None,
+    # every step is one full LM iteration of the same workload (~1.7 s at C5 on 16 cores); the run is bounded at 40
+    # iterations in all so that it ends within a few minutes, and the line reports the counts actually run
+    steps = max(1, min(args.steps, 30)); warmup = max(0, min(args.warmup, 10))
+    base = cpu_baseline_sample(args.config, steps=steps, scale=args.scale, warmup=warmup)
+    line = dict(metric=METRIC, value=base['value'], unit='iterations/s', n_gpus=args.gpus, steps=base['steps_run'],
+                warmup=base['warmup_run'], steps_requested=args.steps, warmup_requested=args.warmup,
+                ms_per_step=1000.0 / base['value'] if base['value'] else None,
                 higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
-                impl='reference', config=dict(workload=workload_name(args.config, args.scale), note='CPU restatement of the reference path, see cpu_baseline.sample'),
+                impl='reference', config=dict(workload=workload_name(args.config, args.scale), note='CPU restatement of the reference path, see cpu_baseline.sample; '
+                                              'timed region = the five phases of each iteration (setup outside)'),
                 cpu_baseline=base,
                 e2e=dict(value=base['value'], unit='iterations/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 wall_s=time.perf_counter() - t0)
@@ -214,6 +221,7 @@ def main():
         for t in types:
             ctx.set_values(t, pinned[t].numpy())
 
+    fp64_meas = abi.fp64_peak(local)
     # ---- device-resident arm
     ctx.optimize(max_iterations=max(args.warmup, 3), force_iterations=1)
     reset()
@@ -254,14 +262,17 @@ def main():
     state_bytes = int(sum(init[t].nbytes for t in types))
     value = args.steps / dt
     peak, peak_src = measured_peaks()
-    sizes = dict(M=int(rep.n_projections) * world, L=int(rep.n_landmarks) * world, P=spec['n_poses'], nnz=int(rep.nnz_L))
-    ab = algorithmic_bytes(sizes)
+    # the byte model of SURVEY 8d twice: with nnz(S) (the reduced Hessian as assembled: algorithmic) and with nnz(L) (what this
+    # solver stores, nested-dissection fill included)
+    M_all = len(spec.get('proj_pose', [])); L_all = len(spec.get('point_init', []))
+    ab = algorithmic_bytes(dict(M=M_all, L=L_all, P=spec['n_poses'], nnz=int(rep.nnz_S)))
+    ab_fill = algorithmic_bytes(dict(M=M_all, L=L_all, P=spec['n_poses'], nnz=int(rep.nnz_L)))
     trials = max(rep.trials, 1)
     phases = dict(linearize=rep.ms_linearize / max(rep.iterations, 1), schur=rep.ms_schur / trials,
                   factor=rep.ms_factor / trials, backsolve=rep.ms_solve / trials,
                   retract_error=rep.ms_retract_error / trials)
     # Rooflines.  Times are CUDA-event durations measured live around the single kernels on the
-    # context's stream (fg_lm_report.ms_proj_obs / ms_schur_blocks) or around the phase for k_chol_reg / k_backsolve.
+    # context's stream (fg_lm_report.ms_proj_obs / ms_schur_blocks) or around the phase for the factorisation / k_backsolve_w.
     m_rank, l_rank = int(rep.n_projections), int(rep.n_landmarks)
     iters = max(rep.iterations, 1)
     t_obs = rep.ms_proj_obs / iters                       # k_proj_obs<JAC>: 176 B per observation (idx 8, uv 16, w 8, W 144)
@@ -274,12 +285,13 @@ def main():
 
     # dram__bytes_read+write per launch from the committed ncu --set full capture (single GPU, C5 only)
     traffic = {}
-    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')   # refreshed with every committed ncu --set full capture
+    tp = os.path.join(ROOT, 'profiles', 'r2_traffic.json')   # refreshed with every committed ncu --set full capture
     if os.path.exists(tp) and args.config == 'C5' and args.scale == 1.0 and world == 1:
         traffic = json.load(open(tp)).get('dram_bytes_per_launch', {})
 
-    # fp64 arithmetic peak measured on this pool's B200 with profiles/tools/fp64_peak.cu (MEASURED_PEAKS.json has bf16 only)
-    fp64_peak = dict(dfma=36.17, dmma=37.14, source='profiles/r1_fp64_peak.txt')
+    # fp64 arithmetic peak of this GPU, measured in this run (fg_debug_fp64_peak: register-only DFMA / DMMA loops on every SM;
+    # MEASURED_PEAKS.json has HBM and bf16 only)
+    fp64_peak = dict(zip(('dfma', 'dmma'), fp64_meas), source='measured in this run (fg_debug_fp64_peak)')
     f_cho = float(ctx.debug_sizes()[5])                   # flops of one factorisation (fg_symbolic.cpp)
 
     def roof(name, nbytes, ms, note, flops=None, pipe='dfma'):
@@ -292,8 +304,8 @@ def main():
                              flops=flops, peak_source=fp64_peak['source'])
         return r
     roofs = [roof('k_chol_rs', b_cho, t_cho, 'factorisation phase (k_chol_rs x2 + k_front_syrk): dependency chain of %d levels; the leaf phase streams ~12 GB of descendant panels through L2 per factorisation (profiles/r1_ncu_full_summary.md), fp64 on DMMA' % int(rep.n_levels), flops=f_cho, pipe='dmma'),
-             roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA bound: %d pairs x 216 flop = %.1f TFLOP/s achieved (fp64 peak measured on this B200: 36.2 TFLOP/s DFMA, profiles/r1_fp64_peak.txt; not in MEASURED_PEAKS.json)' % (
-                 int(rep.n_schur_pairs), f_sch / (t_sch * 1e-3) / 1e12 if t_sch > 0 else 0.0), flops=f_sch, pipe='dfma'),
+             roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA bound: %d pairs x 216 flop = %.1f TFLOP/s achieved (fp64 DFMA peak measured in this run: %.1f TFLOP/s)' % (
+                 int(rep.n_schur_pairs), f_sch / (t_sch * 1e-3) / 1e12 if t_sch > 0 else 0.0, fp64_meas[0]), flops=f_sch, pipe='dfma'),
              roof('k_proj_obs<1>', b_obs, t_obs, 'streaming pass over the observations')]
     dominant = max(roofs, key=lambda r: r['ms'])
     line = dict(metric=METRIC, value=value, unit='iterations/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -312,11 +324,15 @@ def main():
                                  trials * (20 + ('between_i' in spec) + 2 * ('plane_init' in spec))),
                 clocks=sampler.summary(),
                 roofline=dict(dominant, peak_source=peak_src, iteration_algorithmic_bytes=ab['total'],
-                              iteration_frac=ab['total'] / (dt / args.steps) / 1e9 / peak),
+                              iteration_frac=ab['total'] / (dt / args.steps) / 1e9 / peak,
+                              iteration_bytes_with_fill=ab_fill['total'], iteration_frac_with_fill=ab_fill['total'] / (dt / args.steps) / 1e9 / peak),
                 roofline_all=roofs,
                 phases_ms=phases, lm=dict(iterations=rep.iterations, trials=rep.trials, initial_error=rep.initial_error,
                                           final_error=rep.final_error, e2e_last_error=r1.final_error),
-                sizes=dict(reduced_dims=int(rep.n_reduced_dims), supernodes=int(rep.n_supernodes), nnz_L=int(rep.nnz_L)))
+                sizes=dict(reduced_dims=int(rep.n_reduced_dims), supernodes=int(rep.n_supernodes), nnz_L=int(rep.nnz_L), nnz_S=int(rep.nnz_S)),
+                collectives=dict(per_trial=['ncclAllReduce f64 x %d (packed reduced Hessian + rhs + chi2)' % (int(rep.allreduce_bytes) // 8),
+                                            'ncclAllReduce f64 x 3 (g.delta, |delta|^2, new chi2)'] if world > 1 else [],
+                                 allreduce_bytes=int(rep.allreduce_bytes)))
     if not args.no_cpu_baseline and world == 1:                      # the CPU baseline is reported at N = 1 only
         try:
             line['cpu_baseline'] = cpu_baseline_sample(args.config, steps=2, spec=spec, scale=args.scale, one_thread=True)

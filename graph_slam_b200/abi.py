@@ -48,7 +48,7 @@ class LMReport(C.Structure):
                 ('ms_solve', C.c_double), ('ms_retract_error', C.c_double), ('ms_total', C.c_double),
                 ('n_reduced_dims', C.c_int64), ('n_supernodes', C.c_int64), ('nnz_L', C.c_int64),
                 ('n_projections', C.c_int64), ('n_landmarks', C.c_int64),
-                ('ms_proj_obs', C.c_double), ('ms_schur_blocks', C.c_double), ('n_schur_pairs', C.c_int64), ('n_levels', C.c_int64)]
+                ('ms_proj_obs', C.c_double), ('ms_schur_blocks', C.c_double), ('n_schur_pairs', C.c_int64), ('n_levels', C.c_int64), ('allreduce_bytes', C.c_int64), ('nnz_S', C.c_int64)]
 
     def trace(self):
         n = self.trace_len
@@ -98,6 +98,7 @@ SIGNATURES = {
     'fg_optimize_lm': (C.c_int, [_vp, C.POINTER(LMParams), C.POINTER(LMReport)]),
     'fg_error': (C.c_int, [_vp, _dp]),
     'fg_marginal_cov': (C.c_int, [_vp, C.c_uint64, _dp, C.POINTER(C.c_int)]),
+    'fg_debug_fp64_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     'fg_comm_unique_id': (C.c_int, [C.c_char_p]),
     'fg_comm_init': (C.c_int, [_vp, C.c_char_p]),
     'fg_add_structure_edges': (C.c_int, [_vp, C.c_int64, _kp, _kp]),
@@ -281,6 +282,15 @@ class Context:
         out = np.zeros(max(n, 1), dtype=np.int64)
         self.l.fg_debug_symbolic(self.h, which, out.ctypes.data_as(C.POINTER(C.c_int64)), n)
         return out[:n]
+
+
+def fp64_peak(device=0):
+    """(DFMA, DMMA) TFLOP/s measured on `device` now (fg_debug_fp64_peak)."""
+    out = (C.c_double * 2)()
+    rc = lib().fg_debug_fp64_peak(device, out)
+    if rc != 0:
+        raise FgError(rc, 'fg_debug_fp64_peak failed')
+    return float(out[0]), float(out[1])
 
 
 def comm_unique_id():

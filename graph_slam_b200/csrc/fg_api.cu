@@ -653,6 +653,10 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload(c, &d.rs_colinv, S.rs_colinv)) ||
         (rc = dev_upload<int>(c, &d.rs_done, nullptr, S.rs_units.size())) || (rc = dev_upload(c, &d.rs_sn_units, S.rs_sn_units))) return rc;
   }
+  if (c->nranks > 1) {
+    d.n_pk = (int64_t)S.pk_idx.size();
+    if ((rc = dev_upload(c, &d.pk_idx, S.pk_idx)) || (rc = dev_upload<double>(c, &d.pk_buf, nullptr, (size_t)d.n_pk + 1))) return rc;
+  }
   CK(cudaStreamSynchronize(c->stream));
   c->epoch = 0;
   c->finalized = true;
@@ -674,6 +678,18 @@ static int allreduce(fg_ctx* c, double* buf, size_t n) {
   if (!c->nccl_comm) return fail(c, FG_ERR_NCCL, "nranks > 1 but fg_comm_init was not called");
   int r = g_nccl.AllReduce(buf, buf, n, kNcclDouble, kNcclSum, c->nccl_comm, c->stream);
   return r == 0 ? FG_OK : fail(c, FG_ERR_NCCL, "ncclAllReduce failed");
+}
+
+// The one large collective of a trial: every rank holds its partial reduced system in d.L; only the entries
+// that can be non-zero before the factorisation travel (packed), with the chi2 of the linearisation point in the same
+// buffer when it is fresh.
+static int reduce_system(fg_ctx* c, bool with_chi2) {
+  if (c->nranks <= 1) return FG_OK;
+  launch_pack(c, with_chi2);
+  int rc = allreduce(c, c->d.pk_buf, (size_t)c->d.n_pk + 1);
+  if (rc != FG_OK) return rc;
+  launch_unpack(c, with_chi2);
+  return FG_OK;
 }
 
 static int read_scalars(fg_ctx* c, double* hs, int* status) {
@@ -717,7 +733,9 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   bool have_err = false;
   rep->n_reduced_dims = c->sym.n_r; rep->n_supernodes = c->sym.n_sn; rep->nnz_L = c->sym.nnz;
   rep->n_projections = d.n_obs; rep->n_landmarks = d.n[T_POINT];
-  rep->n_schur_pairs = d.n_pairs; rep->n_levels = c->sym.n_levels;
+  rep->n_schur_pairs = d.n_pairs; rep->n_levels = c->sym.n_levels_rs;
+  rep->nnz_S = c->sym.nnz_S;
+  rep->allreduce_bytes = c->nranks > 1 ? (int64_t)sizeof(double) * (d.n_pk + 1) : 0;
   double lam = p.lambda_initial;
   const double inf = std::numeric_limits<double>::infinity();
   int it = 0;
@@ -734,7 +752,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
     while (true) {
       if (!first) CK(cudaEventRecord(ev[1], c->stream));
       launch_build_and_schur(c, lam);
-      if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) break;
+      if ((rc = reduce_system(c, first)) != FG_OK) break;
       CK(cudaEventRecord(ev[2], c->stream));
       launch_factor_rs(c);
       CK(cudaEventRecord(ev[3], c->stream));
@@ -742,7 +760,7 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
       CK(cudaEventRecord(ev[4], c->stream));
       launch_retract_error(c, lam);
       // [0] chi2 at the linearisation point (fresh only on the first trial of an iteration), [1] g^T delta, [2] |delta|^2, [3] new chi2
-      if ((rc = first ? allreduce(c, d.scal, 4) : allreduce(c, d.scal + 1, 3)) != FG_OK) break;
+      if ((rc = allreduce(c, d.scal + 1, 3)) != FG_OK) break;     // the small collective: the three scalars that depend on the solve
       CK(cudaEventRecord(ev[5], c->stream));
       double hs[4]; int st = 0;
       if ((rc = read_scalars(c, hs, &st)) != FG_OK) break;
@@ -835,7 +853,7 @@ extern "C" int fg_marginal_cov(fg_ctx* c, fg_key key, double* cov, int* dim) {
   const int col0 = c->sym.off[type][it->second.idx], dm = kDim[type];
   launch_linearize(c);
   launch_build_and_schur(c, 0.0);
-  if ((rc = allreduce(c, d.L, (size_t)c->sym.nnz)) != FG_OK) return rc;
+  if ((rc = reduce_system(c, false)) != FG_OK) return rc;
   launch_factor_rs(c);
   double* work = nullptr;
   CK(cudaMalloc((void**)&work, sizeof(double) * (6 * ((size_t)c->sym.n_r + 1) + 36)));
@@ -928,6 +946,7 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 40: v.assign(S.rs_colinv.begin(), S.rs_colinv.end()); break;
     case 39: v = {S.rs_ok ? 1 : 0, S.rs_units_a, (int64_t)S.rs_units.size(), S.n_levels_rs}; break;
     case 47: put(S.rsu_ptr); break;
+    case 49: v.assign(S.pk_idx.begin(), S.pk_idx.end()); break;
     case 48: v.clear(); for (size_t q = 0; q < S.rsu_d.size(); ++q) { const UpdRec& r = S.rsu_rec[q]; v.push_back(S.rsu_d[q]); v.push_back(S.rsu_src[q]); v.push_back(r.pad[1]); v.push_back(r.K); v.push_back(r.pad[0]); } break;
     case 41: case 42: case 43: case 44: case 45: case 46: {
       // Schur tile tables of the projection factors held by this context (host only): 41 header [CH, n_tiles, n_pairs],

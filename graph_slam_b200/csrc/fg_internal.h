@@ -63,6 +63,7 @@ struct Symbolic {
   int n_r = 0;                       // reduced scalar dimension (poses, vels, biases, planes)
   int n_sn = 0;                      // supernodes
   int64_t nnz = 0;                   // doubles in panel storage (incl. rhs rows)
+  int64_t nnz_S = 0;                 // structural non-zeros of the reduced system before the factorisation (lower + rhs row)
   std::vector<int> off[T_COUNT];     // scalar offset of each reduced variable (T_POINT unused)
   std::vector<int> sn_col0, sn_ncols, sn_nrows, sn_rowptr;  // nrows includes diag rows and the rhs row
   std::vector<int64_t> sn_valptr;
@@ -102,6 +103,7 @@ struct Symbolic {
   // the update list k_chol_rs walks: the list in use (upd_* or updr_*) with descendants wider than 16 columns cut into
   // column slices (UpdRec.val_off points at the slice, pad[0] = 8-column groups of the target it reaches, pad[1] = k0)
   std::vector<int> rsu_ptr, rsu_d, rsu_src; std::vector<UpdRec> rsu_rec;
+  std::vector<int64_t> pk_idx;                     // multi-GPU: sorted panel offsets of the entries exchanged by the allreduce
   int n_levels_rs = 0;                             // dependency levels of the factorisation as run (fronts included)
 };
 
@@ -235,6 +237,7 @@ struct DevGraph {
   int *sched = nullptr;
   int4* rs_units = nullptr; int64_t* rs_moff = nullptr; short* rs_map = nullptr; signed char* rs_colinv = nullptr; int* rs_done = nullptr;   // rs_done: one done flag per unit
   int2* rs_sn_units = nullptr;   // per supernode: (first unit, number of units)
+  int64_t n_pk = 0; int64_t* pk_idx = nullptr; double* pk_buf = nullptr;   // packed exchange buffer: n_pk entries + 1 scalar (chi2)
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
   int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve)
 };
@@ -278,6 +281,8 @@ void launch_front_syrk(fg_ctx* c);                        // fg_front.cu: dense 
 void launch_backsolve(fg_ctx* c);
 void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);   // fg_chol.cu: [S^-1] block of one variable from the factor in d.L                         // backward solve -> delta
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
+void launch_pack(fg_ctx* c, bool with_chi2);               // multi-GPU: gather the exchanged entries of d.L (+ scal[0]) into d.pk_buf
+void launch_unpack(fg_ctx* c, bool with_chi2);             // ... and scatter the reduced values back
 void launch_error_only(fg_ctx* c, bool trial);            // chi2 of val (or val_new) -> scal[0] (or scal[3])
 void launch_preintegrate(int n, const int* d_off, const double* d_imu, double dt, const ImuParamsDev* d_par,
                          const double* d_bias, fg_pim* d_out, cudaStream_t st);

@@ -755,6 +755,28 @@ void launch_build_and_schur(fg_ctx* c, double lambda) {
   if (L) launch_schur(c, lambda);
 }
 
+// ------------------------------------------------------------------ packed exchange (multi-GPU)
+__global__ void k_pack(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ L, double* __restrict__ buf,
+                       const double* __restrict__ scal, int with_chi2) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = L[idx[i]];
+  if (i == n) buf[n] = with_chi2 ? scal[0] : 0.0;
+}
+__global__ void k_unpack(int64_t n, const int64_t* __restrict__ idx, double* __restrict__ L, const double* __restrict__ buf,
+                         double* __restrict__ scal, int with_chi2) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) L[idx[i]] = buf[i];
+  if (i == n && with_chi2) scal[0] = buf[n];
+}
+void launch_pack(fg_ctx* c, bool with_chi2) {
+  DevGraph& d = c->d;
+  k_pack<<<cdiv(d.n_pk + 1, 256), 256, 0, c->stream>>>(d.n_pk, d.pk_idx, d.L, d.pk_buf, d.scal, with_chi2 ? 1 : 0);
+}
+void launch_unpack(fg_ctx* c, bool with_chi2) {
+  DevGraph& d = c->d;
+  k_unpack<<<cdiv(d.n_pk + 1, 256), 256, 0, c->stream>>>(d.n_pk, d.pk_idx, d.L, d.pk_buf, d.scal, with_chi2 ? 1 : 0);
+}
+
 void launch_retract_error(fg_ctx* c, double lambda) {
   DevGraph& d = c->d;
   cudaStream_t st = c->stream;

@@ -156,6 +156,7 @@ int build_symbolic(fg_ctx* c) {
     for (int u : adj[b]) if (posb[u] > posb[b]) hadj[posb[b]].push_back(posb[u]);
   adj.clear(); adj.shrink_to_fit();
   for (auto& a : hadj) std::sort(a.begin(), a.end());
+  const std::vector<std::vector<int>> hadj_keep = hadj;      // later neighbours of every variable: nnz(S) and the packed-exchange index
 
   // ---- symbolic elimination (variable level)
   std::vector<std::vector<int>> st(nv);
@@ -229,6 +230,39 @@ int build_symbolic(fg_ctx* c) {
     for (int j = 0; j < S.sn_ncols[s]; ++j) r[k++] = S.sn_col0[s] + j;
     for (int u : st[sn_last[s]]) for (int j = 0; j < vdim[u]; ++j) r[k++] = voff[u] + j;
     r[k++] = S.n_r;
+  }
+  // ---- packed exchange index (multi-GPU): the panel entries that can be non-zero BEFORE the factorisation on
+  //      any rank -- the blocks of coupled variable pairs, the diagonal blocks and the right-hand-side row.  Only these
+  //      (about nnz(S), not nnz(L) with its fill) travel in the allreduce of the reduced pose Hessian.
+  S.nnz_S = 0;                                         // structural non-zeros of the assembled reduced system (lower triangle + rhs row)
+  for (int v = 0; v < nv; ++v) {
+    int64_t below = 0;
+    for (int u : hadj_keep[v]) below += vdim[u];
+    S.nnz_S += (int64_t)vdim[v] * (vdim[v] + 1) / 2 + vdim[v] + (int64_t)vdim[v] * below;
+  }
+  if (c->nranks > 1) {
+    const std::vector<std::vector<int>>& hadj0 = hadj_keep;
+    auto find = [&](int R, int C) -> int64_t {          // panel offset of entry (R, C), R >= C (host twin of sys_find)
+      const int sn = S.col2sn[C];
+      const int c0 = S.sn_col0[sn], nc = S.sn_ncols[sn], nr = S.sn_nrows[sn];
+      int r;
+      if (R < c0 + nc) r = R - c0;
+      else { const int* rows = &S.rowidx[S.sn_rowptr[sn]]; r = (int)(std::lower_bound(rows + nc, rows + nr, R) - rows); }
+      return S.sn_valptr[sn] + r + (int64_t)(C - c0) * nr;
+    };
+    for (int v = 0; v < nv; ++v) {
+      const int cv = voff[v], dv = vdim[v];
+      for (int j = 0; j < dv; ++j) {
+        const int64_t b0 = find(cv + j, cv + j);
+        for (int i = j; i < dv; ++i) S.pk_idx.push_back(b0 + (i - j));           // diagonal block, lower triangle
+        S.pk_idx.push_back(find(S.n_r, cv + j));                                 // right-hand-side row
+        for (int u : hadj0[v]) {                                                 // later neighbours: rows of u, this column
+          const int64_t bu = find(voff[u], cv + j);
+          for (int i = 0; i < vdim[u]; ++i) S.pk_idx.push_back(bu + i);          // a variable's rows are consecutive in a row list
+        }
+      }
+    }
+    std::sort(S.pk_idx.begin(), S.pk_idx.end());
   }
   // ---- update lists (target <- descendants) and ancestor lists (descendant -> targets)
   std::vector<std::vector<int>> ul(S.n_sn);   // triples (d, a, b)

@@ -169,6 +169,9 @@ typedef struct {
   /* single-kernel device times (ms, summed): the observation pass of the linearisation and the Schur tile kernel */
   double ms_proj_obs, ms_schur_blocks;
   int64_t n_schur_pairs, n_levels;
+  /* multi-GPU: bytes of the per-trial allreduce of the reduced pose Hessian (packed structural non-zeros + rhs + chi2) */
+  int64_t allreduce_bytes;
+  int64_t nnz_S;             /* structural non-zeros of the reduced system before the factorisation (nnz_L includes the fill) */
 } fg_lm_report;
 
 /* Build the symbolic structure and upload the graph (idempotent; called lazily by the functions below). */
@@ -186,6 +189,10 @@ int fg_error(fg_ctx* ctx, double* error);
  * (row-major) covariance of one pose (d = 6), velocity (3), bias (6) or plane (3) variable.  Point3 keys are
  * eliminated by the Schur complement and are not supported (FG_ERR_INVALID).  */
 int fg_marginal_cov(fg_ctx* ctx, fg_key key, double* cov, int* dim);
+
+/* Diagnostic: measured fp64 throughput of `device` in TFLOP/s, out[0] = DFMA (CUDA cores), out[1] = DMMA
+ * (mma.sync.m8n8k4.f64).  bench.py divides its fp64 roofline by these (MEASURED_PEAKS.json holds bf16 only). */
+int fg_debug_fp64_peak(int device, double out[2]);
 
 /* ------------------------------------------------------------------ multi-GPU */
 /* Rank 0 fills a 128-byte NCCL unique id; the host launcher ships it to the other ranks (any transport);

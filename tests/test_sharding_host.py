@@ -1,5 +1,5 @@
 """Host side of the multi-GPU path on CPU: two gloo ranks build their landmark shards in detached contexts and
-must arrive at the SAME reduced-system structure (what makes the single allreduce of the panel buffer legal),
+must arrive at the SAME reduced-system structure and packed exchange index (what makes the single allreduce legal),
 and that structure must equal the unsharded one declared with the same co-visibility band."""
 import hashlib
 import os
@@ -22,15 +22,34 @@ WORKER = textwrap.dedent('''
     pims = (abi.Pim * (P - 1))()
     for i in range(P - 1):
         pims[i].dt = 0.1; pims[i].cov[:] = np.eye(15).ravel().tolist()
-    def digest(sl):
+    def digest(sl, check_pack=False):
         ctx = abi.Context(device=-1, rank=rank, nranks=world)
         abi.load_spec(ctx, spec, landmark_slice=sl, preintegrated=pims)
         h = hashlib.sha256()
-        for w in range(0, 17):
+        for w in list(range(0, 17)) + [49]:
             h.update(ctx.symbolic(w).tobytes())
+        if check_pack:
+            # the packed exchange index must cover every entry of the assembled reduced system (and its rhs row):
+            # place the oracle's full reduced system in the panel layout and look its non-zeros up
+            sys.path.insert(0, os.path.join(%r, 'tests'))
+            from test_symbolic_host import reduced_system, perm_from_offsets
+            g, S, b = reduced_system(spec, 1e-3)
+            perm = perm_from_offsets(ctx, g)
+            n_r = len(perm)
+            Sp = np.zeros((n_r + 1, n_r)); Sp[np.ix_(perm, perm)] = S; Sp[n_r, perm] = b
+            col0, ncols, nrows, rowptr, valptr, rowidx = (ctx.symbolic(w) for w in range(1, 7))
+            pk = set(ctx.symbolic(49).tolist())
+            assert len(pk) < ctx.symbolic(0)[2], 'the packed index is not smaller than the panel storage'
+            for s_ in range(len(col0)):
+                rows = rowidx[rowptr[s_]:rowptr[s_] + nrows[s_]]
+                for c_ in range(ncols[s_]):
+                    col = Sp[rows, col0[s_] + c_]
+                    for r_ in np.nonzero(col)[0]:
+                        if r_ >= c_:
+                            assert int(valptr[s_] + r_ + c_ * nrows[s_]) in pk, 'assembled entry missing from the packed exchange index'
         ctx.close()
         return h.hexdigest()
-    mine = digest((L * rank // world, L * (rank + 1) // world))
+    mine = digest((L * rank // world, L * (rank + 1) // world), check_pack=(rank == 0))
     full = digest((0, L))
     out = [None] * world
     dist.all_gather_object(out, (mine, full))
@@ -39,7 +58,7 @@ WORKER = textwrap.dedent('''
         assert out[0][0] == out[0][1], 'sharded structure differs from the unsharded one'
         print('SHARDING_OK')
     dist.destroy_process_group()
-''') % ROOT
+''') % (ROOT, ROOT)
 
 
 def test_two_rank_structures_agree(fglib, tmp_path):
