@@ -39,6 +39,15 @@ class LMParams(C.Structure):
                 ('force_iterations', C.c_int), ('verbosity', C.c_int)]
 
 
+class Isam2Params(C.Structure):
+    _fields_ = [('relinearize_threshold', C.c_double), ('relinearize_skip', C.c_int)]
+
+
+class IncReport(C.Structure):
+    _fields_ = [('error_before', C.c_double), ('error_after', C.c_double), ('n_variables', C.c_int64), ('n_relinearized', C.c_int64),
+                ('n_new_variables', C.c_int64), ('ms_update', C.c_double), ('ms_rebuild', C.c_double), ('status', C.c_int)]
+
+
 class LMReport(C.Structure):
     _fields_ = [('iterations', C.c_int), ('trials', C.c_int), ('initial_error', C.c_double),
                 ('final_error', C.c_double), ('lambda_', C.c_double), ('status', C.c_int), ('trace_len', C.c_int),
@@ -98,6 +107,9 @@ SIGNATURES = {
     'fg_optimize_lm': (C.c_int, [_vp, C.POINTER(LMParams), C.POINTER(LMReport)]),
     'fg_error': (C.c_int, [_vp, _dp]),
     'fg_marginal_cov': (C.c_int, [_vp, C.c_uint64, _dp, C.POINTER(C.c_int)]),
+    'fg_isam2_params_default': (None, [C.POINTER(Isam2Params)]),
+    'fg_update_incremental': (C.c_int, [_vp, C.POINTER(Isam2Params), C.POINTER(IncReport)]),
+    'fg_debug_counts': (C.c_int64, [_vp, C.c_int]),
     'fg_debug_fp64_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     'fg_comm_unique_id': (C.c_int, [C.c_char_p]),
     'fg_comm_init': (C.c_int, [_vp, C.c_char_p]),
@@ -254,6 +266,16 @@ class Context:
             setattr(p, k, v)
         rep = LMReport()
         self.call('fg_optimize_lm', C.byref(p), C.byref(rep))
+        return rep
+
+    def update_incremental(self, **kw):
+        """isam2->update(new factors, new values) + calculateEstimate() (CGraphGT::optimizeGraphIncremental, gtsam_graph.cpp:1768-1776)."""
+        p = Isam2Params()
+        self.l.fg_isam2_params_default(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        rep = IncReport()
+        self.call('fg_update_incremental', C.byref(p), C.byref(rep))
         return rep
 
     def marginal_covariance(self, key):

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <climits>
 #include <cstdlib>
 #include <dlfcn.h>
@@ -64,12 +65,30 @@ const int kNcclDouble = 8, kNcclSum = 0;   // ncclFloat64, ncclSum
 }  // namespace
 
 // ------------------------------------------------------------------ device memory helpers
+// Device buffers come from the context's pool when a buffer of the previous build fits (a graph that grows by one frame
+// per fg_update_incremental re-uploads ~100 arrays per frame: no cudaMalloc / cudaFree churn); fresh buffers get 25 %
+// headroom for the same reason.
+static int dev_alloc(fg_ctx* c, void** dst, size_t bytes) {
+  size_t best = (size_t)-1, bi = 0;
+  for (size_t i = 0; i < c->pool.size(); ++i)
+    if (c->pool[i].second >= bytes && c->pool[i].second <= 2 * bytes + 4096 && c->pool[i].second < best) { best = c->pool[i].second; bi = i; }
+  if (best != (size_t)-1) {
+    *dst = c->pool[bi].first;
+    c->allocs.push_back(*dst); c->alloc_bytes.push_back(best);
+    c->pool[bi] = c->pool.back(); c->pool.pop_back();
+    return FG_OK;
+  }
+  const size_t cap = bytes + bytes / 4 + 256;
+  CK(cudaMalloc(dst, cap));
+  c->allocs.push_back(*dst); c->alloc_bytes.push_back(cap);
+  return FG_OK;
+}
 template <typename T>
 static int dev_upload(fg_ctx* c, T** dst, const T* src, size_t n) {
   *dst = nullptr;
   if (n == 0) n = 1;
-  CK(cudaMalloc((void**)dst, n * sizeof(T)));
-  c->allocs.push_back(*dst);
+  int rc = dev_alloc(c, (void**)dst, n * sizeof(T));
+  if (rc != FG_OK) return rc;
   if (src) CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
   else CK(cudaMemsetAsync(*dst, 0, n * sizeof(T), c->stream));
   return FG_OK;
@@ -78,16 +97,38 @@ template <typename T>
 static int dev_upload(fg_ctx* c, T** dst, const std::vector<T>& v) {
   return dev_upload(c, dst, v.empty() ? (const T*)nullptr : v.data(), v.size());
 }
-static void dev_free_all(fg_ctx* c) {
-  for (void* p : c->allocs) cudaFree(p);
-  c->allocs.clear();
+// retire the buffers of the current build into the pool (keep = true) or release everything
+static void dev_free_all(fg_ctx* c, bool keep = false) {
+  if (keep) {
+    for (size_t i = 0; i < c->allocs.size(); ++i) c->pool.push_back({c->allocs[i], c->alloc_bytes[i]});
+  } else {
+    for (void* p : c->allocs) cudaFree(p);
+    for (auto& p : c->pool) cudaFree(p.first);
+    c->pool.clear();
+  }
+  c->allocs.clear(); c->alloc_bytes.clear();
   c->d = DevGraph();
 }
+// buffers of the previous build that the new one did not take
+static void pool_trim(fg_ctx* c) {
+  for (auto& p : c->pool) cudaFree(p.first);
+  c->pool.clear();
+}
 
+// During an incremental session the device holds two states per variable: d.val = linearisation point theta (host mirror
+// h.lin), d.val_new = estimate (host mirror h.val -- what fg_get_value returns).  Otherwise d.val <-> h.val.
 static int pull_values(fg_ctx* c) {
   if (!c->device_newer) return FG_OK;
   for (int t = 0; t < T_COUNT; ++t)
-    if (c->d.n[t]) CK(cudaMemcpyAsync(c->h.val[t].data(), c->d.val[t], sizeof(double) * c->h.val[t].size(), cudaMemcpyDeviceToHost, c->stream));
+    if (c->d.n[t]) {
+      const size_t nb = sizeof(double) * c->h.val[t].size();
+      if (c->inc_active) {
+        CK(cudaMemcpyAsync(c->h.val[t].data(), c->d.val_new[t], nb, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h.lin[t].data(), c->d.val[t], nb, cudaMemcpyDeviceToHost, c->stream));
+      } else {
+        CK(cudaMemcpyAsync(c->h.val[t].data(), c->d.val[t], nb, cudaMemcpyDeviceToHost, c->stream));
+      }
+    }
   CK(cudaStreamSynchronize(c->stream));
   c->device_newer = false;
   return FG_OK;
@@ -95,8 +136,29 @@ static int pull_values(fg_ctx* c) {
 static int push_values(fg_ctx* c) {
   if (!c->finalized || !c->values_dirty) return FG_OK;
   for (int t = 0; t < T_COUNT; ++t)
-    if (c->d.n[t]) CK(cudaMemcpyAsync(c->d.val[t], c->h.val[t].data(), sizeof(double) * c->h.val[t].size(), cudaMemcpyHostToDevice, c->stream));
+    if (c->d.n[t]) {
+      const size_t nb = sizeof(double) * c->h.val[t].size();
+      if (c->inc_active) {
+        CK(cudaMemcpyAsync(c->d.val[t], c->h.lin[t].data(), nb, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d.val_new[t], c->h.val[t].data(), nb, cudaMemcpyHostToDevice, c->stream));
+      } else {
+        CK(cudaMemcpyAsync(c->d.val[t], c->h.val[t].data(), nb, cudaMemcpyHostToDevice, c->stream));
+      }
+    }
   c->values_dirty = false;
+  return FG_OK;
+}
+// leave the incremental session: the estimate becomes the (single) state -- the reference copies calculateEstimate() into
+// mp_node_values (gtsam_graph.cpp:1773) and every batch entry point starts from there
+static int end_incremental(fg_ctx* c) {
+  if (!c->inc_active) return FG_OK;
+  if (c->finalized && !c->values_dirty) {
+    for (int t = 0; t < T_COUNT; ++t)
+      if (c->d.n[t]) CK(cudaMemcpyAsync(c->d.val[t], c->d.val_new[t], sizeof(double) * c->h.val[t].size(), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  for (int t = 0; t < T_COUNT; ++t) { c->h.lin[t].clear(); c->h.lin[t].shrink_to_fit(); }
+  c->inc_active = false;
+  c->inc_updates = 0;
   return FG_OK;
 }
 
@@ -146,6 +208,7 @@ static int add_value(fg_ctx* c, fg_key key, int type, const double* v) {
   c->h.index[key] = VarRef{type, idx};
   c->h.keys[type].push_back(key);
   c->h.val[type].insert(c->h.val[type].end(), v, v + kStore[type]);
+  if (c->inc_active) c->h.lin[type].insert(c->h.lin[type].end(), v, v + kStore[type]);     // a new variable: theta = estimate = initial value
   c->finalized = false;
   return FG_OK;
 }
@@ -163,13 +226,18 @@ extern "C" int fg_add_plane(fg_ctx* c, fg_key k, const double pl[4]) {
 extern "C" int fg_add_points(fg_ctx* c, int64_t n, const fg_key* keys, const double* p3) {
   if (!c || !keys || !p3 || n < 0) return fail(c, FG_ERR_INVALID, "bad argument");
   if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
+  // all or nothing: a duplicate (against Values or inside the batch) leaves the graph untouched
+  const size_t n0 = c->h.keys[T_POINT].size();
   c->h.index.reserve(c->h.index.size() + (size_t)n);
   for (int64_t i = 0; i < n; ++i) {
-    if (c->h.index.count(keys[i])) return fail(c, FG_ERR_DUPLICATE_KEY, "key already exists in Values");
-    c->h.index[keys[i]] = VarRef{T_POINT, (int)c->h.keys[T_POINT].size()};
-    c->h.keys[T_POINT].push_back(keys[i]);
+    if (!c->h.index.emplace(keys[i], VarRef{T_POINT, (int)(n0 + i)}).second) {
+      for (int64_t j = 0; j < i; ++j) c->h.index.erase(keys[j]);
+      return fail(c, FG_ERR_DUPLICATE_KEY, "key already exists in Values");
+    }
   }
+  c->h.keys[T_POINT].insert(c->h.keys[T_POINT].end(), keys, keys + n);
   c->h.val[T_POINT].insert(c->h.val[T_POINT].end(), p3, p3 + 3 * n);
+  if (c->inc_active) c->h.lin[T_POINT].insert(c->h.lin[T_POINT].end(), p3, p3 + 3 * n);
   c->finalized = false;
   return FG_OK;
 }
@@ -180,6 +248,7 @@ extern "C" int fg_update_value(fg_ctx* c, fg_key key, const double* v) {
   if (pull_values(c) != FG_OK) return FG_ERR_CUDA;
   int t = it->second.type;
   std::copy(v, v + kStore[t], c->h.val[t].begin() + (size_t)it->second.idx * kStore[t]);
+  if (c->inc_active) std::copy(v, v + kStore[t], c->h.lin[t].begin() + (size_t)it->second.idx * kStore[t]);   // Values::update: both states
   c->values_dirty = true;
   return FG_OK;
 }
@@ -203,7 +272,7 @@ extern "C" int fg_get_values(fg_ctx* c, int type, double* out) {
   if (!c || !out || type < 0 || type >= T_COUNT) return fail(c, FG_ERR_INVALID, "bad argument");
   size_t nb = sizeof(double) * c->h.val[type].size();
   if (c->finalized && c->device_newer && c->d.n[type]) {
-    CK(cudaMemcpyAsync(out, c->d.val[type], nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out, c->inc_active ? c->d.val_new[type] : c->d.val[type], nb, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   } else {
     std::memcpy(out, c->h.val[type].data(), nb);
@@ -213,6 +282,7 @@ extern "C" int fg_get_values(fg_ctx* c, int type, double* out) {
 extern "C" int fg_set_values(fg_ctx* c, int type, const double* in) {
   if (!c || !in || type < 0 || type >= T_COUNT) return fail(c, FG_ERR_INVALID, "bad argument");
   const size_t nb = sizeof(double) * c->h.val[type].size();
+  if (c->inc_active) { if (pull_values(c) != FG_OK) return FG_ERR_CUDA; end_incremental(c); }
   if (c->finalized && c->d.n[type] && !c->values_dirty) {
     // fast path: one host -> device copy of this array straight from the caller's buffer (which may be pinned); the
     // device copy becomes the authoritative one, the host mirror is refreshed lazily by pull_values
@@ -276,8 +346,11 @@ extern "C" int fg_add_prior_point(fg_ctx* c, fg_key key, const double m[3], doub
 }
 extern "C" int fg_add_prior_points(fg_ctx* c, int64_t n, const fg_key* keys, const double* m3, double sigma) {
   if (!c || !keys || !m3 || n < 0 || !(sigma > 0)) return fail(c, FG_ERR_INVALID, "bad argument");
+  const size_t n0 = c->h.pq_var.size();
   for (int64_t i = 0; i < n; ++i) {
-    int v; FIND(keys[i], T_POINT, &v);
+    int v;
+    const int rc = find_var(c, keys[i], T_POINT, &v);
+    if (rc != FG_OK) { c->h.pq_var.resize(n0); return rc; }      // all or nothing
     c->h.pq_var.push_back(v);
   }
   c->h.pq_mean.insert(c->h.pq_mean.end(), m3, m3 + 3 * n);
@@ -476,7 +549,7 @@ extern "C" int fg_pim_predict(const fg_pim* pim, const double Xi[12], const doub
 // pose-major position and the bit mask of the landmarks seen; tiles are pairs of 16-pose groups that share a landmark.
 namespace fg {
 int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::vector<int64_t>& lm_ptr, const std::vector<int64_t>& pose_ptr,
-                   const std::vector<int64_t>& pose_obs, const std::vector<int>& s_point, SchurTables& T) {
+                   const std::vector<int>& pose_nprim, const std::vector<int64_t>& pose_obs, const std::vector<int>& s_point, SchurTables& T) {
   const Symbolic& S = c->sym;
   std::vector<int>& ppos = T.ppos; std::vector<int>& pzp = T.pzp; std::vector<int>& pc_lo = T.pc_lo; std::vector<int>& pc_n = T.pc_n;
   std::vector<int64_t>& pc_ptr = T.pc_ptr; std::vector<uint2>& pc_ent = T.pc_ent; std::vector<int4>& tiles = T.tiles;
@@ -487,20 +560,23 @@ int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::ve
   for (int64_t k = 0; k < M; ++k) { ppos[pose_obs[k]] = (int)k; pzp[k] = s_point[pose_obs[k]]; }
   pc_lo.assign(P, 0); pc_n.assign(P, 0);
   pc_ptr.assign(P + 1, 0);
+  // the first pose_nprim[p] pose-major records of a pose are its PRIMARY observations, one per landmark, sorted by
+  // landmark; further factors on an already seen (pose, landmark) pair sit behind them (their W is folded into the
+  // primary's by k_merge_dup, so they take no part in the tile products)
   for (int64_t p = 0; p < P; ++p) {
-    if (pose_ptr[p + 1] > pose_ptr[p]) {
+    if (pose_nprim[p] > 0) {
       pc_lo[p] = pzp[pose_ptr[p]] / CH;
-      pc_n[p] = pzp[pose_ptr[p + 1] - 1] / CH - pc_lo[p] + 1;
+      pc_n[p] = pzp[pose_ptr[p] + pose_nprim[p] - 1] / CH - pc_lo[p] + 1;
     }
     pc_ptr[p + 1] = pc_ptr[p] + pc_n[p];
   }
   pc_ent.assign(pc_ptr[P] ? pc_ptr[P] : 1, make_uint2(0u, 0u));
   for (int64_t p = 0; p < P; ++p)
-    for (int64_t k = pose_ptr[p]; k < pose_ptr[p + 1]; ++k) {
+    for (int64_t k = pose_ptr[p]; k < pose_ptr[p] + pose_nprim[p]; ++k) {
       const int l = pzp[k];
       uint2& e = pc_ent[pc_ptr[p] + (l / CH - pc_lo[p])];
       if (e.y == 0u) e.x = (unsigned)k;
-      if (e.y & (1u << (l % CH))) return fail(c, FG_ERR_INVALID, "two projection factors on the same (pose, landmark) pair are not supported by the Schur tables");
+      if (e.y & (1u << (l % CH))) return fail(c, FG_ERR_STATE, "internal: duplicate primary observation in the Schur tables");
       e.y |= 1u << (l % CH);
     }
   // tiles: pairs of 16-pose groups that share a landmark, with the chunk range both sides cover
@@ -532,7 +608,9 @@ int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::ve
   std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
   T.ch = CH;
   T.npairs = 0;
-  for (int64_t l = 0; l < L; ++l) { const int64_t k = lm_ptr[l + 1] - lm_ptr[l]; T.npairs += k * (k + 1) / 2; }
+  std::vector<int64_t> nprim_l(L, 0);
+  for (int64_t p = 0; p < P; ++p) for (int64_t k = pose_ptr[p]; k < pose_ptr[p] + pose_nprim[p]; ++k) nprim_l[pzp[k]]++;
+  for (int64_t l = 0; l < L; ++l) T.npairs += nprim_l[l] * (nprim_l[l] + 1) / 2;
   return FG_OK;
 }
 }  // namespace fg
@@ -547,7 +625,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
   HostGraph& h = c->h;
   if (h.count(T_POSE) + h.count(T_VEC3) + h.count(T_BIAS) + h.count(T_PLANE) == 0)
     return fail(c, FG_ERR_STATE, "graph has no pose-side variables");
-  dev_free_all(c);
+  dev_free_all(c, /*keep=*/true);
   int rc = build_symbolic(c);
   if (rc != FG_OK) return fail(c, rc, "symbolic analysis failed");
   Symbolic& S = c->sym;
@@ -555,8 +633,9 @@ extern "C" int fg_finalize(fg_ctx* c) {
   // values
   for (int t = 0; t < T_COUNT; ++t) {
     d.n[t] = h.count(t);
-    if ((rc = dev_upload(c, &d.val[t], h.val[t])) != FG_OK) return rc;
-    if ((rc = dev_upload<double>(c, &d.val_new[t], nullptr, h.val[t].size())) != FG_OK) return rc;
+    if ((rc = dev_upload(c, &d.val[t], c->inc_active ? h.lin[t] : h.val[t])) != FG_OK) return rc;
+    if (c->inc_active) { if ((rc = dev_upload(c, &d.val_new[t], h.val[t])) != FG_OK) return rc; }
+    else if ((rc = dev_upload<double>(c, &d.val_new[t], nullptr, h.val[t].size())) != FG_OK) return rc;
     if (t != T_POINT) if ((rc = dev_upload(c, &d.off[t], S.off[t])) != FG_OK) return rc;
   }
   // pose-side factors
@@ -590,11 +669,37 @@ extern "C" int fg_finalize(fg_ctx* c) {
         s_uv[2 * k] = h.pj_uv[2 * o]; s_uv[2 * k + 1] = h.pj_uv[2 * o + 1]; s_w[k] = h.pj_w[o];
       }
     }
+    // several projection factors on one (pose, landmark) pair (GTSAM accepts them; CGraphGT's BA builder can produce them
+    // when two features of a frame match the same landmark, gtsam_graph.cpp:398-434): the first is the PRIMARY
+    // observation, the others are folded into it where the pair acts as one block (W), and are kept as observations
+    // everywhere else (residuals, V_l, g_l, U_pp, g_p)
+    std::vector<int> dup_prim, dup_sec, pose_nprim(P, 0);
+    std::vector<char> is_sec(M, 0);
+    {
+      std::vector<int64_t> seen_l(P, -1); std::vector<int> seen_k(P, 0);
+      for (int64_t l = 0; l < L; ++l)
+        for (int64_t k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k) {
+          const int p = s_pose[k];
+          if (seen_l[p] == l) { is_sec[k] = 1; dup_prim.push_back(seen_k[p]); dup_sec.push_back((int)k); }
+          else { seen_l[p] = l; seen_k[p] = (int)k; pose_nprim[p]++; }
+        }
+    }
     std::vector<int64_t> pose_obs(M);
     {
       std::vector<int64_t> cur(pose_ptr.begin(), pose_ptr.end() - 1);
-      for (int64_t k = 0; k < M; ++k) pose_obs[cur[s_pose[k]]++] = k;
+      for (int64_t k = 0; k < M; ++k) if (!is_sec[k]) pose_obs[cur[s_pose[k]]++] = k;
+      for (int64_t k = 0; k < M; ++k) if (is_sec[k]) pose_obs[cur[s_pose[k]]++] = k;
     }
+    if (!dup_sec.empty()) {                                  // pairs of one primary consecutive, in observation order (k_merge_dup)
+      std::vector<int> ord(dup_sec.size());
+      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return dup_prim[a] != dup_prim[b] ? dup_prim[a] < dup_prim[b] : dup_sec[a] < dup_sec[b]; });
+      std::vector<int> a(ord.size()), b(ord.size());
+      for (size_t i = 0; i < ord.size(); ++i) { a[i] = dup_prim[ord[i]]; b[i] = dup_sec[ord[i]]; }
+      dup_prim.swap(a); dup_sec.swap(b);
+    }
+    d.n_dup = (int)dup_sec.size();
+    if ((rc = dev_upload(c, &d.dup_prim, dup_prim)) || (rc = dev_upload(c, &d.dup_sec, dup_sec))) return rc;
     std::vector<double> pm(3 * L, 0.0), pw(L, 0.0);
     for (size_t i = 0; i < h.pq_var.size(); ++i) {
       int l = h.pq_var[i];
@@ -613,7 +718,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<double>(c, &d.Zp, nullptr, (size_t)18 * M))) return rc;
     {
       SchurTables T;
-      if ((rc = build_schur_tables(c, L, M, P, lm_ptr, pose_ptr, pose_obs, s_point, T)) != FG_OK) return rc;
+      if ((rc = build_schur_tables(c, L, M, P, lm_ptr, pose_ptr, pose_nprim, pose_obs, s_point, T)) != FG_OK) return rc;
       d.schur_ch = T.ch; d.n_tiles = (int)T.tiles.size(); d.n_pairs = T.npairs;
       if ((rc = dev_upload(c, &d.obs_ppos, T.ppos)) || (rc = dev_upload(c, &d.pz_point, T.pzp)) || (rc = dev_upload(c, &d.pc_lo, T.pc_lo)) ||
           (rc = dev_upload(c, &d.pc_n, T.pc_n)) || (rc = dev_upload(c, &d.pc_ptr, T.pc_ptr)) || (rc = dev_upload(c, &d.pc_ent, T.pc_ent)) ||
@@ -633,7 +738,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
       (rc = dev_upload(c, &d.upd_a, S.upd_a)) || (rc = dev_upload(c, &d.upd_b, S.upd_b)) ||
       (rc = dev_upload(c, &d.anc_ptr, S.anc_ptr)) || (rc = dev_upload(c, &d.anc_t, S.anc_t)) || (rc = dev_upload(c, &d.anc_a, S.anc_a)) ||
       (rc = dev_upload(c, &d.anc_b, S.anc_b)) || (rc = dev_upload(c, &d.sched, S.sched)) ||
-      (rc = dev_upload<int>(c, &d.flags2, nullptr, S.n_sn)) || (rc = dev_upload<int>(c, &d.counters, nullptr, 4))) return rc;
+      (rc = dev_upload<int>(c, &d.flags2, nullptr, S.n_sn)) || (rc = dev_upload<int>(c, &d.counters, nullptr, 8))) return rc;
   if (S.use_fronts) {
     if ((rc = dev_upload(c, &d.updr_ptr, S.updr_ptr)) || (rc = dev_upload(c, &d.updr_d, S.updr_d)) ||
         (rc = dev_upload(c, &d.sched_a, S.sched_a)) || (rc = dev_upload(c, &d.sched_c, S.sched_c)) ||
@@ -658,6 +763,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
     if ((rc = dev_upload(c, &d.pk_idx, S.pk_idx)) || (rc = dev_upload<double>(c, &d.pk_buf, nullptr, (size_t)d.n_pk + 1))) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));
+  pool_trim(c);
   c->epoch = 0;
   c->finalized = true;
   c->values_dirty = false;
@@ -704,6 +810,7 @@ extern "C" int fg_error(fg_ctx* c, double* error) {
   int rc = fg_finalize(c);
   if (rc != FG_OK) return rc;
   CK(cudaSetDevice(c->device));
+  if ((rc = end_incremental(c)) != FG_OK) return rc;
   launch_error_only(c, false);
   if ((rc = allreduce(c, c->d.scal, 1)) != FG_OK) return rc;
   double hs[4];
@@ -723,10 +830,15 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   int rc = fg_finalize(c);
   if (rc != FG_OK) { rep->status = rc; return rc; }
   CK(cudaSetDevice(c->device));
+  if ((rc = end_incremental(c)) != FG_OK) { rep->status = rc; return rc; }
   DevGraph& d = c->d;
-  cudaEvent_t ev[6];
-  for (auto& e : ev) CK(cudaEventCreate(&e));
-  auto cleanup = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
+  struct Events {          // destroyed on every return path (CK returns early)
+    cudaEvent_t e[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+  } evs;
+  for (auto& e : evs.e) CK(cudaEventCreate(&e));
+  cudaEvent_t* ev = evs.e;
+  const cudaEvent_t ev_begin = evs.e[6], ev_end = evs.e[7];
 
   // graph.error(values) of the starting point comes out of the first linearisation (scal[0]): no separate error pass
   double err = std::numeric_limits<double>::quiet_NaN();
@@ -739,8 +851,6 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   double lam = p.lambda_initial;
   const double inf = std::numeric_limits<double>::infinity();
   int it = 0;
-  cudaEvent_t ev_begin, ev_end;
-  CK(cudaEventCreate(&ev_begin)); CK(cudaEventCreate(&ev_end));
   CK(cudaEventRecord(ev_begin, c->stream));
   while (true) {
     double cur = err;
@@ -829,14 +939,83 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   cudaEventSynchronize(ev_end);
   float total = 0;
   cudaEventElapsedTime(&total, ev_begin, ev_end);
-  cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
-  cleanup();
   rep->ms_total = total;
   rep->iterations = it;
   rep->final_error = err;
   rep->lambda = lam;
   rep->status = rc;
   return rc;
+}
+
+// ------------------------------------------------------------------ incremental update (ISAM2 semantics)
+extern "C" void fg_isam2_params_default(fg_isam2_params* p) {
+  if (!p) return;
+  p->relinearize_threshold = 0.1; p->relinearize_skip = 1;       // initISAM2Params, gtsam_graph.cpp:96-97
+}
+
+extern "C" int fg_update_incremental(fg_ctx* c, const fg_isam2_params* params, fg_inc_report* rep) {
+  if (!c) return FG_ERR_INVALID;
+  fg_isam2_params p;
+  if (params) p = *params; else fg_isam2_params_default(&p);
+  fg_inc_report local;
+  if (!rep) rep = &local;
+  std::memset(rep, 0, sizeof *rep);
+  if (c->device < 0) return fail(c, FG_ERR_CUDA, "detached context (device -1): no CUDA device, and there is no CPU solver");
+  CK(cudaSetDevice(c->device));
+  int rc;
+  if (!c->inc_active) {
+    // first update of a session: theta = estimate = the current values
+    if ((rc = pull_values(c)) != FG_OK) return rc;
+    for (int t = 0; t < T_COUNT; ++t) c->h.lin[t] = c->h.val[t];
+    c->inc_active = true; c->inc_updates = 0;
+    for (int t = 0; t < T_COUNT; ++t) c->inc_known[t] = 0;
+    if (c->finalized) c->values_dirty = true;        // the device has no estimate array content yet
+  }
+  const auto t_host = std::chrono::steady_clock::now();
+  if ((rc = fg_finalize(c)) != FG_OK) { rep->status = rc; return rc; }
+  rep->ms_rebuild = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host).count();
+  DevGraph& d = c->d;
+  for (int t = 0; t < T_COUNT; ++t) { rep->n_variables += d.n[t]; rep->n_new_variables += d.n[t] - c->inc_known[t]; c->inc_known[t] = d.n[t]; }
+  struct Events {
+    cudaEvent_t e[2] = {nullptr, nullptr};
+    ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+  } ev;
+  for (auto& e : ev.e) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev.e[0], c->stream));
+  // ---- fluid relinearisation: theta_j <- estimate_j where |delta_j| reaches the threshold
+  c->inc_updates += 1;
+  CK(cudaMemsetAsync(d.counters + 5, 0, sizeof(int), c->stream));     // [5]: relinearised variables (the factorisation owns [0..3])
+  if (p.relinearize_skip <= 1 || c->inc_updates % p.relinearize_skip == 0) launch_inc_gate(c, p.relinearize_threshold, d.counters + 5);
+  // ---- one undamped Gauss-Newton system at theta; estimate = theta (+) delta
+  launch_linearize(c);
+  launch_build_and_schur(c, 0.0);
+  if ((rc = reduce_system(c, true)) != FG_OK) { rep->status = rc; return rc; }
+  launch_factor_rs(c);
+  launch_backsolve(c);
+  launch_retract_error(c, 0.0);
+  if ((rc = allreduce(c, d.scal + 1, 3)) != FG_OK) { rep->status = rc; return rc; }
+  CK(cudaEventRecord(ev.e[1], c->stream));
+  double hs[4]; int st = 0, nrel = 0;
+  CK(cudaMemcpyAsync(&nrel, d.counters + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = read_scalars(c, hs, &st)) != FG_OK) { rep->status = rc; return rc; }
+  CK(cudaGetLastError());
+  float ms = 0; cudaEventElapsedTime(&ms, ev.e[0], ev.e[1]);
+  rep->ms_update = ms;
+  rep->n_relinearized = nrel;
+  rep->error_before = 0.5 * hs[0];
+  c->device_newer = true;
+  if (st != 0 || !std::isfinite(hs[1]) || !std::isfinite(hs[2]) || !std::isfinite(hs[3])) {
+    // IndeterminantLinearSystemException in GTSAM: the estimate stays where the linearisation point is
+    for (int t = 0; t < T_COUNT; ++t)
+      if (d.n[t]) CK(cudaMemcpyAsync(d.val_new[t], d.val[t], sizeof(double) * c->h.val[t].size(), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    rep->error_after = rep->error_before;
+    rep->status = FG_ERR_INDETERMINATE;
+    return fail(c, FG_ERR_INDETERMINATE, "the undamped system of the incremental update is not positive definite (IndeterminantLinearSystemException in GTSAM)");
+  }
+  rep->error_after = 0.5 * hs[3];
+  rep->status = FG_OK;
+  return FG_OK;
 }
 
 // ------------------------------------------------------------------ marginal covariance
@@ -849,6 +1028,7 @@ extern "C" int fg_marginal_cov(fg_ctx* c, fg_key key, double* cov, int* dim) {
   int rc = fg_finalize(c);
   if (rc != FG_OK) return rc;
   CK(cudaSetDevice(c->device));
+  if ((rc = end_incremental(c)) != FG_OK) return rc;
   DevGraph& d = c->d;
   const int col0 = c->sym.off[type][it->second.idx], dm = kDim[type];
   launch_linearize(c);
@@ -960,9 +1140,18 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
       std::vector<int> s_pose(M), s_point(M);
       { std::vector<int64_t> cur(lm_ptr.begin(), lm_ptr.end() - 1); for (int64_t o = 0; o < M; ++o) { int64_t k = cur[h.pj_point[o]]++; s_pose[k] = h.pj_pose[o]; s_point[k] = h.pj_point[o]; } }
       std::vector<int64_t> pose_obs(M);
-      { std::vector<int64_t> cur(pose_ptr.begin(), pose_ptr.end() - 1); for (int64_t k = 0; k < M; ++k) pose_obs[cur[s_pose[k]]++] = k; }
+      std::vector<int> pose_nprim(P, 0);
+      {
+        std::vector<char> is_sec(M, 0);
+        std::vector<int64_t> seen_l(P, -1);
+        for (int64_t l = 0; l < L; ++l)
+          for (int64_t k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k) { const int p = s_pose[k]; if (seen_l[p] == l) is_sec[k] = 1; else { seen_l[p] = l; pose_nprim[p]++; } }
+        std::vector<int64_t> cur(pose_ptr.begin(), pose_ptr.end() - 1);
+        for (int64_t k = 0; k < M; ++k) if (!is_sec[k]) pose_obs[cur[s_pose[k]]++] = k;
+        for (int64_t k = 0; k < M; ++k) if (is_sec[k]) pose_obs[cur[s_pose[k]]++] = k;
+      }
       SchurTables T;
-      int rc = build_schur_tables(c, L, M, P, lm_ptr, pose_ptr, pose_obs, s_point, T);
+      int rc = build_schur_tables(c, L, M, P, lm_ptr, pose_ptr, pose_nprim, pose_obs, s_point, T);
       if (rc != FG_OK) return rc;
       if (which == 41) v = {T.ch, (int64_t)T.tiles.size(), T.npairs};
       else if (which == 42) { for (const int4& t : T.tiles) { v.push_back(t.x); v.push_back(t.y); v.push_back(t.z); v.push_back(t.w); } }
@@ -976,6 +1165,21 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
   }
   if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];
   return (int64_t)v.size();
+}
+
+// Host-side factor counts for tests: 0 point priors, 1 projections, 2 betweens, 3 imu, 4 plane factors, 5 pose priors.
+extern "C" int64_t fg_debug_counts(fg_ctx* c, int which) {
+  if (!c) return FG_ERR_INVALID;
+  const HostGraph& h = c->h;
+  switch (which) {
+    case 0: return (h.pq_var.size() == h.pq_w.size() && 3 * h.pq_var.size() == h.pq_mean.size()) ? (int64_t)h.pq_var.size() : -1;
+    case 1: return (int64_t)h.pj_pose.size();
+    case 2: return (int64_t)h.bt_i.size();
+    case 3: return (int64_t)h.imu_rec.size();
+    case 4: return (int64_t)h.pl_pose.size();
+    case 5: return (int64_t)h.pp_var.size();
+    default: return FG_ERR_INVALID;
+  }
 }
 
 extern "C" int fg_debug_sizes(fg_ctx* c, int64_t out[8]) {

@@ -19,7 +19,8 @@ struct VarRef { int type; int idx; };
 // ------------------------------------------------------------------ host graph store
 struct HostGraph {
   std::unordered_map<fg_key, VarRef> index;
-  std::vector<double> val[T_COUNT];          // kStore[t] doubles per value
+  std::vector<double> val[T_COUNT];          // kStore[t] doubles per value (during an incremental session: the ESTIMATE)
+  std::vector<double> lin[T_COUNT];          // incremental session only: the linearisation point theta of every value
   std::vector<fg_key> keys[T_COUNT];
 
   // factor SoA (host)
@@ -188,6 +189,7 @@ struct DevGraph {
   int64_t* pose_obs_ptr = nullptr;  // P+1
   int64_t* pose_obs = nullptr;      // M  observation ids grouped by pose
   int* obs_point = nullptr;         // M
+  int n_dup = 0; int* dup_prim = nullptr; int* dup_sec = nullptr;   // extra factors on an already seen (pose, landmark) pair: (primary, secondary) observation ids
   double* lm_prior_mean = nullptr;  // 3L (NaN weight = no prior)
   double* lm_prior_w = nullptr;     // L
   double* W = nullptr;              // M x 18 (AoS): w Jp^T Jl per observation
@@ -239,7 +241,7 @@ struct DevGraph {
   int2* rs_sn_units = nullptr;   // per supernode: (first unit, number of units)
   int64_t n_pk = 0; int64_t* pk_idx = nullptr; double* pk_buf = nullptr;   // packed exchange buffer: n_pk entries + 1 scalar (chi2)
   int *flags2 = nullptr;            // per supernode epoch flags of the backward solve
-  int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve)
+  int *counters = nullptr;          // [0] next schedule slot (factor), [1] next schedule slot (backsolve), [2] phase C slot, [5] relinearised variables
 };
 
 }  // namespace fg
@@ -254,12 +256,18 @@ struct fg_ctx {
   bool finalized = false;
   bool values_dirty = false;     // host values newer than device
   bool device_newer = false;     // device values newer than host
+  // incremental session (fg_update_incremental): d.val holds theta, d.val_new the estimate; h.val / h.lin mirror them
+  bool inc_active = false;
+  int inc_updates = 0;
+  int64_t inc_known[fg::T_COUNT] = {0, 0, 0, 0, 0};   // variables per type at the previous update
+  std::vector<std::pair<void*, size_t>> pool;          // device buffers of the previous build, reused by the next (a graph that grows by one frame per update)
   cudaStream_t stream = nullptr;
   int epoch = 0;
   int num_sms = 148;
   void* nccl_comm = nullptr;
   cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // around k_proj_obs<JAC> and k_schur_tiles (roofline timing)
   std::vector<void*> allocs;
+  std::vector<size_t> alloc_bytes;
 };
 
 namespace fg {
@@ -269,7 +277,7 @@ struct SchurTables {
   std::vector<int> ppos, pzp, pc_lo, pc_n; std::vector<int64_t> pc_ptr; std::vector<uint2> pc_ent; std::vector<int4> tiles;
 };
 int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::vector<int64_t>& lm_ptr, const std::vector<int64_t>& pose_ptr,
-                       const std::vector<int64_t>& pose_obs, const std::vector<int>& s_point, SchurTables& T);
+                       const std::vector<int>& pose_nprim, const std::vector<int64_t>& pose_obs, const std::vector<int>& s_point, SchurTables& T);
 // host.cpp
 int build_symbolic(fg_ctx* c);
 // kernels (launch wrappers), all asynchronous on c->stream
@@ -283,6 +291,7 @@ void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
 void launch_pack(fg_ctx* c, bool with_chi2);               // multi-GPU: gather the exchanged entries of d.L (+ scal[0]) into d.pk_buf
 void launch_unpack(fg_ctx* c, bool with_chi2);             // ... and scatter the reduced values back
+void launch_inc_gate(fg_ctx* c, double threshold, int* d_count);   // move theta to the estimate where |delta| >= threshold
 void launch_error_only(fg_ctx* c, bool trial);            // chi2 of val (or val_new) -> scal[0] (or scal[3])
 void launch_preintegrate(int n, const int* d_off, const double* d_imu, double dt, const ImuParamsDev* d_par,
                          const double* d_bias, fg_pim* d_out, cudaStream_t st);

@@ -405,6 +405,21 @@ __global__ void __launch_bounds__(256, 3) k_proj_obs(int64_t M, const int* __res
   chi2_accumulate(e, chi2);
 }
 
+// Several projection factors on one (pose, landmark) pair act as ONE coupling block W = sum of their W records: fold the
+// secondaries into the primary and clear them (rare; a secondary chain on one pair is walked by the thread of its last link
+// only when the list is ordered, which fg_finalize guarantees: the pairs of one primary are consecutive).
+__global__ void k_merge_dup(int n, const int* __restrict__ prim, const int* __restrict__ sec, double* __restrict__ W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i > 0 && prim[i - 1] == prim[i]) return;           // the first pair of a primary does the whole group, in list order
+  double* wp = W + 18 * (int64_t)prim[i];
+  for (int j = i; j < n && prim[j] == prim[i]; ++j) {
+    double* ws = W + 18 * (int64_t)sec[j];
+#pragma unroll
+    for (int e = 0; e < 18; ++e) { wp[e] += ws[e]; ws[e] = 0.0; }
+  }
+}
+
 // one warp per pose: U_pp = sum w Jp^T Jp, g_p = sum w Jp^T r over the pose's observations (recomputed)
 __global__ void __launch_bounds__(256, 2) k_proj_pose(int P, const int64_t* __restrict__ pose_obs_ptr, const int64_t* __restrict__ pose_obs,
                                                    const int* __restrict__ obs_point, const double* __restrict__ obs_uv,
@@ -720,6 +735,7 @@ static void run_factors(fg_ctx* c, bool trial, double* chi2) {
       if (JAC && c->kev[0]) cudaEventRecord(c->kev[0], st);
       k_proj_obs<JAC><<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, chi2);
       if (JAC && c->kev[1]) cudaEventRecord(c->kev[1], st);
+      if (JAC && d.n_dup) k_merge_dup<<<cdiv(d.n_dup, 128), 128, 0, st>>>(d.n_dup, d.dup_prim, d.dup_sec, d.W);
       if (JAC) {
         int P = (int)d.n[T_POSE];
         k_proj_pose<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.off[T_POSE], sys, d.g_r);
@@ -753,6 +769,49 @@ void launch_build_and_schur(fg_ctx* c, double lambda) {
   k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, st>>>(sys, d.g_r, c->rank == 0 ? lambda : 0.0, 1);
   int64_t L = d.n[T_POINT];
   if (L) launch_schur(c, lambda);
+}
+
+// ------------------------------------------------------------------ incremental update: relinearisation gating
+// ISAM2's fluid relinearisation (gtsam_graph.cpp:93-99: relinearizeThreshold 0.1): delta_j = local(theta_j, estimate_j);
+// where a component reaches the threshold the linearisation point moves to the estimate.
+template <int TYPE>
+__global__ void k_inc_gate(int64_t n, double* __restrict__ theta, const double* __restrict__ est, double thr, int* count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int S = (TYPE == T_POSE) ? 12 : (TYPE == T_PLANE ? 4 : (TYPE == T_BIAS ? 6 : 3));
+  const int D = (TYPE == T_POSE || TYPE == T_BIAS) ? 6 : 3;
+  double a[12], b[12], dl[6];
+#pragma unroll
+  for (int k = 0; k < S; ++k) { a[k] = theta[S * i + k]; b[k] = est[S * i + k]; }
+  if (TYPE == T_POSE) {
+    double R[9], t[3];
+    pose_between(a, a + 9, b, b + 9, R, t);
+    se3_log(R, t, dl);
+  } else if (TYPE == T_PLANE) {
+    unit3_local(a, b, dl);
+    dl[2] = b[3] - a[3];
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) dl[k] = b[k] - a[k];
+  }
+  double m = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) m = fmax(m, fabs(dl[k]));
+  if (m >= thr) {
+#pragma unroll
+    for (int k = 0; k < S; ++k) theta[S * i + k] = b[k];
+    atomicAdd(count, 1);
+  }
+}
+void launch_inc_gate(fg_ctx* c, double thr, int* d_count) {
+  DevGraph& d = c->d;
+  cudaStream_t st = c->stream;
+  const int T = 128;
+  if (d.n[T_POSE]) k_inc_gate<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], thr, d_count);
+  if (d.n[T_VEC3]) k_inc_gate<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], thr, d_count);
+  if (d.n[T_BIAS]) k_inc_gate<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], thr, d_count);
+  if (d.n[T_POINT]) k_inc_gate<T_POINT><<<cdiv(d.n[T_POINT], T), T, 0, st>>>(d.n[T_POINT], d.val[T_POINT], d.val_new[T_POINT], thr, d_count);
+  if (d.n[T_PLANE]) k_inc_gate<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], thr, d_count);
 }
 
 // ------------------------------------------------------------------ packed exchange (multi-GPU)

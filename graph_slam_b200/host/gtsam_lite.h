@@ -19,6 +19,7 @@
 #include <map>
 #include <memory>
 #include <stdexcept>
+#include <cstring>
 #include <string>
 #include <vector>
 #include "../../include/fg_abi.h"
@@ -487,21 +488,50 @@ class Marginals {
   }
 };
 
-// ISAM2 stand-in ("next"): update() appends the new factors/values to the accumulated graph and
-// calculateEstimate() runs the batch LM from the current estimate.  The converged estimate equals the batch
-// optimum; the incremental Bayes-tree bookkeeping (relinearizeThreshold/relinearizeSkip) is not reproduced.
+// ISAM2 (gtsam/gtsam_graph.cpp:93-99,1768-1776): one persistent device context.  update() hands the new
+// values and factors to it and runs fg_update_incremental -- new variables enter at their initial value, variables whose
+// delta reaches relinearizeThreshold move their linearisation point, one undamped Gauss-Newton system is solved on the
+// device; calculateEstimate() reads theta (+) delta back.  (A full re-factorisation per update instead of the partial
+// Bayes-tree re-elimination: see include/fg_abi.h.)
 struct ISAM2Params { double relinearizeThreshold = 0.1; int relinearizeSkip = 10; };
 class ISAM2 {
  public:
-  ISAM2Params params; NonlinearFactorGraph graph; Values estimate; bool dirty = false;
-  ISAM2() {}
-  explicit ISAM2(const ISAM2Params& p) : params(p) {}
-  void update(const NonlinearFactorGraph& nf, const Values& nv) { for (auto& x : nf.f) graph.f.push_back(x); estimate.insert(nv); dirty = true; }
-  void update() {}
+  ISAM2Params params; Values estimate; fg_inc_report report;
+  ISAM2() { std::memset(&report, 0, sizeof report); }
+  explicit ISAM2(const ISAM2Params& p) : params(p) { std::memset(&report, 0, sizeof report); }
+  ISAM2(const ISAM2&) = delete;
+  ISAM2& operator=(const ISAM2&) = delete;
+  ~ISAM2() { if (c_) fg_destroy(c_); }
+  void update(const NonlinearFactorGraph& nf, const Values& nv) {
+    if (!c_) {
+      c_ = fg_create(0, 0, 1);
+      if (!c_) throw std::runtime_error("fg_create failed: no CUDA device (this backend has no CPU fallback)");
+    }
+    for (auto& kv : nv.m) {
+      int rc = FG_OK;
+      switch (kv.second.type) {
+        case FG_T_POSE: rc = fg_add_pose(c_, kv.first, kv.second.v); break;
+        case FG_T_VEC3: rc = fg_add_vec3(c_, kv.first, kv.second.v); break;
+        case FG_T_BIAS: rc = fg_add_bias(c_, kv.first, kv.second.v); break;
+        case FG_T_POINT: rc = fg_add_point(c_, kv.first, kv.second.v); break;
+        case FG_T_PLANE: rc = fg_add_plane(c_, kv.first, kv.second.v); break;
+      }
+      detail::check(c_, rc, "ISAM2::update (new value)");
+    }
+    estimate.insert(nv);
+    for (auto& fac : nf.f) if (fac) detail::check(c_, fac->emit(c_), "ISAM2::update (new factor)");
+    fg_isam2_params p; p.relinearize_threshold = params.relinearizeThreshold; p.relinearize_skip = params.relinearizeSkip;
+    detail::check(c_, fg_update_incremental(c_, &p, &report), "fg_update_incremental");
+    fresh_ = false;
+  }
+  void update() { NonlinearFactorGraph none; Values nov; update(none, nov); }
   Values calculateEstimate() {
-    if (dirty) { LevenbergMarquardtOptimizer opt(graph, estimate); estimate = opt.optimize(); dirty = false; }
+    if (!fresh_ && c_) { detail::readback(c_, estimate); fresh_ = true; }
     return estimate;
   }
+ private:
+  fg_ctx* c_ = nullptr;
+  bool fresh_ = true;
 };
 
 }  // namespace gtsam

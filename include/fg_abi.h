@@ -182,6 +182,36 @@ int fg_optimize_lm(fg_ctx* ctx, const fg_lm_params* params, fg_lm_report* report
 /* graph.error(values) = 1/2 sum |r|^2_Sigma     CGraphGT::error  gtsam_graph.cpp:173-176 */
 int fg_error(fg_ctx* ctx, double* error);
 
+/* ISAM2Params as CGraphGT sets them (initISAM2Params, gtsam_graph.cpp:93-99). */
+typedef struct {
+  double relinearize_threshold;   /* 0.1 */
+  int relinearize_skip;           /* 1   */
+} fg_isam2_params;
+void fg_isam2_params_default(fg_isam2_params* p);
+typedef struct {
+  double error_before;       /* graph.error at the linearisation point of this update        */
+  double error_after;        /* graph.error at the new estimate                              */
+  int64_t n_variables;       /* variables in the graph (all types)                           */
+  int64_t n_relinearized;    /* variables whose linearisation point moved in this update     */
+  int64_t n_new_variables;   /* variables that entered since the previous update             */
+  double ms_update;          /* device time of the update (gating, linearise, solve, retract) */
+  double ms_rebuild;         /* host time spent re-analysing / uploading the grown graph      */
+  int status;
+} fg_inc_report;
+/* isam2->update(new factors, new values); values <- isam2->calculateEstimate()
+ *   CGraphGT::optimizeGraphIncremental  gtsam_graph.cpp:1768-1776 (called once per frame by
+ *   test_vro_imu_graph.cpp:344 and test_ba_imu_graph.cpp:427).
+ * The factors and values added through fg_add_* since the previous call are the "new" ones.  The context keeps ISAM2's
+ * two states per variable -- the linearisation point theta and the estimate theta (+) delta; fg_get_value(s) return the
+ * estimate.  One call = one update(): new variables enter at their initial value, every variable whose delta has a
+ * component >= relinearize_threshold moves its linearisation point (every relinearize_skip calls), the graph is
+ * linearised at theta and ONE undamped Gauss-Newton system is solved on the device (full re-factorisation instead of
+ * ISAM2's partial Bayes-tree re-elimination: the same delta when ISAM2's wildfire threshold is 0).  An indefinite
+ * system returns FG_ERR_INDETERMINATE (IndeterminantLinearSystemException) and leaves the estimate unchanged.
+ * fg_optimize_lm / fg_error / fg_marginal_cov afterwards start from the estimate (the reference copies it into
+ * mp_node_values) and end the incremental session. */
+int fg_update_incremental(fg_ctx* ctx, const fg_isam2_params* params, fg_inc_report* report);
+
 /* Marginals(graph, values, Marginals::CHOLESKY).marginalCovariance(key)
  *   CGraphGT::bundleAdjust gtsam_graph.cpp:598-601 (edge information = inverse of pose 1's marginal covariance),
  *   planeNodeAssociation :1357, gtsam/test/convert_vo2ba.cpp:413-416.

@@ -1,8 +1,13 @@
 // vio_driver.cpp -- test program in the shape of the reference's offline VIO driver
 // (gtsam/test_vro_imu_graph.cpp:76-360, without images, planes and ROS): VRO edge log + IMU log + image time
 // log -> CGraphGT / CImuVn100 -> optimizeGraphBatch, through the host mirror in graph_slam_b200/host.
-//   usage: vio_driver <vro.log> <imu.log> <times.log> <out_poses.txt>
+//   usage: vio_driver <vro.log> <imu.log> <times.log> <out_poses.txt> [incremental]
+// With "incremental" the loop also does what the reference does at the end of every frame
+// (test_vro_imu_graph.cpp:344-350): optimizeGraphIncremental(), then the integrator is re-seeded from the estimated
+// bias, pose and velocity of the current frame.
+#include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <map>
 #include "../../graph_slam_b200/host/gtsam_graph.h"
@@ -38,6 +43,8 @@ int main(int argc, char** argv) {
     gt_graph.firstNode(pNewNode, false);
     imu->setStartPoint(img_times[g_f_start]);
     int cur_frame_id = g_f_start;
+    const bool incremental = argc > 5 && !strcmp(argv[5], "incremental");
+    double inc_ms_sum = 0, inc_ms_max = 0, inc_dev_ms = 0; long inc_frames = 0, inc_relin = 0;
     for (size_t i = 0; i < gt_graph.mv_vro_res.size(); i++) {
       MatchingResult* pm = gt_graph.mv_vro_res[i];
       if (pm->edge.id2 <= g_f_start) continue;
@@ -49,21 +56,50 @@ int main(int argc, char** argv) {
         NavState cur_p;
         bool imu_available = imu->predictNextFlag(img_times[cur_imu_id], cur_p);
         PreintegratedCombinedMeasurements* preint = dynamic_cast<PreintegratedCombinedMeasurements*>(imu->mp_combined_pre_imu);
+        const int cur_node_id = node->m_id;
         if (imu_available) {
-          int cur_node_id = node->m_id;
           CombinedImuFactor imu_factor(X(cur_node_id - 1), V(cur_node_id - 1), X(cur_node_id), V(cur_node_id),
                                        B(cur_node_id - 1), B(cur_node_id), *preint);
           gt_graph.mp_fac_graph->add(imu_factor);
           gt_graph.mp_new_fac->add(imu_factor);
           gt_graph.addToGTSAM(cur_p, cur_node_id, !valid_match);
-          // re-seed the integrator from the current estimate (test_vro_imu_graph.cpp:346-356)
-          NavState st(gt_graph.mp_node_values->at<Pose3>(X(cur_node_id)), gt_graph.mp_node_values->at<Vector3>(V(cur_node_id)));
-          imu->setState(st);
-          imu->resetPreintegrationAndBias(*gt_graph.mp_prev_bias);
+          if (!incremental) {
+            // re-seed the integrator from the dead-reckoned state
+            NavState st(gt_graph.mp_node_values->at<Pose3>(X(cur_node_id)), gt_graph.mp_node_values->at<Vector3>(V(cur_node_id)));
+            imu->setState(st);
+            imu->resetPreintegrationAndBias(*gt_graph.mp_prev_bias);
+          }
         }
         cur_frame_id = pm->edge.id2;
+        if (incremental) {
+          // the look-back / loop-closure edges of this frame, then one ISAM2 update (test_vro_imu_graph.cpp:323-350)
+          size_t j = i + 1;
+          while (j < gt_graph.mv_vro_res.size() && gt_graph.mv_vro_res[j]->edge.id2 <= cur_frame_id) gt_graph.addEdgeOffline(gt_graph.mv_vro_res[j++]);
+          i = j - 1;
+          const auto t0 = std::chrono::steady_clock::now();
+          gt_graph.optimizeGraphIncremental();
+          const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+          inc_ms_sum += ms; inc_ms_max = ms > inc_ms_max ? ms : inc_ms_max; ++inc_frames;
+          inc_relin += gt_graph.mp_isam2->report.n_relinearized; inc_dev_ms += gt_graph.mp_isam2->report.ms_update;
+          imu->resetPreintegrationAndBias(gt_graph.mp_node_values->at<imuBias::ConstantBias>(B(cur_node_id)));
+          NavState pre_state(gt_graph.mp_node_values->at<Pose3>(X(cur_node_id)), gt_graph.mp_node_values->at<Vector3>(V(cur_node_id)));
+          imu->setState(pre_state);
+        }
       } else {
         gt_graph.addEdgeOffline(pm);               // look-back / loop-closure edge
+      }
+    }
+    if (incremental) {
+      printf("INCREMENTAL frames %ld mean_ms %.4f max_ms %.4f device_ms_mean %.4f relinearized %ld\n", inc_frames, inc_ms_sum / (inc_frames ? inc_frames : 1),
+             inc_ms_max, inc_dev_ms / (inc_frames ? inc_frames : 1), inc_relin);
+      std::ofstream est(std::string(argv[4]) + ".isam2");
+      est.precision(17);
+      for (auto& kv : gt_graph.m_graph_map) {
+        double T[12];
+        gt_graph.mp_node_values->at<Pose3>(X(kv.first)).toArray12(T);
+        est << kv.first;
+        for (int k = 0; k < 12; ++k) est << " " << T[k];
+        est << "\n";
       }
     }
     double e0 = gt_graph.error();

@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import numpy as np
+import pytest
 from graph_slam_b200 import abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,7 +26,7 @@ def test_every_declared_symbol_is_exported(fglib):
 
 def test_ctypes_table_matches_header(fglib):
     names = set(declared_functions())
-    table = set(abi.SIGNATURES) - {'fg_debug_symbolic'}       # test-only introspection entry, not in the public header
+    table = set(abi.SIGNATURES) - {'fg_debug_symbolic', 'fg_debug_counts'}       # test-only introspection entries, not in the public header
     assert names == table, (sorted(names - table), sorted(table - names))
 
 
@@ -61,4 +62,26 @@ def test_host_only_graph_store(fglib):
             raise AssertionError('expected FgError %d' % code)
         except abi.FgError as e:
             assert e.code == code
+    ctx.close()
+
+
+def test_batch_inserts_are_all_or_nothing(fglib):
+    """A failing fg_add_points / fg_add_prior_points batch leaves the graph exactly as it was (no half-registered keys)."""
+    ctx = abi.Context(device=-1)
+    q = abi.symbols('q', np.arange(4))
+    ctx.add_points(q[:2], np.arange(6.0).reshape(2, 3))
+    for keys in (np.array([q[2], q[3], q[2]], dtype=np.uint64), np.array([q[2], q[0]], dtype=np.uint64)):   # repeated inside the batch / already in Values
+        with pytest.raises(abi.FgError) as e:
+            ctx.add_points(keys, np.ones((len(keys), 3)))
+        assert e.value.code == -2
+        assert ctx.num_values(abi.T_POINT) == 2 and not ctx.exists(int(q[2])) and not ctx.exists(int(q[3]))
+        assert np.allclose(ctx.get_values(abi.T_POINT), np.arange(6.0).reshape(2, 3))
+    ctx.add_points(q[2:], np.ones((2, 3)))                       # the retry of a clean batch succeeds
+    assert ctx.num_values(abi.T_POINT) == 4 and np.allclose(ctx.get_value(int(q[3])), 1.0)
+    with pytest.raises(abi.FgError) as e:                        # unknown key in the middle of a prior batch
+        ctx.add_prior_points(np.array([q[0], abi.symbol('q', 77), q[1]], dtype=np.uint64), np.zeros((3, 3)), 0.1)
+    assert e.value.code == -3
+    assert ctx.l.fg_debug_counts(ctx.h, 0) == 0                 # no point prior was registered
+    ctx.add_prior_points(q, np.zeros((4, 3)), 0.1)
+    assert ctx.l.fg_debug_counts(ctx.h, 0) == 4
     ctx.close()

@@ -87,7 +87,7 @@ def test_c1_pose_graph():
 
 
 def test_c2_vio():
-    check(synth.make_config('C2', seed=1, scale=0.1), 1e-9, 1e-8)
+    check(synth.make_config("C2", seed=1, scale=0.1), 1e-9, 1e-8)        # full size: tests/test_gpu_fullsize_oracle.py
 
 
 def test_c3_vio_planes():
@@ -156,6 +156,20 @@ def test_single_pose_and_empty_landmark():
     keep = spec['proj_point'] != 3
     for k in ('proj_pose', 'proj_point', 'proj_uv'):
         spec[k] = spec[k][keep]
+    check(spec, 1e-7, 1e-6, solver='schur')
+
+
+def test_duplicate_pose_landmark_factors_match_oracle():
+    """Several GenericProjectionFactors on one (pose, landmark) pair -- GTSAM accepts them and CGraphGT's BA builder can
+    produce them (two features of frame i matched to one landmark, gtsam_graph.cpp:398-434): every one of them counts."""
+    spec = synth.make_config('C4', seed=5, scale=0.03)
+    rng = np.random.default_rng(11)
+    M = len(spec['proj_pose'])
+    pick = rng.choice(M, size=40, replace=False)
+    pick = np.concatenate([pick, pick[:7], pick[:3]])         # some pairs three and four times
+    spec['proj_pose'] = np.concatenate([spec['proj_pose'], spec['proj_pose'][pick]])
+    spec['proj_point'] = np.concatenate([spec['proj_point'], spec['proj_point'][pick]])
+    spec['proj_uv'] = np.concatenate([spec['proj_uv'], spec['proj_uv'][pick] + rng.normal(size=(len(pick), 2))])
     check(spec, 1e-7, 1e-6, solver='schur')
 
 
@@ -252,15 +266,3 @@ def test_dense_visibility_splits_schur_chunks():
     check(spec, 1e-7, 1e-6, solver='schur')
 
 
-def test_duplicate_projection_factor_is_rejected():
-    """Two GenericProjectionFactor on one (pose, landmark) pair would break the landmark bit masks of k_schur_tiles: the
-    library must say so instead of solving something else."""
-    spec = synth.make_config('C4', seed=6, scale=0.02)
-    for k in ('proj_pose', 'proj_point', 'proj_uv'):
-        spec[k] = np.concatenate([spec[k], spec[k][:1]])
-    ctx = abi.Context(device=0)
-    abi.load_spec(ctx, spec)
-    with pytest.raises(abi.FgError) as e:
-        ctx.optimize()
-    assert e.value.code == -1
-    ctx.close()

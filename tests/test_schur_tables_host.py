@@ -23,9 +23,16 @@ def tables(spec, landmark_slice=None):
     return t
 
 
-@pytest.mark.parametrize('scale,sl', [(0.03, None), (0.05, None), (0.05, (0.3, 0.8))])
-def test_tiles_visit_every_observation_pair_once(fglib, scale, sl):
+@pytest.mark.parametrize('scale,sl,dup', [(0.03, None, 0), (0.05, None, 0), (0.05, (0.3, 0.8), 0), (0.03, None, 60)])
+def test_tiles_visit_every_observation_pair_once(fglib, scale, sl, dup):
     spec = synth.make_config('C4', seed=5, scale=scale)
+    if dup:
+        # extra projection factors on (pose, landmark) pairs that already have one: the tables hold one PRIMARY record per
+        # pair (the extras sit behind the primaries of their pose and take no part in the tile products)
+        pick = np.random.default_rng(3).choice(len(spec['proj_pose']), size=dup, replace=False)
+        pick = np.concatenate([pick, pick[:9]])
+        for k in ('proj_pose', 'proj_point', 'proj_uv'):
+            spec[k] = np.concatenate([spec[k], spec[k][pick]])
     L = len(spec['point_init']); P = spec['n_poses']
     lo, hi = (0, L) if sl is None else (int(sl[0] * L), int(sl[1] * L))
     t = tables(spec, None if sl is None else (lo, hi))
@@ -36,8 +43,12 @@ def test_tiles_visit_every_observation_pair_once(fglib, scale, sl):
     vis = np.zeros((P, hi - lo), dtype=bool); vis[pose, pt] = True
     common = vis.astype(np.int64) @ vis.T.astype(np.int64)
     assert t['n_pairs'] == int(sum(k * (k + 1) // 2 for k in vis.sum(0)))
-    order = np.lexsort((pt, pose))
-    pm_pose, pm_pt = pose[order], pt[order]
+    # pose-major order: per pose its primaries sorted by landmark, then the extra factors
+    pm_pose, pm_pt = [], []
+    for p in range(P):
+        mine = np.sort(pt[pose == p])
+        prim = np.unique(mine)
+        pm_pose += [p] * len(mine); pm_pt += prim.tolist() + [-1] * (len(mine) - len(prim))
     # entries: for every pose and chunk, mask == landmarks seen in the chunk, start == first pose-major position
     for p in range(P):
         seen = np.nonzero(vis[p])[0]
