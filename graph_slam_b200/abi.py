@@ -48,6 +48,16 @@ class IncReport(C.Structure):
                 ('n_new_variables', C.c_int64), ('ms_update', C.c_double), ('ms_rebuild', C.c_double), ('status', C.c_int)]
 
 
+class G2OParams(C.Structure):
+    _fields_ = [('iterations', C.c_int), ('iterations_per_call', C.c_int), ('tau', C.c_double), ('max_trials', C.c_int)]
+
+
+class G2OReport(C.Structure):
+    _fields_ = [('iterations', C.c_int), ('calls', C.c_int), ('initial_chi2', C.c_double), ('final_chi2', C.c_double), ('lambda_', C.c_double),
+                ('status', C.c_int), ('trace_len', C.c_int), ('trace_chi2', C.c_double * 64), ('trace_lambda', C.c_double * 64),
+                ('trace_trials', C.c_int * 64), ('ms_total', C.c_double)]
+
+
 class LMReport(C.Structure):
     _fields_ = [('iterations', C.c_int), ('trials', C.c_int), ('initial_error', C.c_double),
                 ('final_error', C.c_double), ('lambda_', C.c_double), ('status', C.c_int), ('trace_len', C.c_int),
@@ -107,6 +117,11 @@ SIGNATURES = {
     'fg_optimize_lm': (C.c_int, [_vp, C.POINTER(LMParams), C.POINTER(LMReport)]),
     'fg_error': (C.c_int, [_vp, _dp]),
     'fg_marginal_cov': (C.c_int, [_vp, C.c_uint64, _dp, C.POINTER(C.c_int)]),
+    'fg_add_g2o_edge': (C.c_int, [_vp, C.c_uint64, C.c_uint64, _dp, _dp]),
+    'fg_set_fixed': (C.c_int, [_vp, C.c_uint64, C.c_int]),
+    'fg_g2o_params_default': (None, [C.POINTER(G2OParams)]),
+    'fg_optimize_g2o': (C.c_int, [_vp, C.POINTER(G2OParams), C.POINTER(G2OReport)]),
+    'fg_g2o_chi2': (C.c_int, [_vp, _dp]),
     'fg_isam2_params_default': (None, [C.POINTER(Isam2Params)]),
     'fg_update_incremental': (C.c_int, [_vp, C.POINTER(Isam2Params), C.POINTER(IncReport)]),
     'fg_debug_counts': (C.c_int64, [_vp, C.c_int]),
@@ -267,6 +282,24 @@ class Context:
         rep = LMReport()
         self.call('fg_optimize_lm', C.byref(p), C.byref(rep))
         return rep
+
+    def add_g2o_edge(self, k1, k2, T12, info): a, p = _d(T12); b, q = _d(info); self.call('fg_add_g2o_edge', k1, k2, p, q)
+    def set_fixed(self, key, fixed=True): self.call('fg_set_fixed', key, int(bool(fixed)))
+
+    def optimize_g2o(self, **kw):
+        """CGraphG2O::optimizeGraph (g2o/g2o_graph.cpp:241-252)."""
+        p = G2OParams()
+        self.l.fg_g2o_params_default(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        rep = G2OReport()
+        self.call('fg_optimize_g2o', C.byref(p), C.byref(rep))
+        return rep
+
+    def g2o_chi2(self):
+        out = C.c_double(0)
+        self.call('fg_g2o_chi2', C.byref(out))
+        return out.value
 
     def update_incremental(self, **kw):
         """isam2->update(new factors, new values) + calculateEstimate() (CGraphGT::optimizeGraphIncremental, gtsam_graph.cpp:1768-1776)."""

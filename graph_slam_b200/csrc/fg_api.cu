@@ -367,6 +367,23 @@ extern "C" int fg_add_between(fg_ctx* c, fg_key k1, fg_key k2, const double T[12
   c->finalized = false;
   return FG_OK;
 }
+extern "C" int fg_add_g2o_edge(fg_ctx* c, fg_key k1, fg_key k2, const double T[12], const double info[36]) {
+  if (!c || !T || !info) return fail(c, FG_ERR_INVALID, "null argument");
+  int a, b; FIND(k1, T_POSE, &a); FIND(k2, T_POSE, &b);
+  c->h.ge_i.push_back(a); c->h.ge_j.push_back(b);
+  c->h.ge_meas.insert(c->h.ge_meas.end(), T, T + 12);
+  c->h.ge_info.insert(c->h.ge_info.end(), info, info + 36);
+  c->finalized = false;
+  return FG_OK;
+}
+extern "C" int fg_set_fixed(fg_ctx* c, fg_key key, int fixed) {
+  if (!c) return FG_ERR_INVALID;
+  int v; FIND(key, T_POSE, &v);
+  if (c->h.fixed_pose.size() <= (size_t)v) c->h.fixed_pose.resize((size_t)v + 1, 0);
+  c->h.fixed_pose[v] = fixed ? 1 : 0;
+  c->finalized = false;
+  return FG_OK;
+}
 extern "C" int fg_add_structure_edges(fg_ctx* c, int64_t n, const fg_key* ka, const fg_key* kb) {
   if (!c || !ka || !kb || n < 0) return fail(c, FG_ERR_INVALID, "bad argument");
   for (int64_t i = 0; i < n; ++i) {
@@ -646,6 +663,24 @@ extern "C" int fg_finalize(fg_ctx* c) {
   if ((rc = dev_upload(c, &d.pb_var, h.pb_var)) || (rc = dev_upload(c, &d.pb_mean, h.pb_mean)) || (rc = dev_upload(c, &d.pb_info, h.pb_info))) return rc;
   if ((rc = dev_upload(c, &d.bt_i, h.bt_i)) || (rc = dev_upload(c, &d.bt_j, h.bt_j)) || (rc = dev_upload(c, &d.bt_meas, h.bt_meas)) || (rc = dev_upload(c, &d.bt_info, h.bt_info))) return rc;
   if ((rc = dev_upload(c, &d.imu_var, h.imu_var)) || (rc = dev_upload(c, &d.imu_rec, h.imu_rec))) return rc;
+  // g2o back-end: EdgeSE3 factors, fixed vertices, VertexSE3::oplus as the pose retraction
+  d.n_ge = (int)h.ge_i.size();
+  d.pose_chart = d.n_ge ? 1 : 0;
+  if (d.n_ge && (h.pp_var.size() + h.bt_i.size() + h.imu_rec.size() + h.pl_pose.size() + h.pj_pose.size()))
+    return fail(c, FG_ERR_INVALID, "g2o edges and GTSAM pose factors cannot share a graph (different pose charts)");
+  {
+    std::vector<int> fixed_list;
+    h.fixed_pose.resize(h.count(T_POSE), 0);
+    for (size_t i = 0; i < h.fixed_pose.size(); ++i) if (h.fixed_pose[i]) fixed_list.push_back((int)i);
+    d.n_fixed = (int)fixed_list.size();
+    if (d.n_fixed) {
+      if (!d.n_ge) return fail(c, FG_ERR_INVALID, "fg_set_fixed: only g2o edges may touch a fixed vertex");
+      std::vector<char> fixed_col(S.n_r, 0);
+      for (int i : fixed_list) for (int k = 0; k < 6; ++k) fixed_col[S.off[T_POSE][i] + k] = 1;
+      if ((rc = dev_upload(c, &d.fixed_list, fixed_list)) || (rc = dev_upload(c, &d.fixed_pose, h.fixed_pose)) || (rc = dev_upload(c, &d.fixed_col, fixed_col))) return rc;
+    }
+  }
+  if ((rc = dev_upload(c, &d.ge_i, h.ge_i)) || (rc = dev_upload(c, &d.ge_j, h.ge_j)) || (rc = dev_upload(c, &d.ge_meas, h.ge_meas)) || (rc = dev_upload(c, &d.ge_info, h.ge_info))) return rc;
   if ((rc = dev_upload(c, &d.pl_pose, h.pl_pose)) || (rc = dev_upload(c, &d.pl_plane, h.pl_plane)) || (rc = dev_upload(c, &d.pl_meas, h.pl_meas)) || (rc = dev_upload(c, &d.pl_info, h.pl_info))) return rc;
   // landmarks: sort observations by landmark (stable), CSR by pose
   const int64_t L = h.count(T_POINT), M = (int64_t)h.pj_pose.size(), P = h.count(T_POSE);
@@ -945,6 +980,108 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   rep->lambda = lam;
   rep->status = rc;
   return rc;
+}
+
+// ------------------------------------------------------------------ g2o Levenberg (config 1)
+extern "C" void fg_g2o_params_default(fg_g2o_params* p) {
+  if (!p) return;
+  p->iterations = 20; p->iterations_per_call = 2; p->tau = 1e-5; p->max_trials = 10;
+}
+
+extern "C" int fg_g2o_chi2(fg_ctx* c, double* chi2) {
+  if (!c || !chi2) return fail(c, FG_ERR_INVALID, "null argument");
+  double e;
+  int rc = fg_error(c, &e);
+  if (rc != FG_OK) return rc;
+  *chi2 = 2.0 * e;            // fg_error reports GTSAM's 1/2 sum; g2o's chi2() has no 1/2
+  return FG_OK;
+}
+
+extern "C" int fg_optimize_g2o(fg_ctx* c, const fg_g2o_params* params, fg_g2o_report* rep) {
+  if (!c) return FG_ERR_INVALID;
+  fg_g2o_params p;
+  if (params) p = *params; else fg_g2o_params_default(&p);
+  fg_g2o_report local;
+  if (!rep) rep = &local;
+  std::memset(rep, 0, sizeof *rep);
+  if (p.iterations_per_call < 1 || p.max_trials < 1) return fail(c, FG_ERR_INVALID, "bad g2o parameters");
+  int rc = fg_finalize(c);
+  if (rc != FG_OK) { rep->status = rc; return rc; }
+  CK(cudaSetDevice(c->device));
+  if ((rc = end_incremental(c)) != FG_OK) { rep->status = rc; return rc; }
+  DevGraph& d = c->d;
+  if (!d.n_ge) return fail(c, FG_ERR_STATE, "fg_optimize_g2o: the graph has no g2o edges");
+  struct Events {
+    cudaEvent_t e[2] = {nullptr, nullptr};
+    ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+  } ev;
+  for (auto& e : ev.e) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev.e[0], c->stream));
+  double lam = 0.0, ni = 2.0, cur = 0.0;
+  bool have_initial = false;
+  int done_total = 0;
+  while (done_total < p.iterations) {                      // for (i = 0; i < iter; i += currIt) currIt = optimize(per_call)
+    int done = 0;
+    bool ok = true;
+    for (int it = 0; it < p.iterations_per_call && ok; ++it) {
+      // ---- OptimizationAlgorithmLevenberg::solve(it)
+      launch_linearize(c);
+      if (it == 0) launch_max_diag(c, d.scal + 4);
+      double hs0[5];
+      CK(cudaMemcpyAsync(hs0, d.scal, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      cur = hs0[0];
+      if (!have_initial) { rep->initial_chi2 = cur; have_initial = true; }
+      if (it == 0) { lam = p.tau * hs0[4]; ni = 2.0; }     // computeLambdaInit
+      double rho = 0.0;
+      int qmax = 0;
+      do {
+        launch_build_and_schur(c, lam);
+        launch_factor_rs(c);
+        launch_backsolve(c);
+        launch_retract_error(c, lam);
+        double hs[4]; int st = 0;
+        if ((rc = read_scalars(c, hs, &st)) != FG_OK) { rep->status = rc; return rc; }
+        CK(cudaGetLastError());
+        const bool solved = st == 0 && std::isfinite(hs[1]) && std::isfinite(hs[2]);
+        const double temp = solved ? hs[3] : std::numeric_limits<double>::max();
+        const double scale = (solved ? lam * hs[2] - hs[1] : 0.0) + 1e-3;        // computeScale: sum dx_j (lambda dx_j + b_j), b = -g
+        rho = (cur - temp) / scale;
+        if (rho > 0 && std::isfinite(temp)) {
+          double alpha = 1.0 - std::pow(2.0 * rho - 1.0, 3);
+          alpha = std::min(alpha, 2.0 / 3.0);
+          lam *= std::max(1.0 / 3.0, alpha);
+          ni = 2.0;
+          cur = temp;
+          for (int t = 0; t < T_COUNT; ++t) std::swap(d.val[t], d.val_new[t]);
+          c->device_newer = true;
+        } else {
+          lam *= ni;
+          ni *= 2.0;
+          if (!std::isfinite(lam)) break;
+        }
+        ++qmax;
+      } while (rho < 0 && qmax < p.max_trials);
+      ok = !(qmax == p.max_trials || rho == 0 || !std::isfinite(lam));          // otherwise: Terminate
+      ++done;
+      if (rep->trace_len < FG_G2O_TRACE_MAX) {
+        const int k = rep->trace_len++;
+        rep->trace_chi2[k] = cur; rep->trace_lambda[k] = lam; rep->trace_trials[k] = qmax;
+      }
+    }
+    rep->calls += 1;
+    done_total += done;
+    if (done == 0) break;
+  }
+  CK(cudaEventRecord(ev.e[1], c->stream));
+  CK(cudaEventSynchronize(ev.e[1]));
+  float ms = 0; cudaEventElapsedTime(&ms, ev.e[0], ev.e[1]);
+  rep->ms_total = ms;
+  rep->iterations = done_total;
+  rep->final_chi2 = cur;
+  rep->lambda = lam;
+  rep->status = FG_OK;
+  return FG_OK;
 }
 
 // ------------------------------------------------------------------ incremental update (ISAM2 semantics)

@@ -28,6 +28,37 @@ FG_HD void between_eval(const double* X1, const double* X2, const double* Z, dou
   }
 }
 
+// g2o::EdgeSE3  (g2o/g2o_graph.cpp:125-132): e = toVectorMQT(Z^-1 X1^-1 X2) = [t, q_xyz], tangent order
+// [trans, rot]; Jacobians w.r.t. VertexSE3::oplus (X <- X * fromVectorMQT(d)) of both ends, 6x6 row-major, at d = 0:
+//   E = A B, A = Z^-1, B = X1^-1 X2;  q_e = (w, v) the quaternion of R_E, Q = w I + [v]x
+//   J2 = [[R_E, 0], [0, Q]]        J1 = [[-R_A, 2 R_A [t_B]x], [0, -Q R_B^T]]
+// (the exact derivatives of the error map, which is what g2o's analytic EdgeSE3 Jacobians are).
+template <bool JAC>
+FG_HD void g2o_edge_eval(const double* X1, const double* X2, const double* Z, double* e, double* J1, double* J2) {
+  double Rb[9], tb[3], Re[9], te[3], q[4];
+  pose_between(X1, X1 + 9, X2, X2 + 9, Rb, tb);
+  pose_between(Z, Z + 9, Rb, tb, Re, te);
+  quat_from_rot(Re, q);
+  e[0] = te[0]; e[1] = te[1]; e[2] = te[2]; e[3] = q[1]; e[4] = q[2]; e[5] = q[3];
+  if (JAC) {
+    double Q[9], S[9], RaS[9], QRbt[9];
+    skew3(q + 1, Q);
+    Q[0] += q[0]; Q[4] += q[0]; Q[8] += q[0];
+    skew3(tb, S);
+    m3_tmul(Z, S, RaS);                 // R_A = R_Z^T
+    m3_mult(Q, Rb, QRbt);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        J2[6 * i + j] = Re[3 * i + j];  J2[6 * i + 3 + j] = 0.0;
+        J2[6 * (i + 3) + j] = 0.0;      J2[6 * (i + 3) + 3 + j] = Q[3 * i + j];
+        J1[6 * i + j] = -Z[3 * j + i];  J1[6 * i + 3 + j] = 2.0 * RaS[3 * i + j];
+        J1[6 * (i + 3) + j] = 0.0;      J1[6 * (i + 3) + 3 + j] = -QRbt[3 * i + j];
+      }
+  }
+}
+
 // PriorFactor<Pose3>  (gtsam/gtsam_graph.cpp:341; A.3): r = Logmap(prior^-1 x), H = I.
 FG_HD void prior_pose_eval(const double* X, const double* Pm, double* r) {
   double R[9], t[3];

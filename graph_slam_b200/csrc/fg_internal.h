@@ -29,6 +29,8 @@ struct HostGraph {
   std::vector<int> pb_var;  std::vector<double> pb_mean, pb_info;                 // prior bias: 6, 36
   std::vector<int> pq_var;  std::vector<double> pq_mean, pq_w;                    // prior point: 3, 1 (1/sigma^2)
   std::vector<int> bt_i, bt_j; std::vector<double> bt_meas, bt_info;             // between: 12, 36
+  std::vector<int> ge_i, ge_j; std::vector<double> ge_meas, ge_info;             // g2o EdgeSE3: 12, 36 (tangent order [trans, rot])
+  std::vector<char> fixed_pose;                                                   // VertexSE3::setFixed (sized on demand; g2o graphs only)
   std::vector<int> imu_var;                                                       // 6 per factor (pose_i, vel_i, pose_j, vel_j, bias_i, bias_j)
   std::vector<ImuRec> imu_rec;
   std::vector<int> pj_pose, pj_point; std::vector<double> pj_uv; std::vector<double> pj_w;  // projection: uv 2, w = 1/sigma^2
@@ -178,6 +180,9 @@ struct DevGraph {
   int n_pv = 0; int* pv_var = nullptr; double* pv_mean = nullptr; double* pv_info = nullptr;
   int n_pb = 0; int* pb_var = nullptr; double* pb_mean = nullptr; double* pb_info = nullptr;
   int n_bt = 0; int* bt_i = nullptr; int* bt_j = nullptr; double* bt_meas = nullptr; double* bt_info = nullptr;
+  int n_ge = 0; int* ge_i = nullptr; int* ge_j = nullptr; double* ge_meas = nullptr; double* ge_info = nullptr;
+  int n_fixed = 0; int* fixed_list = nullptr; char* fixed_pose = nullptr; char* fixed_col = nullptr;   // fixed poses: list, per-pose flag, per reduced column flag
+  int pose_chart = 0;               // retraction of Pose3 values: 0 = Pose3 EXPMAP (GTSAM), 1 = g2o VertexSE3::oplus ([t, q_xyz])
   int n_imu = 0; int* imu_var = nullptr; ImuRec* imu_rec = nullptr;
   int n_pl = 0; int* pl_pose = nullptr; int* pl_plane = nullptr; double* pl_meas = nullptr; double* pl_info = nullptr;
   // landmarks: observations sorted by landmark (CSR), plus CSR by pose
@@ -291,6 +296,7 @@ void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
 void launch_pack(fg_ctx* c, bool with_chi2);               // multi-GPU: gather the exchanged entries of d.L (+ scal[0]) into d.pk_buf
 void launch_unpack(fg_ctx* c, bool with_chi2);             // ... and scatter the reduced values back
+void launch_max_diag(fg_ctx* c, double* d_out);          // g2o computeLambdaInit: max diagonal entry of the assembled Hessian (free variables) -> *d_out
 void launch_inc_gate(fg_ctx* c, double threshold, int* d_count);   // move theta to the estimate where |delta| >= threshold
 void launch_error_only(fg_ctx* c, bool trial);            // chi2 of val (or val_new) -> scal[0] (or scal[3])
 void launch_preintegrate(int n, const int* d_off, const double* d_imu, double dt, const ImuParamsDev* d_par,

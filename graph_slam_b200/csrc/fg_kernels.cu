@@ -171,6 +171,83 @@ __global__ void k_between(int n, const int* __restrict__ vi, const int* __restri
   chi2_accumulate(e, chi2);
 }
 
+// ------------------------------------------------------------------ g2o EdgeSE3 (config 1: CGraphG2O, g2o/g2o_graph.cpp:96-134)
+// chi2 = sum e^T Omega e (no 1/2: g2o's chi2(), g2o_graph.cpp:254-258).  A fixed end (VertexSE3::setFixed, :90) takes no
+// Hessian or gradient contribution: its delta stays 0 (k_fix_identity keeps its diagonal block non-singular).
+template <bool JAC>
+__global__ void k_g2o_edge(int n, const int* __restrict__ vi, const int* __restrict__ vj, const double* __restrict__ meas,
+                           const double* __restrict__ info, Vals vals, const int* __restrict__ off, const char* __restrict__ fixed,
+                           SysView sys, double* g_r, double* chi2) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (f < n) {
+    double X1[12], X2[12], Z[12], r[6], J1[36], J2[36], wr[6], O[36];
+    load_pose(vals.v[T_POSE], vi[f], X1);
+    load_pose(vals.v[T_POSE], vj[f], X2);
+    load_pose(meas, f, Z);
+    g2o_edge_eval<JAC>(X1, X2, Z, r, J1, J2);
+#pragma unroll
+    for (int i = 0; i < 36; ++i) O[i] = info[36 * (int64_t)f + i];
+    matvec<6, 6>(O, r, wr);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e += r[i] * wr[i];
+    if (JAC) {
+      const bool free1 = !fixed || !fixed[vi[f]], free2 = !fixed || !fixed[vj[f]];
+      const int o1 = off[vi[f]], o2 = off[vj[f]];
+      double M1[36], M2[36], H[36], g[6];
+      auto mul = [](const double* A, const double* B, double* C, bool at) {     // C = A B or A^T B (6x6)
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) {
+            double s = 0;
+            for (int k = 0; k < 6; ++k) s += (at ? A[6 * k + i] : A[6 * i + k]) * B[6 * k + j];
+            C[6 * i + j] = s;
+          }
+      };
+      mul(O, J1, M1, false);
+      mul(O, J2, M2, false);
+      if (free1) {
+        mul(J1, M1, H, true);
+        sys_add_block(sys, o1, 6, o1, 6, H, 6);
+        for (int i = 0; i < 6; ++i) { double s = 0; for (int k = 0; k < 6; ++k) s += J1[6 * k + i] * wr[k]; g[i] = s; }
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_r[o1 + i], g[i]);
+      }
+      if (free2) {
+        mul(J2, M2, H, true);
+        sys_add_block(sys, o2, 6, o2, 6, H, 6);
+        for (int i = 0; i < 6; ++i) { double s = 0; for (int k = 0; k < 6; ++k) s += J2[6 * k + i] * wr[k]; g[i] = s; }
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_r[o2 + i], g[i]);
+      }
+      if (free1 && free2) {
+        mul(J2, M1, H, true);                      // rows of vertex 2, columns of vertex 1
+        sys_add_block(sys, o2, 6, o1, 6, H, 6);
+      }
+    }
+  }
+  chi2_accumulate(e, chi2);
+}
+// identity on the diagonal block of every fixed pose (the block has no other contribution)
+__global__ void k_fix_identity(int n, const int* __restrict__ list, const int* __restrict__ off, SysView sys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 6 * n) return;
+  const int C = off[list[i / 6]] + i % 6;
+  int ld;
+  sys.L[sys_find(sys, C, C, &ld)] += 1.0;
+}
+// max diagonal entry over the free columns (g2o: OptimizationAlgorithmLevenberg::computeLambdaInit); doubles >= 0 order
+// like their bit patterns
+__global__ void k_max_diag(SysView sys, const char* __restrict__ fixed_col, unsigned long long* out) {
+  const int C = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (C < sys.n_r && !(fixed_col && fixed_col[C])) {
+    const int sn = sys.col2sn[C];
+    const int c = C - sys.sn_col0[sn];
+    v = fabs(sys.L[sys.sn_valptr[sn] + c + (int64_t)c * sys.sn_nrows[sn]]);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, d));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+
 // ------------------------------------------------------------------ K5 plane
 template <bool JAC>
 __global__ void k_plane(int n, const int* __restrict__ vp, const int* __restrict__ vl,
@@ -544,7 +621,7 @@ __global__ void k_lm_update(int64_t L, const double* __restrict__ pts, const dou
 // Values::retract for the reduced variables; accumulates g_r^T delta and |delta|^2 (once per scalar)
 template <int TYPE>
 __global__ void k_retract_reduced(int64_t n, const double* __restrict__ val, double* val_new, const int* __restrict__ off,
-                                  const double* __restrict__ delta, const double* __restrict__ g_r, double* scal, int count_scal) {
+                                  const double* __restrict__ delta, const double* __restrict__ g_r, double* scal, int count_scal, int chart) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double gd = 0.0, dd = 0.0;
   if (i < n) {
@@ -557,7 +634,8 @@ __global__ void k_retract_reduced(int64_t n, const double* __restrict__ val, dou
     if (TYPE == T_POSE) {
       double X[12], Y[12];
       load_pose(val, (int)i, X);
-      pose_retract(X, X + 9, dl, Y, Y + 9);
+      if (chart == 1) g2o_oplus(X, X + 9, dl, Y, Y + 9);      // VertexSE3::oplus
+      else pose_retract(X, X + 9, dl, Y, Y + 9);             // Pose3::Retract, EXPMAP chart
 #pragma unroll
       for (int k = 0; k < 12; ++k) val_new[12 * i + k] = Y[k];
     } else if (TYPE == T_PLANE) {
@@ -725,6 +803,8 @@ static void run_factors(fg_ctx* c, bool trial, double* chi2) {
     if (d.n_pv) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(d.n_pv, T), T, 0, st>>>(d.n_pv, d.pv_var, d.pv_mean, d.pv_info, v, d.off[T_VEC3], sys, d.g_r, chi2);
     if (d.n_pb) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(d.n_pb, T), T, 0, st>>>(d.n_pb, d.pb_var, d.pb_mean, d.pb_info, v, d.off[T_BIAS], sys, d.g_r, chi2);
     if (d.n_bt) k_between<JAC><<<cdiv(d.n_bt, T), T, 0, st>>>(d.n_bt, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, chi2);
+    if (d.n_ge) k_g2o_edge<JAC><<<cdiv(d.n_ge, 64), 64, 0, st>>>(d.n_ge, d.ge_i, d.ge_j, d.ge_meas, d.ge_info, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, chi2);
+    if (JAC && d.n_fixed) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, st>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
     if (d.n_imu) k_imu<JAC><<<cdiv(d.n_imu, IMU_WPB), 32 * IMU_WPB, 0, st>>>(d.n_imu, d.imu_var, d.imu_rec, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, chi2);
     if (d.n_pl) k_plane<JAC><<<cdiv(d.n_pl, T), T, 0, st>>>(d.n_pl, d.pl_pose, d.pl_plane, d.pl_meas, d.pl_info, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, chi2);
   }
@@ -769,6 +849,12 @@ void launch_build_and_schur(fg_ctx* c, double lambda) {
   k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, st>>>(sys, d.g_r, c->rank == 0 ? lambda : 0.0, 1);
   int64_t L = d.n[T_POINT];
   if (L) launch_schur(c, lambda);
+}
+
+void launch_max_diag(fg_ctx* c, double* d_out) {
+  cudaMemsetAsync(d_out, 0, sizeof(double), c->stream);
+  SysView sys = make_view(c, c->d.U0);
+  k_max_diag<<<cdiv(c->sym.n_r, 256), 256, 0, c->stream>>>(sys, c->d.fixed_col, reinterpret_cast<unsigned long long*>(d_out));
 }
 
 // ------------------------------------------------------------------ incremental update: relinearisation gating
@@ -842,10 +928,10 @@ void launch_retract_error(fg_ctx* c, double lambda) {
   cudaMemsetAsync(d.scal + 1, 0, sizeof(double) * 3, st);
   const int T = 128;
   int cnt = (c->rank == 0) ? 1 : 0;
-  if (d.n[T_POSE]) k_retract_reduced<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], d.off[T_POSE], d.delta, d.g_r, d.scal, cnt);
-  if (d.n[T_VEC3]) k_retract_reduced<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], d.off[T_VEC3], d.delta, d.g_r, d.scal, cnt);
-  if (d.n[T_BIAS]) k_retract_reduced<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], d.off[T_BIAS], d.delta, d.g_r, d.scal, cnt);
-  if (d.n[T_PLANE]) k_retract_reduced<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], d.off[T_PLANE], d.delta, d.g_r, d.scal, cnt);
+  if (d.n[T_POSE]) k_retract_reduced<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], d.off[T_POSE], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
+  if (d.n[T_VEC3]) k_retract_reduced<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], d.off[T_VEC3], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
+  if (d.n[T_BIAS]) k_retract_reduced<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], d.off[T_BIAS], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
+  if (d.n[T_PLANE]) k_retract_reduced<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], d.off[T_PLANE], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
   int64_t L = d.n[T_POINT];
   if (L) {
     cudaMemsetAsync(d.tl, 0, sizeof(double) * 3 * L, st);

@@ -179,6 +179,42 @@ FG_HD void pose_retract(const double* R, const double* t, const double* xi, doub
   se3_exp(xi, dR, dt);
   pose_compose(R, t, dR, dt, Ro, to);
 }
+// ---- g2o's SE3 chart (g2o/types/slam3d/isometry3d_mappings: toVectorMQT / fromVectorMQT)
+// unit quaternion (w, x, y, z) with w >= 0 of a rotation matrix (Shepperd's method; g2o normalises the sign the same way)
+FG_HD void quat_from_rot(const double* M, double* q) {
+  const double tr = M[0] + M[4] + M[8];
+  if (tr > 0) {
+    const double s = sqrt(tr + 1.0) * 2;
+    q[0] = 0.25 * s; q[1] = (M[7] - M[5]) / s; q[2] = (M[2] - M[6]) / s; q[3] = (M[3] - M[1]) / s;
+  } else if (M[0] > M[4] && M[0] > M[8]) {
+    const double s = sqrt(1.0 + M[0] - M[4] - M[8]) * 2;
+    q[0] = (M[7] - M[5]) / s; q[1] = 0.25 * s; q[2] = (M[1] + M[3]) / s; q[3] = (M[2] + M[6]) / s;
+  } else if (M[4] > M[8]) {
+    const double s = sqrt(1.0 + M[4] - M[0] - M[8]) * 2;
+    q[0] = (M[2] - M[6]) / s; q[1] = (M[1] + M[3]) / s; q[2] = 0.25 * s; q[3] = (M[5] + M[7]) / s;
+  } else {
+    const double s = sqrt(1.0 + M[8] - M[0] - M[4]) * 2;
+    q[0] = (M[3] - M[1]) / s; q[1] = (M[2] + M[6]) / s; q[2] = (M[5] + M[7]) / s; q[3] = 0.25 * s;
+  }
+  if (q[0] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+}
+FG_HD void rot_from_quat(const double* q, double* R) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+// VertexSE3::oplus: X <- X * fromVectorMQT(d), d = [t, q_xyz]
+FG_HD void g2o_oplus(const double* R, const double* t, const double* d, double* Ro, double* to) {
+  const double w2 = 1.0 - (d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+  double q[4] = {w2 > 0.0 ? sqrt(w2) : 0.0, d[3], d[4], d[5]};
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+  double dR[9];
+  rot_from_quat(q, dR);
+  pose_compose(R, t, dR, d, Ro, to);
+}
+
 // Ad(T) = [[R,0],[[t]x R, R]]  (6x6 row-major)
 FG_HD void adjoint(const double* R, const double* t, double* Ad) {
   double S[9], SR[9];

@@ -54,6 +54,7 @@ int build_symbolic(fg_ctx* c) {
   std::vector<std::vector<int>> adj(nv);
   auto edge = [&](int a, int b) { if (a != b) { adj[a].push_back(b); adj[b].push_back(a); } };
   for (size_t f = 0; f < h.bt_i.size(); ++f) edge(base[T_POSE][h.bt_i[f]], base[T_POSE][h.bt_j[f]]);
+  for (size_t f = 0; f < h.ge_i.size(); ++f) edge(base[T_POSE][h.ge_i[f]], base[T_POSE][h.ge_j[f]]);
   for (size_t f = 0; f < h.imu_rec.size(); ++f) {
     const int* v = &h.imu_var[6 * f];
     int p[6] = {base[T_POSE][v[0]], base[T_VEC3][v[1]], base[T_POSE][v[2]], base[T_VEC3][v[3]], base[T_BIAS][v[4]], base[T_BIAS][v[5]]};

@@ -182,6 +182,44 @@ int fg_optimize_lm(fg_ctx* ctx, const fg_lm_params* params, fg_lm_report* report
 /* graph.error(values) = 1/2 sum |r|^2_Sigma     CGraphGT::error  gtsam_graph.cpp:173-176 */
 int fg_error(fg_ctx* ctx, double* error);
 
+/* ------------------------------------------------------------------ g2o back-end (CGraphG2O, BASELINE config 1) */
+/* g2o::EdgeSE3 between two VertexSE3 (poses added with fg_add_pose):  setMeasurement(mr.edge.transform),
+ * setInformation(mr.edge.informationMatrix)   CGraphG2O::addToGraph  g2o/g2o_graph.cpp:125-132.
+ * Error = toVectorMQT(Z^-1 X1^-1 X2) = [t, q_xyz]; `info` is 6x6 row-major in that [trans, rot] order.  A graph holds
+ * either GTSAM pose factors or g2o edges, not both (fg_finalize rejects the mix). */
+int fg_add_g2o_edge(fg_ctx* ctx, fg_key k1, fg_key k2, const double T[12], const double info[36]);
+/* VertexSE3::setFixed(true)   CGraphG2O::firstNode  g2o/g2o_graph.cpp:90.  Only g2o edges may touch a fixed vertex. */
+int fg_set_fixed(fg_ctx* ctx, fg_key key, int fixed);
+typedef struct {
+  int iterations;           /* 20: `int iter = 20`                                  g2o_graph.cpp:244 */
+  int iterations_per_call;  /* 2 : mp_optimizer->optimize(ceil(iter/10))            g2o_graph.cpp:249 */
+  double tau;               /* 1e-5: OptimizationAlgorithmLevenberg lambda init = tau * max diag(H)    */
+  int max_trials;           /* 10 : maxTrialsAfterFailure                                              */
+} fg_g2o_params;
+void fg_g2o_params_default(fg_g2o_params* p);
+#define FG_G2O_TRACE_MAX 64
+typedef struct {
+  int iterations;            /* LM iterations performed (the reference asks for 20)                       */
+  int calls;                 /* optimize() calls made (lambda is re-initialised at the start of each)     */
+  double initial_chi2, final_chi2;   /* sum e^T Omega e, no 1/2 (g2o chi2())                               */
+  double lambda;
+  int status;
+  int trace_len;
+  double trace_chi2[FG_G2O_TRACE_MAX];     /* chi2 after the iteration  */
+  double trace_lambda[FG_G2O_TRACE_MAX];   /* lambda after the iteration */
+  int trace_trials[FG_G2O_TRACE_MAX];      /* damped solves it took      */
+  double ms_total;
+} fg_g2o_report;
+/* mp_optimizer->initializeOptimization(); for (i = 0; i < iter; i += currIt) currIt = mp_optimizer->optimize(2);
+ *   CGraphG2O::optimizeGraph  g2o/g2o_graph.cpp:241-252  (OptimizationAlgorithmLevenberg + BlockSolver<6,3> + CSparse
+ *   Cholesky, :65-77): gain ratio rho = (chi2 - chi2_new) / (dx.(lambda dx + b) + 1e-3); on success
+ *   lambda *= max(1/3, min(1 - (2 rho - 1)^3, 2/3)), on failure lambda *= nu, nu *= 2, at most max_trials solves; an
+ *   iteration that ends without progress terminates the optimize() call.  (The reference's loop never ends if optimize()
+ *   returns 0; this entry point returns instead.) */
+int fg_optimize_g2o(fg_ctx* ctx, const fg_g2o_params* params, fg_g2o_report* report);
+/* mp_optimizer->computeActiveErrors(); return mp_optimizer->chi2();   CGraphG2O::error  g2o_graph.cpp:254-258 */
+int fg_g2o_chi2(fg_ctx* ctx, double* chi2);
+
 /* ISAM2Params as CGraphGT sets them (initISAM2Params, gtsam_graph.cpp:93-99). */
 typedef struct {
   double relinearize_threshold;   /* 0.1 */

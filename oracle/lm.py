@@ -126,9 +126,23 @@ class PoseGraphG2O:
         e = self.errors(R, t)
         return float(np.einsum('ni,nij,nj->', e, self.info, e))
 
-    def jacobians(self, eps=1e-7):
-        """Central-difference Jacobians w.r.t. the oplus perturbation of each endpoint
-        (g2o's analytic EdgeSE3 Jacobians are the exact derivative of the same map)."""
+    def jacobians(self, eps=None):
+        """Jacobians of the edge error w.r.t. the oplus perturbation of each endpoint, at zero perturbation (g2o's analytic
+        EdgeSE3 Jacobians are the exact derivative of the same map).  Closed form (E = A B, A = Z^-1, B = X1^-1 X2,
+        q_E = (w, v), Q = w I + [v]x):  J2 = [[R_E, 0], [0, Q]],  J1 = [[-R_A, 2 R_A [t_B]x], [0, -Q R_B^T]];
+        with eps: central differences through g2o_oplus instead (tests/test_oracle_g2o.py checks one against the other)."""
+        if eps is None:
+            Ri, ti, Rj, tj = self.R[self.ei], self.t[self.ei], self.R[self.ej], self.t[self.ej]
+            Rb, tb = lie.pose_between(Ri, ti, Rj, tj)
+            Re, te = lie.pose_between(self.Rm, self.tm, Rb, tb)
+            q = lie.quat_from_rot(Re)
+            Q = q[:, 0, None, None] * np.eye(3)[None] + lie.skew(q[:, 1:])
+            Ra = np.swapaxes(self.Rm, -1, -2)
+            n = len(self.ei)
+            Ji = np.zeros((n, 6, 6)); Jj = np.zeros((n, 6, 6))
+            Jj[:, :3, :3] = Re; Jj[:, 3:, 3:] = Q
+            Ji[:, :3, :3] = -Ra; Ji[:, :3, 3:] = 2.0 * Ra @ lie.skew(tb); Ji[:, 3:, 3:] = -Q @ np.swapaxes(Rb, -1, -2)
+            return Ji, Jj
         n = len(self.ei)
         Ji = np.zeros((n, 6, 6)); Jj = np.zeros((n, 6, 6))
         Ri, ti, Rj, tj = self.R[self.ei], self.t[self.ei], self.R[self.ej], self.t[self.ej]
@@ -201,3 +215,57 @@ def optimize_g2o(pg, iterations=20, tau=1e-5, max_trials=10):
         if rho <= 0:
             break
     return pg, dict(iterations=len(trace), chi2=pg.chi2(), trace=trace)
+
+
+def optimize_g2o_calls(pg, iterations=20, per_call=2, tau=1e-5, max_trials=10):
+    """CGraphG2O::optimizeGraph as written (g2o/g2o_graph.cpp:241-252): `for (i = 0; i < iter; i += currIt) currIt =
+    optimize(ceil(iter/10))` -- every optimize() call restarts OptimizationAlgorithmLevenberg at iteration 0, i.e. lambda
+    is re-initialised to tau * max diag(H) and nu to 2 every `per_call` iterations [ext]; an iteration without progress
+    (rho == 0, max_trials failures or lambda overflow) terminates that call only."""
+    n = len(pg.R)
+    trace = []
+    done_total, calls = 0, 0
+    initial = pg.chi2()
+    lam, ni = 0.0, 2.0
+    while done_total < iterations:
+        done, ok, it = 0, True, 0
+        while it < per_call and ok:
+            H, b, idx = pg.build()
+            cur = pg.chi2()
+            if it == 0:
+                lam, ni = tau * float(H.diagonal().max()), 2.0
+            rho, qmax = 0.0, 0
+            R0, t0 = pg.R.copy(), pg.t.copy()
+            while True:
+                A = (H + lam * sp.identity(H.shape[0], format='csc')).tocsc()
+                try:
+                    dx = spla.splu(A).solve(b)
+                    solved = bool(np.all(np.isfinite(dx)))
+                except RuntimeError:
+                    dx, solved = np.zeros_like(b), False
+                full = np.zeros(6 * n); full[idx] = dx
+                Rn, tn = F.g2o_oplus(R0, t0, full.reshape(-1, 6))
+                temp = pg.chi2(Rn, tn) if solved else np.finfo(float).max
+                scale = (float(dx @ (lam * dx + b)) if solved else 0.0) + 1e-3
+                rho = (cur - temp) / scale
+                if rho > 0 and np.isfinite(temp):
+                    lam *= max(1.0 / 3.0, min(1.0 - (2 * rho - 1) ** 3, 2.0 / 3.0))
+                    ni = 2.0
+                    pg.R, pg.t = Rn, tn
+                    cur = temp
+                else:
+                    lam *= ni
+                    ni *= 2
+                    if not np.isfinite(lam):
+                        break
+                qmax += 1
+                if not (rho < 0 and qmax < max_trials):
+                    break
+            ok = not (qmax == max_trials or rho == 0 or not np.isfinite(lam))
+            done += 1; it += 1
+            trace.append(dict(chi2=cur, lam=lam, trials=qmax))
+        calls += 1
+        done_total += done
+        if done == 0:
+            break
+    return pg, dict(iterations=done_total, calls=calls, initial_chi2=initial, chi2=pg.chi2(), trace=trace)

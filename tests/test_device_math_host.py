@@ -124,3 +124,26 @@ def test_d_jr_c(hostmath, rng):
         th = rng.normal(size=3) * rng.choice([1e-7, 0.1, 1.5]); c = rng.normal(size=3)
         D = arr(9); hostmath.hm_d_jr_c(p(th), p(c), p(D))
         assert np.allclose(D.reshape(3, 3), oimu._d_jr_c(th, c), atol=1e-12)
+
+
+def test_g2o_edge_and_oplus(hostmath, rng):
+    """g2o::EdgeSE3 / VertexSE3::oplus as the device evaluates them (SURVEY A.8): the error against the oracle, the analytic
+    Jacobians against central differences of the oracle's error map through the oracle's oplus."""
+    for _ in range(50):
+        R1, t1 = rand_pose(rng); R2, t2 = rand_pose(rng)
+        Rm, tm = lie.pose_compose(*lie.pose_between(R1, t1, R2, t2), *lie.se3_exp(rng.normal(size=6) * rng.choice([0.02, 0.4, 2.0])))
+        e, J1, J2 = arr(6), arr(36), arr(36)
+        hostmath.hm_g2o_edge(p(T12(R1, t1)), p(T12(R2, t2)), p(T12(Rm, tm)), p(e), p(J1), p(J2))
+        ref = F.g2o_edge_se3(R1, t1, R2, t2, Rm, tm)
+        assert np.allclose(e, ref, atol=1e-13)
+        eps = 1e-6
+        N1, N2 = np.zeros((6, 6)), np.zeros((6, 6))
+        for k in range(6):
+            d = np.zeros(6); d[k] = eps
+            N1[:, k] = (F.g2o_edge_se3(*F.g2o_oplus(R1, t1, d), R2, t2, Rm, tm) - F.g2o_edge_se3(*F.g2o_oplus(R1, t1, -d), R2, t2, Rm, tm)) / (2 * eps)
+            N2[:, k] = (F.g2o_edge_se3(R1, t1, *F.g2o_oplus(R2, t2, d), Rm, tm) - F.g2o_edge_se3(R1, t1, *F.g2o_oplus(R2, t2, -d), Rm, tm)) / (2 * eps)
+        assert np.allclose(J1.reshape(6, 6), N1, atol=1e-8) and np.allclose(J2.reshape(6, 6), N2, atol=1e-8)
+        d = rng.normal(size=6) * 0.2
+        To = arr(12); hostmath.hm_g2o_oplus(p(T12(R1, t1)), p(d), p(To))
+        Ro, to = F.g2o_oplus(R1, t1, d)
+        assert np.allclose(To[:9].reshape(3, 3), Ro, atol=1e-14) and np.allclose(To[9:], to, atol=1e-14)

@@ -45,3 +45,13 @@ def test_g2o_and_gtsam_semantics_agree_on_the_optimum():
     pg, _ = lm.optimize_g2o(pg, iterations=20)
     g, _ = lm.optimize_gtsam(build.from_spec(spec))
     assert np.abs(pg.t - g.t).max() < 5e-3
+
+
+def test_closed_form_edge_jacobians_match_central_differences():
+    spec, pg = make_pg(seed=3)
+    rng = np.random.default_rng(0)
+    dR, dt = lie.se3_exp(rng.normal(size=(len(pg.R), 6)) * 0.5)
+    pg.R, pg.t = lie.pose_compose(pg.R, pg.t, dR, dt)          # large residuals: the Jacobians are not near the identity
+    Ji, Jj = pg.jacobians()
+    Ni, Nj = pg.jacobians(eps=1e-6)
+    assert np.abs(Ji - Ni).max() < 1e-8 and np.abs(Jj - Nj).max() < 1e-8
