@@ -55,3 +55,21 @@ def fglib():
     if not os.path.exists(abi.LIB_PATH):
         g.build()
     return abi.lib()
+
+
+@pytest.fixture(scope='session')
+def refbin(fglib):
+    """Path of a binary built by compat/build_ref.py: the reference's own wrapper sources / drivers (and this repository's
+    test programs written against the reference's headers) compiled UNCHANGED over compat/ + the facades.  Built here when
+    /root/reference is present; on the GPU box the prebuilt files that travelled with the snapshot are used."""
+    sys.path.insert(0, os.path.join(ROOT, 'compat'))
+    import build_ref
+    if build_ref.available():
+        build_ref.build()
+
+    def get(name):
+        path = os.path.join(ROOT, 'compat', '_ref', name)
+        if not os.path.exists(path):
+            pytest.skip('%s not built (the reference sources are not on this machine and no prebuilt compat/_ref/ travelled)' % name)
+        return path
+    return get

@@ -1,4 +1,5 @@
-// Multi-frame BA and two-view BA through the C++ mirror of the reference's wrapper API (graph_slam_b200/host):
+// Multi-frame BA and two-view BA through the reference's OWN wrapper (gtsam/gtsam_graph.cpp built unchanged over compat/ +
+// the gtsam facade, compat/build_ref.py):
 //   CGraphGT::firstNode / addNodeOffline (VRO edges)      gtsam_graph.cpp:320-368, 1593-1623
 //   CGraphGT::addToGTSAM(CCameraNodeBA*, CCameraNodeBA*, map<int,int>&, CamModel*)   :370-448
 //   CGraphGT::optimizeGraphBatch                          :1784-1788
@@ -7,12 +8,19 @@
 // usage: ba_driver features.txt vro.log out.txt
 #include <cstdio>
 #include <fstream>
-#include "../../graph_slam_b200/host/gtsam_graph.h"
+#include <ros/ros.h>
+#include <gtsam/nonlinear/NonlinearFactorGraph.h>
+#include <gtsam/nonlinear/Values.h>
+#include <gtsam/inference/Symbol.h>
+#include "gtsam_graph.h"
+#include "camera_node_ba.h"
+#include "matching_result.h"
+#include "cam_model.h"
 using namespace gtsam;
 using symbol_shorthand::X;
 
 struct NodeAll : public CCameraNodeBA {     // "front end": feature k of every frame is the same physical point
-  std::map<int, int> matchNodePairBA(CCameraNodeBA* older, const Matrix4&, CamModel*) override {
+  std::map<int, int> matchNodePairBA(CCameraNodeBA* older, Eigen::Matrix4f&, CamModel*) override {
     std::map<int, int> m;
     for (size_t k = 0; k < m_feature_loc_3d.size() && k < older->m_feature_loc_3d.size(); ++k) m[(int)k] = (int)k;
     return m;
@@ -31,7 +39,7 @@ int main(int argc, char** argv) {
     nodes[p]->m_feature_loc_3d.resize(n); nodes[p]->m_feature_loc_2d.resize(n); nodes[p]->mv_feature_qid.assign(n, -1);
     for (int k = 0; k < n; ++k) {
       double x, y, z, u, v; in >> x >> y >> z >> u >> v;
-      nodes[p]->m_feature_loc_3d[k] = {(float)x, (float)y, (float)z, 1.f};
+      nodes[p]->m_feature_loc_3d[k] = Eigen::Vector4f((float)x, (float)y, (float)z, 1.f);
       nodes[p]->m_feature_loc_2d[k].pt.x = (float)u; nodes[p]->m_feature_loc_2d[k].pt.y = (float)v;
     }
   }
@@ -58,7 +66,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 12; ++i) fprintf(f, "%.17g ", a[i]);
     fprintf(f, "\n");
   }
-  { double a[12]; Pose3(ba.final_trafo).toArray12(a); for (int i = 0; i < 12; ++i) fprintf(f, "%.17g ", a[i]); fprintf(f, "\n"); }
+  { double a[12]; Pose3(Eigen::Matrix4d(ba.final_trafo.cast<double>())).toArray12(a); for (int i = 0; i < 12; ++i) fprintf(f, "%.17g ", a[i]); fprintf(f, "\n"); }
   for (int r = 0; r < 6; ++r) { for (int c = 0; c < 6; ++c) fprintf(f, "%.17g ", ba.edge.informationMatrix(r, c)); fprintf(f, "0 0 0 0 0 0\n"); }
   fclose(f);
   return 0;

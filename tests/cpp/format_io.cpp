@@ -1,8 +1,15 @@
-// Host-only exercise of the text formats on the path through the C++ mirror of CGraphGT:
+// Host-only exercise of the text formats on the path through the reference's own CGraphGT
+// (gtsam/gtsam_graph.cpp built unchanged over compat/ + the gtsam facade, compat/build_ref.py):
 // VRO edge log round trip (printVROResult -> readVRORecord), trajectory log, trajectory PLY, g2o export.  No GPU call.
 #include <cstdio>
 #include <fstream>
-#include "../../graph_slam_b200/host/gtsam_graph.h"
+#include <ros/ros.h>
+#include <gtsam/nonlinear/NonlinearFactorGraph.h>
+#include <gtsam/nonlinear/Values.h>
+#include <gtsam/inference/Symbol.h>
+#include "gtsam_graph.h"
+#include "camera_node.h"
+#include "matching_result.h"
 using namespace gtsam;
 
 int main(int argc, char** argv) {
@@ -15,7 +22,7 @@ int main(int argc, char** argv) {
   for (int k = 0; k < 3; ++k) {
     Vector6 r; for (int i = 0; i < 6; ++i) r(i) = 0.01 * (i + 1) * (k + 1);
     Pose3 p = Pose3::ChartAtOrigin::Retract(r);
-    recs[k].final_trafo = p.matrix(); recs[k].edge.transform = p;
+    recs[k].final_trafo = p.matrix().cast<float>(); recs[k].edge.transform = p.matrix();
     recs[k].edge.id1 = k; recs[k].edge.id2 = k + 1;
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) recs[k].edge.informationMatrix(i, j) = (i == j ? 100.0 + i : 0.5) * (k == 2 && i == 0 && j == 0 ? 0 : 1);
   }

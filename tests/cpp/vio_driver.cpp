@@ -1,6 +1,8 @@
 // vio_driver.cpp -- test program in the shape of the reference's offline VIO driver
-// (gtsam/test_vro_imu_graph.cpp:76-360, without images, planes and ROS): VRO edge log + IMU log + image time
-// log -> CGraphGT / CImuVn100 -> optimizeGraphBatch, through the host mirror in graph_slam_b200/host.
+// (gtsam/test_vro_imu_graph.cpp:76-360, without images and planes): VRO edge log + IMU log + image time log ->
+// CGraphGT / CImuVn100 -> optimizeGraphBatch.  It is compiled against the REFERENCE's own headers and linked with the
+// reference's own gtsam_graph.cpp / imu_base.cpp / imu_vn100.cpp built unchanged over compat/ + the gtsam facade
+// (compat/build_ref.py); nothing of CGraphGT is re-implemented in this repository.
 //   usage: vio_driver <vro.log> <imu.log> <times.log> <out_poses.txt> [incremental]
 // With "incremental" the loop also does what the reference does at the end of every frame
 // (test_vro_imu_graph.cpp:344-350): optimizeGraphIncremental(), then the integrator is re-seeded from the estimated
@@ -10,7 +12,16 @@
 #include <cstring>
 #include <fstream>
 #include <map>
-#include "../../graph_slam_b200/host/gtsam_graph.h"
+#include <ros/ros.h>
+#include <gtsam/navigation/CombinedImuFactor.h>
+#include <gtsam/nonlinear/NonlinearFactorGraph.h>
+#include <gtsam/nonlinear/Values.h>
+#include <gtsam/nonlinear/ISAM2.h>
+#include <gtsam/inference/Symbol.h>
+#include "gtsam_graph.h"
+#include "imu_vn100.h"
+#include "camera_node.h"
+#include "matching_result.h"
 
 using namespace gtsam;
 using symbol_shorthand::B;

@@ -1,5 +1,6 @@
-"""Text formats on the path through the C++ mirror of CGraphGT -- host only, no GPU:
-VRO edge log round trip with the failed-match sentinel, trajectory log, trajectory PLY, g2o export."""
+"""Text formats on the path through the reference's own CGraphGT (gtsam/gtsam_graph.cpp
+compiled unchanged over compat/ + the gtsam facade, compat/build_ref.py) -- host only, no GPU: VRO edge log round trip with
+the failed-match sentinel, trajectory log, trajectory PLY, g2o export."""
 import os
 import subprocess
 import numpy as np
@@ -8,13 +9,8 @@ from oracle import lie
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_vro_log_trajectory_ply_g2o(fglib, tmp_path):
-    out_dir = os.path.join(ROOT, 'tests', 'hostmath', '_build')
-    os.makedirs(out_dir, exist_ok=True)
-    exe = os.path.join(out_dir, 'format_io')
-    libdir = os.path.join(ROOT, 'graph_slam_b200')
-    subprocess.check_call(['g++', '-std=c++17', '-O1', '-I' + os.path.join(ROOT, 'include'), os.path.join(ROOT, 'tests', 'cpp', 'format_io.cpp'),
-                           os.path.join(ROOT, 'graph_slam_b200', 'host', 'gtsam_graph.cpp'), '-L' + libdir, '-lfg_b200', '-Wl,-rpath,' + libdir, '-o', exe])
+def test_vro_log_trajectory_ply_g2o(refbin, tmp_path):
+    exe = refbin('format_io')
     res = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stderr[-2000:]
     out = dict(l.split(' ', 1) for l in res.stdout.splitlines() if l.split(' ')[0] in ('RECORDS', 'ADDED', 'X2', 'WRITE'))
