@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_sources_compile_unchanged_and_link(refbin):
     """CPU-side check: every reference file on the path builds from /root/reference with -Icompat and
     links libfg_b200.so -- the wrapper libraries, both offline drivers and this repository's test programs."""
-    for name in ('libgraphslam_gt.so', 'libgraphslam_g2o.so', 'test_vro_imu_graph', 'test_ba_imu_graph', 'vio_driver', 'ba_driver', 'format_io', 'g2o_driver'):
+    for name in ('libgraphslam_gt.so', 'libgraphslam_g2o.so', 'test_vro_imu_graph', 'test_ba_imu_graph', 'vio_driver', 'ba_driver', 'format_io', 'plane_driver', 'g2o_driver'):
         assert os.path.exists(refbin(name))
 
 
@@ -203,3 +203,80 @@ def test_g2o_driver_matches_oracle(refbin, tmp_path):
     assert np.abs(a[:, 1:4] - pg.t).max() <= 1e-6
     g2o = [l.split() for l in open(tmp_path / 'graph.g2o')]
     assert sum(l[0] == 'VERTEX_SE3:QUAT' for l in g2o) == spec['n_poses'] and sum(l[0] == 'EDGE_SE3:QUAT' for l in g2o) == len(ei)
+
+
+def _plane_transform(pl, R, t):
+    """OrientedPlane3::transform(pose) with the 3x3 Jacobian w.r.t. the plane (A.4): n' = R^T n, d' = n.t + d."""
+    from oracle import factors as ofac
+    n = pl[:3]
+    q = R.T @ n
+    out = np.concatenate([q, [n @ t + pl[3]]])
+    Bn, Bq = ofac.unit3_basis(n), ofac.unit3_basis(q)
+    Hp = np.zeros((3, 3))
+    Hp[:2, :2] = Bq.T @ R.T @ Bn
+    Hp[2, :2] = Bn.T @ t
+    Hp[2, 2] = 1.0
+    return out, Hp, Bn
+
+
+@pytest.mark.gpu
+def test_plane_branch_through_reference_add_plane_factor(refbin, tmp_path):
+    """BASELINE config 3 (plane-aided VIO) through the reference's own CGraphGT::addPlaneFactor (gtsam_graph.cpp:1118-1298):
+    the covariance J blkdiag(B^T S_n B, S_d) J^T, its conditioning (off-diagonal (0,1) dropped, diagonal truncated through a
+    float), the world-frame landmark initialisation -- restated here in numpy for the oracle graph -- then batch LM on the
+    device against the oracle."""
+    from oracle import factors as ofac
+    exe = refbin('plane_driver')
+    spec = synth.make_config('C3', seed=2, scale=0.06)
+    vro, imu, times = (str(tmp_path / n) for n in ('vro.log', 'imu.log', 'times.log'))
+    recs = driver_logs.write_logs(spec, vro, imu, times)
+    g0 = driver_logs.oracle_graph_from_logs(spec, recs)
+    Ruc, tuc = spec['Rs'], spec['ts']                      # mp_u2c: camera pose in the IMU frame
+    Rcu, tcu = lie.pose_inverse(Ruc, tuc)
+    rng = np.random.default_rng(7)
+    opose, opl = spec['plane_obs_pose'], spec['plane_obs_plane']
+    order = np.lexsort((np.arange(len(opose)), opose))      # the driver adds the observations frame by frame, in file order within a frame
+    # landmark ids in order of first appearance (the driver's file carries them)
+    first_seen, lm_id = {}, []
+    for k in order:
+        first_seen.setdefault(int(opl[k]), len(first_seen))
+    meas, infos, obs_i, obs_l, init = [], [], [], [], {}
+    with open(tmp_path / 'planes.txt', 'w') as f:
+        for k in order:
+            zb = spec['plane_meas'][k]                       # plane in the IMU frame
+            zc, _, _ = _plane_transform(zb, Ruc, tuc)        # ... as the camera sees it
+            A = rng.normal(size=(4, 4)) * 0.003
+            S = A @ A.T + np.diag([2e-5, 3e-5, 2.5e-5, 1e-4])
+            lid = first_seen[int(opl[k])]
+            f.write('%d %d %s %s\n' % (opose[k], lid, ' '.join(repr(float(v)) for v in zc), ' '.join(repr(float(v)) for v in S.ravel())))
+            # --- what addPlaneFactor does with it
+            onj, J, Bn = _plane_transform(zc, Rcu, tcu)      # ONJ = ONI.transform(Tcu, J)
+            S_upi = np.zeros((3, 3)); S_upi[:2, :2] = Bn.T @ S[:3, :3] @ Bn; S_upi[2, 2] = S[3, 3]
+            S_upj = J @ S_upi @ J.T
+            dom = all(abs(S_upj[i, i]) >= sum(abs(S_upj[i, j]) for j in range(3) if j != i) for i in range(3))
+            if not dom:
+                S_upj = np.diag(np.diag(S_upj))
+            S_upj[0, 1] = S_upj[1, 0] = 0.0
+            for i in range(3):
+                S_upj[i, i] = float(np.float32(int(S_upj[i, i] * 1e8))) * 1e-8 + 1e-8
+            meas.append(onj); infos.append(np.linalg.inv(S_upj)); obs_i.append(int(opose[k])); obs_l.append(lid)
+            if lid not in init:                              # new landmark: ONW = ONJ.transform(Twu^-1) at the pose's current value
+                Rw, tw = lie.pose_inverse(g0.R[opose[k]], g0.t[opose[k]])
+                init[lid] = _plane_transform(onj, Rw, tw)[0]
+    g0.plane = np.array([init[l] for l in range(len(init))])
+    g0.f['plane'] = dict(i=np.array(obs_i), l=np.array(obs_l), meas=np.array(meas), info=np.array(infos))
+    res = subprocess.run([exe, vro, imu, times, str(tmp_path / 'planes.txt'), str(tmp_path / 'poses.txt'), str(tmp_path / 'planes_out.txt')],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith('RESULT')][0].split()
+    assert int(line[2]) == spec['n_poses'] and int(line[4]) == len(init) and int(line[6]) == len(order) and int(line[8]) == 0
+    ini = np.loadtxt(str(tmp_path / 'planes_out.txt') + '.init')
+    assert np.abs(ini[:, 1:] - g0.plane).max() <= 1e-12
+    e0, e1 = float(line[10]), float(line[12])
+    assert abs(e0 - g0.error()) <= 1e-9 * g0.error(), (e0, g0.error())
+    g1, rep = lm.optimize_gtsam(g0)
+    assert abs(e1 - rep['error']) <= 1e-9 * rep['error']
+    got = np.loadtxt(tmp_path / 'poses.txt')
+    assert np.abs(got[:, 10:13] - g1.t).max() <= 1e-8 and np.abs(got[:, 1:10].reshape(-1, 3, 3) - g1.R).max() <= 1e-8
+    pl = np.loadtxt(tmp_path / 'planes_out.txt')
+    assert np.abs(pl[:, 1:] - g1.plane).max() <= 1e-7
