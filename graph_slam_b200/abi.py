@@ -117,6 +117,7 @@ SIGNATURES = {
     'fg_optimize_lm': (C.c_int, [_vp, C.POINTER(LMParams), C.POINTER(LMReport)]),
     'fg_error': (C.c_int, [_vp, _dp]),
     'fg_marginal_cov': (C.c_int, [_vp, C.c_uint64, _dp, C.POINTER(C.c_int)]),
+    'fg_set_pose_chart': (C.c_int, [_vp, C.c_int]),
     'fg_add_g2o_edge': (C.c_int, [_vp, C.c_uint64, C.c_uint64, _dp, _dp]),
     'fg_set_fixed': (C.c_int, [_vp, C.c_uint64, C.c_int]),
     'fg_g2o_params_default': (None, [C.POINTER(G2OParams)]),
@@ -283,6 +284,7 @@ class Context:
         self.call('fg_optimize_lm', C.byref(p), C.byref(rep))
         return rep
 
+    def set_pose_chart(self, chart): self.call('fg_set_pose_chart', int(chart))
     def add_g2o_edge(self, k1, k2, T12, info): a, p = _d(T12); b, q = _d(info); self.call('fg_add_g2o_edge', k1, k2, p, q)
     def set_fixed(self, key, fixed=True): self.call('fg_set_fixed', key, int(bool(fixed)))
 

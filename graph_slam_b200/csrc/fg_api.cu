@@ -367,6 +367,13 @@ extern "C" int fg_add_between(fg_ctx* c, fg_key k1, fg_key k2, const double T[12
   c->finalized = false;
   return FG_OK;
 }
+extern "C" int fg_set_pose_chart(fg_ctx* c, int chart) {
+  if (!c) return FG_ERR_INVALID;
+  if (chart != FG_CHART_EXPMAP && chart != FG_CHART_FIRST_ORDER_EXPMAP && chart != FG_CHART_FIRST_ORDER_CAYLEY) return fail(c, FG_ERR_INVALID, "unknown Pose3 chart");
+  c->pose_chart = chart;
+  c->d.pose_chart = c->d.n_ge ? 1 : chart;      // takes effect at once on a finalized graph too
+  return FG_OK;
+}
 extern "C" int fg_add_g2o_edge(fg_ctx* c, fg_key k1, fg_key k2, const double T[12], const double info[36]) {
   if (!c || !T || !info) return fail(c, FG_ERR_INVALID, "null argument");
   int a, b; FIND(k1, T_POSE, &a); FIND(k2, T_POSE, &b);
@@ -665,7 +672,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
   if ((rc = dev_upload(c, &d.imu_var, h.imu_var)) || (rc = dev_upload(c, &d.imu_rec, h.imu_rec))) return rc;
   // g2o back-end: EdgeSE3 factors, fixed vertices, VertexSE3::oplus as the pose retraction
   d.n_ge = (int)h.ge_i.size();
-  d.pose_chart = d.n_ge ? 1 : 0;
+  d.pose_chart = d.n_ge ? 1 : c->pose_chart;
   if (d.n_ge && (h.pp_var.size() + h.bt_i.size() + h.imu_rec.size() + h.pl_pose.size() + h.pj_pose.size()))
     return fail(c, FG_ERR_INVALID, "g2o edges and GTSAM pose factors cannot share a graph (different pose charts)");
   {

@@ -7,13 +7,14 @@
 namespace fg {
 
 // BetweenFactor<Pose3>  (gtsam/gtsam_graph.cpp:691-692; A.3)
-//   r = Logmap(Z^-1 X1^-1 X2), H1 = -Ad(h^-1), H2 = I.  J1 is 6x6 row-major (only if JAC).
+//   r = Local(Z, h) = ChartAtOrigin::Local(Z^-1 X1^-1 X2) under the context's chart (fg_math.cuh), H1 = -Ad(h^-1), H2 = I
+//   (GTSAM's fast path: the derivative of Local is not chained in).  J1 is 6x6 row-major (only if JAC).
 template <bool JAC>
-FG_HD void between_eval(const double* X1, const double* X2, const double* Z, double* r, double* J1) {
+FG_HD void between_eval(const double* X1, const double* X2, const double* Z, double* r, double* J1, int chart = 0) {
   double Rh[9], th[3], Re[9], te[3];
   pose_between(X1, X1 + 9, X2, X2 + 9, Rh, th);
   pose_between(Z, Z + 9, Rh, th, Re, te);
-  se3_log(Re, te, r);
+  pose_chart_local0(Re, te, chart, r);
   if (JAC) {
     double Rhi[9], thi[3];
 #pragma unroll
@@ -59,11 +60,11 @@ FG_HD void g2o_edge_eval(const double* X1, const double* X2, const double* Z, do
   }
 }
 
-// PriorFactor<Pose3>  (gtsam/gtsam_graph.cpp:341; A.3): r = Logmap(prior^-1 x), H = I.
-FG_HD void prior_pose_eval(const double* X, const double* Pm, double* r) {
+// PriorFactor<Pose3>  (gtsam/gtsam_graph.cpp:341; A.3): r = Local(prior, x) = ChartAtOrigin::Local(prior^-1 x), H = I.
+FG_HD void prior_pose_eval(const double* X, const double* Pm, double* r, int chart = 0) {
   double R[9], t[3];
   pose_between(Pm, Pm + 9, X, X + 9, R, t);
-  se3_log(R, t, r);
+  pose_chart_local0(R, t, chart, r);
 }
 
 // Camera model: Cal3DS2 K = (fx,fy,s,u0,v0,k1,k2,p1,p2); sensor = body_P_sensor pose (12).

@@ -182,7 +182,7 @@ struct DevGraph {
   int n_bt = 0; int* bt_i = nullptr; int* bt_j = nullptr; double* bt_meas = nullptr; double* bt_info = nullptr;
   int n_ge = 0; int* ge_i = nullptr; int* ge_j = nullptr; double* ge_meas = nullptr; double* ge_info = nullptr;
   int n_fixed = 0; int* fixed_list = nullptr; char* fixed_pose = nullptr; char* fixed_col = nullptr;   // fixed poses: list, per-pose flag, per reduced column flag
-  int pose_chart = 0;               // retraction of Pose3 values: 0 = Pose3 EXPMAP (GTSAM), 1 = g2o VertexSE3::oplus ([t, q_xyz])
+  int pose_chart = 0;               // Pose3 chart (fg_math.cuh): 0 EXPMAP, 1 g2o VertexSE3::oplus, 2 FIRST_ORDER / Rot3 EXPMAP, 3 FIRST_ORDER / Rot3 CAYLEY
   int n_imu = 0; int* imu_var = nullptr; ImuRec* imu_rec = nullptr;
   int n_pl = 0; int* pl_pose = nullptr; int* pl_plane = nullptr; double* pl_meas = nullptr; double* pl_info = nullptr;
   // landmarks: observations sorted by landmark (CSR), plus CSR by pose
@@ -262,6 +262,7 @@ struct fg_ctx {
   bool values_dirty = false;     // host values newer than device
   bool device_newer = false;     // device values newer than host
   // incremental session (fg_update_incremental): d.val holds theta, d.val_new the estimate; h.val / h.lin mirror them
+  int pose_chart = 0;            // fg_set_pose_chart (GTSAM graphs; the g2o back-end uses its own)
   bool inc_active = false;
   int inc_updates = 0;
   int64_t inc_known[fg::T_COUNT] = {0, 0, 0, 0, 0};   // variables per type at the previous update

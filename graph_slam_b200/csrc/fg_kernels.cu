@@ -63,7 +63,7 @@ __device__ __forceinline__ void matvec(const double* A, const double* x, double*
 template <bool JAC>
 __global__ void k_prior_pose(int n, const int* __restrict__ var, const double* __restrict__ mean,
                              const double* __restrict__ info, Vals vals, const int* __restrict__ off,
-                             SysView sys, double* g_r, double* chi2) {
+                             SysView sys, double* g_r, double* chi2, int chart) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0;
   if (f < n) {
@@ -71,7 +71,7 @@ __global__ void k_prior_pose(int n, const int* __restrict__ var, const double* _
     load_pose(vals.v[T_POSE], var[f], X);
 #pragma unroll
     for (int i = 0; i < 12; ++i) Pm[i] = mean[12 * f + i];
-    prior_pose_eval(X, Pm, r);
+    prior_pose_eval(X, Pm, r, chart);
     const double* Om = info + 36 * f;
     matvec<6, 6>(Om, r, wr);
 #pragma unroll
@@ -115,7 +115,7 @@ __global__ void k_prior_vec(int n, const int* __restrict__ var, const double* __
 template <bool JAC>
 __global__ void k_between(int n, const int* __restrict__ vi, const int* __restrict__ vj,
                           const double* __restrict__ meas, const double* __restrict__ info, Vals vals,
-                          const int* __restrict__ off, SysView sys, double* g_r, double* chi2) {
+                          const int* __restrict__ off, SysView sys, double* g_r, double* chi2, int chart) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0;
   if (f < n) {
@@ -123,7 +123,7 @@ __global__ void k_between(int n, const int* __restrict__ vi, const int* __restri
     load_pose(vals.v[T_POSE], vi[f], X1);
     load_pose(vals.v[T_POSE], vj[f], X2);
     load_pose(meas, f, Z);
-    between_eval<JAC>(X1, X2, Z, r, J1);
+    between_eval<JAC>(X1, X2, Z, r, J1, chart);
     const double* Om = info + 36 * (int64_t)f;
     double O[36];
 #pragma unroll
@@ -634,8 +634,8 @@ __global__ void k_retract_reduced(int64_t n, const double* __restrict__ val, dou
     if (TYPE == T_POSE) {
       double X[12], Y[12];
       load_pose(val, (int)i, X);
-      if (chart == 1) g2o_oplus(X, X + 9, dl, Y, Y + 9);      // VertexSE3::oplus
-      else pose_retract(X, X + 9, dl, Y, Y + 9);             // Pose3::Retract, EXPMAP chart
+      if (chart == 1) g2o_oplus(X, X + 9, dl, Y, Y + 9);                 // VertexSE3::oplus
+      else pose_chart_retract(X, X + 9, dl, chart, Y, Y + 9);           // Pose3::Retract under the context's chart
 #pragma unroll
       for (int k = 0; k < 12; ++k) val_new[12 * i + k] = Y[k];
     } else if (TYPE == T_PLANE) {
@@ -799,10 +799,10 @@ static void run_factors(fg_ctx* c, bool trial, double* chi2) {
   const bool pose_side = (c->rank == 0);     // replicated factors are counted once
   const int T = 128;
   if (pose_side) {
-    if (d.n_pp) k_prior_pose<JAC><<<cdiv(d.n_pp, T), T, 0, st>>>(d.n_pp, d.pp_var, d.pp_mean, d.pp_info, v, d.off[T_POSE], sys, d.g_r, chi2);
+    if (d.n_pp) k_prior_pose<JAC><<<cdiv(d.n_pp, T), T, 0, st>>>(d.n_pp, d.pp_var, d.pp_mean, d.pp_info, v, d.off[T_POSE], sys, d.g_r, chi2, d.pose_chart);
     if (d.n_pv) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(d.n_pv, T), T, 0, st>>>(d.n_pv, d.pv_var, d.pv_mean, d.pv_info, v, d.off[T_VEC3], sys, d.g_r, chi2);
     if (d.n_pb) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(d.n_pb, T), T, 0, st>>>(d.n_pb, d.pb_var, d.pb_mean, d.pb_info, v, d.off[T_BIAS], sys, d.g_r, chi2);
-    if (d.n_bt) k_between<JAC><<<cdiv(d.n_bt, T), T, 0, st>>>(d.n_bt, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, chi2);
+    if (d.n_bt) k_between<JAC><<<cdiv(d.n_bt, T), T, 0, st>>>(d.n_bt, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, chi2, d.pose_chart);
     if (d.n_ge) k_g2o_edge<JAC><<<cdiv(d.n_ge, 64), 64, 0, st>>>(d.n_ge, d.ge_i, d.ge_j, d.ge_meas, d.ge_info, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, chi2);
     if (JAC && d.n_fixed) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, st>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
     if (d.n_imu) k_imu<JAC><<<cdiv(d.n_imu, IMU_WPB), 32 * IMU_WPB, 0, st>>>(d.n_imu, d.imu_var, d.imu_rec, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, chi2);
@@ -861,7 +861,7 @@ void launch_max_diag(fg_ctx* c, double* d_out) {
 // ISAM2's fluid relinearisation (gtsam_graph.cpp:93-99: relinearizeThreshold 0.1): delta_j = local(theta_j, estimate_j);
 // where a component reaches the threshold the linearisation point moves to the estimate.
 template <int TYPE>
-__global__ void k_inc_gate(int64_t n, double* __restrict__ theta, const double* __restrict__ est, double thr, int* count) {
+__global__ void k_inc_gate(int64_t n, double* __restrict__ theta, const double* __restrict__ est, double thr, int* count, int chart) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int S = (TYPE == T_POSE) ? 12 : (TYPE == T_PLANE ? 4 : (TYPE == T_BIAS ? 6 : 3));
@@ -872,7 +872,7 @@ __global__ void k_inc_gate(int64_t n, double* __restrict__ theta, const double* 
   if (TYPE == T_POSE) {
     double R[9], t[3];
     pose_between(a, a + 9, b, b + 9, R, t);
-    se3_log(R, t, dl);
+    pose_chart_local0(R, t, chart, dl);
   } else if (TYPE == T_PLANE) {
     unit3_local(a, b, dl);
     dl[2] = b[3] - a[3];
@@ -893,11 +893,11 @@ void launch_inc_gate(fg_ctx* c, double thr, int* d_count) {
   DevGraph& d = c->d;
   cudaStream_t st = c->stream;
   const int T = 128;
-  if (d.n[T_POSE]) k_inc_gate<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], thr, d_count);
-  if (d.n[T_VEC3]) k_inc_gate<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], thr, d_count);
-  if (d.n[T_BIAS]) k_inc_gate<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], thr, d_count);
-  if (d.n[T_POINT]) k_inc_gate<T_POINT><<<cdiv(d.n[T_POINT], T), T, 0, st>>>(d.n[T_POINT], d.val[T_POINT], d.val_new[T_POINT], thr, d_count);
-  if (d.n[T_PLANE]) k_inc_gate<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], thr, d_count);
+  if (d.n[T_POSE]) k_inc_gate<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], thr, d_count, d.pose_chart);
+  if (d.n[T_VEC3]) k_inc_gate<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], thr, d_count, d.pose_chart);
+  if (d.n[T_BIAS]) k_inc_gate<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], thr, d_count, d.pose_chart);
+  if (d.n[T_POINT]) k_inc_gate<T_POINT><<<cdiv(d.n[T_POINT], T), T, 0, st>>>(d.n[T_POINT], d.val[T_POINT], d.val_new[T_POINT], thr, d_count, d.pose_chart);
+  if (d.n[T_PLANE]) k_inc_gate<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], thr, d_count, d.pose_chart);
 }
 
 // ------------------------------------------------------------------ packed exchange (multi-GPU)

@@ -215,6 +215,48 @@ FG_HD void g2o_oplus(const double* R, const double* t, const double* d, double* 
   pose_compose(R, t, dR, d, Ro, to);
 }
 
+// ---- chart options: GTSAM picks the Pose3 / Rot3 retraction at compile time (GTSAM_POSE3_EXPMAP,
+// GTSAM_ROT3_EXPMAP) and the reference's build flags are unknown, so the chart is a context option (fg_set_pose_chart):
+//   0 full EXPMAP (default)   2 Pose3 FIRST_ORDER over Rot3 EXPMAP   3 Pose3 FIRST_ORDER over Rot3 CAYLEY (GTSAM 4.0's
+//   default build)            1 is g2o's [t, q_xyz] chart (set by the g2o back-end, g2o_oplus above)
+// Rot3::CayleyChart::Retract: the Cayley transform of [w/2]x
+FG_HD void cayley_retract(const double* w, double* R) {
+  const double x = w[0], y = w[1], z = w[2];
+  const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z;
+  const double f = 1.0 / (4.0 + x2 + y2 + z2), f2 = 2.0 * f;
+  R[0] = (4 + x2 - y2 - z2) * f; R[1] = (xy - 2 * z) * f2;       R[2] = (xz + 2 * y) * f2;
+  R[3] = (xy + 2 * z) * f2;       R[4] = (4 - x2 + y2 - z2) * f; R[5] = (yz - 2 * x) * f2;
+  R[6] = (xz - 2 * y) * f2;       R[7] = (yz + 2 * x) * f2;       R[8] = (4 - x2 - y2 + z2) * f;
+}
+// Rot3::CayleyChart::Local: its inverse.  With R = (I + A)(I - A)^-1, A = [a]x, a = w / 2:  a = vee(R - R^T) / (1 + tr R)
+FG_HD void cayley_local(const double* R, double* w) {
+  const double k = 2.0 / (1.0 + R[0] + R[4] + R[8]);
+  w[0] = k * (R[7] - R[5]); w[1] = k * (R[2] - R[6]); w[2] = k * (R[3] - R[1]);
+}
+// Pose3::ChartAtOrigin::Retract / Local under the chosen chart, tangent [rot, trans]
+FG_HD void pose_chart_retract0(const double* xi, int chart, double* R, double* t) {
+  if (chart == 2 || chart == 3) {
+    if (chart == 2) so3_exp(xi, R); else cayley_retract(xi, R);
+    t[0] = xi[3]; t[1] = xi[4]; t[2] = xi[5];
+  } else {
+    se3_exp(xi, R, t);
+  }
+}
+FG_HD void pose_chart_local0(const double* R, const double* t, int chart, double* xi) {
+  if (chart == 2 || chart == 3) {
+    if (chart == 2) so3_log(R, xi); else cayley_local(R, xi);
+    xi[3] = t[0]; xi[4] = t[1]; xi[5] = t[2];
+  } else {
+    se3_log(R, t, xi);
+  }
+}
+// X (+) xi under the chosen chart (Values::retract of a Pose3)
+FG_HD void pose_chart_retract(const double* R, const double* t, const double* xi, int chart, double* Ro, double* to) {
+  double dR[9], dt[3];
+  pose_chart_retract0(xi, chart, dR, dt);
+  pose_compose(R, t, dR, dt, Ro, to);
+}
+
 // Ad(T) = [[R,0],[[t]x R, R]]  (6x6 row-major)
 FG_HD void adjoint(const double* R, const double* t, double* Ad) {
   double S[9], SR[9];

@@ -34,6 +34,13 @@
 #include <boost/shared_ptr.hpp>
 #include "../../include/fg_abi.h"
 
+// Which of GTSAM's compile-time charts this facade plays (include/fg_abi.h FG_CHART_*): 0 full EXPMAP (default),
+// 2 Pose3 FIRST_ORDER over Rot3 EXPMAP, 3 Pose3 FIRST_ORDER over Rot3 CAYLEY (GTSAM 4.0's default build).  One switch for the
+// host side (Pose3::ChartAtOrigin -- the 6-vector of the VRO log) and the device side (every context is created with it).
+#ifndef FG_POSE3_CHART
+#define FG_POSE3_CHART 0
+#endif
+
 namespace gtsam {
 
 typedef uint64_t Key;
@@ -155,6 +162,18 @@ class Rot3 {
   static Rot3 Quaternion(double w, double x, double y, double z) { return Rot3(Eigen::Quaterniond(w, x, y, z).toRotationMatrix()); }
   static Rot3 Expmap(const Vector3& w) { return Rot3(detail::so3_exp(w)); }
   static Vector3 Logmap(const Rot3& R) { return detail::so3_log(R.R_); }
+  // Rot3::CayleyChart (the Rot3 chart of GTSAM 4.0's default build): the Cayley transform of [w/2]x and its inverse
+  static Rot3 CayleyRetract(const Vector3& w) {
+    const double x = w(0), y = w(1), z = w(2), x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z;
+    const double f = 1.0 / (4.0 + x2 + y2 + z2), f2 = 2.0 * f;
+    return Rot3((4 + x2 - y2 - z2) * f, (xy - 2 * z) * f2, (xz + 2 * y) * f2, (xy + 2 * z) * f2, (4 - x2 + y2 - z2) * f, (yz - 2 * x) * f2,
+                (xz - 2 * y) * f2, (yz + 2 * x) * f2, (4 - x2 - y2 + z2) * f);
+  }
+  static Vector3 CayleyLocal(const Rot3& R) {
+    const Matrix3& M = R.R_;
+    const double k = 2.0 / (1.0 + M(0, 0) + M(1, 1) + M(2, 2));
+    return Vector3(k * (M(2, 1) - M(1, 2)), k * (M(0, 2) - M(2, 0)), k * (M(1, 0) - M(0, 1)));
+  }
   const Matrix3& matrix() const { return R_; }
   Matrix3 transpose() const { return R_.transpose(); }
   Rot3 operator*(const Rot3& o) const { return Rot3(Matrix3(R_ * o.R_)); }
@@ -230,11 +249,20 @@ class Pose3 {
   // Pose3::ChartAtOrigin::{Retract, Local}: the full EXPMAP chart (GTSAM_POSE3_EXPMAP build) -- the chart the
   // device uses for BetweenFactor residuals and Values::retract, and the encoding of the VRO log (gtsam_graph.cpp:60,1532)
   struct ChartAtOrigin {
-    static Pose3 Retract(const Vector6& xi) { return Pose3::Expmap(xi); }
-    static Vector6 Local(const Pose3& p) { return Pose3::Logmap(p); }
+    static Pose3 Retract(const Vector6& xi) {
+      if (FG_POSE3_CHART == 0) return Pose3::Expmap(xi);
+      const Vector3 w(xi(0), xi(1), xi(2));
+      return Pose3(FG_POSE3_CHART == 2 ? Rot3::Expmap(w) : Rot3::CayleyRetract(w), Point3(xi(3), xi(4), xi(5)));
+    }
+    static Vector6 Local(const Pose3& p) {
+      if (FG_POSE3_CHART == 0) return Pose3::Logmap(p);
+      const Vector3 w = FG_POSE3_CHART == 2 ? Rot3::Logmap(p.r_) : Rot3::CayleyLocal(p.r_);
+      Vector6 xi; for (int i = 0; i < 3; ++i) { xi(i) = w(i); xi(3 + i) = p.t_(i); }
+      return xi;
+    }
   };
-  Pose3 retract(const Vector6& xi) const { return *this * Expmap(xi); }
-  Vector6 localCoordinates(const Pose3& o) const { return Logmap(between(o)); }
+  Pose3 retract(const Vector6& xi) const { return *this * ChartAtOrigin::Retract(xi); }
+  Vector6 localCoordinates(const Pose3& o) const { return ChartAtOrigin::Local(between(o)); }
 };
 
 // ------------------------------------------------------------------ NavState / ConstantBias / Unit3 / OrientedPlane3
@@ -666,7 +694,10 @@ inline void add_value(fg_ctx* c, Key k, const Value& v, const char* what) {
 }
 struct Ctx {          // owns a context for the duration of one call
   fg_ctx* c;
-  Ctx() : c(fg_create(0, 0, 1)) { if (!c) throw std::runtime_error("fg_create failed: no CUDA device (this backend has no CPU fallback)"); }
+  Ctx() : c(fg_create(0, 0, 1)) {
+    if (!c) throw std::runtime_error("fg_create failed: no CUDA device (this backend has no CPU fallback)");
+    fg_set_pose_chart(c, FG_POSE3_CHART);
+  }
   ~Ctx() { if (c) { camera_slots().erase(c); fg_destroy(c); } }
   Ctx(const Ctx&) = delete;
 };
@@ -758,6 +789,7 @@ class ISAM2 {
     if (!c_) {
       c_ = fg_create(0, 0, 1);
       if (!c_) throw std::runtime_error("fg_create failed: no CUDA device (this backend has no CPU fallback)");
+      fg_set_pose_chart(c_, FG_POSE3_CHART);
     }
     for (auto& kv : nv.m) detail::add_value(c_, kv.first, kv.second, "ISAM2::update (new value)");
     estimate.insert(nv);

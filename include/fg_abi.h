@@ -182,6 +182,18 @@ int fg_optimize_lm(fg_ctx* ctx, const fg_lm_params* params, fg_lm_report* report
 /* graph.error(values) = 1/2 sum |r|^2_Sigma     CGraphGT::error  gtsam_graph.cpp:173-176 */
 int fg_error(fg_ctx* ctx, double* error);
 
+/* ------------------------------------------------------------------ manifold charts */
+/* GTSAM chooses the Pose3 / Rot3 retraction at COMPILE time (GTSAM_POSE3_EXPMAP, GTSAM_ROT3_EXPMAP); the reference links an
+ * author-local GTSAM 4.0 whose flags are unknown (gtsam/CMakeLists.txt:12-18).  The chart decides Values::retract of a
+ * Pose3, the residual Local(measured, h) of BetweenFactor / PriorFactor<Pose3> at non-zero error, and the 6-vector of the
+ * VRO log (gtsam_graph.cpp:60,1532), not the minimiser.  Default: full EXPMAP. */
+enum {
+  FG_CHART_EXPMAP = 0,              /* Pose3 EXPMAP (Rot3 chart irrelevant): GTSAM 4.1+ default           */
+  FG_CHART_FIRST_ORDER_EXPMAP = 2,  /* Pose3 FIRST_ORDER over Rot3 EXPMAP                                  */
+  FG_CHART_FIRST_ORDER_CAYLEY = 3   /* Pose3 FIRST_ORDER over Rot3 CAYLEY: GTSAM 4.0's default build       */
+};
+int fg_set_pose_chart(fg_ctx* ctx, int chart);
+
 /* ------------------------------------------------------------------ g2o back-end (CGraphG2O, BASELINE config 1) */
 /* g2o::EdgeSE3 between two VertexSE3 (poses added with fg_add_pose):  setMeasurement(mr.edge.transform),
  * setInformation(mr.edge.informationMatrix)   CGraphG2O::addToGraph  g2o/g2o_graph.cpp:125-132.

@@ -15,11 +15,12 @@ from . import lie
 
 
 # --------------------------------------------------------------------------- Between / Prior
-def between_pose(R1, t1, R2, t2, Rm, tm, jac=True):
-    """r = Logmap(Z^-1 * X1^-1 * X2);  H1 = -Ad(h^-1), H2 = I  (A.3, fast path)."""
+def between_pose(R1, t1, R2, t2, Rm, tm, jac=True, chart=0):
+    """r = Local(Z, X1^-1 * X2) = ChartAtOrigin::Local(Z^-1 h);  H1 = -Ad(h^-1), H2 = I  (A.3, fast path: the derivative of
+    Local is not chained in, whatever the chart)."""
     Rh, th = lie.pose_between(R1, t1, R2, t2)
     Re, te = lie.pose_between(Rm, tm, Rh, th)
-    r = lie.se3_log(Re, te)
+    r = lie.chart_local0(Re, te, chart)
     if not jac:
         return r
     Rhi, thi = lie.pose_inverse(Rh, th)
@@ -28,9 +29,9 @@ def between_pose(R1, t1, R2, t2, Rm, tm, jac=True):
     return r, H1, H2
 
 
-def prior_pose(R, t, Rp, tp, jac=True):
-    """r = Logmap(prior^-1 x) (== -Local(x, prior) under EXPMAP), H = I."""
-    r = lie.pose_local(Rp, tp, R, t)
+def prior_pose(R, t, Rp, tp, jac=True, chart=0):
+    """r = Local(prior, x) = ChartAtOrigin::Local(prior^-1 x), H = I."""
+    r = lie.pose_local(Rp, tp, R, t, chart)
     if not jac:
         return r
     return r, np.broadcast_to(np.eye(6), r.shape[:-1] + (6, 6)).copy()

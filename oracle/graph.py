@@ -29,6 +29,7 @@ class Graph:
         self.f = {}          # factor groups
         self.K = CAL_SR4K
         self.Rs = np.eye(3); self.ts = np.zeros(3)   # body_P_sensor (mp_u2c)
+        self.chart = 0                               # Pose3 / Rot3 charts (oracle/lie.py: EXPMAP, FIRST_ORDER_EXPMAP, FIRST_ORDER_CAYLEY)
 
     # ---- sizes / offsets
     @property
@@ -48,7 +49,7 @@ class Graph:
         d = self.dims
         g = self.copy()
         if d['P']:
-            g.R, g.t = lie.pose_retract(self.R, self.t, delta[:d['o_v']].reshape(-1, 6))
+            g.R, g.t = lie.pose_retract(self.R, self.t, delta[:d['o_v']].reshape(-1, 6), self.chart)
         g.vel = self.vel + delta[d['o_v']:d['o_b']].reshape(-1, 3)
         g.bias = self.bias + delta[d['o_b']:d['o_pl']].reshape(-1, 6)
         if d['Npl']:
@@ -63,7 +64,7 @@ class Graph:
         f = self.f
         if 'prior_pose' in f:
             q = f['prior_pose']; i = q['i']
-            res = F.prior_pose(self.R[i], self.t[i], q['R'], q['t'], jac)
+            res = F.prior_pose(self.R[i], self.t[i], q['R'], q['t'], jac, self.chart)
             out.append((res[0], q['info'], [(6 * i, res[1])]) if jac else (res, q['info'], None))
         if 'prior_vel' in f:
             q = f['prior_vel']; i = q['i']
@@ -79,7 +80,7 @@ class Graph:
             out.append((res[0], q['info'], [(d['o_pt'] + 3 * i, res[1])]) if jac else (res, q['info'], None))
         if 'between' in f:
             q = f['between']; i, j = q['i'], q['j']
-            res = F.between_pose(self.R[i], self.t[i], self.R[j], self.t[j], q['R'], q['t'], jac)
+            res = F.between_pose(self.R[i], self.t[i], self.R[j], self.t[j], q['R'], q['t'], jac, self.chart)
             out.append((res[0], q['info'], [(6 * i, res[1]), (6 * j, res[2])]) if jac else (res, q['info'], None))
         if 'imu' in f:
             q = f['imu']

@@ -149,16 +149,16 @@ def adjoint(R, t):
     return Ad
 
 
-def pose_retract(R, t, xi):
-    """Values::retract for Pose3 (EXPMAP chart): X * Expmap(xi)."""
-    dR, dt = se3_exp(xi)
+def pose_retract(R, t, xi, chart=0):
+    """Values::retract for Pose3: X * ChartAtOrigin::Retract(xi)  (chart 0 = full EXPMAP, see the end of this file)."""
+    dR, dt = chart_retract0(xi, chart)
     return pose_compose(R, t, dR, dt)
 
 
-def pose_local(Ra, ta, Rb, tb):
-    """Pose3::localCoordinates: Logmap(a^-1 b)."""
+def pose_local(Ra, ta, Rb, tb, chart=0):
+    """Pose3::localCoordinates: ChartAtOrigin::Local(a^-1 b)."""
     R, t = pose_between(Ra, ta, Rb, tb)
-    return se3_log(R, t)
+    return chart_local0(R, t, chart)
 
 
 def rzryrx(x, y, z):
@@ -201,3 +201,46 @@ def rot_from_quat(q):
         np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
         np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
         np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], -2)
+
+
+# --------------------------------------------------------------------------- chart options
+# GTSAM chooses the Pose3 / Rot3 retraction at compile time (GTSAM_POSE3_EXPMAP, GTSAM_ROT3_EXPMAP); the reference's build
+# flags are unknown, so the charts are an explicit option everywhere a chart is used (Values::retract of a Pose3, the
+# residual Local(measured, h) of BetweenFactor / PriorFactor<Pose3>, the 6-vector of the VRO log):
+EXPMAP, FIRST_ORDER_EXPMAP, FIRST_ORDER_CAYLEY = 0, 2, 3        # ids shared with include/fg_abi.h (1 is g2o's chart)
+
+
+def cayley_retract(w):
+    """Rot3::CayleyChart::Retract: the Cayley transform of [w/2]x."""
+    w = np.asarray(w, dtype=np.float64)
+    x, y, z = w[..., 0], w[..., 1], w[..., 2]
+    x2, y2, z2, xy, xz, yz = x * x, y * y, z * z, x * y, x * z, y * z
+    f = 1.0 / (4.0 + x2 + y2 + z2); f2 = 2.0 * f
+    return np.stack([np.stack([(4 + x2 - y2 - z2) * f, (xy - 2 * z) * f2, (xz + 2 * y) * f2], -1),
+                     np.stack([(xy + 2 * z) * f2, (4 - x2 + y2 - z2) * f, (yz - 2 * x) * f2], -1),
+                     np.stack([(xz - 2 * y) * f2, (yz + 2 * x) * f2, (4 - x2 - y2 + z2) * f], -1)], -2)
+
+
+def cayley_local(R):
+    """Rot3::CayleyChart::Local: the inverse of cayley_retract, [w/2]x = (R - I)(R + I)^-1."""
+    R = np.asarray(R, dtype=np.float64)
+    I = np.eye(3)
+    A = (R - I) @ np.linalg.inv(R + I)
+    return np.stack([A[..., 2, 1] - A[..., 1, 2], A[..., 0, 2] - A[..., 2, 0], A[..., 1, 0] - A[..., 0, 1]], -1)      # vee: [a]x -> 2a = w
+
+
+def chart_retract0(xi, chart=EXPMAP):
+    """Pose3::ChartAtOrigin::Retract under the chosen charts."""
+    if chart == EXPMAP:
+        return se3_exp(xi)
+    xi = np.asarray(xi, dtype=np.float64)
+    R = so3_exp(xi[..., :3]) if chart == FIRST_ORDER_EXPMAP else cayley_retract(xi[..., :3])
+    return R, xi[..., 3:].copy()
+
+
+def chart_local0(R, t, chart=EXPMAP):
+    """Pose3::ChartAtOrigin::Local under the chosen charts."""
+    if chart == EXPMAP:
+        return se3_log(R, t)
+    w = so3_log(R) if chart == FIRST_ORDER_EXPMAP else cayley_local(R)
+    return np.concatenate([w, np.asarray(t, dtype=np.float64)], -1)

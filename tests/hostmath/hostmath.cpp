@@ -30,6 +30,9 @@ void hm_imu(const double* Xi, const double* vi, const double* Xj, const double* 
   imu_eval<true>(Xi, vi, Xj, vj, bi, bj, &f, r, J);
 }
 void hm_d_jr_c(const double* th, const double* c, double* D) { d_jr_c(th, c, D); }
+void hm_chart_retract(const double* T, const double* xi, int chart, double* To) { pose_chart_retract(T, T + 9, xi, chart, To, To + 9); }
+void hm_chart_local0(const double* T, int chart, double* xi) { pose_chart_local0(T, T + 9, chart, xi); }
+void hm_between_chart(const double* X1, const double* X2, const double* Z, int chart, double* r, double* J1) { between_eval<true>(X1, X2, Z, r, J1, chart); }
 void hm_g2o_edge(const double* X1, const double* X2, const double* Z, double* e, double* J1, double* J2) { g2o_edge_eval<true>(X1, X2, Z, e, J1, J2); }
 void hm_g2o_oplus(const double* T, const double* d, double* To) { g2o_oplus(T, T + 9, d, To, To + 9); }
 }

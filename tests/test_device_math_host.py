@@ -147,3 +147,25 @@ def test_g2o_edge_and_oplus(hostmath, rng):
         To = arr(12); hostmath.hm_g2o_oplus(p(T12(R1, t1)), p(d), p(To))
         Ro, to = F.g2o_oplus(R1, t1, d)
         assert np.allclose(To[:9].reshape(3, 3), Ro, atol=1e-14) and np.allclose(To[9:], to, atol=1e-14)
+
+
+@pytest.mark.parametrize('chart', [lie.EXPMAP, lie.FIRST_ORDER_EXPMAP, lie.FIRST_ORDER_CAYLEY])
+def test_pose_charts(hostmath, rng, chart):
+    """Pose3::ChartAtOrigin::{Retract, Local} under the three chart options as the device evaluates them, against the oracle;
+    Local inverts Retract; every chart agrees with EXPMAP to first order (so the Jacobians are chart independent)."""
+    for _ in range(100):
+        R, t = rand_pose(rng)
+        xi = rng.normal(size=6) * rng.choice([1e-6, 0.05, 0.8])
+        To = arr(12); hostmath.hm_chart_retract(p(T12(R, t)), p(xi), C.c_int(chart), p(To))
+        Ro, to = lie.pose_retract(R, t, xi, chart)
+        assert np.allclose(To[:9].reshape(3, 3), Ro, atol=1e-14) and np.allclose(To[9:], to, atol=1e-14)
+        R0, t0 = lie.chart_retract0(xi, chart)
+        back = arr(6); hostmath.hm_chart_local0(p(T12(R0, t0)), C.c_int(chart), p(back))
+        assert np.allclose(back, xi, atol=1e-12) and np.allclose(back, lie.chart_local0(R0, t0, chart), atol=1e-12)
+        Re, te = lie.se3_exp(xi)
+        assert np.abs(R0 - Re).max() <= 2 * np.linalg.norm(xi) ** 2 + 1e-15 and np.abs(t0 - te).max() <= 2 * np.linalg.norm(xi) ** 2 + 1e-15
+        R2, t2 = rand_pose(rng); Rm, tm = rand_pose(rng, 0.3)
+        r, J1 = arr(6), arr(36)
+        hostmath.hm_between_chart(p(T12(R, t)), p(T12(R2, t2)), p(T12(Rm, tm)), C.c_int(chart), p(r), p(J1))
+        ro, H1, H2 = F.between_pose(R, t, R2, t2, Rm, tm, chart=chart)
+        assert np.allclose(r, ro, atol=1e-12) and np.allclose(J1.reshape(6, 6), H1, atol=1e-13)

@@ -13,18 +13,20 @@ def rot_angle(Ra, Rb):
     return np.linalg.norm(lie.so3_log(np.swapaxes(Ra, -1, -2) @ Rb), axis=-1)
 
 
-def run_both(spec, solver='direct', **lm_kw):
+def run_both(spec, solver='direct', chart=0, **lm_kw):
     ctx = abi.Context(device=0)
     abi.load_spec(ctx, spec)
     g0 = build.from_spec(spec)
+    if chart:
+        ctx.set_pose_chart(chart); g0.chart = chart
     e_dev, e_orc = ctx.error(), g0.error()
     rep = ctx.optimize(**lm_kw)
     g1, orep = lm.optimize_gtsam(g0, lm.LMParams(**lm_kw), solver=solver)
     return ctx, rep, g0, g1, orep, e_dev, e_orc
 
 
-def check(spec, tol_chi2, tol_pose, solver='direct', **lm_kw):
-    ctx, rep, g0, g1, orep, e_dev, e_orc = run_both(spec, solver, **lm_kw)
+def check(spec, tol_chi2, tol_pose, solver='direct', chart=0, **lm_kw):
+    ctx, rep, g0, g1, orep, e_dev, e_orc = run_both(spec, solver, chart, **lm_kw)
     assert abs(e_dev - e_orc) <= 1e-11 * e_orc, (e_dev, e_orc)
     dt, ot = rep.trace(), orep['trace']
     assert [t['accepted'] for t in dt] == [t['accepted'] for t in ot]
@@ -92,6 +94,19 @@ def test_c2_vio():
 
 def test_c3_vio_planes():
     check(synth.make_config('C3', seed=1, scale=0.1), 1e-9, 1e-8)
+
+
+@pytest.mark.parametrize('chart', [lie.FIRST_ORDER_EXPMAP, lie.FIRST_ORDER_CAYLEY])
+@pytest.mark.parametrize('name,scale', [('C1', 1.0), ('C3', 0.1)])
+def test_pose_chart_options(name, scale, chart):
+    """SURVEY A.1 / hard part 1: GTSAM's compile-time Pose3 / Rot3 charts as a context option -- FIRST_ORDER over Rot3 EXPMAP
+    and over Rot3 CAYLEY (GTSAM 4.0's default build) against the oracle run with the same chart; the initial error differs
+    from the EXPMAP one (non-zero residuals are chart dependent), the optimum does not."""
+    spec = synth.make_config(name, seed=4, scale=scale)
+    rep = check(spec, 1e-9, 1e-8, chart=chart)
+    ctx = abi.Context(device=0); abi.load_spec(ctx, spec); rep0 = ctx.optimize(); ctx.close()
+    assert abs(rep.initial_error - rep0.initial_error) > 1e-9 * rep0.initial_error
+    assert abs(rep.final_error - rep0.final_error) < 1e-3 * rep0.final_error
 
 
 def test_c4_ba_imu_schur():
