@@ -662,14 +662,70 @@ extern "C" int fg_finalize(fg_ctx* c) {
     else if ((rc = dev_upload<double>(c, &d.val_new[t], nullptr, h.val[t].size())) != FG_OK) return rc;
     if (t != T_POINT) if ((rc = dev_upload(c, &d.off[t], S.off[t])) != FG_OK) return rc;
   }
-  // pose-side factors
+  // pose-side factors, uploaded COLOUR-SORTED: within a colour no two factors share a variable, so the assembly kernels
+  // (launched colour by colour, fg_kernels.cu: run_factors) never add to one address from two threads of a launch --
+  // the assembled system is bitwise repeatable without giving up the thread-per-factor kernels (greedy colouring in
+  // insertion order over all kinds; a VIO graph with 5 look-back edges takes ~14 colours)
   d.n_pp = (int)h.pp_var.size(); d.n_pv = (int)h.pv_var.size(); d.n_pb = (int)h.pb_var.size();
   d.n_bt = (int)h.bt_i.size(); d.n_imu = (int)h.imu_rec.size(); d.n_pl = (int)h.pl_pose.size();
-  if ((rc = dev_upload(c, &d.pp_var, h.pp_var)) || (rc = dev_upload(c, &d.pp_mean, h.pp_mean)) || (rc = dev_upload(c, &d.pp_info, h.pp_info))) return rc;
-  if ((rc = dev_upload(c, &d.pv_var, h.pv_var)) || (rc = dev_upload(c, &d.pv_mean, h.pv_mean)) || (rc = dev_upload(c, &d.pv_info, h.pv_info))) return rc;
-  if ((rc = dev_upload(c, &d.pb_var, h.pb_var)) || (rc = dev_upload(c, &d.pb_mean, h.pb_mean)) || (rc = dev_upload(c, &d.pb_info, h.pb_info))) return rc;
-  if ((rc = dev_upload(c, &d.bt_i, h.bt_i)) || (rc = dev_upload(c, &d.bt_j, h.bt_j)) || (rc = dev_upload(c, &d.bt_meas, h.bt_meas)) || (rc = dev_upload(c, &d.bt_info, h.bt_info))) return rc;
-  if ((rc = dev_upload(c, &d.imu_var, h.imu_var)) || (rc = dev_upload(c, &d.imu_rec, h.imu_rec))) return rc;
+  {
+    const int64_t nP = h.count(T_POSE), nV = h.count(T_VEC3), nB = h.count(T_BIAS);
+    std::vector<std::vector<uint64_t>> used((size_t)(nP + nV + nB + h.count(T_PLANE)));
+    auto pick = [&](const int* vars, int nv) {
+      for (int col = 0;; ++col) {
+        const size_t w = (size_t)col >> 6; const uint64_t bit = 1ull << (col & 63);
+        bool free_ = true;
+        for (int k = 0; k < nv && free_; ++k) { const auto& u = used[vars[k]]; if (w < u.size() && (u[w] & bit)) free_ = false; }
+        if (!free_) continue;
+        for (int k = 0; k < nv; ++k) { auto& u = used[vars[k]]; if (u.size() <= w) u.resize(w + 1, 0); u[w] |= bit; }
+        return col;
+      }
+    };
+    auto sort_kind = [&](int kind, const std::vector<int>& col) {
+      std::vector<int> ord(col.size());
+      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return col[a] < col[b]; });
+      std::vector<int>& cp = c->color_ptr[kind];
+      cp.assign(1, 0);
+      for (size_t i = 0; i < ord.size(); ++i) { while ((int)cp.size() <= col[ord[i]]) cp.push_back((int)i); }
+      cp.push_back((int)ord.size());
+      return ord;
+    };
+    auto permute_i = [](const std::vector<int>& a, const std::vector<int>& ord, int w) { std::vector<int> o(a.size()); for (size_t i = 0; i < ord.size(); ++i) for (int k = 0; k < w; ++k) o[i * w + k] = a[(size_t)ord[i] * w + k]; return o; };
+    auto permute_d = [](const std::vector<double>& a, const std::vector<int>& ord, int w) { std::vector<double> o(a.size()); for (size_t i = 0; i < ord.size(); ++i) for (int k = 0; k < w; ++k) o[i * w + k] = a[(size_t)ord[i] * w + k]; return o; };
+    std::vector<int> col_pp(d.n_pp), col_pv(d.n_pv), col_pb(d.n_pb), col_bt(d.n_bt), col_ge(h.ge_i.size()), col_imu(d.n_imu), col_pl(d.n_pl);
+    for (int f = 0; f < d.n_pp; ++f) { int v[1] = {h.pp_var[f]}; col_pp[f] = pick(v, 1); }
+    for (int f = 0; f < d.n_pv; ++f) { int v[1] = {(int)(nP + h.pv_var[f])}; col_pv[f] = pick(v, 1); }
+    for (int f = 0; f < d.n_pb; ++f) { int v[1] = {(int)(nP + nV + h.pb_var[f])}; col_pb[f] = pick(v, 1); }
+    for (int f = 0; f < d.n_bt; ++f) { int v[2] = {h.bt_i[f], h.bt_j[f]}; col_bt[f] = pick(v, 2); }
+    for (size_t f = 0; f < h.ge_i.size(); ++f) { int v[2] = {h.ge_i[f], h.ge_j[f]}; col_ge[f] = pick(v, 2); }
+    for (int f = 0; f < d.n_imu; ++f) {
+      const int* q = &h.imu_var[6 * (size_t)f];
+      int v[6] = {q[0], (int)(nP + q[1]), q[2], (int)(nP + q[3]), (int)(nP + nV + q[4]), (int)(nP + nV + q[5])};
+      col_imu[f] = pick(v, 6);
+    }
+    for (int f = 0; f < d.n_pl; ++f) { int v[2] = {h.pl_pose[f], (int)(nP + nV + nB + h.pl_plane[f])}; col_pl[f] = pick(v, 2); }
+    std::vector<int> o;
+    o = sort_kind(K_PP, col_pp);
+    if ((rc = dev_upload(c, &d.pp_var, permute_i(h.pp_var, o, 1))) || (rc = dev_upload(c, &d.pp_mean, permute_d(h.pp_mean, o, 12))) || (rc = dev_upload(c, &d.pp_info, permute_d(h.pp_info, o, 36)))) return rc;
+    o = sort_kind(K_PV, col_pv);
+    if ((rc = dev_upload(c, &d.pv_var, permute_i(h.pv_var, o, 1))) || (rc = dev_upload(c, &d.pv_mean, permute_d(h.pv_mean, o, 3))) || (rc = dev_upload(c, &d.pv_info, permute_d(h.pv_info, o, 9)))) return rc;
+    o = sort_kind(K_PB, col_pb);
+    if ((rc = dev_upload(c, &d.pb_var, permute_i(h.pb_var, o, 1))) || (rc = dev_upload(c, &d.pb_mean, permute_d(h.pb_mean, o, 6))) || (rc = dev_upload(c, &d.pb_info, permute_d(h.pb_info, o, 36)))) return rc;
+    o = sort_kind(K_BT, col_bt);
+    if ((rc = dev_upload(c, &d.bt_i, permute_i(h.bt_i, o, 1))) || (rc = dev_upload(c, &d.bt_j, permute_i(h.bt_j, o, 1))) || (rc = dev_upload(c, &d.bt_meas, permute_d(h.bt_meas, o, 12))) || (rc = dev_upload(c, &d.bt_info, permute_d(h.bt_info, o, 36)))) return rc;
+    o = sort_kind(K_GE, col_ge);
+    if ((rc = dev_upload(c, &d.ge_i, permute_i(h.ge_i, o, 1))) || (rc = dev_upload(c, &d.ge_j, permute_i(h.ge_j, o, 1))) || (rc = dev_upload(c, &d.ge_meas, permute_d(h.ge_meas, o, 12))) || (rc = dev_upload(c, &d.ge_info, permute_d(h.ge_info, o, 36)))) return rc;
+    o = sort_kind(K_IMU, col_imu);
+    {
+      std::vector<ImuRec> recs(h.imu_rec.size());
+      for (size_t i = 0; i < o.size(); ++i) recs[i] = h.imu_rec[o[i]];
+      if ((rc = dev_upload(c, &d.imu_var, permute_i(h.imu_var, o, 6))) || (rc = dev_upload(c, &d.imu_rec, recs))) return rc;
+    }
+    o = sort_kind(K_PL, col_pl);
+    if ((rc = dev_upload(c, &d.pl_pose, permute_i(h.pl_pose, o, 1))) || (rc = dev_upload(c, &d.pl_plane, permute_i(h.pl_plane, o, 1))) || (rc = dev_upload(c, &d.pl_meas, permute_d(h.pl_meas, o, 4))) || (rc = dev_upload(c, &d.pl_info, permute_d(h.pl_info, o, 9)))) return rc;
+    CK(cudaStreamSynchronize(c->stream));       // the permuted host copies go out of scope
+  }
   // g2o back-end: EdgeSE3 factors, fixed vertices, VertexSE3::oplus as the pose retraction
   d.n_ge = (int)h.ge_i.size();
   d.pose_chart = d.n_ge ? 1 : c->pose_chart;
@@ -687,7 +743,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
       if ((rc = dev_upload(c, &d.fixed_list, fixed_list)) || (rc = dev_upload(c, &d.fixed_pose, h.fixed_pose)) || (rc = dev_upload(c, &d.fixed_col, fixed_col))) return rc;
     }
   }
-  if ((rc = dev_upload(c, &d.ge_i, h.ge_i)) || (rc = dev_upload(c, &d.ge_j, h.ge_j)) || (rc = dev_upload(c, &d.ge_meas, h.ge_meas)) || (rc = dev_upload(c, &d.ge_info, h.ge_info))) return rc;
+
   if ((rc = dev_upload(c, &d.pl_pose, h.pl_pose)) || (rc = dev_upload(c, &d.pl_plane, h.pl_plane)) || (rc = dev_upload(c, &d.pl_meas, h.pl_meas)) || (rc = dev_upload(c, &d.pl_info, h.pl_info))) return rc;
   // landmarks: sort observations by landmark (stable), CSR by pose
   const int64_t L = h.count(T_POINT), M = (int64_t)h.pj_pose.size(), P = h.count(T_POSE);
@@ -740,6 +796,21 @@ extern "C" int fg_finalize(fg_ctx* c) {
       for (size_t i = 0; i < ord.size(); ++i) { a[i] = dup_prim[ord[i]]; b[i] = dup_sec[ord[i]]; }
       dup_prim.swap(a); dup_sec.swap(b);
     }
+    // observation ranges of the blocks of k_proj_obs / k_lm_backsub_obs: whole landmarks, at most 256 observations (a landmark
+    // with more gets a block of its own), so that every per-landmark sum is formed inside one block in a fixed order
+    {
+      std::vector<int64_t> ob(1, 0);
+      int64_t cur = 0;
+      for (int64_t l = 0; l < L; ++l) {
+        const int64_t k = lm_ptr[l + 1] - lm_ptr[l];
+        if (k == 0) continue;
+        if (cur > 0 && cur + k > 256) { ob.push_back(lm_ptr[l]); cur = 0; }
+        cur += k;
+      }
+      if (M > 0) ob.push_back(M);
+      d.n_oblk = (int)ob.size() - 1;
+      if ((rc = dev_upload(c, &d.oblk_ptr, ob)) != FG_OK) return rc;
+    }
     d.n_dup = (int)dup_sec.size();
     if ((rc = dev_upload(c, &d.dup_prim, dup_prim)) || (rc = dev_upload(c, &d.dup_sec, dup_sec))) return rc;
     std::vector<double> pm(3 * L, 0.0), pw(L, 0.0);
@@ -768,6 +839,15 @@ extern "C" int fg_finalize(fg_ctx* c) {
       CK(cudaStreamSynchronize(c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
+  }
+  // per-block partial sums of the scalar reductions (one slot per block of every kernel of a pass)
+  {
+    size_t cap = 64;
+    for (int k = 0; k < K_COUNT; ++k) cap += c->color_ptr[k].size() + (size_t)c->color_ptr[k].back() / 4 + 4;      // >= sum over colours of cdiv(n, 64) or cdiv(n, 4)
+    cap += (size_t)h.count(T_POINT) / 256 + 2 + (size_t)d.n_oblk;
+    for (int t = 0; t < T_COUNT; ++t) cap += (size_t)h.count(t) / 128 + 2;
+    d.part_cap = (int)cap;
+    if ((rc = dev_upload<double>(c, &d.part, nullptr, cap)) || (rc = dev_upload<double>(c, &d.part2, nullptr, cap))) return rc;
   }
   // reduced system
   if ((rc = dev_upload<double>(c, &d.L, nullptr, (size_t)S.nnz + 8)) || (rc = dev_upload<double>(c, &d.U0, nullptr, (size_t)S.nnz + 8)) ||

@@ -10,6 +10,7 @@
 
 namespace fg {
 
+enum FactorKind { K_PP = 0, K_PV, K_PB, K_BT, K_GE, K_IMU, K_PL, K_COUNT };     // pose-side factor kinds (colour tables)
 enum VarType { T_POSE = 0, T_VEC3 = 1, T_BIAS = 2, T_POINT = 3, T_PLANE = 4, T_COUNT = 5 };
 static const int kStore[T_COUNT] = {12, 3, 6, 3, 4};   // doubles stored per value
 static const int kDim[T_COUNT] = {6, 3, 6, 3, 3};      // tangent dimension
@@ -194,6 +195,8 @@ struct DevGraph {
   int64_t* pose_obs_ptr = nullptr;  // P+1
   int64_t* pose_obs = nullptr;      // M  observation ids grouped by pose
   int* obs_point = nullptr;         // M
+  int n_oblk = 0; int64_t* oblk_ptr = nullptr;   // observation ranges of the blocks of k_proj_obs / k_lm_backsub_obs (on landmark boundaries)
+  double* part = nullptr; double* part2 = nullptr; int part_cap = 0;   // per-block partial sums of the scalar reductions
   int n_dup = 0; int* dup_prim = nullptr; int* dup_sec = nullptr;   // extra factors on an already seen (pose, landmark) pair: (primary, secondary) observation ids
   double* lm_prior_mean = nullptr;  // 3L (NaN weight = no prior)
   double* lm_prior_w = nullptr;     // L
@@ -263,6 +266,7 @@ struct fg_ctx {
   bool device_newer = false;     // device values newer than host
   // incremental session (fg_update_incremental): d.val holds theta, d.val_new the estimate; h.val / h.lin mirror them
   int pose_chart = 0;            // fg_set_pose_chart (GTSAM graphs; the g2o back-end uses its own)
+  std::vector<int> color_ptr[fg::K_COUNT];   // per pose-side factor kind: offsets of its colour classes in the (colour-sorted) device arrays
   bool inc_active = false;
   int inc_updates = 0;
   int64_t inc_known[fg::T_COUNT] = {0, 0, 0, 0, 0};   // variables per type at the previous update

@@ -28,19 +28,32 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
   return v;
 }
-// every thread of the block must call; one atomic per BLOCK (all warps of all blocks adding to one address made the
-// chi2-only pass atomic bound: 312 k serialised fp64 atomics per pass at C5)
-__device__ __forceinline__ void chi2_accumulate(double e, double* target) {
-  __shared__ double chi2_part[32];
+// Scalar sums (chi2, g^T delta, |delta|^2) are deterministic: every block of every kernel of a pass writes its own partial
+// into a slot (no fp64 atomics, whose arrival order varies from run to run), and k_sum_partials adds the slots in a fixed order.
+// Every thread of the block must call.
+__device__ __forceinline__ double block_sum(double e) {
+  __shared__ double bs_part[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   e = warp_sum(e);
-  if (lane == 0) chi2_part[w] = e;
+  __syncthreads();                       // a second call in the same kernel reuses bs_part
+  if (lane == 0) bs_part[w] = e;
   __syncthreads();
-  if (w == 0) {
-    double v = lane < nw ? chi2_part[lane] : 0.0;
-    v = warp_sum(v);
-    if (lane == 0 && v != 0.0) atomicAdd(target, v);
-  }
+  double v = 0.0;
+  if (w == 0) { v = lane < nw ? bs_part[lane] : 0.0; v = warp_sum(v); }
+  return v;                              // valid in thread 0
+}
+__device__ __forceinline__ void chi2_accumulate(double e, double* part) {
+  const double v = block_sum(e);
+  if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ part, int n, double* target) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += part[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) { if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d]; __syncthreads(); }
+  if (threadIdx.x == 0) *target = sh[0];
 }
 
 // 128-bit loads of a pose record (12 doubles, 96 B, 16 B aligned)
@@ -410,76 +423,116 @@ __device__ __forceinline__ double seg_sum(double v, int key, int lane) {
   return v;
 }
 
-// one thread per observation (observations sorted by landmark): residual, Jp, Jl; W = w Jp^T Jl stored SoA;
-// V_l, g_l by warp-segmented reduction.
+// In-block ordered merge of per-landmark sums (deterministic: no atomics).  Observations are sorted by landmark and a block's
+// range starts and ends on landmark boundaries (fg_finalize: oblk_ptr), so every landmark is summed inside ONE block: the
+// warp-segmented reduction leaves a partial in the head lane of every (warp, landmark) run; the heads are numbered in
+// observation order, parked in shared memory, and the first head of each landmark adds its pieces in that order.
+template <int NV>
+__device__ __forceinline__ void landmark_merge(const double (&v)[NV], int l, bool act, double* hbuf, int* hl, int* wcnt, double* dst0, int stride0, int n0,
+                                               double* dst1, int stride1) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int prev = __shfl_up_sync(FULL, l, 1);
+  const bool head = act && (lane == 0 || prev != l);
+  const unsigned hm = __ballot_sync(FULL, head);
+  if (lane == 0) wcnt[w] = __popc(hm);
+  double sums[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sums[i] = seg_sum(v[i], l, lane);
+  __syncthreads();
+  int base = 0, nh = 0;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { if (k < w) base += wcnt[k]; nh += wcnt[k]; }
+  if (head) {
+    const int ord = base + __popc(hm & ((1u << lane) - 1u));
+    hl[ord] = l;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) hbuf[ord * (NV + 1) + i] = sums[i];
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < nh && (t == 0 || hl[t - 1] != hl[t])) {
+    const int lm = hl[t];
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = hbuf[t * (NV + 1) + i];
+    for (int k = t + 1; k < nh && hl[k] == lm; ++k)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += hbuf[k * (NV + 1) + i];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < n0) dst0[(int64_t)stride0 * lm + i] += acc[i];          // single owner: a plain read-modify-write
+      else dst1[(int64_t)stride1 * lm + (i - n0)] += acc[i];
+    }
+  }
+  __syncthreads();
+}
+
+// one thread per observation (observations sorted by landmark): residual, Jp, Jl; W = w Jp^T Jl stored AoS;
+// V_l, g_l by the in-block ordered merge above.  Block b owns observations [oblk_ptr[b], oblk_ptr[b + 1]) (<= 256 unless a
+// single landmark has more).
 template <bool JAC>
-__global__ void __launch_bounds__(256, 3) k_proj_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+__global__ void __launch_bounds__(256, 3) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
                                                   Vals vals, const double* __restrict__ calib, const double* __restrict__ sensor,
-                                                  double* __restrict__ W, double* V, double* gl, double* chi2) {
-  int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int lane = threadIdx.x & 31;
-  double e = 0.0;
-  bool act = o < M;
-  int l = act ? obs_point[o] : -1;
-  double r[2], Jp[12], Jl[6], w = 0.0;
-  if (act) {
-    double X[12], K[9], S[12], p[3];
-    load_pose(vals.v[T_POSE], obs_pose[o], X);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) K[i] = __ldg(calib + i);
-#pragma unroll
-    for (int i = 0; i < 12; ++i) S[i] = __ldg(sensor + i);
-    p[0] = vals.v[T_POINT][3 * (int64_t)l]; p[1] = vals.v[T_POINT][3 * (int64_t)l + 1]; p[2] = vals.v[T_POINT][3 * (int64_t)l + 2];
-    double2 uvv = __ldg(reinterpret_cast<const double2*>(obs_uv) + o);
-    double uv[2] = {uvv.x, uvv.y};
-    w = obs_w[o];
-    projection_eval<JAC>(X, p, uv, K, S, r, Jp, Jl);
-    e = w * (r[0] * r[0] + r[1] * r[1]);
-  }
-  // W records (144 B each) of the block's 256 consecutive observations go through shared memory so that the global
+                                                  double* __restrict__ W, double* V, double* gl, double* part) {
+  // W records (144 B each) of the block's consecutive observations go through shared memory so that the global
   // store is coalesced (a thread writing its own record costs 32 cache-line wavefronts per store instruction)
   __shared__ double wbuf[JAC ? 256 * 19 : 1];
-  if (JAC) {
+  __shared__ int hl[JAC ? 256 : 1];
+  __shared__ int wcnt[8];
+  const int64_t s0 = oblk_ptr[blockIdx.x], s1 = oblk_ptr[blockIdx.x + 1];
+  double e = 0.0;
+  for (int64_t base = s0; base < s1; base += 256) {
+    const int64_t o = base + threadIdx.x;
+    const bool act = o < s1;
+    const int l = act ? obs_point[o] : -1;
+    double r[2], Jp[12], Jl[6], w = 0.0;
     if (act) {
+      double X[12], K[9], S[12], p[3];
+      load_pose(vals.v[T_POSE], obs_pose[o], X);
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 9; ++i) K[i] = __ldg(calib + i);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          wbuf[threadIdx.x * 19 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
+      for (int i = 0; i < 12; ++i) S[i] = __ldg(sensor + i);
+      p[0] = vals.v[T_POINT][3 * (int64_t)l]; p[1] = vals.v[T_POINT][3 * (int64_t)l + 1]; p[2] = vals.v[T_POINT][3 * (int64_t)l + 2];
+      double2 uvv = __ldg(reinterpret_cast<const double2*>(obs_uv) + o);
+      double uv[2] = {uvv.x, uvv.y};
+      w = obs_w[o];
+      projection_eval<JAC>(X, p, uv, K, S, r, Jp, Jl);
+      e += w * (r[0] * r[0] + r[1] * r[1]);
     }
-    // V (upper: 00 01 02 11 12 22) and gl
-    double c9[9];
-    if (act) {
-      c9[0] = w * (Jl[0] * Jl[0] + Jl[3] * Jl[3]);
-      c9[1] = w * (Jl[0] * Jl[1] + Jl[3] * Jl[4]);
-      c9[2] = w * (Jl[0] * Jl[2] + Jl[3] * Jl[5]);
-      c9[3] = w * (Jl[1] * Jl[1] + Jl[4] * Jl[4]);
-      c9[4] = w * (Jl[1] * Jl[2] + Jl[4] * Jl[5]);
-      c9[5] = w * (Jl[2] * Jl[2] + Jl[5] * Jl[5]);
-      c9[6] = w * (Jl[0] * r[0] + Jl[3] * r[1]);
-      c9[7] = w * (Jl[1] * r[0] + Jl[4] * r[1]);
-      c9[8] = w * (Jl[2] * r[0] + Jl[5] * r[1]);
-    } else {
+    if (JAC) {
+      if (act) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) c9[i] = 0.0;
-    }
-    int prev = __shfl_up_sync(0xffffffffu, l, 1);
-    bool head = act && (lane == 0 || prev != l);
+        for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      double s = seg_sum(c9[i], l, lane);
-      if (head) {
-        if (i < 6) atomicAdd(&V[6 * (int64_t)l + i], s);
-        else atomicAdd(&gl[3 * (int64_t)l + (i - 6)], s);
+          for (int c = 0; c < 3; ++c)
+            wbuf[threadIdx.x * 19 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
       }
+      __syncthreads();
+      const int n = (int)min((int64_t)256, s1 - base);
+      for (int i = threadIdx.x; i < n * 18; i += blockDim.x) W[base * 18 + i] = wbuf[(i / 18) * 19 + (i % 18)];
+      __syncthreads();                       // wbuf is free: the merge parks its head partials there
+      // V (upper: 00 01 02 11 12 22) and gl
+      double c9[9];
+      if (act) {
+        c9[0] = w * (Jl[0] * Jl[0] + Jl[3] * Jl[3]);
+        c9[1] = w * (Jl[0] * Jl[1] + Jl[3] * Jl[4]);
+        c9[2] = w * (Jl[0] * Jl[2] + Jl[3] * Jl[5]);
+        c9[3] = w * (Jl[1] * Jl[1] + Jl[4] * Jl[4]);
+        c9[4] = w * (Jl[1] * Jl[2] + Jl[4] * Jl[5]);
+        c9[5] = w * (Jl[2] * Jl[2] + Jl[5] * Jl[5]);
+        c9[6] = w * (Jl[0] * r[0] + Jl[3] * r[1]);
+        c9[7] = w * (Jl[1] * r[0] + Jl[4] * r[1]);
+        c9[8] = w * (Jl[2] * r[0] + Jl[5] * r[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c9[i] = 0.0;
+      }
+      landmark_merge<9>(c9, l, act, wbuf, hl, wcnt, V, 6, 6, gl, 3);
     }
-    __syncthreads();
-    const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
-    const int n = (int)min((int64_t)blockDim.x, M - o0);
-    for (int i = threadIdx.x; i < n * 18; i += blockDim.x) W[o0 * 18 + i] = wbuf[(i / 18) * 19 + (i % 18)];
   }
-  chi2_accumulate(e, chi2);
+  chi2_accumulate(e, part);
 }
 
 // Several projection factors on one (pose, landmark) pair act as ONE coupling block W = sum of their W records: fold the
@@ -540,9 +593,9 @@ __global__ void __launch_bounds__(256, 2) k_proj_pose(int P, const int64_t* __re
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int j = 0; j <= i; ++j) atomicAdd(&sys.L[base + i + (int64_t)j * ld], acc[q++]);
+      for (int j = 0; j <= i; ++j) sys.L[base + i + (int64_t)j * ld] += acc[q++];      // the only writer of this block in this kernel
 #pragma unroll
-    for (int i = 0; i < 6; ++i) atomicAdd(&g_r[o + i], acc[21 + i]);
+    for (int i = 0; i < 6; ++i) g_r[o + i] += acc[21 + i];
   }
 }
 
@@ -558,50 +611,48 @@ __global__ void k_damp_rhs(SysView sys, const double* __restrict__ g_r, double l
 }
 
 // ------------------------------------------------------------------ K9/K10 back-substitution and retraction
-// t_l = sum_o W_o^T delta_p(o) by warp-segmented reduction (thread per observation)
-__global__ void __launch_bounds__(256) k_lm_backsub_obs(int64_t M, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+// t_l = sum_o W_o^T delta_p(o) (thread per observation, block ranges on landmark boundaries, in-block ordered merge)
+__global__ void __launch_bounds__(256) k_lm_backsub_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                         const double* __restrict__ W, const double* __restrict__ delta,
                                                         const int* __restrict__ off_pose, double* tl) {
   __shared__ double wbuf[256 * 19];
-  int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int lane = threadIdx.x & 31;
-  bool act = o < M;
-  int l = act ? obs_point[o] : -1;
-  double t3[3] = {0, 0, 0};
-  // the dependent gather obs_pose -> off_pose -> delta is issued first so that it overlaps the streaming W loads
-  double dl[6];
-  {
-    const double* d = delta + (act ? off_pose[obs_pose[o]] : 0);
+  __shared__ int hl[256];
+  __shared__ int wcnt[8];
+  const int64_t s0 = oblk_ptr[blockIdx.x], s1 = oblk_ptr[blockIdx.x + 1];
+  for (int64_t base = s0; base < s1; base += 256) {
+    const int64_t o = base + threadIdx.x;
+    const bool act = o < s1;
+    const int l = act ? obs_point[o] : -1;
+    double t3[3] = {0, 0, 0};
+    // the dependent gather obs_pose -> off_pose -> delta is issued first so that it overlaps the streaming W loads
+    double dl[6];
+    {
+      const double* d = delta + (act ? off_pose[obs_pose[o]] : 0);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) dl[i] = act ? d[i] : 0.0;
-  }
-  {
-    // coalesced load of the block's 256 consecutive W records, transposed through shared memory
-    const int64_t o0 = blockIdx.x * (int64_t)blockDim.x;
-    const int n = (int)min((int64_t)blockDim.x, M - o0);
-    for (int i = threadIdx.x; i < n * 18; i += blockDim.x) wbuf[(i / 18) * 19 + (i % 18)] = __ldg(W + o0 * 18 + i);
-    __syncthreads();
-  }
-  if (act) {
-    const double* wr = wbuf + threadIdx.x * 19;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) t3[c] += wr[3 * i + c] * dl[i];
+      for (int i = 0; i < 6; ++i) dl[i] = act ? d[i] : 0.0;
     }
-  }
-  int prev = __shfl_up_sync(0xffffffffu, l, 1);
-  bool head = act && (lane == 0 || prev != l);
+    {
+      // coalesced load of the block's consecutive W records, transposed through shared memory
+      const int n = (int)min((int64_t)256, s1 - base);
+      for (int i = threadIdx.x; i < n * 18; i += blockDim.x) wbuf[(i / 18) * 19 + (i % 18)] = __ldg(W + base * 18 + i);
+      __syncthreads();
+    }
+    if (act) {
+      const double* wr = wbuf + threadIdx.x * 19;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    double s = seg_sum(t3[c], l, lane);
-    if (head) atomicAdd(&tl[3 * (int64_t)l + c], s);
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t3[c] += wr[3 * i + c] * dl[i];
+      }
+    }
+    __syncthreads();
+    landmark_merge<3>(t3, l, act, wbuf, hl, wcnt, tl, 3, 3, tl, 3);
   }
 }
 
 // delta_l = -Vinv (g_l + t_l) ; p_new = p + delta_l ; accumulates g^T delta and |delta|^2
 __global__ void k_lm_update(int64_t L, const double* __restrict__ pts, const double* __restrict__ Vinv,
-                            const double* __restrict__ gl, const double* __restrict__ tl, double* pts_new, double* scal) {
+                            const double* __restrict__ gl, const double* __restrict__ tl, double* pts_new, double* part_gd, double* part_dd) {
   int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double gd = 0.0, dd = 0.0;
   if (l < L) {
@@ -614,14 +665,14 @@ __global__ void k_lm_update(int64_t L, const double* __restrict__ pts, const dou
     gd = gl[3 * l] * d0 + gl[3 * l + 1] * d1 + gl[3 * l + 2] * d2;
     dd = d0 * d0 + d1 * d1 + d2 * d2;
   }
-  gd = warp_sum(gd); dd = warp_sum(dd);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&scal[1], gd); atomicAdd(&scal[2], dd); }
+  gd = block_sum(gd); dd = block_sum(dd);
+  if (threadIdx.x == 0) { part_gd[blockIdx.x] = gd; part_dd[blockIdx.x] = dd; }
 }
 
 // Values::retract for the reduced variables; accumulates g_r^T delta and |delta|^2 (once per scalar)
 template <int TYPE>
 __global__ void k_retract_reduced(int64_t n, const double* __restrict__ val, double* val_new, const int* __restrict__ off,
-                                  const double* __restrict__ delta, const double* __restrict__ g_r, double* scal, int count_scal, int chart) {
+                                  const double* __restrict__ delta, const double* __restrict__ g_r, double* part_gd, double* part_dd, int count_scal, int chart) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   double gd = 0.0, dd = 0.0;
   if (i < n) {
@@ -649,8 +700,8 @@ __global__ void k_retract_reduced(int64_t n, const double* __restrict__ val, dou
     }
   }
   // g_r is this rank's share of the gradient (always counted); |delta_r|^2 is replicated (rank 0 only)
-  gd = warp_sum(gd); dd = warp_sum(dd);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&scal[1], gd); if (count_scal) atomicAdd(&scal[2], dd); }
+  gd = block_sum(gd); dd = block_sum(dd);
+  if (threadIdx.x == 0) { part_gd[blockIdx.x] = gd; part_dd[blockIdx.x] = count_scal ? dd : 0.0; }
 }
 
 // ------------------------------------------------------------------ K3 IMU preintegration
@@ -789,8 +840,12 @@ static SysView make_view(fg_ctx* c, double* Lbuf) {
   return s;
 }
 
+// All factors of the graph at `val` (or the trial state): chi2 -> *target, and with JAC the linearisation.
+// Pose-side factors are launched COLOUR BY COLOUR (fg_finalize: no two factors of a colour share a variable), so the
+// read-modify-writes of sys_add_block / g_r never meet inside a launch and the assembled system is bitwise repeatable;
+// the launches of a kind walk its colour-sorted arrays through [cp[k], cp[k + 1]).
 template <bool JAC>
-static void run_factors(fg_ctx* c, bool trial, double* chi2) {
+static void run_factors(fg_ctx* c, bool trial, double* target) {
   DevGraph& d = c->d;
   cudaStream_t st = c->stream;
   Vals v;
@@ -798,22 +853,45 @@ static void run_factors(fg_ctx* c, bool trial, double* chi2) {
   SysView sys = make_view(c, d.U0);
   const bool pose_side = (c->rank == 0);     // replicated factors are counted once
   const int T = 128;
+  int np = 0;                                // partial-sum slots handed out so far
+  auto slots = [&](int grid) { double* p = d.part + np; np += grid; return p; };
   if (pose_side) {
-    if (d.n_pp) k_prior_pose<JAC><<<cdiv(d.n_pp, T), T, 0, st>>>(d.n_pp, d.pp_var, d.pp_mean, d.pp_info, v, d.off[T_POSE], sys, d.g_r, chi2, d.pose_chart);
-    if (d.n_pv) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(d.n_pv, T), T, 0, st>>>(d.n_pv, d.pv_var, d.pv_mean, d.pv_info, v, d.off[T_VEC3], sys, d.g_r, chi2);
-    if (d.n_pb) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(d.n_pb, T), T, 0, st>>>(d.n_pb, d.pb_var, d.pb_mean, d.pb_info, v, d.off[T_BIAS], sys, d.g_r, chi2);
-    if (d.n_bt) k_between<JAC><<<cdiv(d.n_bt, T), T, 0, st>>>(d.n_bt, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, chi2, d.pose_chart);
-    if (d.n_ge) k_g2o_edge<JAC><<<cdiv(d.n_ge, 64), 64, 0, st>>>(d.n_ge, d.ge_i, d.ge_j, d.ge_meas, d.ge_info, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, chi2);
+    for (size_t k = 0; k + 1 < c->color_ptr[K_PP].size(); ++k) {
+      const int b = c->color_ptr[K_PP][k], n = c->color_ptr[K_PP][k + 1] - b;
+      if (n) k_prior_pose<JAC><<<cdiv(n, T), T, 0, st>>>(n, d.pp_var + b, d.pp_mean + 12 * (size_t)b, d.pp_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
+    }
+    for (size_t k = 0; k + 1 < c->color_ptr[K_PV].size(); ++k) {
+      const int b = c->color_ptr[K_PV][k], n = c->color_ptr[K_PV][k + 1] - b;
+      if (n) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(n, T), T, 0, st>>>(n, d.pv_var + b, d.pv_mean + 3 * (size_t)b, d.pv_info + 9 * (size_t)b, v, d.off[T_VEC3], sys, d.g_r, slots(cdiv(n, T)));
+    }
+    for (size_t k = 0; k + 1 < c->color_ptr[K_PB].size(); ++k) {
+      const int b = c->color_ptr[K_PB][k], n = c->color_ptr[K_PB][k + 1] - b;
+      if (n) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(n, T), T, 0, st>>>(n, d.pb_var + b, d.pb_mean + 6 * (size_t)b, d.pb_info + 36 * (size_t)b, v, d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, T)));
+    }
+    for (size_t k = 0; k + 1 < c->color_ptr[K_BT].size(); ++k) {
+      const int b = c->color_ptr[K_BT][k], n = c->color_ptr[K_BT][k + 1] - b;
+      if (n) k_between<JAC><<<cdiv(n, T), T, 0, st>>>(n, d.bt_i + b, d.bt_j + b, d.bt_meas + 12 * (size_t)b, d.bt_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
+    }
+    for (size_t k = 0; k + 1 < c->color_ptr[K_GE].size(); ++k) {
+      const int b = c->color_ptr[K_GE][k], n = c->color_ptr[K_GE][k + 1] - b;
+      if (n) k_g2o_edge<JAC><<<cdiv(n, 64), 64, 0, st>>>(n, d.ge_i + b, d.ge_j + b, d.ge_meas + 12 * (size_t)b, d.ge_info + 36 * (size_t)b, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, slots(cdiv(n, 64)));
+    }
     if (JAC && d.n_fixed) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, st>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
-    if (d.n_imu) k_imu<JAC><<<cdiv(d.n_imu, IMU_WPB), 32 * IMU_WPB, 0, st>>>(d.n_imu, d.imu_var, d.imu_rec, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, chi2);
-    if (d.n_pl) k_plane<JAC><<<cdiv(d.n_pl, T), T, 0, st>>>(d.n_pl, d.pl_pose, d.pl_plane, d.pl_meas, d.pl_info, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, chi2);
+    for (size_t k = 0; k + 1 < c->color_ptr[K_IMU].size(); ++k) {
+      const int b = c->color_ptr[K_IMU][k], n = c->color_ptr[K_IMU][k + 1] - b;
+      if (n) k_imu<JAC><<<cdiv(n, IMU_WPB), 32 * IMU_WPB, 0, st>>>(n, d.imu_var + 6 * (size_t)b, d.imu_rec + b, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, IMU_WPB)));
+    }
+    for (size_t k = 0; k + 1 < c->color_ptr[K_PL].size(); ++k) {
+      const int b = c->color_ptr[K_PL][k], n = c->color_ptr[K_PL][k + 1] - b;
+      if (n) k_plane<JAC><<<cdiv(n, T), T, 0, st>>>(n, d.pl_pose + b, d.pl_plane + b, d.pl_meas + 4 * (size_t)b, d.pl_info + 9 * (size_t)b, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, slots(cdiv(n, T)));
+    }
   }
   int64_t L = d.n[T_POINT];
   if (L) {
-    k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, st>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, chi2);
+    k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, st>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, slots(cdiv(L, 256)));
     if (d.n_obs) {
       if (JAC && c->kev[0]) cudaEventRecord(c->kev[0], st);
-      k_proj_obs<JAC><<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, chi2);
+      k_proj_obs<JAC><<<d.n_oblk, 256, 0, st>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, slots(d.n_oblk));
       if (JAC && c->kev[1]) cudaEventRecord(c->kev[1], st);
       if (JAC && d.n_dup) k_merge_dup<<<cdiv(d.n_dup, 128), 128, 0, st>>>(d.n_dup, d.dup_prim, d.dup_sec, d.W);
       if (JAC) {
@@ -822,6 +900,7 @@ static void run_factors(fg_ctx* c, bool trial, double* chi2) {
       }
     }
   }
+  k_sum_partials<<<1, 256, 0, st>>>(d.part, np, target);
 }
 
 void launch_linearize(fg_ctx* c) {
@@ -835,7 +914,6 @@ void launch_linearize(fg_ctx* c) {
 void launch_error_only(fg_ctx* c, bool trial) {
   DevGraph& d = c->d;
   double* target = d.scal + (trial ? 3 : 0);
-  cudaMemsetAsync(target, 0, sizeof(double), c->stream);
   run_factors<false>(c, trial, target);
 }
 
@@ -925,19 +1003,23 @@ void launch_unpack(fg_ctx* c, bool with_chi2) {
 void launch_retract_error(fg_ctx* c, double lambda) {
   DevGraph& d = c->d;
   cudaStream_t st = c->stream;
-  cudaMemsetAsync(d.scal + 1, 0, sizeof(double) * 3, st);
   const int T = 128;
   int cnt = (c->rank == 0) ? 1 : 0;
-  if (d.n[T_POSE]) k_retract_reduced<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], d.off[T_POSE], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
-  if (d.n[T_VEC3]) k_retract_reduced<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], d.off[T_VEC3], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
-  if (d.n[T_BIAS]) k_retract_reduced<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], d.off[T_BIAS], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
-  if (d.n[T_PLANE]) k_retract_reduced<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], d.off[T_PLANE], d.delta, d.g_r, d.scal, cnt, d.pose_chart);
+  int np = 0;                                // slots of g^T delta (d.part) and |delta|^2 (d.part2)
+  auto at = [&](int grid) { int o = np; np += grid; return o; };
+  if (d.n[T_POSE]) { const int g = cdiv(d.n[T_POSE], T), o = at(g); k_retract_reduced<T_POSE><<<g, T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], d.off[T_POSE], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
+  if (d.n[T_VEC3]) { const int g = cdiv(d.n[T_VEC3], T), o = at(g); k_retract_reduced<T_VEC3><<<g, T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], d.off[T_VEC3], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
+  if (d.n[T_BIAS]) { const int g = cdiv(d.n[T_BIAS], T), o = at(g); k_retract_reduced<T_BIAS><<<g, T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], d.off[T_BIAS], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
+  if (d.n[T_PLANE]) { const int g = cdiv(d.n[T_PLANE], T), o = at(g); k_retract_reduced<T_PLANE><<<g, T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], d.off[T_PLANE], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
   int64_t L = d.n[T_POINT];
   if (L) {
     cudaMemsetAsync(d.tl, 0, sizeof(double) * 3 * L, st);
-    if (d.n_obs) k_lm_backsub_obs<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_pose, d.obs_point, d.W, d.delta, d.off[T_POSE], d.tl);
-    k_lm_update<<<cdiv(L, 256), 256, 0, st>>>(L, d.val[T_POINT], d.Vinv, d.gl, d.tl, d.val_new[T_POINT], d.scal);
+    if (d.n_obs) k_lm_backsub_obs<<<d.n_oblk, 256, 0, st>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.W, d.delta, d.off[T_POSE], d.tl);
+    const int g = cdiv(L, 256), o = at(g);
+    k_lm_update<<<g, 256, 0, st>>>(L, d.val[T_POINT], d.Vinv, d.gl, d.tl, d.val_new[T_POINT], d.part + o, d.part2 + o);
   }
+  k_sum_partials<<<1, 256, 0, st>>>(d.part, np, d.scal + 1);
+  k_sum_partials<<<1, 256, 0, st>>>(d.part2, np, d.scal + 2);
   run_factors<false>(c, true, d.scal + 3);
 }
 

@@ -5,7 +5,9 @@ from oracle import lie, imu as oimu
 from oracle.graph import Graph
 
 
-def write_logs(spec, vro_path, imu_path, times_path):
+def write_logs(spec, vro_path, imu_path, times_path, fmt=None):
+    """fmt: number formatter (default repr = round-trip exact); the returned records hold the values AS WRITTEN."""
+    rp = fmt or (lambda x: repr(float(x)))
     P = spec['n_poses']
     Ruc, tuc = spec['Rs'], spec['ts']
     Ric, tic = lie.pose_inverse(Ruc, tuc)
@@ -21,23 +23,23 @@ def write_logs(spec, vro_path, imu_path, times_path):
             r = lie.se3_log(R, t)
             info = Adi @ spec['between_info'][n] @ Adi.T
             info = 0.5 * (info + info.T)
-            vals = [repr(float(x)) for x in r] + [repr(float(info[i, j])) for i in range(6) for j in range(i, 6)]
+            vals = [rp(x) for x in r] + [rp(info[i, j]) for i in range(6) for j in range(i, 6)]
             f.write('%d %d %s\n' % (ej[n], ei[n], ' '.join(vals)))
-            recs.append((int(ei[n]), int(ej[n]), r.copy(), info.copy()))
+            back = np.array([float(v) for v in vals])
+            iw = np.zeros((6, 6)); iw[np.triu_indices(6)] = back[6:]; iw = iw + np.triu(iw, 1).T
+            recs.append((int(ei[n]), int(ej[n]), back[:6].copy(), iw))
     S = spec['imu_samples'].shape[1]
     flat = spec['imu_samples'].reshape(-1, 6)
+    # the reference reads the samples into float variables (gtsam/imu_vn100.cpp:86-90): 9 significant digits carry a float exactly
+    ri = (lambda x: '%.9g' % float(np.float32(x))) if fmt else (lambda x: repr(float(x)))
     with open(imu_path, 'w') as f:
-        for k, m in enumerate(flat):
-            f.write('%r %r %r %r %r %r %r 0 0 0\n' % (float(k * spec['imu_dt']), float(m[3]), float(m[4]), float(m[5]),
-                                                      float(m[0]), float(m[1]), float(m[2])))
         # the recordings' IMU logs run past the last image; two trailing samples let findIndexAt bracket it
-        for k in range(len(flat), len(flat) + 2):
-            m = flat[-1]
-            f.write('%r %r %r %r %r %r %r 0 0 0\n' % (float(k * spec['imu_dt']), float(m[3]), float(m[4]), float(m[5]),
-                                                      float(m[0]), float(m[1]), float(m[2])))
+        for k in range(len(flat) + 2):
+            m = flat[min(k, len(flat) - 1)]
+            f.write('%s %s %s %s %s %s %s 0 0 0\n' % (rp(k * spec['imu_dt']), ri(m[3]), ri(m[4]), ri(m[5]), ri(m[0]), ri(m[1]), ri(m[2])))
     with open(times_path, 'w') as f:
         for j in range(P):
-            f.write('%d %r\n' % (j, float(j * S * spec['imu_dt'])))
+            f.write('%d %s\n' % (j, rp(j * S * spec['imu_dt'])))
     return recs
 
 
@@ -78,3 +80,26 @@ def oracle_graph_from_logs(spec, recs):
         between=dict(i=np.array(bi), j=np.array(bj), R=np.array(bR), t=np.array(bt), info=np.array(binfo)),
         imu=dict(pi=a, vi=a, pj=a + 1, vj=a + 1, bi=a, bj=a + 1, pim=pim, info=np.linalg.inv(pim['cov'])))
     return g
+
+
+def read_vro_log(path):
+    """VRO edge log: `id_to id_from r(6) upper-triangular information(21)` per line -> [(i, j, r, info)]."""
+    recs = []
+    for line in open(path):
+        v = line.split()
+        if len(v) < 29:
+            continue
+        iw = np.zeros((6, 6)); iw[np.triu_indices(6)] = [float(x) for x in v[8:29]]; iw = iw + np.triu(iw, 1).T
+        recs.append((int(v[1]), int(v[0]), np.array([float(x) for x in v[2:8]]), iw))
+    return recs
+
+
+def read_imu_log(imu_path, times_path):
+    """IMU log `t ax ay az gx gy gz ...` + image time log `id t` -> samples (P-1, S, 6) as [gx gy gz ax ay az], dt."""
+    a = np.loadtxt(imu_path)
+    t_img = np.loadtxt(times_path)[:, 1]
+    dt = float(a[1, 0] - a[0, 0])
+    idx = np.rint(t_img / dt).astype(int)
+    S = int(idx[1] - idx[0])
+    flat = np.concatenate([a[:, 4:7], a[:, 1:4]], 1)
+    return np.stack([flat[idx[k]:idx[k] + S] for k in range(len(t_img) - 1)]), dt

@@ -281,3 +281,21 @@ def test_dense_visibility_splits_schur_chunks():
     check(spec, 1e-7, 1e-6, solver='schur')
 
 
+
+
+@pytest.mark.parametrize('name,scale', [('C2', 0.2), ('C3', 0.1), ('C4', 0.06)])
+def test_runs_are_bitwise_repeatable(name, scale):
+    """No fp64 atomics on the accumulation paths (fixed-order reductions): pose-side factors are assembled colour
+    by colour, per-landmark sums are merged in order inside one block, scalars go through per-block partials -- two runs of
+    the same graph give bit-identical errors, traces and states."""
+    spec = synth.make_config(name, seed=3, scale=scale)
+    out = []
+    for _ in range(2):
+        ctx = abi.Context(device=0)
+        abi.load_spec(ctx, spec)
+        e0 = ctx.error()
+        rep = ctx.optimize()
+        out.append((e0, rep.initial_error, rep.final_error, [t['new_err'] for t in rep.trace()], ctx.get_values(abi.T_POSE).tobytes(),
+                    ctx.get_values(abi.T_POINT).tobytes() if ctx.num_values(abi.T_POINT) else b''))
+        ctx.close()
+    assert out[0] == out[1]
