@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) k_backsolve_w(SysView s, con
     if (lane == 0) slot = atomicAdd(&counters[1], 1);
     slot = __shfl_sync(FULL, slot, 0);
     if (slot >= n_sn) break;
-    const int sn = sched[n_sn - 1 - slot];
+    const int sn = sched[slot];                            // processing order: reverse level order (this rank's supernodes)
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     const double* Lp = s.L + s.sn_valptr[sn];
     const int* rows = s.rowidx + s.sn_rowptr[sn];
@@ -175,13 +175,17 @@ void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36) 
   k_marginal<<<1, 256, 0, c->stream>>>(s, col0, dim, work, out36);
 }
 
-void launch_backsolve(fg_ctx* c) {
+void launch_backsolve(fg_ctx* c, bool distribute) {
   DevGraph& d = c->d;
   SysView s = chol_view(c);
+  // multi-GPU: the separators are solved on every rank, a leaf only on the rank that factored it; the leaf solutions travel
+  // by gather_delta
+  const bool dist = distribute && c->dist_ok;
+  const int n = dist ? c->n_bs_mine : c->sym.n_sn;
   int gridw = c->num_sms;                                // measured: 1.19 / 1.26 / 1.32 ms at 1 / 2 / 4 CTAs per SM (fewer pollers)
-  if (gridw * BW_WARPS > c->sym.n_sn) gridw = (c->sym.n_sn + BW_WARPS - 1) / BW_WARPS;
-  k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, c->stream>>>(s, d.sched, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch,
-                                                       c->sym.n_sn, d.delta);
+  if (gridw * BW_WARPS > n) gridw = (n + BW_WARPS - 1) / BW_WARPS;
+  k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, c->stream>>>(s, dist ? d.bs_mine : d.bs_full, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch, n, d.delta);
+  if (dist) gather_delta(c);
 }
 
 }  // namespace fg

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(RS_T, 3)
 k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__ unit_moff, const short* __restrict__ rowmap,
           const int* __restrict__ upd_ptr, const int* __restrict__ upd_d, const UpdRec* __restrict__ upd_rec,
           const signed char* __restrict__ colinv, const int2* __restrict__ sn_units, int* done, int unit_base,
-          int* counter, int n_units, int* status, FrontView fv, long long* dbg) {
+          int* counter, int n_units, int* status, FrontView fv, long long* dbg, const int* __restrict__ slot_idx) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
   const int tid = threadIdx.x;
@@ -117,7 +117,8 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     if (slot >= n_units) break;
 #define RS_STAMP(k) if (dbg && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[8 * slot + (k)] = t_; }
     RS_STAMP(0)
-    const int4 un = units[slot];
+    const int uidx = slot_idx ? slot_idx[slot] : slot;      // multi-GPU: this rank's leaves only (fg_api.cu: distributed leaf phase)
+    const int4 un = units[uidx];
     const int sn = un.x, r0 = un.y, r1 = un.z;               // rows [r0, r1) of the panel; r0 == 0: the diagonal block [0, nc)
     const bool is_diag = (r0 == 0);
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
@@ -179,7 +180,7 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
       for (int n = 0; n < RS_NT; ++n)
 #pragma unroll
         for (int e = 0; e < 2; ++e) fr[m][n][e] = slab[(8 * m + fgi) * RS_SP + 8 * n + 2 * fti + e];
-    const short* umap = rowmap + unit_moff[slot] + tid;
+    const short* umap = rowmap + unit_moff[uidx] + tid;
     const int bk = tid / RS_NC, bc = tid % RS_NC;          // this thread's elements of the B tile: (bk + 4 h, bc), h = 0..3
 
     int u = upd_ptr[sn];
@@ -348,12 +349,12 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + unit_base + slot), "r"(1) : "memory");
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + unit_base + uidx), "r"(1) : "memory");
     RS_STAMP(6)
   }
 }
 
-void launch_factor_rs(fg_ctx* c) {
+void launch_factor_rs(fg_ctx* c, bool distribute) {
   DevGraph& d = c->d;
   const Symbolic& S = c->sym;
   SysView s;
@@ -400,16 +401,20 @@ void launch_factor_rs(fg_ctx* c) {
   const int cap = c->num_sms * per_sm;
   if (!S.use_fronts) {
     k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
-                                                                d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg);
+                                                                d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg, nullptr);
     return;
   }
   // phase A: the leaves; phase B: one dense update matrix per leaf; phase C: the separators
-  if (na) k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
-                                                                      d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg);
-  launch_front_syrk(c);
+  // phase A: the leaves (multi-GPU: this rank's leaves only, the fronts of the others arrive by fg_gather_fronts)
+  const bool dist = distribute && c->dist_ok;
+  const int na_run = dist ? c->n_my_units_a : na;
+  if (na_run) k_chol_rs<<<std::min(cap, na_run), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
+                                                                              d.rs_sn_units, d.rs_done, 0, d.counters, na_run, d.status, none, dbg, dist ? d.my_units_a : nullptr);
+  launch_front_syrk(c, dist);
+  if (dist) gather_fronts(c);
   FrontView fv = {d.tf_ptr, d.tf_leaf, d.fr_rowptr, d.fr_rows, d.fr_uptr, d.U};
   if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.rsu_ptr, d.rsu_d,
-                                                                      d.rsu_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr);
+                                                                      d.rsu_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr, nullptr);
 }
 
 }  // namespace fg
