@@ -228,10 +228,12 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
+    launches0 = abi.launch_count()
     t0 = time.perf_counter()
     rep = ctx.optimize(max_iterations=args.steps, force_iterations=1)
     barrier()
     dt = time.perf_counter() - t0
+    launches = abi.launch_count() - launches0            # counted at every <<<>>> of the library (FGS() in fg_internal.h), rank 0's
     # ---- end-to-end arm: host buffers in and out every step
     reset()
     for _ in range(2):
@@ -318,10 +320,7 @@ def main():
                     graph_build_s=t_build),
                 e2e=dict(value=args.steps / dt_e2e, unit='iterations/s', h2d_bytes_per_step=state_bytes,
                          d2h_bytes_per_step=state_bytes),
-                # kernels per outer iteration (linearise) and per lambda trial (build, Schur, factor x3, solve, retract, error pass),
-                # counted on the ncu launch list (profiles/r1_launch_summary.md: 27 per one-trial iteration at C5)
-                gpu_launches=int(rep.iterations * (7 + ('between_i' in spec) + ('plane_init' in spec)) +
-                                 trials * (20 + ('between_i' in spec) + 2 * ('plane_init' in spec))),
+                gpu_launches=int(launches),
                 clocks=sampler.summary(),
                 roofline=dict(dominant, peak_source=peak_src, iteration_algorithmic_bytes=ab['total'],
                               iteration_frac=ab['total'] / (dt / args.steps) / 1e9 / peak,

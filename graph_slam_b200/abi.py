@@ -350,6 +350,11 @@ def fp64_peak(device=0):
     return float(out[0]), float(out[1])
 
 
+def launch_count():
+    """Kernels this process has launched through the library so far (fg_debug_counts(NULL, 100))."""
+    return int(lib().fg_debug_counts(None, 100))
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(128)
     rc = lib().fg_comm_unique_id(buf)

@@ -918,7 +918,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
     if ((rc = dev_upload(c, &d.rsu_ptr, S.rsu_ptr)) || (rc = dev_upload(c, &d.rsu_d, S.rsu_d)) || (rc = dev_upload(c, &d.rsu_rec, S.rsu_rec)) ||
         (rc = dev_upload(c, &d.rs_units, S.rs_units)) || (rc = dev_upload(c, &d.rs_moff, S.rs_moff)) || (rc = dev_upload(c, &d.rs_map, S.rs_map)) ||
         (rc = dev_upload(c, &d.rs_colinv, S.rs_colinv)) ||
-        (rc = dev_upload<int>(c, &d.rs_done, nullptr, S.rs_units.size())) || (rc = dev_upload(c, &d.rs_sn_units, S.rs_sn_units))) return rc;
+        (rc = dev_upload<int>(c, &d.rs_done, nullptr, S.rs_units.size() + S.n_sn)) || (rc = dev_upload(c, &d.rs_sn_units, S.rs_sn_units))) return rc;
   }
   {
     DistTables T;
@@ -1473,8 +1473,12 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
   return (int64_t)v.size();
 }
 
-// Host-side factor counts for tests: 0 point priors, 1 projections, 2 betweens, 3 imu, 4 plane factors, 5 pose priors.
+long long g_fg_launches = 0;
+
+// Host-side factor counts for tests: 0 point priors, 1 projections, 2 betweens, 3 imu, 4 plane factors, 5 pose priors;
+// 100: kernels this process has launched so far (FGS() in fg_internal.h).
 extern "C" int64_t fg_debug_counts(fg_ctx* c, int which) {
+  if (which == 100) return (int64_t)g_fg_launches;
   if (!c) return FG_ERR_INVALID;
   const HostGraph& h = c->h;
   switch (which) {

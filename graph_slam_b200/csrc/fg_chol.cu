@@ -172,7 +172,7 @@ static SysView chol_view(fg_ctx* c) {
 void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36) {
   SysView s = chol_view(c);
   cudaMemsetAsync(work, 0, sizeof(double) * 6 * ((size_t)c->sym.n_r + 1), c->stream);
-  k_marginal<<<1, 256, 0, c->stream>>>(s, col0, dim, work, out36);
+  k_marginal<<<1, 256, 0, FGS(c->stream)>>>(s, col0, dim, work, out36);
 }
 
 void launch_backsolve(fg_ctx* c, bool distribute) {
@@ -184,7 +184,7 @@ void launch_backsolve(fg_ctx* c, bool distribute) {
   const int n = dist ? c->n_bs_mine : c->sym.n_sn;
   int gridw = c->num_sms;                                // measured: 1.19 / 1.26 / 1.32 ms at 1 / 2 / 4 CTAs per SM (fewer pollers)
   if (gridw * BW_WARPS > n) gridw = (n + BW_WARPS - 1) / BW_WARPS;
-  k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, c->stream>>>(s, dist ? d.bs_mine : d.bs_full, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch, n, d.delta);
+  k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, FGS(c->stream)>>>(s, dist ? d.bs_mine : d.bs_full, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch, n, d.delta);
   if (dist) gather_delta(c);
 }
 

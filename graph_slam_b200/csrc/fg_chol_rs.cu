@@ -31,7 +31,7 @@ namespace fg {
 #define RS_NC 32                       // columns of a target supernode (fg_symbolic.cpp: kMaxSnCols)
 #define RS_KC 16                       // columns of one update step (fg_symbolic.cpp: kUpdK)
 #define RS_NT (RS_NC / 8)              // 8-column MMA tiles of the target
-#define RS_DP 34                       // row stride of the diagonal block in shared memory (even: 16-byte row starts)
+#define RS_DP 34                       // column stride of the diagonal factor in shared memory (even: 16-byte column starts)
 #define RS_SP 33                       // row stride of the layout-conversion slabs
 
 __device__ __forceinline__ int rs_ld_relaxed(const int* p) {
@@ -46,7 +46,7 @@ __device__ __forceinline__ int rs_ld_relaxed(const int* p) {
 struct RsSmem {
   double Xs[RS_ST][RS_KC * RS_XLD];     // [stage][k][row]: the descendant row that lands on each local row (gathered by the host row map)
   double Bs[RS_ST][RS_KC * RS_BS];      // [stage][k][c]: descendant rows that fall in the target's columns, scattered to TARGET columns
-  double Ds[RS_NC * RS_DP];
+  double Dt[RS_NC * RS_DP];              // the diagonal factor, transposed: Dt[c * RS_DP + r] = L[r][c], r >= c (a column of L is contiguous)
   double dinv[RS_NC];
   int colidx[RS_NC];
   int slot, first_not_ready;
@@ -68,41 +68,49 @@ __device__ __forceinline__ void rs_cp_async8(double* smem_dst, const double* gsr
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-// Cholesky of the nc x nc (nc <= 32) diagonal block by one warp, the matrix in registers: lane r holds row r, the pivot
-// and the scaled column travel by shuffles, every index is static (fully unrolled).  Rows / columns beyond nc are padded
-// with the identity.  Entries above the diagonal hold garbage that never feeds a used value.
-__device__ __forceinline__ void rs_potrf_warp(RsSmem& sm, int nc, int lane, int* status) {
+// Right-looking Cholesky of the first 32 rows of a head unit by its first warp, in the registers that already hold them: lane r
+// has panel row r.  Rows [0, nc) are the diagonal block; the lanes beyond it hold the first rows below the block, and the same
+// recurrence (scale by 1 / L_cc, subtract the scaled column times L_jc) is their triangular solve.  The pivot of column c + 1 is
+// updated, broadcast and its reciprocal square root started BEFORE the rest of column c's update is issued, so that the
+// rsqrt / shuffle latency chain (the critical path of the whole factorisation) hides behind those independent updates.
+// Entries above the diagonal hold garbage that never feeds a used value.  Returns 1 / L[lane][lane].
+__device__ __forceinline__ double rs_potrf_rows(double (&a)[RS_NC], int nc, int lane, bool& bad) {
   const unsigned FULL = 0xffffffffu;
-  double a[RS_NC];
-#pragma unroll
-  for (int c = 0; c < RS_NC; ++c) a[c] = (lane < nc && c < nc) ? sm.Ds[lane * RS_DP + c] : (lane == c ? 1.0 : 0.0);
-  bool bad = false;
+  // every index and every trip count below is static: the columns beyond nc run too, with pivot 1, on entries that are never
+  // stored and never feed a column below nc
+  double myinv = 1.0;
+  double d = __shfl_sync(FULL, a[0], 0);
+  if (!(d > 0.0)) { bad = true; d = 1.0; }          // not positive definite (or NaN): flag and keep going with a safe pivot
+  double inv = rsqrt(d);
 #pragma unroll
   for (int c = 0; c < RS_NC; ++c) {
-    double d = __shfl_sync(FULL, a[c], c);
-    if (!(d > 0.0)) { bad = true; d = 1.0; }       // not positive definite (or NaN): flag and keep going with a safe pivot
-    const double inv = rsqrt(d);
     const double l = (lane == c) ? d * inv : a[c] * inv;
     a[c] = l;
+    if (lane == c) myinv = inv;
+    if (c + 1 < RS_NC) {
+      const double l1 = __shfl_sync(FULL, l, (c + 1) & 31);
+      a[(c + 1) & 31] = fma(-l, l1, a[(c + 1) & 31]);
+      d = __shfl_sync(FULL, a[(c + 1) & 31], (c + 1) & 31);
+      if (c + 1 >= nc) d = 1.0;
+      else if (!(d > 0.0)) { bad = true; d = 1.0; }
+      inv = rsqrt(d);
+    }
 #pragma unroll
-    for (int j = c + 1; j < RS_NC; ++j) {
-      const double lj = __shfl_sync(FULL, l, j);
-      a[j] = fma(-l, lj, a[j]);
+    for (int j = 0; j < RS_NC; ++j) {
+      if (j >= c + 2) {
+        const double lj = __shfl_sync(FULL, l, j);
+        a[j] = fma(-l, lj, a[j]);
+      }
     }
   }
-  if (bad && lane == 0) atomicExch(status, 1);
-  if (lane < nc) {
-#pragma unroll
-    for (int c = 0; c < RS_NC; ++c)
-      if (c <= lane) sm.Ds[lane * RS_DP + c] = a[c];
-  }
+  return myinv;
 }
 
 __global__ void __launch_bounds__(RS_T, 3)
 k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__ unit_moff, const short* __restrict__ rowmap,
           const int* __restrict__ upd_ptr, const int* __restrict__ upd_d, const UpdRec* __restrict__ upd_rec,
           const signed char* __restrict__ colinv, const int2* __restrict__ sn_units, int* done, int unit_base,
-          int* counter, int n_units, int* status, FrontView fv, long long* dbg, const int* __restrict__ slot_idx) {
+          int* counter, int n_units, int* status, FrontView fv, long long* dbg, const int* __restrict__ slot_idx, int* diag_done) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
   const int tid = threadIdx.x;
@@ -115,11 +123,12 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     const int slot = sm.slot;
     __syncthreads();
     if (slot >= n_units) break;
-#define RS_STAMP(k) if (dbg && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[8 * slot + (k)] = t_; }
+// (the __syncwarp matters: a warp left diverged by the one-lane branch would take the slow divergent path of every following shuffle)
+#define RS_STAMP(k) if (dbg) { if (tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[8 * slot + (k)] = t_; } __syncwarp(); }
     RS_STAMP(0)
     const int uidx = slot_idx ? slot_idx[slot] : slot;      // multi-GPU: this rank's leaves only (fg_api.cu: distributed leaf phase)
     const int4 un = units[uidx];
-    const int sn = un.x, r0 = un.y, r1 = un.z;               // rows [r0, r1) of the panel; r0 == 0: the diagonal block [0, nc)
+    const int sn = un.x, r0 = un.y, r1 = un.z;               // rows [r0, r1) of the panel; r0 == 0: the head unit (diagonal block [0, nc) + rows below it)
     const bool is_diag = (r0 == 0);
     const int c0 = s.sn_col0[sn], nc = s.sn_ncols[sn], nr = s.sn_nrows[sn];
     const int nloc = r1 - r0;
@@ -295,58 +304,70 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
     RS_STAMP(2)
 
     if (is_diag) {
-      // ---- the diagonal block: factor it (one warp, registers) and store it into the panel; the blocks of below-diagonal
-      //      rows of this supernode wait for this unit's flag
-      if (tid < nc) {
+      // ---- the head unit: its first warp factors the diagonal block (and solves the rows it holds beyond it) in registers, hands
+      //      the factor to the other warps through shared memory, stores its rows and raises the supernode's diagonal flag -- the
+      //      further row blocks of this supernode wait for it
+      if (wrp == 0) {
+        bool bad = false;
+        const double myinv = rs_potrf_rows(acc, nc, lane, bad);
+        if (bad) atomicExch(status, 1);
 #pragma unroll
-        for (int c = 0; c < RS_NC; ++c) if (c <= tid) sm.Ds[tid * RS_DP + c] = acc[c];
+        for (int c = 0; c < RS_NC; ++c) sm.Dt[c * RS_DP + lane] = (lane < nc && c <= lane) ? acc[c] : 0.0;      // padded: no bounds in the solve
+        sm.dinv[lane] = myinv;
       }
-      __syncthreads();
-      if (tid < 32) rs_potrf_warp(sm, nc, tid, status);
       __syncthreads();
       RS_STAMP(3)
-      for (int i = tid; i < nc * nc; i += RS_T) {
-        const int r = i % nc, c = i / nc;
-        if (c <= r) Lp[r + (int64_t)c * nr] = sm.Ds[r * RS_DP + c];
+      if (wrp == 0) {
+        if (has_row) {
+#pragma unroll
+          for (int c = 0; c < RS_NC; ++c) if (c < nc && (prow >= nc || c <= prow)) Lp[prow + (int64_t)c * nr] = acc[c];
+        }
+        if (r1 < nr) {                                   // somebody is waiting
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(diag_done + sn), "r"(1) : "memory");
+        }
       }
-      RS_STAMP(4)
     } else {
-      // ---- below-diagonal rows: wait for the diagonal factor of this supernode, solve the own row against it in
-      //      registers and store it (coalesced per column)
+      // ---- further rows: wait for the diagonal factor of this supernode
       if (tid == 0) {
-        const int* fp = done + sn_units[sn].x;
+        const int* fp = diag_done + sn;
         while (rs_ld_relaxed(fp) == 0) { }
         __threadfence();
       }
       __syncthreads();
-      for (int i = tid; i < nc * nc; i += RS_T) {
-        const int r = i % nc, c = i / nc;
-        if (c <= r) sm.Ds[r * RS_DP + c] = __ldcg(&Lp[r + (int64_t)c * nr]);
+      for (int i = tid; i < RS_NC * RS_NC; i += RS_T) {
+        const int r = i % RS_NC, c = i / RS_NC;
+        sm.Dt[c * RS_DP + r] = (r < nc && c <= r) ? __ldcg(&Lp[r + (int64_t)c * nr]) : 0.0;       // padded: no bounds in the solve
       }
       __syncthreads();
-      if (tid < nc) sm.dinv[tid] = 1.0 / sm.Ds[tid * RS_DP + tid];
+      if (tid < RS_NC) sm.dinv[tid] = tid < nc ? 1.0 / sm.Dt[tid * RS_DP + tid] : 1.0;
       __syncthreads();
       RS_STAMP(3)
-      if (has_row) {
+    }
+    // ---- rows below the diagonal block: right-looking triangular solve of the own row in registers (the updates of one column are
+    //      independent: the dependency chain is one multiply and one FMA per column), then the store (coalesced per column)
+    if (has_row && !(is_diag && wrp == 0)) {
 #pragma unroll
-        for (int c = 0; c < RS_NC; ++c) {
-          if (c < nc) {
-            double v = acc[c];
-            const double2* dr = reinterpret_cast<const double2*>(&sm.Ds[c * RS_DP]);
+      for (int c = 0; c < RS_NC; ++c) {
+        const double x = acc[c] * sm.dinv[c];
+        acc[c] = x;
+        if (c < nc) Lp[prow + (int64_t)c * nr] = x;
+        const double* dc = &sm.Dt[c * RS_DP];
 #pragma unroll
-            for (int k2 = 0; k2 < c / 2; ++k2) {
-              const double2 dd = dr[k2];
-              v = fma(-acc[2 * k2], dd.x, v);
-              v = fma(-acc[2 * k2 + 1], dd.y, v);
-            }
-            if (c & 1) v = fma(-acc[c - 1], sm.Ds[c * RS_DP + c - 1], v);
-            acc[c] = v * sm.dinv[c];
-            Lp[prow + (int64_t)c * nr] = acc[c];
+        for (int jj = 0; jj < RS_NC / 2; ++jj) {          // columns (j, j + 1) of the row, one 16-byte read of the factor's column c
+          const int j = 2 * jj;
+          if (j > c) {
+            const double2 dd = *reinterpret_cast<const double2*>(dc + j);
+            acc[j] = fma(-x, dd.x, acc[j]);
+            acc[j + 1] = fma(-x, dd.y, acc[j + 1]);
+          } else if (j + 1 > c) {
+            acc[j + 1] = fma(-x, dc[j + 1], acc[j + 1]);
           }
         }
       }
-      RS_STAMP(4)
     }
+    RS_STAMP(4)
     __threadfence();
     __syncthreads();
     if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + unit_base + uidx), "r"(1) : "memory");
@@ -369,15 +390,17 @@ void launch_factor_rs(fg_ctx* c, bool distribute) {
   cudaStream_t st = c->stream;
   c->epoch += 1;                                   // k_backsolve's flags are epoch stamped
   cudaMemsetAsync(d.status, 0, sizeof(int), st);
-  cudaMemsetAsync(d.rs_done, 0, sizeof(int) * S.rs_units.size(), st);     // one done flag per unit
+  cudaMemsetAsync(d.rs_done, 0, sizeof(int) * (S.rs_units.size() + S.n_sn), st);     // one done flag per unit, then one diagonal flag per supernode
+  int* const diag_done = d.rs_done + S.rs_units.size();
   cudaMemsetAsync(d.counters, 0, sizeof(int) * 4, st);
   const int na = S.rs_units_a, nc = (int)S.rs_units.size() - S.rs_units_a;
-  // FG_CHOL_TRACE=<file>: per-unit %globaltimer stamps of the 3rd factorisation (dev tool, profiles/tools/chol_trace.py)
+  // FG_CHOL_TRACE=<file>: per-unit %globaltimer stamps of the 3rd (FG_CHOL_TRACE_CALL-th) factorisation (dev tool, profiles/tools/chol_trace.py)
   static int n_calls = 0;
   long long* dbg = nullptr;
   const char* trace = getenv("FG_CHOL_TRACE");
   const size_t n_all = S.rs_units.size();
-  if (trace && ++n_calls == 3) { cudaMalloc((void**)&dbg, sizeof(long long) * 8 * n_all); cudaMemset(dbg, 0, sizeof(long long) * 8 * n_all); }
+  static const int trace_call = getenv("FG_CHOL_TRACE_CALL") ? atoi(getenv("FG_CHOL_TRACE_CALL")) : 3;
+  if (trace && ++n_calls == trace_call) { cudaMalloc((void**)&dbg, sizeof(long long) * 8 * n_all); cudaMemset(dbg, 0, sizeof(long long) * 8 * n_all); }
   struct TraceDump {
     long long* dbg; const char* path; const Symbolic& S; cudaStream_t st;
     ~TraceDump() {
@@ -400,21 +423,21 @@ void launch_factor_rs(fg_ctx* c, bool distribute) {
   FrontView none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const int cap = c->num_sms * per_sm;
   if (!S.use_fronts) {
-    k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
-                                                                d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg, nullptr);
+    k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), FGS(st)>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
+                                                                d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg, nullptr, diag_done);
     return;
   }
   // phase A: the leaves; phase B: one dense update matrix per leaf; phase C: the separators
   // phase A: the leaves (multi-GPU: this rank's leaves only, the fronts of the others arrive by fg_gather_fronts)
   const bool dist = distribute && c->dist_ok;
   const int na_run = dist ? c->n_my_units_a : na;
-  if (na_run) k_chol_rs<<<std::min(cap, na_run), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
-                                                                              d.rs_sn_units, d.rs_done, 0, d.counters, na_run, d.status, none, dbg, dist ? d.my_units_a : nullptr);
+  if (na_run) k_chol_rs<<<std::min(cap, na_run), RS_T, sizeof(RsSmem), FGS(st)>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
+                                                                              d.rs_sn_units, d.rs_done, 0, d.counters, na_run, d.status, none, dbg, dist ? d.my_units_a : nullptr, diag_done);
   launch_front_syrk(c, dist);
   if (dist) gather_fronts(c);
   FrontView fv = {d.tf_ptr, d.tf_leaf, d.fr_rowptr, d.fr_rows, d.fr_uptr, d.U};
-  if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), st>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.rsu_ptr, d.rsu_d,
-                                                                      d.rsu_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr, nullptr);
+  if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), FGS(st)>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.rsu_ptr, d.rsu_d,
+                                                                      d.rsu_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr, nullptr, diag_done);
 }
 
 }  // namespace fg

@@ -102,7 +102,7 @@ void launch_front_syrk(fg_ctx* c, bool dist) {
   if (!n_tiles) return;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_front_syrk, cudaFuncAttributePreferredSharedMemoryCarveout, 100); attr = true; }
-  k_front_syrk<<<n_tiles, 256, 0, c->stream>>>(n_tiles, d.tile_leaf, d.tile_i, d.tile_j, d.tile_mptr, d.tile_mrec, d.fr_rowptr, d.fr_uptr,
+  k_front_syrk<<<n_tiles, 256, 0, FGS(c->stream)>>>(n_tiles, d.tile_leaf, d.tile_i, d.tile_j, d.tile_mptr, d.tile_mrec, d.fr_rowptr, d.fr_uptr,
                                                d.posmap, d.L, d.U, dist ? d.my_tiles : nullptr);
 }
 

@@ -8,6 +8,11 @@
 #include "../../include/fg_abi.h"
 #include "fg_factors.cuh"
 
+// Every kernel launch of the library passes its stream through FGS(): the process-wide launch count that bench.py reports as
+// `gpu_launches` (fg_debug_counts(ctx, 100)) is counted, not estimated.
+extern long long g_fg_launches;
+#define FGS(stream) (++g_fg_launches, (stream))
+
 namespace fg {
 
 enum FactorKind { K_PP = 0, K_PV, K_PB, K_BT, K_GE, K_IMU, K_PL, K_COUNT };     // pose-side factor kinds (colour tables)

@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(32 * PI_WPB, 4) k_preintegrate(int n, const in
 void launch_preintegrate(int n, const int* d_off, const double* d_imu, double dt, const ImuParamsDev* d_par,
                          const double* d_bias, fg_pim* d_out, cudaStream_t st) {
   if (n <= 0) return;
-  k_preintegrate<<<cdiv(n, PI_WPB), 32 * PI_WPB, 0, st>>>(n, d_off, d_imu, dt, d_par, d_bias, d_out);
+  k_preintegrate<<<cdiv(n, PI_WPB), 32 * PI_WPB, 0, FGS(st)>>>(n, d_off, d_imu, dt, d_par, d_bias, d_out);
 }
 
 // ------------------------------------------------------------------ launch wrappers
@@ -879,49 +879,49 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
   if (pose_side) {
     for (size_t k = 0; k + 1 < c->color_ptr[K_PP].size(); ++k) {
       const int b = c->color_ptr[K_PP][k], n = c->color_ptr[K_PP][k + 1] - b;
-      if (n) k_prior_pose<JAC><<<cdiv(n, T), T, 0, st>>>(n, d.pp_var + b, d.pp_mean + 12 * (size_t)b, d.pp_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
+      if (n) k_prior_pose<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pp_var + b, d.pp_mean + 12 * (size_t)b, d.pp_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
     }
     for (size_t k = 0; k + 1 < c->color_ptr[K_PV].size(); ++k) {
       const int b = c->color_ptr[K_PV][k], n = c->color_ptr[K_PV][k + 1] - b;
-      if (n) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(n, T), T, 0, st>>>(n, d.pv_var + b, d.pv_mean + 3 * (size_t)b, d.pv_info + 9 * (size_t)b, v, d.off[T_VEC3], sys, d.g_r, slots(cdiv(n, T)));
+      if (n) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pv_var + b, d.pv_mean + 3 * (size_t)b, d.pv_info + 9 * (size_t)b, v, d.off[T_VEC3], sys, d.g_r, slots(cdiv(n, T)));
     }
     for (size_t k = 0; k + 1 < c->color_ptr[K_PB].size(); ++k) {
       const int b = c->color_ptr[K_PB][k], n = c->color_ptr[K_PB][k + 1] - b;
-      if (n) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(n, T), T, 0, st>>>(n, d.pb_var + b, d.pb_mean + 6 * (size_t)b, d.pb_info + 36 * (size_t)b, v, d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, T)));
+      if (n) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pb_var + b, d.pb_mean + 6 * (size_t)b, d.pb_info + 36 * (size_t)b, v, d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, T)));
     }
     for (size_t k = 0; k + 1 < c->color_ptr[K_BT].size(); ++k) {
       const int b = c->color_ptr[K_BT][k], n = c->color_ptr[K_BT][k + 1] - b;
-      if (n) k_between<JAC><<<cdiv(n, T), T, 0, st>>>(n, d.bt_i + b, d.bt_j + b, d.bt_meas + 12 * (size_t)b, d.bt_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
+      if (n) k_between<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.bt_i + b, d.bt_j + b, d.bt_meas + 12 * (size_t)b, d.bt_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
     }
     for (size_t k = 0; k + 1 < c->color_ptr[K_GE].size(); ++k) {
       const int b = c->color_ptr[K_GE][k], n = c->color_ptr[K_GE][k + 1] - b;
-      if (n) k_g2o_edge<JAC><<<cdiv(n, 64), 64, 0, st>>>(n, d.ge_i + b, d.ge_j + b, d.ge_meas + 12 * (size_t)b, d.ge_info + 36 * (size_t)b, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, slots(cdiv(n, 64)));
+      if (n) k_g2o_edge<JAC><<<cdiv(n, 64), 64, 0, FGS(st)>>>(n, d.ge_i + b, d.ge_j + b, d.ge_meas + 12 * (size_t)b, d.ge_info + 36 * (size_t)b, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, slots(cdiv(n, 64)));
     }
-    if (JAC && d.n_fixed) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, st>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
+    if (JAC && d.n_fixed) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, FGS(st)>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
     for (size_t k = 0; k + 1 < c->color_ptr[K_IMU].size(); ++k) {
       const int b = c->color_ptr[K_IMU][k], n = c->color_ptr[K_IMU][k + 1] - b;
-      if (n) k_imu<JAC><<<cdiv(n, IMU_WPB), 32 * IMU_WPB, 0, st>>>(n, d.imu_var + 6 * (size_t)b, d.imu_rec + b, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, IMU_WPB)));
+      if (n) k_imu<JAC><<<cdiv(n, IMU_WPB), 32 * IMU_WPB, 0, FGS(st)>>>(n, d.imu_var + 6 * (size_t)b, d.imu_rec + b, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, IMU_WPB)));
     }
     for (size_t k = 0; k + 1 < c->color_ptr[K_PL].size(); ++k) {
       const int b = c->color_ptr[K_PL][k], n = c->color_ptr[K_PL][k + 1] - b;
-      if (n) k_plane<JAC><<<cdiv(n, T), T, 0, st>>>(n, d.pl_pose + b, d.pl_plane + b, d.pl_meas + 4 * (size_t)b, d.pl_info + 9 * (size_t)b, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, slots(cdiv(n, T)));
+      if (n) k_plane<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pl_pose + b, d.pl_plane + b, d.pl_meas + 4 * (size_t)b, d.pl_info + 9 * (size_t)b, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, slots(cdiv(n, T)));
     }
   }
   int64_t L = d.n[T_POINT];
   if (L) {
-    k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, st>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, slots(cdiv(L, 256)));
+    k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, FGS(st)>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, slots(cdiv(L, 256)));
     if (d.n_obs) {
       if (JAC && c->kev[0]) cudaEventRecord(c->kev[0], st);
-      k_proj_obs<JAC><<<d.n_oblk, 256, 0, st>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, slots(d.n_oblk));
+      k_proj_obs<JAC><<<d.n_oblk, 256, 0, FGS(st)>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, slots(d.n_oblk));
       if (JAC && c->kev[1]) cudaEventRecord(c->kev[1], st);
-      if (JAC && d.n_dup) k_merge_dup<<<cdiv(d.n_dup, 128), 128, 0, st>>>(d.n_dup, d.dup_prim, d.dup_sec, d.W);
+      if (JAC && d.n_dup) k_merge_dup<<<cdiv(d.n_dup, 128), 128, 0, FGS(st)>>>(d.n_dup, d.dup_prim, d.dup_sec, d.W);
       if (JAC) {
         int P = (int)d.n[T_POSE];
-        k_proj_pose<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.off[T_POSE], sys, d.g_r);
+        k_proj_pose<<<cdiv((int64_t)P * 32, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.off[T_POSE], sys, d.g_r);
       }
     }
   }
-  k_sum_partials<<<1, 256, 0, st>>>(d.part, np, target);
+  k_sum_partials<<<1, 256, 0, FGS(st)>>>(d.part, np, target);
 }
 
 void launch_linearize(fg_ctx* c) {
@@ -945,7 +945,7 @@ void launch_build_and_schur(fg_ctx* c, double lambda) {
   SysView sys = make_view(c, d.L);
   // damping and the pose-side gradient are replicated terms: added by rank 0 only
   // damping is a replicated term (rank 0 only); every rank contributes its own share of the gradient
-  k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, st>>>(sys, d.g_r, c->rank == 0 ? lambda : 0.0, 1);
+  k_damp_rhs<<<cdiv(c->sym.n_r, 256), 256, 0, FGS(st)>>>(sys, d.g_r, c->rank == 0 ? lambda : 0.0, 1);
   int64_t L = d.n[T_POINT];
   if (L) launch_schur(c, lambda);
 }
@@ -953,7 +953,7 @@ void launch_build_and_schur(fg_ctx* c, double lambda) {
 void launch_max_diag(fg_ctx* c, double* d_out) {
   cudaMemsetAsync(d_out, 0, sizeof(double), c->stream);
   SysView sys = make_view(c, c->d.U0);
-  k_max_diag<<<cdiv(c->sym.n_r, 256), 256, 0, c->stream>>>(sys, c->d.fixed_col, reinterpret_cast<unsigned long long*>(d_out));
+  k_max_diag<<<cdiv(c->sym.n_r, 256), 256, 0, FGS(c->stream)>>>(sys, c->d.fixed_col, reinterpret_cast<unsigned long long*>(d_out));
 }
 
 // ------------------------------------------------------------------ incremental update: relinearisation gating
@@ -992,11 +992,11 @@ void launch_inc_gate(fg_ctx* c, double thr, int* d_count) {
   DevGraph& d = c->d;
   cudaStream_t st = c->stream;
   const int T = 128;
-  if (d.n[T_POSE]) k_inc_gate<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], thr, d_count, d.pose_chart);
-  if (d.n[T_VEC3]) k_inc_gate<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], thr, d_count, d.pose_chart);
-  if (d.n[T_BIAS]) k_inc_gate<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], thr, d_count, d.pose_chart);
-  if (d.n[T_POINT]) k_inc_gate<T_POINT><<<cdiv(d.n[T_POINT], T), T, 0, st>>>(d.n[T_POINT], d.val[T_POINT], d.val_new[T_POINT], thr, d_count, d.pose_chart);
-  if (d.n[T_PLANE]) k_inc_gate<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], thr, d_count, d.pose_chart);
+  if (d.n[T_POSE]) k_inc_gate<T_POSE><<<cdiv(d.n[T_POSE], T), T, 0, FGS(st)>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], thr, d_count, d.pose_chart);
+  if (d.n[T_VEC3]) k_inc_gate<T_VEC3><<<cdiv(d.n[T_VEC3], T), T, 0, FGS(st)>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], thr, d_count, d.pose_chart);
+  if (d.n[T_BIAS]) k_inc_gate<T_BIAS><<<cdiv(d.n[T_BIAS], T), T, 0, FGS(st)>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], thr, d_count, d.pose_chart);
+  if (d.n[T_POINT]) k_inc_gate<T_POINT><<<cdiv(d.n[T_POINT], T), T, 0, FGS(st)>>>(d.n[T_POINT], d.val[T_POINT], d.val_new[T_POINT], thr, d_count, d.pose_chart);
+  if (d.n[T_PLANE]) k_inc_gate<T_PLANE><<<cdiv(d.n[T_PLANE], T), T, 0, FGS(st)>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], thr, d_count, d.pose_chart);
 }
 
 // ------------------------------------------------------------------ packed exchange (multi-GPU)
@@ -1014,11 +1014,11 @@ __global__ void k_unpack(int64_t n, const int64_t* __restrict__ idx, double* __r
 }
 void launch_pack(fg_ctx* c, bool with_chi2) {
   DevGraph& d = c->d;
-  k_pack<<<cdiv(d.n_pk + 1, 256), 256, 0, c->stream>>>(d.n_pk, d.pk_idx, d.L, d.pk_buf, d.scal, with_chi2 ? 1 : 0);
+  k_pack<<<cdiv(d.n_pk + 1, 256), 256, 0, FGS(c->stream)>>>(d.n_pk, d.pk_idx, d.L, d.pk_buf, d.scal, with_chi2 ? 1 : 0);
 }
 void launch_unpack(fg_ctx* c, bool with_chi2) {
   DevGraph& d = c->d;
-  k_unpack<<<cdiv(d.n_pk + 1, 256), 256, 0, c->stream>>>(d.n_pk, d.pk_idx, d.L, d.pk_buf, d.scal, with_chi2 ? 1 : 0);
+  k_unpack<<<cdiv(d.n_pk + 1, 256), 256, 0, FGS(c->stream)>>>(d.n_pk, d.pk_idx, d.L, d.pk_buf, d.scal, with_chi2 ? 1 : 0);
 }
 
 void launch_retract_error(fg_ctx* c, double lambda) {
@@ -1028,19 +1028,19 @@ void launch_retract_error(fg_ctx* c, double lambda) {
   int cnt = (c->rank == 0) ? 1 : 0;
   int np = 0;                                // slots of g^T delta (d.part) and |delta|^2 (d.part2)
   auto at = [&](int grid) { int o = np; np += grid; return o; };
-  if (d.n[T_POSE]) { const int g = cdiv(d.n[T_POSE], T), o = at(g); k_retract_reduced<T_POSE><<<g, T, 0, st>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], d.off[T_POSE], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
-  if (d.n[T_VEC3]) { const int g = cdiv(d.n[T_VEC3], T), o = at(g); k_retract_reduced<T_VEC3><<<g, T, 0, st>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], d.off[T_VEC3], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
-  if (d.n[T_BIAS]) { const int g = cdiv(d.n[T_BIAS], T), o = at(g); k_retract_reduced<T_BIAS><<<g, T, 0, st>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], d.off[T_BIAS], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
-  if (d.n[T_PLANE]) { const int g = cdiv(d.n[T_PLANE], T), o = at(g); k_retract_reduced<T_PLANE><<<g, T, 0, st>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], d.off[T_PLANE], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
+  if (d.n[T_POSE]) { const int g = cdiv(d.n[T_POSE], T), o = at(g); k_retract_reduced<T_POSE><<<g, T, 0, FGS(st)>>>(d.n[T_POSE], d.val[T_POSE], d.val_new[T_POSE], d.off[T_POSE], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
+  if (d.n[T_VEC3]) { const int g = cdiv(d.n[T_VEC3], T), o = at(g); k_retract_reduced<T_VEC3><<<g, T, 0, FGS(st)>>>(d.n[T_VEC3], d.val[T_VEC3], d.val_new[T_VEC3], d.off[T_VEC3], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
+  if (d.n[T_BIAS]) { const int g = cdiv(d.n[T_BIAS], T), o = at(g); k_retract_reduced<T_BIAS><<<g, T, 0, FGS(st)>>>(d.n[T_BIAS], d.val[T_BIAS], d.val_new[T_BIAS], d.off[T_BIAS], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
+  if (d.n[T_PLANE]) { const int g = cdiv(d.n[T_PLANE], T), o = at(g); k_retract_reduced<T_PLANE><<<g, T, 0, FGS(st)>>>(d.n[T_PLANE], d.val[T_PLANE], d.val_new[T_PLANE], d.off[T_PLANE], d.delta, d.g_r, d.part + o, d.part2 + o, cnt, d.pose_chart); }
   int64_t L = d.n[T_POINT];
   if (L) {
     cudaMemsetAsync(d.tl, 0, sizeof(double) * 3 * L, st);
-    if (d.n_obs) k_lm_backsub_obs<<<d.n_oblk, 256, 0, st>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.W, d.delta, d.off[T_POSE], d.tl);
+    if (d.n_obs) k_lm_backsub_obs<<<d.n_oblk, 256, 0, FGS(st)>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.W, d.delta, d.off[T_POSE], d.tl);
     const int g = cdiv(L, 256), o = at(g);
-    k_lm_update<<<g, 256, 0, st>>>(L, d.val[T_POINT], d.Vinv, d.gl, d.tl, d.val_new[T_POINT], d.part + o, d.part2 + o);
+    k_lm_update<<<g, 256, 0, FGS(st)>>>(L, d.val[T_POINT], d.Vinv, d.gl, d.tl, d.val_new[T_POINT], d.part + o, d.part2 + o);
   }
-  k_sum_partials<<<1, 256, 0, st>>>(d.part, np, d.scal + 1);
-  k_sum_partials<<<1, 256, 0, st>>>(d.part2, np, d.scal + 2);
+  k_sum_partials<<<1, 256, 0, FGS(st)>>>(d.part, np, d.scal + 1);
+  k_sum_partials<<<1, 256, 0, FGS(st)>>>(d.part2, np, d.scal + 2);
   run_factors<false>(c, true, d.scal + 3);
 }
 

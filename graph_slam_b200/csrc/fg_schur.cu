@@ -327,7 +327,7 @@ static void launch_tiles(fg_ctx* c, const SysView& sys) {
     cudaFuncSetAttribute(k_schur_tiles<CH, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchurSmem<CH, KMAX>));
     attr_set = true;
   }
-  k_schur_tiles<CH, KMAX><<<d.n_tiles, ST_THREADS, sizeof(SchurSmem<CH, KMAX>), c->stream>>>(d.tile_desc, (int)d.n[T_POSE], d.pc_lo, d.pc_n, d.pc_ptr, d.pc_ent,
+  k_schur_tiles<CH, KMAX><<<d.n_tiles, ST_THREADS, sizeof(SchurSmem<CH, KMAX>), FGS(c->stream)>>>(d.tile_desc, (int)d.n[T_POSE], d.pc_lo, d.pc_n, d.pc_ptr, d.pc_ent,
                                                                                  d.Zp, d.off[T_POSE], sys);
 }
 
@@ -338,8 +338,8 @@ void launch_schur(fg_ctx* c, double lambda) {
   sys.L = d.L; sys.col2sn = d.col2sn; sys.sn_col0 = d.sn_col0; sys.sn_ncols = d.sn_ncols; sys.sn_nrows = d.sn_nrows;
   sys.sn_rowptr = d.sn_rowptr; sys.sn_valptr = d.sn_valptr; sys.rowidx = d.rowidx; sys.n_r = c->sym.n_r;
   const int64_t L = d.n[T_POINT];
-  k_vinv<<<cdiv(L, 256), 256, 0, st>>>(L, d.V, d.gl, lambda, d.Vinv, d.Cf, d.ul);
-  if (d.n_obs) k_zmat<<<cdiv(d.n_obs, 256), 256, 0, st>>>(d.n_obs, d.obs_point, d.obs_ppos, d.W, d.Cf, d.Zp);
+  k_vinv<<<cdiv(L, 256), 256, 0, FGS(st)>>>(L, d.V, d.gl, lambda, d.Vinv, d.Cf, d.ul);
+  if (d.n_obs) k_zmat<<<cdiv(d.n_obs, 256), 256, 0, FGS(st)>>>(d.n_obs, d.obs_point, d.obs_ppos, d.W, d.Cf, d.Zp);
   if (c->kev[2]) cudaEventRecord(c->kev[2], st);
   if (d.n_tiles) {
     if (d.schur_ch == 32) launch_tiles<32, 24>(c, sys);
@@ -347,7 +347,7 @@ void launch_schur(fg_ctx* c, double lambda) {
   }
   if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];
-  if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, st>>>(P, d.pose_obs_ptr, d.pz_point, d.Zp, d.ul, d.off[T_POSE], sys);
+  if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pz_point, d.Zp, d.ul, d.off[T_POSE], sys);
 }
 
 }  // namespace fg

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <functional>
 #include <numeric>
+#include <tuple>
 #include "fg_internal.h"
 
 namespace fg {
@@ -113,7 +114,6 @@ int build_symbolic(fg_ctx* c) {
     std::vector<int> region(nv, -1);
     int next_region = 0;
     leaf_of.assign(nv, -1);
-    auto dims = [&](const std::vector<std::vector<int>>& F) { int d = 0; for (auto& f : F) for (int v : f) d += bdim[v]; return d; };
     std::function<void(std::vector<std::vector<int>>&)> nd = [&](std::vector<std::vector<int>>& F) {
       auto emit = [&]() { for (auto& f : F) for (int v : f) { elim.push_back(v); leaf_of[v] = n_leaves; } ++n_leaves; };
       if (F.size() < 8) { emit(); return; }
@@ -122,19 +122,20 @@ int build_symbolic(fg_ctx* c) {
       for (size_t i = 0; i < F.size(); ++i) for (int v : F[i]) region[v] = i < mid ? ra : rb;
       std::vector<char> inS;
       std::vector<std::vector<int>> A(F.begin(), F.begin() + mid), B, Sep;
-      int dS = 0, dB = 0;
+      int dS = 0;
       for (size_t i = mid; i < F.size(); ++i) {
         std::vector<int> keep, sep;
         for (int v : F[i]) {
           bool touch = false;
           for (int u : adj[v]) if (region[u] == ra) { touch = true; break; }
-          if (touch) { sep.push_back(v); dS += bdim[v]; } else { keep.push_back(v); dB += bdim[v]; }
+          if (touch) { sep.push_back(v); dS += bdim[v]; } else { keep.push_back(v); }
         }
         if (!keep.empty()) B.push_back(keep);
         if (!sep.empty()) Sep.push_back(sep);
       }
-      int dA = dims(A);
-      if (dS == 0 || 4 * dS > std::min(dA, dB) || B.size() < 4) { emit(); return; }
+      // dissect all the way down: measured at C5 (profiles/r2_nd_depth.md) stopping early at a separator-to-part ratio left 32 long
+      // leaf chains with 1.5x the fill and 1.5x the dependency levels of the full recursion
+      if (dS == 0 || B.size() < 4) { emit(); return; }
       nd(A);
       nd(B);
       for (auto& f : Sep) for (int v : f) elim.push_back(v);
@@ -398,7 +399,7 @@ int build_symbolic(fg_ctx* c) {
       for (int l = 0; l < n_leaves; ++l) if (S.fr_rowptr[l + 1] - S.fr_rowptr[l] > 1024) S.use_fronts = false;   // k_chol_reg stages a front's row list in shared memory
     }
   }
-  // ---- row-split work units for k_chol_rs: blocks of <= kRsRows below-diagonal rows per supernode
+  // ---- row-split work units for k_chol_rs: blocks of <= kRsRows panel rows per supernode
   {
     const int kRsRows = 128;                  // RS_T: one panel row per thread
     const bool fr = S.use_fronts;
@@ -406,10 +407,27 @@ int build_symbolic(fg_ctx* c) {
     const std::vector<int>& UD = fr ? S.updr_d : S.upd_d;
     const std::vector<int>& UA = fr ? S.updr_a : S.upd_a;
     const std::vector<int>& UB = fr ? S.updr_b : S.upd_b;
-    // the kernel's update list: the list in use with every descendant wider than kUpdK cut into column slices
-    S.rsu_ptr.assign(S.n_sn + 1, 0);
+    // levels of the supernodes under the update lists in use
+    std::vector<int> lv(S.n_sn, 0);
     for (int s = 0; s < S.n_sn; ++s) {
-      for (int u = UP[s]; u < UP[s + 1]; ++u) {
+      for (int u = UP[s]; u < UP[s + 1]; ++u) lv[s] = std::max(lv[s], lv[UD[u]] + 1);
+      if (fr)
+        for (int e = S.tf_ptr[s]; e < S.tf_ptr[s + 1]; ++e) {
+          const int l = S.tf_leaf[e];
+          for (int m = S.leaf_sn_lo[l]; m < S.leaf_sn_hi[l]; ++m) lv[s] = std::max(lv[s], lv[m] + 1);
+        }
+    }
+    // the kernel's update list: the list in use with every descendant wider than kUpdK cut into column slices, in the order the
+    // descendants are handed out (phase, level, index) -- a unit pulls its updates in list order and waits at the first one that is
+    // not there yet, so a list in index order would park the whole second subtree of a separator behind the top of the first
+    auto rank_of = [&](int d) { return std::make_tuple((fr && S.sn_leaf[d] < 0) ? 1 : 0, lv[d], d); };
+    S.rsu_ptr.assign(S.n_sn + 1, 0);
+    std::vector<int> us;
+    for (int s = 0; s < S.n_sn; ++s) {
+      us.resize(UP[s + 1] - UP[s]);
+      std::iota(us.begin(), us.end(), UP[s]);
+      std::sort(us.begin(), us.end(), [&](int x, int y) { return rank_of(UD[x]) < rank_of(UD[y]); });
+      for (int u : us) {
         const int d = UD[u], a = UA[u], b = UB[u];
         const int* rd = &S.rowidx[S.sn_rowptr[d]];
         // which 8-column groups of the target the descendant's rows [a, b) reach, and where each target column comes from
@@ -429,17 +447,8 @@ int build_symbolic(fg_ctx* c) {
       S.rsu_ptr[s + 1] = (int)S.rsu_d.size();
     }
     std::vector<int> nblk(S.n_sn);
-    for (int s = 0; s < S.n_sn; ++s) nblk[s] = std::max(1, (S.sn_nrows[s] - S.sn_ncols[s] + kRsRows - 1) / kRsRows);
-    // level-sorted supernode order of each phase (levels under the update lists in use)
-    std::vector<int> lv(S.n_sn, 0);
-    for (int s = 0; s < S.n_sn; ++s) {
-      for (int u = UP[s]; u < UP[s + 1]; ++u) lv[s] = std::max(lv[s], lv[UD[u]] + 1);
-      if (fr)
-        for (int e = S.tf_ptr[s]; e < S.tf_ptr[s + 1]; ++e) {
-          const int l = S.tf_leaf[e];
-          for (int m = S.leaf_sn_lo[l]; m < S.leaf_sn_hi[l]; ++m) lv[s] = std::max(lv[s], lv[m] + 1);
-        }
-    }
+    // the head unit takes the diagonal block and the rows right below it (rows [0, kRsRows) of the panel), the rest is cut evenly
+    for (int s = 0; s < S.n_sn; ++s) nblk[s] = (std::max(0, S.sn_nrows[s] - kRsRows) + kRsRows - 1) / kRsRows;
     S.n_levels_rs = S.n_sn ? *std::max_element(lv.begin(), lv.end()) + 1 : 0;
     std::vector<int> order_a, order_c;
     for (int s = 0; s < S.n_sn; ++s) ((fr && S.sn_leaf[s] < 0) ? order_c : order_a).push_back(s);
@@ -447,15 +456,17 @@ int build_symbolic(fg_ctx* c) {
     std::stable_sort(order_a.begin(), order_a.end(), bylevel);
     std::stable_sort(order_c.begin(), order_c.end(), bylevel);
     std::vector<short> one;
-    // units of a supernode: the diagonal block [0, nc) first (it factors the block and publishes it), then the blocks of
-    // below-diagonal rows (they wait for the diagonal factor before their triangular solve)
+    // units of a supernode: the head unit first -- the diagonal block and the rows right below it, i.e. the rows the next supernodes of
+    // the chain need: it factors the block, publishes it (diagonal flag), then solves its other rows -- then the blocks of further
+    // rows (they wait for the diagonal flag before their triangular solve)
     auto emit = [&](const std::vector<int>& order) {
       for (int s : order) {
-        const int nc = S.sn_ncols[s], nr = S.sn_nrows[s], nb = nblk[s];
-        const int per = (nr - nc + nb - 1) / nb;
+        const int nr = S.sn_nrows[s], nb = nblk[s];
+        const int head = std::min(nr, kRsRows);
+        const int per = nb ? (nr - head + nb - 1) / nb : 0;
         const int* rows = &S.rowidx[S.sn_rowptr[s]];
         for (int b = -1; b < nb; ++b) {
-          const int r0 = b < 0 ? 0 : nc + b * per, r1 = b < 0 ? nc : std::min(nr, r0 + per);
+          const int r0 = b < 0 ? 0 : head + b * per, r1 = b < 0 ? head : std::min(nr, r0 + per);
           S.rs_units.push_back(make_int4(s, r0, r1, nb + 1));
           S.rs_moff.push_back((int64_t)S.rs_map.size());
           const int nloc = r1 - r0;
@@ -464,20 +475,17 @@ int build_symbolic(fg_ctx* c) {
             const int u = S.rsu_src[q];
             if (u != last_src) {
               last_src = u;
-              const int d = UD[u], a = UA[u], bb = UB[u];
+              const int d = UD[u], a = UA[u];
               const int* rd = &S.rowidx[S.sn_rowptr[d]];
               const int nrd = S.sn_nrows[d];
               one.assign(nloc, (short)-1);
-              if (b < 0) {
-                for (int i = a; i < bb; ++i) one[rd[i] - S.sn_col0[s]] = (short)(i - a);      // rows landing on the diagonal block
-              } else {
-                // both lists are sorted, the descendant's rows inside the block are a subset of the block's rows
-                int i = (int)(std::lower_bound(rd + bb, rd + nrd, rows[r0]) - rd);
-                for (int lr = 0; lr < nloc && i < nrd; ++lr) {
-                  const int g = rows[r0 + lr];
-                  while (i < nrd && rd[i] < g) { ++i; }
-                  if (i < nrd && rd[i] == g) { one[lr] = (short)(i - a); ++i; }
-                }
+              // both row lists are sorted (a panel's rows: its own columns, then the structure below), and the descendant's rows from
+              // a on are a subset of the target's rows
+              int i = (int)(std::lower_bound(rd + a, rd + nrd, rows[r0]) - rd);
+              for (int lr = 0; lr < nloc && i < nrd; ++lr) {
+                const int g = rows[r0 + lr];
+                while (i < nrd && rd[i] < g) { ++i; }
+                if (i < nrd && rd[i] == g) { one[lr] = (short)(i - a); ++i; }
               }
             }
             S.rs_map.insert(S.rs_map.end(), one.begin(), one.end());      // a column slice of the same descendant: same rows
@@ -492,7 +500,7 @@ int build_symbolic(fg_ctx* c) {
     for (int k = (int)S.rs_units.size() - 1; k >= 0; --k) { int2& e = S.rs_sn_units[S.rs_units[k].x]; e.x = k; e.y += 1; }
     S.rs_ok = S.max_ncols <= kMaxSnCols && S.max_nrows <= 32767;      // row maps are int16
     for (const int4& un : S.rs_units) if (un.z - un.y > kRsRows || un.z <= un.y) S.rs_ok = false;
-    static_assert(kMaxSnCols <= 128, "the diagonal unit holds one diagonal row per thread");
+    static_assert(kMaxSnCols <= 32, "the head unit factors the diagonal block in its first warp");
   }
   // ---- schedule: supernodes by dependency level (longest path), a topological order that interleaves
   //      the independent chains so that the persistent kernel works on all of them at once

@@ -15,6 +15,11 @@ for ph in (0, 1):
          'potrf': T[:, 3] - T[:, 2], 'solve': T[:, 4] - T[:, 3], 'store + fence + flag': T[:, 6] - T[:, 4]}
     for k, v in d.items():
         print('   %-45s mean %7.2f  median %7.2f  p90 %7.2f us' % (k, np.nanmean(v), np.nanmedian(v), np.nanpercentile(v, 90)))
+    head = m[:, 3] == 0                      # head units (diagonal block + first rows) against the further row blocks
+    for nm, sel in (('head units', head), ('row blocks', ~head)):
+        if sel.any():
+            print('   %-12s n %5d  updates-done -> factor/diag-ready median %6.2f  -> solved %6.2f  -> flagged %6.2f us' % (
+                nm, sel.sum(), np.nanmedian((T[:, 3] - T[:, 2])[sel]), np.nanmedian((T[:, 4] - T[:, 3])[sel]), np.nanmedian((T[:, 6] - T[:, 4])[sel])))
     # chain step: per leaf (phase A), time between consecutive supernodes' flags
     if ph == 0:
         for leaf in np.unique(m[:, 7])[:3]:

@@ -162,10 +162,10 @@ def emulate_fronts(ctx, sym, Sp, bp):
 
 
 def emulate_rowsplit(ctx, sym, Sp, bp):
-    """numpy emulation of k_chol_rs (fg_chol_rs.cu): the unit of work is a block of below-diagonal rows of a
-    supernode.  A unit reads the ASSEMBLED diagonal block and its own rows, applies every descendant update restricted
-    to the descendant rows the host mapped onto its rows (rs_map / rs_colinv), the diagonal block included, factors its own
-    copy of the diagonal block and solves its rows; the diagonal factor is stored once per supernode."""
+    """numpy emulation of k_chol_rs (fg_chol_rs.cu): the unit of work is a block of <= 128 panel rows of a supernode.
+    A unit reads its ASSEMBLED rows and applies every descendant update restricted to the descendant rows the host mapped
+    onto its rows (rs_map / rs_colinv).  The head unit (rows [0, min(nr, 128)): the diagonal block and the rows right below
+    it) factors the diagonal block, then solves its other rows; the further row blocks solve theirs against that factor."""
     n_r, n_sn = int(sym[0][0]), int(sym[0][1])
     col0, ncols, nrows, rowptr, valptr, rowidx = sym[1:7]
     use_fr = bool(ctx.symbolic(33)[0])
@@ -178,8 +178,13 @@ def emulate_rowsplit(ctx, sym, Sp, bp):
     # the kernel's own list: every update of the list in use, cut into column slices of <= 16
     qptr = ctx.symbolic(47); qrec = ctx.symbolic(48).reshape(-1, 5)       # (d, source update, k0, K, 8-column group mask)
     assert len(colinv) == len(qrec) and np.all(ncols <= 32)
+    # ... in the order the descendants' units are handed out (a unit pulls its updates in list order)
+    first_unit = {}
+    for k, un in enumerate(units.tolist()):
+        first_unit.setdefault(un[0], k)
     for s in range(n_sn):
-        want = [(int(ud[u]), u, k0, min(16, int(ncols[ud[u]]) - k0)) for u in range(uptr[s], uptr[s + 1]) for k0 in range(0, int(ncols[ud[u]]), 16)]
+        us = sorted(range(uptr[s], uptr[s + 1]), key=lambda u: first_unit[int(ud[u])])
+        want = [(int(ud[u]), u, k0, min(16, int(ncols[ud[u]]) - k0)) for u in us for k0 in range(0, int(ncols[ud[u]]), 16)]
         assert [tuple(r[:4]) for r in qrec[qptr[s]:qptr[s + 1]].tolist()] == want
     aug = np.zeros((n_r + 1, n_r + 1)); aug[:n_r, :n_r] = Sp; aug[n_r, :n_r] = bp
     rows_of = [rowidx[rowptr[s]:rowptr[s] + nrows[s]] for s in range(n_sn)]
@@ -212,7 +217,7 @@ def emulate_rowsplit(ctx, sym, Sp, bp):
             U = fronts()
         nc = int(ncols[s])
         diag = r0 == 0
-        assert (r1 == nc if diag else nc <= r0 < r1 <= nrows[s]) and r1 - r0 <= 128
+        assert (r1 == min(int(nrows[s]), 128) if diag else 128 <= r0 < r1 <= nrows[s]) and r1 - r0 <= 128
         loc = list(range(r0, r1))
         P = A0[s][loc].copy()
         g = [int(rows_of[s][i]) for i in loc]
@@ -249,11 +254,13 @@ def emulate_rowsplit(ctx, sym, Sp, bp):
                 if mp[lr] >= 0:
                     upd = Ld[a + mp[lr]] @ Bfull
                     for c in range(nc):
-                        if not diag or c <= lr:
+                        if c <= r0 + lr:            # lower triangle of the diagonal block, every column of the rows below it
                             P[lr, c] -= upd[c]
         if diag:
-            assert arrived[s] == 0, 'the diagonal unit comes first'
-            Lf[s][:nc] = np.linalg.cholesky(P + np.tril(P, -1).T)
+            assert arrived[s] == 0, 'the head unit comes first'
+            D = np.tril(P[:nc])
+            Lf[s][:nc] = np.linalg.cholesky(D + np.tril(D, -1).T)
+            Lf[s][nc:r1] = np.linalg.solve(Lf[s][:nc], P[nc:].T).T
         else:
             assert arrived[s] >= 1, 'the diagonal factor is not there yet'
             Lf[s][r0:r1] = np.linalg.solve(Lf[s][:nc], P.T).T
