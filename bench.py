@@ -315,7 +315,7 @@ def main():
                 higher_is_better=True, scaling='strong', vs_baseline=None,
                 dtype='f64', data='synthetic',
                 config=dict(workload=workload_name(args.config, args.scale), projections=len(spec.get('proj_pose', [])),
-                    l2='inputs_exceed_L2' if ab['total'] > 126e6 else 'smaller_than_L2', parallelism='landmark-shard x%d%s' % (world, ', leaf chains of the reduced Cholesky distributed' if int(rep.leaf_exchange_bytes) else ''),
+                    l2='inputs_exceed_L2' if ab['total'] > 126e6 else 'smaller_than_L2', parallelism='landmark-shard x%d, reduced solve replicated' % world,
                     charts='Pose3 EXPMAP / Rot3 EXPMAP', lm='GTSAM defaults, forced iterations',
                     graph_build_s=t_build),
                 e2e=dict(value=args.steps / dt_e2e, unit='iterations/s', h2d_bytes_per_step=state_bytes,
@@ -330,10 +330,8 @@ def main():
                                           final_error=rep.final_error, e2e_last_error=r1.final_error),
                 sizes=dict(reduced_dims=int(rep.n_reduced_dims), supernodes=int(rep.n_supernodes), nnz_L=int(rep.nnz_L), nnz_S=int(rep.nnz_S)),
                 collectives=dict(per_trial=['ncclAllReduce f64 x %d (packed reduced Hessian + rhs + chi2)' % (int(rep.allreduce_bytes) // 8),
-                                            'ncclAllReduce f64 x 3 (g.delta, |delta|^2, new chi2)'] +
-                                           (['grouped ncclBroadcast (all-gather) of the leaf fronts and of the leaf part of delta: %d bytes' % int(rep.leaf_exchange_bytes)]
-                                            if int(rep.leaf_exchange_bytes) else []) if world > 1 else [],
-                                 allreduce_bytes=int(rep.allreduce_bytes), leaf_exchange_bytes=int(rep.leaf_exchange_bytes)))
+                                            'ncclAllReduce f64 x 3 (g.delta, |delta|^2, new chi2)'] if world > 1 else [],
+                                 allreduce_bytes=int(rep.allreduce_bytes)))
     if not args.no_cpu_baseline and world == 1:                      # the CPU baseline is reported at N = 1 only
         try:
             line['cpu_baseline'] = cpu_baseline_sample(args.config, steps=2, spec=spec, scale=args.scale, one_thread=True)

@@ -67,7 +67,7 @@ class LMReport(C.Structure):
                 ('ms_solve', C.c_double), ('ms_retract_error', C.c_double), ('ms_total', C.c_double),
                 ('n_reduced_dims', C.c_int64), ('n_supernodes', C.c_int64), ('nnz_L', C.c_int64),
                 ('n_projections', C.c_int64), ('n_landmarks', C.c_int64),
-                ('ms_proj_obs', C.c_double), ('ms_schur_blocks', C.c_double), ('n_schur_pairs', C.c_int64), ('n_levels', C.c_int64), ('allreduce_bytes', C.c_int64), ('nnz_S', C.c_int64), ('leaf_exchange_bytes', C.c_int64)]
+                ('ms_proj_obs', C.c_double), ('ms_schur_blocks', C.c_double), ('n_schur_pairs', C.c_int64), ('n_levels', C.c_int64), ('allreduce_bytes', C.c_int64), ('nnz_S', C.c_int64)]
 
     def trace(self):
         n = self.trace_len

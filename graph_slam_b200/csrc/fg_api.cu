@@ -40,16 +40,12 @@ typedef int (*p_ncclGetUniqueId)(nccl_uid*);
 typedef int (*p_ncclCommInitRank)(void**, int, nccl_uid, int);
 typedef int (*p_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*p_ncclCommDestroy)(void*);
-typedef int (*p_ncclBroadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-typedef int (*p_ncclGroup)(void);
 struct NcclApi {
   void* h = nullptr;
   p_ncclGetUniqueId GetUniqueId = nullptr;
   p_ncclCommInitRank CommInitRank = nullptr;
   p_ncclAllReduce AllReduce = nullptr;
   p_ncclCommDestroy CommDestroy = nullptr;
-  p_ncclBroadcast Broadcast = nullptr;
-  p_ncclGroup GroupStart = nullptr, GroupEnd = nullptr;
 } g_nccl;
 bool load_nccl() {
   if (g_nccl.h) return true;
@@ -63,10 +59,7 @@ bool load_nccl() {
   g_nccl.CommInitRank = (p_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
   g_nccl.AllReduce = (p_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
   g_nccl.CommDestroy = (p_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
-  g_nccl.Broadcast = (p_ncclBroadcast)dlsym(g_nccl.h, "ncclBroadcast");
-  g_nccl.GroupStart = (p_ncclGroup)dlsym(g_nccl.h, "ncclGroupStart");
-  g_nccl.GroupEnd = (p_ncclGroup)dlsym(g_nccl.h, "ncclGroupEnd");
-  return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy && g_nccl.Broadcast && g_nccl.GroupStart && g_nccl.GroupEnd;
+  return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
 }
 const int kNcclDouble = 8, kNcclSum = 0;   // ncclFloat64, ncclSum
 }  // namespace
@@ -647,38 +640,6 @@ int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::ve
 }  // namespace fg
 
 // ------------------------------------------------------------------ distribution of the leaf phase (multi-GPU; host only)
-// Backward-solve processing order (reverse level order) and, with more than one rank, who does what in the reduced Cholesky:
-// rank r factors and solves the nested-dissection leaves [n_leaves r / N, n_leaves (r + 1) / N) (their row-block units, their
-// front tiles, their supernodes in the backward solve); the separators stay replicated.  Every rank derives the same tables.
-namespace {
-struct DistTables { std::vector<int> bs_full, units_a, tiles_m, bs_mine; };
-void build_dist_tables(fg_ctx* c, DistTables& T) {
-  const Symbolic& S = c->sym;
-  T.bs_full.assign(S.sched.rbegin(), S.sched.rend());
-  c->dist_ok = false;
-  if (c->nranks <= 1 || !S.use_fronts || S.n_leaves < c->nranks) return;
-  const int N = c->nranks, nl = S.n_leaves;
-  auto leaf_lo = [&](int r) { return (int)((int64_t)nl * r / N); };
-  const int my_lo = leaf_lo(c->rank), my_hi = leaf_lo(c->rank + 1);
-  auto mine = [&](int leaf) { return leaf >= my_lo && leaf < my_hi; };
-  for (int k = 0; k < S.rs_units_a; ++k) if (mine(S.sn_leaf[S.rs_units[k].x])) T.units_a.push_back(k);
-  for (size_t t = 0; t < S.tile_leaf.size(); ++t) if (mine(S.tile_leaf[t])) T.tiles_m.push_back((int)t);
-  for (int sn : T.bs_full) if (S.sn_leaf[sn] < 0 || mine(S.sn_leaf[sn])) T.bs_mine.push_back(sn);
-  c->n_my_units_a = (int)T.units_a.size(); c->n_my_tiles = (int)T.tiles_m.size(); c->n_bs_mine = (int)T.bs_mine.size();
-  c->dist_u_off.assign(N + 1, 0); c->dist_col_off.assign(2 * N, 0);
-  for (int r = 0; r <= N; ++r) c->dist_u_off[r] = S.fr_uptr[leaf_lo(r)];
-  for (int r = 0; r < N; ++r) {
-    const int l0 = leaf_lo(r), l1 = leaf_lo(r + 1);
-    if (l1 > l0) {
-      c->dist_col_off[2 * r] = S.sn_col0[S.leaf_sn_lo[l0]];
-      const int last = S.leaf_sn_hi[l1 - 1] - 1;
-      c->dist_col_off[2 * r + 1] = S.sn_col0[last] + S.sn_ncols[last];
-    }
-  }
-  c->dist_ok = true;
-}
-}  // namespace
-
 // ------------------------------------------------------------------ finalize: symbolic + upload
 extern "C" int fg_finalize(fg_ctx* c) {
   if (!c) return FG_ERR_INVALID;
@@ -921,10 +882,8 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<int>(c, &d.rs_done, nullptr, S.rs_units.size() + S.n_sn)) || (rc = dev_upload(c, &d.rs_sn_units, S.rs_sn_units))) return rc;
   }
   {
-    DistTables T;
-    build_dist_tables(c, T);
-    if ((rc = dev_upload(c, &d.bs_full, T.bs_full)) != FG_OK) return rc;
-    if (c->dist_ok && ((rc = dev_upload(c, &d.my_units_a, T.units_a)) || (rc = dev_upload(c, &d.my_tiles, T.tiles_m)) || (rc = dev_upload(c, &d.bs_mine, T.bs_mine)))) return rc;
+    const std::vector<int> bs_order(S.sched.rbegin(), S.sched.rend());      // backward solve: reverse level order
+    if ((rc = dev_upload(c, &d.bs_order, bs_order)) != FG_OK) return rc;
   }
   if (c->nranks > 1) {
     d.n_pk = (int64_t)S.pk_idx.size();
@@ -953,27 +912,6 @@ static int allreduce(fg_ctx* c, double* buf, size_t n) {
   int r = g_nccl.AllReduce(buf, buf, n, kNcclDouble, kNcclSum, c->nccl_comm, c->stream);
   return r == 0 ? FG_OK : fail(c, FG_ERR_NCCL, "ncclAllReduce failed");
 }
-
-// Distributed leaf phase (multi-GPU): all-gather-v as one group of broadcasts, rank r the root of its own contiguous chunk.
-namespace fg {
-static void gather_chunks(fg_ctx* c, double* buf, const std::vector<int64_t>& lo, const std::vector<int64_t>& hi) {
-  if (c->nranks <= 1 || !c->nccl_comm) return;
-  int rc = g_nccl.GroupStart();
-  for (int r = 0; r < c->nranks && rc == 0; ++r)
-    if (hi[r] > lo[r]) rc = g_nccl.Broadcast(buf + lo[r], buf + lo[r], (size_t)(hi[r] - lo[r]), kNcclDouble, r, c->nccl_comm, c->stream);
-  const int rc2 = g_nccl.GroupEnd();
-  if (rc != 0 || rc2 != 0) c->nccl_error = rc != 0 ? rc : rc2;
-}
-void gather_fronts(fg_ctx* c) {
-  std::vector<int64_t> lo(c->dist_u_off.begin(), c->dist_u_off.end() - 1), hi(c->dist_u_off.begin() + 1, c->dist_u_off.end());
-  gather_chunks(c, c->d.U, lo, hi);
-}
-void gather_delta(fg_ctx* c) {
-  std::vector<int64_t> lo(c->nranks), hi(c->nranks);
-  for (int r = 0; r < c->nranks; ++r) { lo[r] = c->dist_col_off[2 * r]; hi[r] = c->dist_col_off[2 * r + 1]; }
-  gather_chunks(c, c->d.delta, lo, hi);
-}
-}  // namespace fg
 
 // The one large collective of a trial: every rank holds its partial reduced system in d.L; only the entries
 // that can be non-zero before the factorisation travel (packed), with the chi2 of the linearisation point in the same
@@ -1036,7 +974,6 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
   rep->n_projections = d.n_obs; rep->n_landmarks = d.n[T_POINT];
   rep->n_schur_pairs = d.n_pairs; rep->n_levels = c->sym.n_levels_rs;
   rep->nnz_S = c->sym.nnz_S;
-  rep->leaf_exchange_bytes = c->dist_ok ? (int64_t)sizeof(double) * (c->dist_u_off.back() + c->sym.n_r) : 0;
   rep->allreduce_bytes = c->nranks > 1 ? (int64_t)sizeof(double) * (d.n_pk + 1) : 0;
   double lam = p.lambda_initial;
   const double inf = std::numeric_limits<double>::infinity();
@@ -1054,10 +991,9 @@ extern "C" int fg_optimize_lm(fg_ctx* c, const fg_lm_params* params, fg_lm_repor
       launch_build_and_schur(c, lam);
       if ((rc = reduce_system(c, first)) != FG_OK) break;
       CK(cudaEventRecord(ev[2], c->stream));
-      launch_factor_rs(c, /*distribute=*/true);
+      launch_factor_rs(c);
       CK(cudaEventRecord(ev[3], c->stream));
-      launch_backsolve(c, /*distribute=*/true);
-      if (c->nccl_error) { rc = fail(c, FG_ERR_NCCL, "ncclBroadcast failed in the distributed leaf phase"); break; }
+      launch_backsolve(c);
       CK(cudaEventRecord(ev[4], c->stream));
       launch_retract_error(c, lam);
       // [0] chi2 at the linearisation point (fresh only on the first trial of an iteration), [1] g^T delta, [2] |delta|^2, [3] new chi2
@@ -1420,19 +1356,6 @@ extern "C" int64_t fg_debug_symbolic(fg_ctx* c, int which, int64_t* out, int64_t
     case 39: v = {S.rs_ok ? 1 : 0, S.rs_units_a, (int64_t)S.rs_units.size(), S.n_levels_rs}; break;
     case 47: put(S.rsu_ptr); break;
     case 49: v.assign(S.pk_idx.begin(), S.pk_idx.end()); break;
-    case 50: case 51: case 52: case 53: {
-      // distribution of the leaf phase for this context's (rank, nranks): 50 header [dist_ok, n_leaves] + per rank [u_lo, col_lo, col_hi] + u_end,
-      // 51 phase-A units of this rank, 52 front tiles of this rank, 53 backward-solve order of this rank
-      DistTables T;
-      build_dist_tables(c, T);
-      if (which == 50) {
-        v = {c->dist_ok ? 1 : 0, S.n_leaves};
-        if (c->dist_ok) { for (int r = 0; r < c->nranks; ++r) { v.push_back(c->dist_u_off[r]); v.push_back(c->dist_col_off[2 * r]); v.push_back(c->dist_col_off[2 * r + 1]); } v.push_back(c->dist_u_off[c->nranks]); }
-      } else if (which == 51) put(T.units_a);
-      else if (which == 52) put(T.tiles_m);
-      else put(c->dist_ok ? T.bs_mine : T.bs_full);
-      break;
-    }
     case 48: v.clear(); for (size_t q = 0; q < S.rsu_d.size(); ++q) { const UpdRec& r = S.rsu_rec[q]; v.push_back(S.rsu_d[q]); v.push_back(S.rsu_src[q]); v.push_back(r.pad[1]); v.push_back(r.K); v.push_back(r.pad[0]); } break;
     case 41: case 42: case 43: case 44: case 45: case 46: {
       // Schur tile tables of the projection factors held by this context (host only): 41 header [CH, n_tiles, n_pairs],

@@ -175,17 +175,13 @@ void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36) 
   k_marginal<<<1, 256, 0, FGS(c->stream)>>>(s, col0, dim, work, out36);
 }
 
-void launch_backsolve(fg_ctx* c, bool distribute) {
+void launch_backsolve(fg_ctx* c) {
   DevGraph& d = c->d;
   SysView s = chol_view(c);
-  // multi-GPU: the separators are solved on every rank, a leaf only on the rank that factored it; the leaf solutions travel
-  // by gather_delta
-  const bool dist = distribute && c->dist_ok;
-  const int n = dist ? c->n_bs_mine : c->sym.n_sn;
+  const int n = c->sym.n_sn;
   int gridw = c->num_sms;                                // measured: 1.19 / 1.26 / 1.32 ms at 1 / 2 / 4 CTAs per SM (fewer pollers)
   if (gridw * BW_WARPS > n) gridw = (n + BW_WARPS - 1) / BW_WARPS;
-  k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, FGS(c->stream)>>>(s, dist ? d.bs_mine : d.bs_full, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch, n, d.delta);
-  if (dist) gather_delta(c);
+  k_backsolve_w<<<gridw, 32 * BW_WARPS, 0, FGS(c->stream)>>>(s, d.bs_order, d.anc_ptr, d.anc_t, d.anc_b, d.flags2, d.counters, c->epoch, n, d.delta);
 }
 
 }  // namespace fg

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(RS_T, 3)
 k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__ unit_moff, const short* __restrict__ rowmap,
           const int* __restrict__ upd_ptr, const int* __restrict__ upd_d, const UpdRec* __restrict__ upd_rec,
           const signed char* __restrict__ colinv, const int2* __restrict__ sn_units, int* done, int unit_base,
-          int* counter, int n_units, int* status, FrontView fv, long long* dbg, const int* __restrict__ slot_idx, int* diag_done) {
+          int* counter, int n_units, int* status, FrontView fv, long long* dbg, int* diag_done) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
   const int tid = threadIdx.x;
@@ -126,7 +126,7 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
 // (the __syncwarp matters: a warp left diverged by the one-lane branch would take the slow divergent path of every following shuffle)
 #define RS_STAMP(k) if (dbg) { if (tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[8 * slot + (k)] = t_; } __syncwarp(); }
     RS_STAMP(0)
-    const int uidx = slot_idx ? slot_idx[slot] : slot;      // multi-GPU: this rank's leaves only (fg_api.cu: distributed leaf phase)
+    const int uidx = slot;
     const int4 un = units[uidx];
     const int sn = un.x, r0 = un.y, r1 = un.z;               // rows [r0, r1) of the panel; r0 == 0: the head unit (diagonal block [0, nc) + rows below it)
     const bool is_diag = (r0 == 0);
@@ -375,7 +375,7 @@ k_chol_rs(SysView s, const int4* __restrict__ units, const int64_t* __restrict__
   }
 }
 
-void launch_factor_rs(fg_ctx* c, bool distribute) {
+void launch_factor_rs(fg_ctx* c) {
   DevGraph& d = c->d;
   const Symbolic& S = c->sym;
   SysView s;
@@ -424,20 +424,16 @@ void launch_factor_rs(fg_ctx* c, bool distribute) {
   const int cap = c->num_sms * per_sm;
   if (!S.use_fronts) {
     k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), FGS(st)>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
-                                                                d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg, nullptr, diag_done);
+                                                                d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg, diag_done);
     return;
   }
   // phase A: the leaves; phase B: one dense update matrix per leaf; phase C: the separators
-  // phase A: the leaves (multi-GPU: this rank's leaves only, the fronts of the others arrive by fg_gather_fronts)
-  const bool dist = distribute && c->dist_ok;
-  const int na_run = dist ? c->n_my_units_a : na;
-  if (na_run) k_chol_rs<<<std::min(cap, na_run), RS_T, sizeof(RsSmem), FGS(st)>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
-                                                                              d.rs_sn_units, d.rs_done, 0, d.counters, na_run, d.status, none, dbg, dist ? d.my_units_a : nullptr, diag_done);
-  launch_front_syrk(c, dist);
-  if (dist) gather_fronts(c);
+  if (na) k_chol_rs<<<std::min(cap, na), RS_T, sizeof(RsSmem), FGS(st)>>>(s, d.rs_units, d.rs_moff, d.rs_map, d.rsu_ptr, d.rsu_d, d.rsu_rec, d.rs_colinv,
+                                                                      d.rs_sn_units, d.rs_done, 0, d.counters, na, d.status, none, dbg, diag_done);
+  launch_front_syrk(c);
   FrontView fv = {d.tf_ptr, d.tf_leaf, d.fr_rowptr, d.fr_rows, d.fr_uptr, d.U};
   if (nc) k_chol_rs<<<std::min(cap, nc), RS_T, sizeof(RsSmem), FGS(st)>>>(s, d.rs_units + na, d.rs_moff + na, d.rs_map, d.rsu_ptr, d.rsu_d,
-                                                                      d.rsu_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr, nullptr, diag_done);
+                                                                      d.rsu_rec, d.rs_colinv, d.rs_sn_units, d.rs_done, na, d.counters + 2, nc, d.status, fv, dbg ? dbg + 8 * (size_t)na : nullptr, diag_done);
 }
 
 }  // namespace fg

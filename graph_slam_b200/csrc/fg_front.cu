@@ -31,11 +31,11 @@ __global__ void __launch_bounds__(256) k_front_syrk(int n_tiles, const int* __re
                                                     const int* __restrict__ tile_j, const int* __restrict__ tile_mptr,
                                                     const FrontRec* __restrict__ tile_mrec, const int* __restrict__ fr_rowptr,
                                                     const int64_t* __restrict__ fr_uptr, const int* __restrict__ posmap,
-                                                    const double* __restrict__ L, double* __restrict__ U, const int* __restrict__ tile_idx) {
+                                                    const double* __restrict__ L, double* __restrict__ U) {
   __shared__ __align__(16) double Ai[FM][FK][FS];
   __shared__ __align__(16) double Aj[FM][FK][FS];
   if ((int)blockIdx.x >= n_tiles) return;
-  const int t = tile_idx ? tile_idx[blockIdx.x] : blockIdx.x;      // multi-GPU: the tiles of this rank's leaves
+  const int t = blockIdx.x;
   const int l = tile_leaf[t], ti = tile_i[t], tj = tile_j[t];
   const int nR = fr_rowptr[l + 1] - fr_rowptr[l];
   const int tid = threadIdx.x;
@@ -96,14 +96,14 @@ __global__ void __launch_bounds__(256) k_front_syrk(int n_tiles, const int* __re
   }
 }
 
-void launch_front_syrk(fg_ctx* c, bool dist) {
+void launch_front_syrk(fg_ctx* c) {
   DevGraph& d = c->d;
-  const int n_tiles = dist ? c->n_my_tiles : (int)c->sym.tile_leaf.size();
+  const int n_tiles = (int)c->sym.tile_leaf.size();
   if (!n_tiles) return;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_front_syrk, cudaFuncAttributePreferredSharedMemoryCarveout, 100); attr = true; }
   k_front_syrk<<<n_tiles, 256, 0, FGS(c->stream)>>>(n_tiles, d.tile_leaf, d.tile_i, d.tile_j, d.tile_mptr, d.tile_mrec, d.fr_rowptr, d.fr_uptr,
-                                               d.posmap, d.L, d.U, dist ? d.my_tiles : nullptr);
+                                               d.posmap, d.L, d.U);
 }
 
 }  // namespace fg

@@ -250,8 +250,7 @@ struct DevGraph {
   double* U = nullptr;              // dense update matrices of all leaves
   int *anc_ptr = nullptr, *anc_t = nullptr, *anc_a = nullptr, *anc_b = nullptr;
   int *sched = nullptr;
-  int *bs_full = nullptr, *bs_mine = nullptr;   // backward-solve processing order: all supernodes / separators + this rank's leaves
-  int *my_units_a = nullptr, *my_tiles = nullptr;   // multi-GPU: phase-A units and front tiles of this rank's leaves
+  int *bs_order = nullptr;          // backward-solve processing order (reverse level order)
   int4* rs_units = nullptr; int64_t* rs_moff = nullptr; short* rs_map = nullptr; signed char* rs_colinv = nullptr; int* rs_done = nullptr;   // rs_done: one done flag per unit
   int2* rs_sn_units = nullptr;   // per supernode: (first unit, number of units)
   int64_t n_pk = 0; int64_t* pk_idx = nullptr; double* pk_buf = nullptr;   // packed exchange buffer: n_pk entries + 1 scalar (chi2)
@@ -273,12 +272,6 @@ struct fg_ctx {
   bool device_newer = false;     // device values newer than host
   // incremental session (fg_update_incremental): d.val holds theta, d.val_new the estimate; h.val / h.lin mirror them
   int pose_chart = 0;            // fg_set_pose_chart (GTSAM graphs; the g2o back-end uses its own)
-  // multi-GPU distribution of the leaf phase (fg_finalize): leaves [leaf_lo[r], leaf_lo[r + 1]) belong to rank r
-  bool dist_ok = false;
-  int n_my_units_a = 0, n_my_tiles = 0, n_bs_mine = 0;
-  std::vector<int64_t> dist_u_off;      // nranks + 1: offsets of the ranks' fronts in d.U
-  std::vector<int> dist_col_off;        // 2 * nranks: [first, end) reduced column of each rank's leaf range
-  int nccl_error = 0;
   std::vector<int> color_ptr[fg::K_COUNT];   // per pose-side factor kind: offsets of its colour classes in the (colour-sorted) device arrays
   bool inc_active = false;
   int inc_updates = 0;
@@ -307,14 +300,10 @@ int build_symbolic(fg_ctx* c);
 void launch_linearize(fg_ctx* c);                         // U0, g_r, V, gl, W, chi2 -> scal[0]
 void launch_build_and_schur(fg_ctx* c, double lambda);    // L = U0 + lambda I - W V'^-1 W^T ; rhs row = -(g_red)
 void launch_schur(fg_ctx* c, double lambda);              // fg_schur.cu: the landmark part of the line above
-// fg_chol_rs.cu: cholesky (row-split units, width <= 32); the rhs row makes it the forward solve too.  distribute (multi-GPU,
-// fg_optimize_lm): every rank factors its own nested-dissection leaves, the leaf fronts are exchanged, the separators are
-// factored everywhere; the panels of foreign leaves are then NOT valid on this rank.
-void launch_factor_rs(fg_ctx* c, bool distribute = false);
-void launch_front_syrk(fg_ctx* c, bool dist);             // fg_front.cu: dense update matrix of every (own) leaf onto its front
-void launch_backsolve(fg_ctx* c, bool distribute = false);
-void gather_fronts(fg_ctx* c);                            // fg_api.cu: all-gather of the leaf fronts U (NCCL, grouped broadcasts)
-void gather_delta(fg_ctx* c);                             // fg_api.cu: all-gather of the leaf parts of the solution
+// fg_chol_rs.cu: cholesky (row-split units, width <= 32); the rhs row makes it the forward solve too
+void launch_factor_rs(fg_ctx* c);
+void launch_front_syrk(fg_ctx* c);                        // fg_front.cu: dense update matrix of every leaf onto its front
+void launch_backsolve(fg_ctx* c);
 void launch_marginal(fg_ctx* c, int col0, int dim, double* work, double* out36);   // fg_chol.cu: [S^-1] block of one variable from the factor in d.L                         // backward solve -> delta
 void launch_retract_error(fg_ctx* c, double lambda);      // val_new = val (+) delta (incl. landmarks), scal[1..3]
 void launch_pack(fg_ctx* c, bool with_chi2);               // multi-GPU: gather the exchanged entries of d.L (+ scal[0]) into d.pk_buf

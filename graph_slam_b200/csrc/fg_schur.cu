@@ -127,11 +127,13 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
   int m_lo = 0, m_n = 0;
   int64_t m_ptr = 0;
   if (mp < P) { m_lo = pc_lo[mp]; m_n = pc_n[mp]; m_ptr = pc_ptr[mp]; }
-  // compute role: half-warp h of warp w works on the wrapped diagonal d = 2 w + h of the tile
-  // (warp w takes diagonals w and 15 - w: pose distance, hence work, grows along d, and the pair sums to a constant).
+  // compute role: half-warp h of warp w works on the wrapped diagonal d = 2 w + h of the tile: pose distance, hence the number
+  // of shared landmarks, changes along d, so the two halves of a warp do about the same work and the lanes stay busy together
+  // (pairing diagonals w and 15 - w balanced the warps instead and left half the lanes of every instruction idle:
+  // 16.3 of 32 threads per instruction in profiles/r1_ncu_full_summary.md); an idle warp gives its issue slots to the other CTA.
   // In a diagonal tile the diagonals d and 16 - d hold the same unordered pose pairs: the two lanes of a pair split its
   // landmarks by bit parity and their sums are joined at the end; the p == q blocks are left to k_schur_rhs.
-  const int i = lane & 15, d = (lane >> 4) ? 15 - warp : warp, j = (i + d) & 15;
+  const int i = lane & 15, d = 2 * warp + (lane >> 4), j = (i + d) & 15;
   bool active = (gi * 16 + i < P) && (gj * 16 + j < P);
   const bool primary = !diag || d < 8 || (d == 8 && i < 8);
   unsigned hit_sel = 0xffffffffu;

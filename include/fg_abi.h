@@ -172,9 +172,6 @@ typedef struct {
   /* multi-GPU: bytes of the per-trial allreduce of the reduced pose Hessian (packed structural non-zeros + rhs + chi2) */
   int64_t allreduce_bytes;
   int64_t nnz_S;             /* structural non-zeros of the reduced system before the factorisation (nnz_L includes the fill) */
-  /* multi-GPU: bytes of the two all-gathers of the distributed leaf phase per trial (leaf fronts, leaf part of delta); 0 when
-   * the factorisation is replicated (fewer nested-dissection leaves than ranks) */
-  int64_t leaf_exchange_bytes;
 } fg_lm_report;
 
 /* Build the symbolic structure and upload the graph (idempotent; called lazily by the functions below). */

@@ -52,43 +52,6 @@ WORKER = textwrap.dedent('''
     mine = digest((L * rank // world, L * (rank + 1) // world), check_pack=(rank == 0))
     full = digest((0, L))
 
-    # distribution of the leaf phase of the reduced Cholesky: the ranks' shares partition the leaf units, the front tiles and the
-    # leaf supernodes of the backward solve; the separators are everybody's; the exchanged ranges are disjoint
-    def dist_tables():
-        spec2 = synth.make_config('C4', seed=3, scale=0.1)            # 200 poses: several nested-dissection leaves
-        L2 = len(spec2['point_init']); P2 = spec2['n_poses']
-        pims2 = (abi.Pim * (P2 - 1))()
-        for i in range(P2 - 1):
-            pims2[i].dt = 0.1; pims2[i].cov[:] = np.eye(15).ravel().tolist()
-        ctx = abi.Context(device=-1, rank=rank, nranks=world)
-        abi.load_spec(ctx, spec2, landmark_slice=(L2 * rank // world, L2 * (rank + 1) // world), preintegrated=pims2)
-        ctx.symbolic(0)
-        out = dict(hdr=ctx.symbolic(50).tolist(), units=ctx.symbolic(51).tolist(), tiles=ctx.symbolic(52).tolist(), bs=ctx.symbolic(53).tolist(),
-                   sn_leaf=ctx.symbolic(21).tolist(), unit_sn=ctx.symbolic(36).reshape(-1, 4)[:, 0].tolist(), n_a=int(ctx.symbolic(39)[1]),
-                   n_tiles=int(ctx.symbolic(33)[3]), col0=ctx.symbolic(1).tolist(), ncols=ctx.symbolic(2).tolist())
-        ctx.close()
-        return out
-    allt = [None] * world
-    dist.all_gather_object(allt, dist_tables())
-    if rank == 0:
-        t0 = allt[0]
-        assert t0['hdr'][0] == 1 and t0['hdr'][1] >= world, 'the test graph must have at least one leaf per rank'
-        assert all(t['hdr'] == t0['hdr'] for t in allt)
-        assert sorted(u for t in allt for u in t['units']) == list(range(t0['n_a']))
-        assert sorted(x for t in allt for x in t['tiles']) == list(range(t0['n_tiles']))
-        n_sn = len(t0['sn_leaf'])
-        seps = [s for s in range(n_sn) if t0['sn_leaf'][s] < 0]
-        leaf_sn = sorted(s for t in allt for s in t['bs'] if t0['sn_leaf'][s] >= 0)
-        assert leaf_sn == [s for s in range(n_sn) if t0['sn_leaf'][s] >= 0]
-        for r, t in enumerate(allt):
-            assert [s for s in t['bs'] if t0['sn_leaf'][s] < 0] == [s for s in allt[0]['bs'] if t0['sn_leaf'][s] < 0] and set(seps) <= set(t['bs'])
-            lo, hi = t0['hdr'][2 + 3 * r + 1], t0['hdr'][2 + 3 * r + 2]
-            for s in t['bs']:
-                if t0['sn_leaf'][s] >= 0:
-                    assert lo <= t0['col0'][s] and t0['col0'][s] + t0['ncols'][s] <= hi, 'a leaf supernode outside the column range its rank broadcasts'
-            if r:
-                assert t0['hdr'][2 + 3 * (r - 1) + 2] <= lo, 'broadcast column ranges overlap'
-        print('DIST_OK')
     out = [None] * world
     dist.all_gather_object(out, (mine, full))
     if rank == 0:
@@ -107,4 +70,4 @@ def test_two_rank_structures_agree(fglib, tmp_path):
                           '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
                          capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-3000:]
-    assert 'SHARDING_OK' in res.stdout and 'DIST_OK' in res.stdout
+    assert 'SHARDING_OK' in res.stdout
