@@ -471,7 +471,7 @@ __device__ __forceinline__ void landmark_merge(const double (&v)[NV], int l, boo
 // V_l, g_l by the in-block ordered merge above.  Block b owns observations [oblk_ptr[b], oblk_ptr[b + 1]) (<= 256 unless a
 // single landmark has more).
 template <bool JAC>
-__global__ void __launch_bounds__(256, 3) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+__global__ void __launch_bounds__(256, JAC ? 2 : 3) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
                                                   Vals vals, const double* __restrict__ calib, const double* __restrict__ sensor,
                                                   double* __restrict__ W, double* V, double* gl, double* part) {
