@@ -666,7 +666,8 @@ extern "C" int fg_finalize(fg_ctx* c) {
   // pose-side factors, uploaded COLOUR-SORTED: within a colour no two factors share a variable, so the assembly kernels
   // (launched colour by colour, fg_kernels.cu: run_factors) never add to one address from two threads of a launch --
   // the assembled system is bitwise repeatable without giving up the thread-per-factor kernels (greedy colouring in
-  // insertion order over all kinds; a VIO graph with 5 look-back edges takes ~14 colours)
+  // insertion order, PER KIND: the kinds are launched one after the other on one stream, so only factors of one kind can meet;
+  // a VIO graph with 5 look-back edges takes ~12 colours for its edges and 2 for its IMU chain)
   d.n_pp = (int)h.pp_var.size(); d.n_pv = (int)h.pv_var.size(); d.n_pb = (int)h.pb_var.size();
   d.n_bt = (int)h.bt_i.size(); d.n_imu = (int)h.imu_rec.size(); d.n_pl = (int)h.pl_pose.size();
   {
@@ -696,15 +697,21 @@ extern "C" int fg_finalize(fg_ctx* c) {
     auto permute_d = [](const std::vector<double>& a, const std::vector<int>& ord, int w) { std::vector<double> o(a.size()); for (size_t i = 0; i < ord.size(); ++i) for (int k = 0; k < w; ++k) o[i * w + k] = a[(size_t)ord[i] * w + k]; return o; };
     std::vector<int> col_pp(d.n_pp), col_pv(d.n_pv), col_pb(d.n_pb), col_bt(d.n_bt), col_ge(h.ge_i.size()), col_imu(d.n_imu), col_pl(d.n_pl);
     for (int f = 0; f < d.n_pp; ++f) { int v[1] = {h.pp_var[f]}; col_pp[f] = pick(v, 1); }
+    for (auto& u : used) u.clear();
     for (int f = 0; f < d.n_pv; ++f) { int v[1] = {(int)(nP + h.pv_var[f])}; col_pv[f] = pick(v, 1); }
+    for (auto& u : used) u.clear();
     for (int f = 0; f < d.n_pb; ++f) { int v[1] = {(int)(nP + nV + h.pb_var[f])}; col_pb[f] = pick(v, 1); }
+    for (auto& u : used) u.clear();
     for (int f = 0; f < d.n_bt; ++f) { int v[2] = {h.bt_i[f], h.bt_j[f]}; col_bt[f] = pick(v, 2); }
+    for (auto& u : used) u.clear();
     for (size_t f = 0; f < h.ge_i.size(); ++f) { int v[2] = {h.ge_i[f], h.ge_j[f]}; col_ge[f] = pick(v, 2); }
+    for (auto& u : used) u.clear();
     for (int f = 0; f < d.n_imu; ++f) {
       const int* q = &h.imu_var[6 * (size_t)f];
       int v[6] = {q[0], (int)(nP + q[1]), q[2], (int)(nP + q[3]), (int)(nP + nV + q[4]), (int)(nP + nV + q[5])};
       col_imu[f] = pick(v, 6);
     }
+    for (auto& u : used) u.clear();
     for (int f = 0; f < d.n_pl; ++f) { int v[2] = {h.pl_pose[f], (int)(nP + nV + nB + h.pl_plane[f])}; col_pl[f] = pick(v, 2); }
     std::vector<int> o;
     o = sort_kind(K_PP, col_pp);

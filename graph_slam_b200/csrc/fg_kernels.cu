@@ -876,36 +876,37 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
   const int T = 128;
   int np = 0;                                // partial-sum slots handed out so far
   auto slots = [&](int grid) { double* p = d.part + np; np += grid; return p; };
+  // Jacobian pass: one launch per colour class (no two factors of a class touch the same variable: plain read-modify-writes,
+  // deterministic).  Error pass: nothing is assembled, the whole (colour-sorted, contiguous) kind goes in one launch.
+  auto classes = [&](int kind, auto&& launch) {
+    const std::vector<int>& cp = c->color_ptr[kind];
+    if (cp.size() < 2) return;
+    if (!JAC) { if (cp.back() > cp.front()) launch(cp.front(), cp.back() - cp.front()); return; }
+    for (size_t k = 0; k + 1 < cp.size(); ++k) if (cp[k + 1] > cp[k]) launch(cp[k], cp[k + 1] - cp[k]);
+  };
   if (pose_side) {
-    for (size_t k = 0; k + 1 < c->color_ptr[K_PP].size(); ++k) {
-      const int b = c->color_ptr[K_PP][k], n = c->color_ptr[K_PP][k + 1] - b;
-      if (n) k_prior_pose<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pp_var + b, d.pp_mean + 12 * (size_t)b, d.pp_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
-    }
-    for (size_t k = 0; k + 1 < c->color_ptr[K_PV].size(); ++k) {
-      const int b = c->color_ptr[K_PV][k], n = c->color_ptr[K_PV][k + 1] - b;
-      if (n) k_prior_vec<JAC, 3, T_VEC3><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pv_var + b, d.pv_mean + 3 * (size_t)b, d.pv_info + 9 * (size_t)b, v, d.off[T_VEC3], sys, d.g_r, slots(cdiv(n, T)));
-    }
-    for (size_t k = 0; k + 1 < c->color_ptr[K_PB].size(); ++k) {
-      const int b = c->color_ptr[K_PB][k], n = c->color_ptr[K_PB][k + 1] - b;
-      if (n) k_prior_vec<JAC, 6, T_BIAS><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pb_var + b, d.pb_mean + 6 * (size_t)b, d.pb_info + 36 * (size_t)b, v, d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, T)));
-    }
-    for (size_t k = 0; k + 1 < c->color_ptr[K_BT].size(); ++k) {
-      const int b = c->color_ptr[K_BT][k], n = c->color_ptr[K_BT][k + 1] - b;
-      if (n) k_between<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.bt_i + b, d.bt_j + b, d.bt_meas + 12 * (size_t)b, d.bt_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
-    }
-    for (size_t k = 0; k + 1 < c->color_ptr[K_GE].size(); ++k) {
-      const int b = c->color_ptr[K_GE][k], n = c->color_ptr[K_GE][k + 1] - b;
-      if (n) k_g2o_edge<JAC><<<cdiv(n, 64), 64, 0, FGS(st)>>>(n, d.ge_i + b, d.ge_j + b, d.ge_meas + 12 * (size_t)b, d.ge_info + 36 * (size_t)b, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, slots(cdiv(n, 64)));
-    }
+    classes(K_PP, [&](int b, int n) {
+      k_prior_pose<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pp_var + b, d.pp_mean + 12 * (size_t)b, d.pp_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
+    });
+    classes(K_PV, [&](int b, int n) {
+      k_prior_vec<JAC, 3, T_VEC3><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pv_var + b, d.pv_mean + 3 * (size_t)b, d.pv_info + 9 * (size_t)b, v, d.off[T_VEC3], sys, d.g_r, slots(cdiv(n, T)));
+    });
+    classes(K_PB, [&](int b, int n) {
+      k_prior_vec<JAC, 6, T_BIAS><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pb_var + b, d.pb_mean + 6 * (size_t)b, d.pb_info + 36 * (size_t)b, v, d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, T)));
+    });
+    classes(K_BT, [&](int b, int n) {
+      k_between<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.bt_i + b, d.bt_j + b, d.bt_meas + 12 * (size_t)b, d.bt_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
+    });
+    classes(K_GE, [&](int b, int n) {
+      k_g2o_edge<JAC><<<cdiv(n, 64), 64, 0, FGS(st)>>>(n, d.ge_i + b, d.ge_j + b, d.ge_meas + 12 * (size_t)b, d.ge_info + 36 * (size_t)b, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, slots(cdiv(n, 64)));
+    });
     if (JAC && d.n_fixed) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, FGS(st)>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
-    for (size_t k = 0; k + 1 < c->color_ptr[K_IMU].size(); ++k) {
-      const int b = c->color_ptr[K_IMU][k], n = c->color_ptr[K_IMU][k + 1] - b;
-      if (n) k_imu<JAC><<<cdiv(n, IMU_WPB), 32 * IMU_WPB, 0, FGS(st)>>>(n, d.imu_var + 6 * (size_t)b, d.imu_rec + b, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, IMU_WPB)));
-    }
-    for (size_t k = 0; k + 1 < c->color_ptr[K_PL].size(); ++k) {
-      const int b = c->color_ptr[K_PL][k], n = c->color_ptr[K_PL][k + 1] - b;
-      if (n) k_plane<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pl_pose + b, d.pl_plane + b, d.pl_meas + 4 * (size_t)b, d.pl_info + 9 * (size_t)b, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, slots(cdiv(n, T)));
-    }
+    classes(K_IMU, [&](int b, int n) {
+      k_imu<JAC><<<cdiv(n, IMU_WPB), 32 * IMU_WPB, 0, FGS(st)>>>(n, d.imu_var + 6 * (size_t)b, d.imu_rec + b, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, IMU_WPB)));
+    });
+    classes(K_PL, [&](int b, int n) {
+      k_plane<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pl_pose + b, d.pl_plane + b, d.pl_meas + 4 * (size_t)b, d.pl_info + 9 * (size_t)b, v, d.off[T_POSE], d.off[T_PLANE], sys, d.g_r, slots(cdiv(n, T)));
+    });
   }
   int64_t L = d.n[T_POINT];
   if (L) {
