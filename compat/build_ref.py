@@ -21,7 +21,7 @@ LIBDIR = os.path.join(ROOT, 'graph_slam_b200')
 GT_SRC = ['gtsam_graph.cpp', 'imu_base.cpp', 'imu_vn100.cpp', 'gt_parameter.cpp', 'color.cpp']
 GT_DRIVERS = ['test_vro_imu_graph', 'test_ba_imu_graph']
 G2O_SRC = ['g2o_graph.cpp', 'g2o_parameter.cpp', 'color.cpp']
-TEST_PROGRAMS = {'vio_driver': 'gt', 'ba_driver': 'gt', 'format_io': 'gt', 'plane_driver': 'gt', 'g2o_driver': 'g2o'}
+TEST_PROGRAMS = {'vio_driver': 'gt', 'ba_driver': 'gt', 'format_io': 'gt', 'plane_driver': 'gt', 'plane_check': 'gt', 'g2o_driver': 'g2o'}
 
 
 def available():

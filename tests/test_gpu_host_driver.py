@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_sources_compile_unchanged_and_link(refbin):
     """CPU-side check: every reference file on the path builds from /root/reference with -Icompat and
     links libfg_b200.so -- the wrapper libraries, both offline drivers and this repository's test programs."""
-    for name in ('libgraphslam_gt.so', 'libgraphslam_g2o.so', 'test_vro_imu_graph', 'test_ba_imu_graph', 'vio_driver', 'ba_driver', 'format_io', 'plane_driver', 'g2o_driver'):
+    for name in ('libgraphslam_gt.so', 'libgraphslam_g2o.so', 'test_vro_imu_graph', 'test_ba_imu_graph', 'vio_driver', 'ba_driver', 'format_io', 'plane_driver', 'plane_check', 'g2o_driver'):
         assert os.path.exists(refbin(name))
 
 
