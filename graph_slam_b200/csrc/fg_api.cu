@@ -722,6 +722,36 @@ extern "C" int fg_finalize(fg_ctx* c) {
     if ((rc = dev_upload(c, &d.pb_var, permute_i(h.pb_var, o, 1))) || (rc = dev_upload(c, &d.pb_mean, permute_d(h.pb_mean, o, 6))) || (rc = dev_upload(c, &d.pb_info, permute_d(h.pb_info, o, 36)))) return rc;
     o = sort_kind(K_BT, col_bt);
     if ((rc = dev_upload(c, &d.bt_i, permute_i(h.bt_i, o, 1))) || (rc = dev_upload(c, &d.bt_j, permute_i(h.bt_j, o, 1))) || (rc = dev_upload(c, &d.bt_meas, permute_d(h.bt_meas, o, 12))) || (rc = dev_upload(c, &d.bt_info, permute_d(h.bt_info, o, 36)))) return rc;
+    {
+      // colour-free Jacobian pass of the between factors (k_between_ends): factor ends sorted by (pose, factor), cut into blocks
+      // of <= 128 ends on pose boundaries.  Needs one factor per pose pair at most (the j-end owns the off-diagonal block);
+      // a graph with parallel or reversed edges on one pair keeps the coloured kernel.
+      const std::vector<int> bi = permute_i(h.bt_i, o, 1), bj = permute_i(h.bt_j, o, 1);
+      std::vector<std::pair<int, int>> pairs(bi.size());
+      bool simple = !bi.empty();
+      for (size_t f = 0; f < bi.size(); ++f) { pairs[f] = {std::min(bi[f], bj[f]), std::max(bi[f], bj[f])}; if (bi[f] == bj[f]) simple = false; }
+      std::sort(pairs.begin(), pairs.end());
+      if (std::adjacent_find(pairs.begin(), pairs.end()) != pairs.end()) simple = false;
+      d.n_bt_eblk = 0;
+      if (simple) {
+        std::vector<std::pair<int, int>> ends;      // (pose, 2 f + end)
+        ends.reserve(2 * bi.size());
+        for (size_t f = 0; f < bi.size(); ++f) { ends.push_back({bi[f], (int)(2 * f)}); ends.push_back({bj[f], (int)(2 * f + 1)}); }
+        std::sort(ends.begin(), ends.end());
+        std::vector<int> rec(ends.size()), blk(1, 0);
+        for (size_t q = 0; q < ends.size(); ++q) rec[q] = ends[q].second;
+        size_t q = 0;
+        while (q < ends.size()) {
+          size_t r = q;
+          while (r < ends.size() && ends[r].first == ends[q].first) ++r;            // the run of one pose
+          if ((int)(r - blk.back()) > 128 && (int)q > blk.back()) blk.push_back((int)q);      // close the block before this pose
+          q = r;
+        }
+        blk.push_back((int)ends.size());
+        if ((rc = dev_upload(c, &d.bt_end, rec)) || (rc = dev_upload(c, &d.bt_eblk, blk))) return rc;
+        d.n_bt_eblk = (int)blk.size() - 1;
+      }
+    }
     o = sort_kind(K_GE, col_ge);
     if ((rc = dev_upload(c, &d.ge_i, permute_i(h.ge_i, o, 1))) || (rc = dev_upload(c, &d.ge_j, permute_i(h.ge_j, o, 1))) || (rc = dev_upload(c, &d.ge_meas, permute_d(h.ge_meas, o, 12))) || (rc = dev_upload(c, &d.ge_info, permute_d(h.ge_info, o, 36)))) return rc;
     o = sort_kind(K_IMU, col_imu);
@@ -852,7 +882,7 @@ extern "C" int fg_finalize(fg_ctx* c) {
   {
     size_t cap = 64;
     for (int k = 0; k < K_COUNT; ++k) cap += c->color_ptr[k].size() + (size_t)c->color_ptr[k].back() / 4 + 4;      // >= sum over colours of cdiv(n, 64) or cdiv(n, 4)
-    cap += (size_t)h.count(T_POINT) / 256 + 2 + (size_t)d.n_oblk;
+    cap += (size_t)h.count(T_POINT) / 256 + 2 + (size_t)d.n_oblk + (size_t)d.n_bt_eblk;
     for (int t = 0; t < T_COUNT; ++t) cap += (size_t)h.count(t) / 128 + 2;
     d.part_cap = (int)cap;
     if ((rc = dev_upload<double>(c, &d.part, nullptr, cap)) || (rc = dev_upload<double>(c, &d.part2, nullptr, cap))) return rc;

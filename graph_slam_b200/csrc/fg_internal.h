@@ -186,6 +186,7 @@ struct DevGraph {
   int n_pv = 0; int* pv_var = nullptr; double* pv_mean = nullptr; double* pv_info = nullptr;
   int n_pb = 0; int* pb_var = nullptr; double* pb_mean = nullptr; double* pb_info = nullptr;
   int n_bt = 0; int* bt_i = nullptr; int* bt_j = nullptr; double* bt_meas = nullptr; double* bt_info = nullptr;
+  int n_bt_eblk = 0; int* bt_end = nullptr; int* bt_eblk = nullptr;   // between factor ends (2 f + end) sorted by (pose, factor); block ranges on pose boundaries (0 blocks: coloured path)
   int n_ge = 0; int* ge_i = nullptr; int* ge_j = nullptr; double* ge_meas = nullptr; double* ge_info = nullptr;
   int n_fixed = 0; int* fixed_list = nullptr; char* fixed_pose = nullptr; char* fixed_col = nullptr;   // fixed poses: list, per-pose flag, per reduced column flag
   int pose_chart = 0;               // Pose3 chart (fg_math.cuh): 0 EXPMAP, 1 g2o VertexSE3::oplus, 2 FIRST_ORDER / Rot3 EXPMAP, 3 FIRST_ORDER / Rot3 CAYLEY

@@ -427,9 +427,8 @@ __device__ __forceinline__ double seg_sum(double v, int key, int lane) {
 // range starts and ends on landmark boundaries (fg_finalize: oblk_ptr), so every landmark is summed inside ONE block: the
 // warp-segmented reduction leaves a partial in the head lane of every (warp, landmark) run; the heads are numbered in
 // observation order, parked in shared memory, and the first head of each landmark adds its pieces in that order.
-template <int NV>
-__device__ __forceinline__ void landmark_merge(const double (&v)[NV], int l, bool act, double* hbuf, int* hl, int* wcnt, double* dst0, int stride0, int n0,
-                                               double* dst1, int stride1) {
+template <int NV, class Write>
+__device__ __forceinline__ void ordered_merge(const double (&v)[NV], int l, bool act, double* hbuf, int* hl, int* wcnt, Write write) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int prev = __shfl_up_sync(FULL, l, 1);
@@ -458,13 +457,125 @@ __device__ __forceinline__ void landmark_merge(const double (&v)[NV], int l, boo
     for (int k = t + 1; k < nh && hl[k] == lm; ++k)
 #pragma unroll
       for (int i = 0; i < NV; ++i) acc[i] += hbuf[k * (NV + 1) + i];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (i < n0) dst0[(int64_t)stride0 * lm + i] += acc[i];          // single owner: a plain read-modify-write
-      else dst1[(int64_t)stride1 * lm + (i - n0)] += acc[i];
-    }
+    write(lm, acc);                                                     // single owner: plain read-modify-writes
   }
   __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void landmark_merge(const double (&v)[NV], int l, bool act, double* hbuf, int* hl, int* wcnt, double* dst0, int stride0, int n0,
+                                               double* dst1, int stride1) {
+  ordered_merge<NV>(v, l, act, hbuf, hl, wcnt, [&](int lm, const double (&acc)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < n0) dst0[(int64_t)stride0 * lm + i] += acc[i];
+      else dst1[(int64_t)stride1 * lm + (i - n0)] += acc[i];
+    }
+  });
+}
+
+// Jacobian pass of the between factors without colours: one thread per factor END, ends sorted by (pose, factor), block ranges
+// cut on pose boundaries (fg_finalize: bt_end, bt_eblk).  Every thread evaluates its factor; the j-end thread owns the factor's
+// off-diagonal block and its chi2 (host guarantee: no two factors on one pose pair -- otherwise the coloured k_between runs);
+// the diagonal block and the gradient of a pose are summed over its ends by the in-block ordered merge.  One launch instead of
+// one per colour (a VIO graph with 5 look-back edges has 11).
+#define BTE_T 128
+__global__ void __launch_bounds__(BTE_T) k_between_ends(const int* __restrict__ eblk_ptr, const int* __restrict__ ends, const int* __restrict__ vi,
+                                                        const int* __restrict__ vj, const double* __restrict__ meas, const double* __restrict__ info,
+                                                        Vals vals, const int* __restrict__ off, SysView sys, double* g_r, double* chi2, int chart) {
+  __shared__ double hbuf[BTE_T * 28];
+  __shared__ int hl[BTE_T];
+  __shared__ int wcnt[BTE_T / 32];
+  const int s0 = eblk_ptr[blockIdx.x], s1 = eblk_ptr[blockIdx.x + 1];
+  double e = 0.0;
+  for (int base = s0; base < s1; base += BTE_T) {
+    const int q = base + threadIdx.x;
+    const bool act = q < s1;
+    int pose = -1;
+    double v27[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) v27[i] = 0.0;
+    if (act) {
+      const int rec = ends[q], f = rec >> 1, end = rec & 1;
+      double X1[12], X2[12], Z[12], r[6], J1[36], wr[6], O[36];
+      const int p1 = vi[f], p2 = vj[f];
+      pose = end ? p2 : p1;
+      load_pose(vals.v[T_POSE], p1, X1);
+      load_pose(vals.v[T_POSE], p2, X2);
+      load_pose(meas, f, Z);
+      between_eval<true>(X1, X2, Z, r, J1, chart);
+      const double* Om = info + 36 * (int64_t)f;
+#pragma unroll
+      for (int i = 0; i < 18; ++i) {
+        double2 v = __ldg(reinterpret_cast<const double2*>(Om) + i);
+        O[2 * i] = v.x; O[2 * i + 1] = v.y;
+      }
+      matvec<6, 6>(O, r, wr);
+      if (end) {
+        // H22 = Omega, g2 = Omega r; the off-diagonal H21 = Omega J1 and the factor's chi2 belong to this end
+        double M[36];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          e += r[i] * wr[i];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sacc += O[6 * i + k] * J1[6 * k + j];
+            M[6 * i + j] = sacc;
+          }
+        }
+        sys_add_block(sys, off[p2], 6, off[p1], 6, M, 6);
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j) v27[t++] = O[6 * i + j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v27[21 + i] = wr[i];
+      } else {
+        // H11 = J1^T Omega J1, g1 = J1^T Omega r
+        double M[36];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sacc += O[6 * i + k] * J1[6 * k + j];
+            M[6 * i + j] = sacc;
+          }
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sacc += J1[6 * k + i] * M[6 * k + j];
+            v27[t++] = sacc;
+          }
+          double sacc = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sacc += J1[6 * k + i] * wr[k];
+          v27[21 + i] = sacc;
+        }
+      }
+    }
+    ordered_merge<27>(v27, pose, act, hbuf, hl, wcnt, [&](int p, const double (&acc)[27]) {
+      const int o = off[p];
+      int ld;
+      const int64_t b0 = sys_find(sys, o, o, &ld);
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) sys.L[b0 + i + (int64_t)j * ld] += acc[t++];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) g_r[o + i] += acc[21 + i];
+    });
+  }
+  chi2_accumulate(e, chi2);
 }
 
 // one thread per observation (observations sorted by landmark): residual, Jp, Jl; W = w Jp^T Jl stored AoS;
@@ -894,7 +1005,9 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
     classes(K_PB, [&](int b, int n) {
       k_prior_vec<JAC, 6, T_BIAS><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pb_var + b, d.pb_mean + 6 * (size_t)b, d.pb_info + 36 * (size_t)b, v, d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, T)));
     });
-    classes(K_BT, [&](int b, int n) {
+    if (JAC && d.n_bt_eblk) {
+      k_between_ends<<<d.n_bt_eblk, BTE_T, 0, FGS(st)>>>(d.bt_eblk, d.bt_end, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, slots(d.n_bt_eblk), d.pose_chart);
+    } else classes(K_BT, [&](int b, int n) {
       k_between<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.bt_i + b, d.bt_j + b, d.bt_meas + 12 * (size_t)b, d.bt_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
     });
     classes(K_GE, [&](int b, int n) {
