@@ -344,8 +344,7 @@ void launch_schur(fg_ctx* c, double lambda) {
   if (d.n_obs) k_zmat<<<cdiv(d.n_obs, 256), 256, 0, FGS(st)>>>(d.n_obs, d.obs_point, d.obs_ppos, d.W, d.Cf, d.Zp);
   if (c->kev[2]) cudaEventRecord(c->kev[2], st);
   if (d.n_tiles) {
-    if (d.schur_ch == 32) launch_tiles<32, 24>(c, sys);
-    else launch_tiles<24, 24>(c, sys);
+    launch_tiles<32, 24>(c, sys);                        // d.schur_ch == 32 (build_schur_tables)
   }
   if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];
