@@ -462,16 +462,39 @@ __device__ __forceinline__ void ordered_merge(const double (&v)[NV], int l, bool
   __syncthreads();
 }
 
+// The same ordered merge for runs that are CONTIGUOUS across the block (observations sorted by landmark), with ONE barrier: a
+// run that crosses a warp boundary continues as the first run of the following warps, so every warp parks the sum of its
+// first run (and the key of its last lane); after the barrier the head of a run that does not continue one from the warp
+// before adds the first-run sums of the following warps while their key matches -- observation order, no atomics.
+// The head with the final sum calls write(key, sums).  `more` = the caller loops and calls again (block-uniform).
 template <int NV>
-__device__ __forceinline__ void landmark_merge(const double (&v)[NV], int l, bool act, double* hbuf, int* hl, int* wcnt, double* dst0, int stride0, int n0,
-                                               double* dst1, int stride1) {
-  ordered_merge<NV>(v, l, act, hbuf, hl, wcnt, [&](int lm, const double (&acc)[NV]) {
+struct RunMergeSmem { double first[8][NV]; int first_key[8]; int last_key[8]; };
+template <int NV, class Write>
+__device__ __forceinline__ void run_merge(const double (&v)[NV], int key, bool act, RunMergeSmem<NV>& sm, bool more, Write write) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int prev = __shfl_up_sync(FULL, key, 1);
+  const bool head = lane == 0 || prev != key;
+  double sums[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (i < n0) dst0[(int64_t)stride0 * lm + i] += acc[i];
-      else dst1[(int64_t)stride1 * lm + (i - n0)] += acc[i];
-    }
-  });
+  for (int i = 0; i < NV; ++i) sums[i] = seg_sum(v[i], key, lane);
+  if (lane == 0) {
+    sm.first_key[w] = act ? key : -1;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sm.first[w][i] = sums[i];
+  }
+  if (lane == 31) sm.last_key[w] = act ? key : -1;
+  const unsigned hm = __ballot_sync(FULL, head);
+  const bool last_run = (hm >> lane) <= 1u;               // no later head in this warp: the run reaches lane 31
+  __syncthreads();
+  if (head && act && !(lane == 0 && w > 0 && sm.last_key[w - 1] == key)) {
+    if (last_run)
+      for (int k = w + 1; k < nw && sm.first_key[k] == key; ++k)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sums[i] += sm.first[k][i];
+    write(key, sums);
+  }
+  if (more) __syncthreads();
 }
 
 // Jacobian pass of the between factors without colours: one thread per factor END, ends sorted by (pose, factor), block ranges
@@ -579,19 +602,20 @@ __global__ void __launch_bounds__(BTE_T) k_between_ends(const int* __restrict__ 
 }
 
 // one thread per observation (observations sorted by landmark): residual, Jp, Jl; W = w Jp^T Jl stored AoS;
-// V_l, g_l by the in-block ordered merge above.  Block b owns observations [oblk_ptr[b], oblk_ptr[b + 1]) (<= 256 unless a
-// single landmark has more).
+// V_l, g_l by the one-barrier run merge above.  Block b owns observations [oblk_ptr[b], oblk_ptr[b + 1]) (<= 256 unless a
+// single landmark has more).  The W records (144 B each) of a warp's 32 consecutive observations are transposed through a
+// warp-private piece of shared memory (no block barrier) so that the global store is coalesced: a thread writing its own
+// record would cost 32 cache-line wavefronts per store instruction.
+struct ProjCal { double K[9], S[12]; };
 template <bool JAC>
 __global__ void __launch_bounds__(256, JAC ? 2 : 3) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
                                                   Vals vals, const double* __restrict__ calib, const double* __restrict__ sensor,
                                                   double* __restrict__ W, double* V, double* gl, double* part) {
-  // W records (144 B each) of the block's consecutive observations go through shared memory so that the global
-  // store is coalesced (a thread writing its own record costs 32 cache-line wavefronts per store instruction)
-  __shared__ double wbuf[JAC ? 256 * 19 : 1];
-  __shared__ int hl[JAC ? 256 : 1];
-  __shared__ int wcnt[8];
+  __shared__ double wbuf[JAC ? 8 : 1][JAC ? 32 * 19 : 1];
+  __shared__ RunMergeSmem<9> ms;
   const int64_t s0 = oblk_ptr[blockIdx.x], s1 = oblk_ptr[blockIdx.x + 1];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   double e = 0.0;
   for (int64_t base = s0; base < s1; base += 256) {
     const int64_t o = base + threadIdx.x;
@@ -613,17 +637,25 @@ __global__ void __launch_bounds__(256, JAC ? 2 : 3) k_proj_obs(const int64_t* __
       e += w * (r[0] * r[0] + r[1] * r[1]);
     }
     if (JAC) {
+      double* wb = wbuf[wp];
       if (act) {
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            wbuf[threadIdx.x * 19 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
+            wb[lane * 19 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
       }
-      __syncthreads();
-      const int n = (int)min((int64_t)256, s1 - base);
-      for (int i = threadIdx.x; i < n * 18; i += blockDim.x) W[base * 18 + i] = wbuf[(i / 18) * 19 + (i % 18)];
-      __syncthreads();                       // wbuf is free: the merge parks its head partials there
+      __syncwarp();
+      {
+        const int64_t o0 = base + 32 * wp;                                  // first observation of this warp
+        const int n2 = (int)max((int64_t)0, min((int64_t)32, s1 - o0)) * 9;    // 16-byte pieces to store
+        double2* dst = reinterpret_cast<double2*>(W + o0 * 18);
+        for (int i = lane; i < n2; i += 32) {
+          const int rr = (2 * i) / 18, pos = 2 * i - 18 * rr;
+          dst[i] = make_double2(wb[rr * 19 + pos], wb[rr * 19 + pos + 1]);
+        }
+      }
+      __syncwarp();
       // V (upper: 00 01 02 11 12 22) and gl
       double c9[9];
       if (act) {
@@ -640,7 +672,12 @@ __global__ void __launch_bounds__(256, JAC ? 2 : 3) k_proj_obs(const int64_t* __
 #pragma unroll
         for (int i = 0; i < 9; ++i) c9[i] = 0.0;
       }
-      landmark_merge<9>(c9, l, act, wbuf, hl, wcnt, V, 6, 6, gl, 3);
+      run_merge<9>(c9, l, act, ms, base + 256 < s1, [&](int lm, const double (&acc)[9]) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) V[6 * (int64_t)lm + i] += acc[i];       // single owner: plain read-modify-writes
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gl[3 * (int64_t)lm + i] += acc[6 + i];
+      });
     }
   }
   chi2_accumulate(e, part);
@@ -722,42 +759,54 @@ __global__ void k_damp_rhs(SysView sys, const double* __restrict__ g_r, double l
 }
 
 // ------------------------------------------------------------------ K9/K10 back-substitution and retraction
-// t_l = sum_o W_o^T delta_p(o) (thread per observation, block ranges on landmark boundaries, in-block ordered merge)
+// t_l = sum_o W_o^T delta_p(o) (thread per observation, block ranges on landmark boundaries, one-barrier run merge); a warp's
+// 32 consecutive W records arrive coalesced and are transposed through its private piece of shared memory
 __global__ void __launch_bounds__(256) k_lm_backsub_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                         const double* __restrict__ W, const double* __restrict__ delta,
                                                         const int* __restrict__ off_pose, double* tl) {
-  __shared__ double wbuf[256 * 19];
-  __shared__ int hl[256];
-  __shared__ int wcnt[8];
+  __shared__ double wbuf[8][32 * 19];
+  __shared__ RunMergeSmem<3> ms;
   const int64_t s0 = oblk_ptr[blockIdx.x], s1 = oblk_ptr[blockIdx.x + 1];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   for (int64_t base = s0; base < s1; base += 256) {
     const int64_t o = base + threadIdx.x;
     const bool act = o < s1;
     const int l = act ? obs_point[o] : -1;
     double t3[3] = {0, 0, 0};
-    // the dependent gather obs_pose -> off_pose -> delta is issued first so that it overlaps the streaming W loads
-    double dl[6];
+    double* wb = wbuf[wp];
     {
+      // coalesced load of the warp's consecutive W records, issued before the dependent gather below
+      const int64_t o0 = base + 32 * wp;
+      const int n2 = (int)max((int64_t)0, min((int64_t)32, s1 - o0)) * 9;
+      const double2* src = reinterpret_cast<const double2*>(W + o0 * 18);
+      double2 v[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { const int i = lane + 32 * q; v[q] = i < n2 ? __ldg(src + i) : make_double2(0.0, 0.0); }
+      // obs_pose -> off_pose -> delta
+      double dl[6];
       const double* d = delta + (act ? off_pose[obs_pose[o]] : 0);
 #pragma unroll
       for (int i = 0; i < 6; ++i) dl[i] = act ? d[i] : 0.0;
-    }
-    {
-      // coalesced load of the block's consecutive W records, transposed through shared memory
-      const int n = (int)min((int64_t)256, s1 - base);
-      for (int i = threadIdx.x; i < n * 18; i += blockDim.x) wbuf[(i / 18) * 19 + (i % 18)] = __ldg(W + base * 18 + i);
-      __syncthreads();
-    }
-    if (act) {
-      const double* wr = wbuf + threadIdx.x * 19;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) t3[c] += wr[3 * i + c] * dl[i];
+      for (int q = 0; q < 9; ++q) {
+        const int i = lane + 32 * q, rr = (2 * i) / 18, pos = 2 * i - 18 * rr;
+        if (i < n2) { wb[rr * 19 + pos] = v[q].x; wb[rr * 19 + pos + 1] = v[q].y; }
       }
+      __syncwarp();
+      if (act) {
+        const double* wr = wb + lane * 19;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) t3[c] += wr[3 * i + c] * dl[i];
+        }
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    landmark_merge<3>(t3, l, act, wbuf, hl, wcnt, tl, 3, 3, tl, 3);
+    run_merge<3>(t3, l, act, ms, base + 256 < s1, [&](int lm, const double (&acc)[3]) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tl[3 * (int64_t)lm + i] += acc[i];
+    });
   }
 }
 

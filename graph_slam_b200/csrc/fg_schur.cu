@@ -84,157 +84,227 @@ __global__ void __launch_bounds__(256) k_zmat(int64_t M, const int* __restrict__
     }
   }
   __syncthreads();
+  // three planes Zk[k][M][6]: column k of every record, 48 contiguous bytes per (record, plane)
   for (int i = tid; i < n * 9; i += 256) {
-    const int r = i / 9, part = i - 9 * r;
-    const double* s = buf + r * RST + 2 * part;
-    reinterpret_cast<double2*>(Zp + (int64_t)ppos[r] * REC)[part] = make_double2(s[0], s[1]);
+    const int r = i / 9, part = i - 9 * r, k = part / 3, pr = part - 3 * k;
+    const double* s = buf + r * RST + 6 * pr + k;
+    reinterpret_cast<double2*>(Zp + ((int64_t)k * M + ppos[r]) * 6)[pr] = make_double2(s[0], s[3]);
   }
 }
 
 // ------------------------------------------------------------------ tile kernel
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 #define ST_THREADS 256
-template <int CH, int KMAX>
+#define ST_NW 3            // 32-landmark table chunks per super-chunk (96 landmarks between two staging rounds)
+#define ST_KMAX 56         // record slots per pose and super-chunk
+#define ST_MAXH 32         // hits per lane and super-chunk the hit list has room for
 struct SchurSmem {
-  static constexpr int PS = KMAX * 16 + 1;        // plane stride (doubles): odd, so bank = (e + i) mod 16
-  double rows[REC * PS];
-  double cols[REC * PS];
-  int src[ST_THREADS / 32][4 * CH];               // per warp: pose-major record index of every record it stages
+  static constexpr int PS2 = ST_KMAX * 16 + 3;       // plane stride in double2 units; = 3 mod 8 spreads the staging writes over the banks
+  double2 rows[3 * PS2];                             // [element pair][slot][pose]: ONE column of Z (6 doubles) per record
+  double2 cols[3 * PS2];
+  unsigned short hits[ST_MAXH * ST_THREADS];         // per lane: (row slot | column slot << 8) of every hit of the super-chunk
+  int src[ST_THREADS / 32][4 * ST_KMAX];             // per warp: pose-major record index of every record it stages
 };
 
-// CH landmarks per chunk, room for KMAX records per pose and chunk.  KMAX < CH (32 / 24) bets that no pose sees more than
-// KMAX of a chunk's landmarks together with the other side of the tile; a chunk that loses the bet is done as two
-// half-chunks of 16 landmarks (<= 16 records per pose).
-template <int CH, int KMAX>
+// Z is stored as three planes Zk[k][M][6] (column k of every 6 x 3 record; pose-major).  S_pq = sum_k sum_l z_pl^k (z_ql^k)^T, so
+// the tile can be built one column at a time: a staging round holds 48 bytes per record instead of 144, which lets a round
+// cover 96 landmarks in the shared memory that held 32 -- the lanes of a warp run until the busiest one is out of hits, and
+// the spread of the hit counts shrinks with the length of the round.  Per super-chunk: the hit list of every lane is
+// built once (bit-mask walk), then three rounds (stage column k, barrier, 36 DFMA per hit from two 3 x LDS.128 operands).
+// A super-chunk that does not fit (a pose with more than ST_KMAX records, a lane with more than ST_MAXH hits) is redone as
+// three single-word rounds.
 __global__ void __launch_bounds__(ST_THREADS, 2)
 k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_lo, const int* __restrict__ pc_n,
-              const int64_t* __restrict__ pc_ptr, const uint2* __restrict__ pc_ent, const double* __restrict__ Zp,
+              const int64_t* __restrict__ pc_ptr, const uint2* __restrict__ pc_ent, const double* __restrict__ Zk, int64_t M,
               const int* __restrict__ off_pose, SysView sys) {
   extern __shared__ __align__(16) unsigned char st_raw[];
-  SchurSmem<CH, KMAX>& sm = *reinterpret_cast<SchurSmem<CH, KMAX>*>(st_raw);
-  constexpr int PS = SchurSmem<CH, KMAX>::PS;
+  SchurSmem& sm = *reinterpret_cast<SchurSmem*>(st_raw);
+  constexpr int PS2 = SchurSmem::PS2;
   const unsigned FULL = 0xffffffffu;
   const int4 td = tiles[blockIdx.x];
   const int gi = td.x, gj = td.y, cb = td.z, ce = td.w;
   const bool diag = gi == gj;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // metadata role: lane s holds the chunk entry of pose s (0..15 row poses, 16..31 column poses)
+  // metadata role: lane s holds the table entries of pose s (0..15 row poses, 16..31 column poses)
   const int mp = ((lane >> 4) ? gj : gi) * 16 + (lane & 15);
   int m_lo = 0, m_n = 0;
   int64_t m_ptr = 0;
   if (mp < P) { m_lo = pc_lo[mp]; m_n = pc_n[mp]; m_ptr = pc_ptr[mp]; }
-  // compute role: half-warp h of warp w works on the wrapped diagonal d = 2 w + h of the tile: pose distance, hence the number
-  // of shared landmarks, changes along d, so the two halves of a warp do about the same work and the lanes stay busy together
-  // (pairing diagonals w and 15 - w balanced the warps instead and left half the lanes of every instruction idle:
-  // 16.3 of 32 threads per instruction in profiles/r1_ncu_full_summary.md); an idle warp gives its issue slots to the other CTA.
-  // In a diagonal tile the diagonals d and 16 - d hold the same unordered pose pairs: the two lanes of a pair split its
-  // landmarks by bit parity and their sums are joined at the end; the p == q blocks are left to k_schur_rhs.
-  const int i = lane & 15, d = 2 * warp + (lane >> 4), j = (i + d) & 15;
+  // compute role: two warps share an 8 x 8 sub-tile; the 8 lanes of a quarter-warp sit on one wrapped diagonal of it (distinct
+  // row pose mod 8, distinct column pose mod 8), which is what makes the 16-byte operand reads bank-conflict free.  A landmark's
+  // window covers ~50 consecutive poses, so at any time a tile is only partly inside it: with 8 x 8 sub-tiles the warps of the
+  // part outside run no steps at all (wrapped diagonals of the whole 16 x 16 tile put every warp half in, half out).
+  // (warps 0-1 and 4-5 issue from schedulers 0-1, warps 2-3 and 6-7 from 2-3: sub-tiles that share a row or a column of the
+  // tile -- the usual shape of the part inside the window -- sit on different schedulers)
+  const int sub = (warp >> 1) < 2 ? (warp >> 1) : 5 - (warp >> 1), ii = lane & 7, dgn = 4 * (warp & 1) + (lane >> 3);
+  const int i = 8 * (sub >> 1) + ii, j = 8 * (sub & 1) + ((ii + dgn) & 7);
   bool active = (gi * 16 + i < P) && (gj * 16 + j < P);
-  const bool primary = !diag || d < 8 || (d == 8 && i < 8);
+  // In a diagonal tile the lanes (i, j) and (j, i) hold the same unordered pose pair: they split its landmarks by bit parity
+  // and their sums are joined at the end; the p == q blocks are left to k_schur_rhs.
+  const bool primary = !diag || i > j;
   unsigned hit_sel = 0xffffffffu;
-  if (diag) { active = active && d != 0; hit_sel = primary ? 0x55555555u : 0xaaaaaaaau; }
+  if (diag) { active = active && i != j; hit_sel = primary ? 0x55555555u : 0xaaaaaaaau; }
   double acc[36];
 #pragma unroll
   for (int q = 0; q < 36; ++q) acc[q] = 0.0;
   bool any = false;
-  const double* cbase = diag ? sm.rows : sm.cols;
-  int* srcl = sm.src[warp];
-  double* stage = sm.rows;                // rows, then cols: one staging area of 2 x REC planes
-  const int n_st = diag ? 16 : 32;        // poses to stage
-  const int spw = n_st / 8;               // poses per warp: s = warp + 8 t
+  const double2* cbase = diag ? sm.rows : sm.cols;
+  int* srcl = sm.src[warp];                         // (M < 2^31 / 6 is checked by build_schur_tables)
+  unsigned short* hl = sm.hits + threadIdx.x;
+  // staging role: warp w copies the records of poses npw w .. npw w + npw - 1 (npw = 4, or 2 in a diagonal tile); a copy step
+  // moves the three 16-byte parts of NR consecutive records of each of these poses
+  const int npw = diag ? 2 : 4;
+  const int st_t = lane % npw, st_part = (lane / npw) % 3, st_r = lane / (3 * npw), st_nr = diag ? 5 : 2;
+  const int st_s = npw * warp + st_t;
+  double2* st_dst = (st_s >> 4 ? sm.cols : sm.rows) + st_part * PS2 + (st_s & 15);
 
   auto fetch = [&](int c) -> uint2 {
     const int r = c - m_lo;
     return (c < ce && r >= 0 && r < m_n) ? __ldg(&pc_ent[m_ptr + r]) : make_uint2(0u, 0u);
   };
-  uint2 ent1 = fetch(cb), ent2 = fetch(cb + 1);
-  for (int c = cb; c < ce; ++c) {
-    const uint2 cur = ent1;
-    ent1 = ent2;
-    ent2 = fetch(c + 2);                          // entries ride two chunks ahead of their use
+  uint2 nxt[ST_NW];
+#pragma unroll
+  for (int wd = 0; wd < ST_NW; ++wd) nxt[wd] = fetch(cb + wd);
+  int c0 = cb, single = -1;                         // single >= 0: the super-chunk at c0 is being redone word by word
+  while (c0 < ce) {
+    uint2 cur[ST_NW];
+    if (single < 0) {
+#pragma unroll
+      for (int wd = 0; wd < ST_NW; ++wd) { cur[wd] = nxt[wd]; nxt[wd] = fetch(c0 + ST_NW + wd); }   // entries ride one super-chunk ahead
+    } else {
+      cur[0] = fetch(c0 + single);
+#pragma unroll
+      for (int wd = 1; wd < ST_NW; ++wd) cur[wd] = make_uint2(0u, 0u);
+    }
     // landmarks seen from both sides of the tile; a pose stages only its records of those
-    unsigned any16 = cur.y;
+    unsigned f[ST_NW];
+    int tot = 0;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) any16 |= __shfl_xor_sync(FULL, any16, o);
-    const unsigned other = __shfl_xor_sync(FULL, any16, 16);
-    const unsigned fall = cur.y & other;
-    if (!__any_sync(FULL, fall != 0u)) continue;  // identical decision in every warp: all hold the same 32 entries
-    int nparts = 1;
-    if (KMAX < CH && __any_sync(FULL, __popc(fall) > KMAX)) nparts = 2;
-    for (int part_i = 0; part_i < nparts; ++part_i) {
-    const unsigned f = nparts == 1 ? fall : (part_i == 0 ? (fall & 0x0000ffffu) : (fall & 0xffff0000u));
-    if (nparts == 2 && !__any_sync(FULL, f != 0u)) continue;
-    __syncthreads();                              // the previous chunk's products are done with the staging area
-    // ---- stage: list the records of this warp's poses, then copy them 3 records (27 lanes x 16 B) per step
-    int base_t[5];
-    base_t[0] = 0;
+    for (int wd = 0; wd < ST_NW; ++wd) {
+      unsigned any16 = cur[wd].y;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      int cnt = 0;
-      if (t < spw) {
-        const int s = warp + 8 * t;
-        const unsigned fm = __shfl_sync(FULL, f, s), mm = __shfl_sync(FULL, cur.y, s);
-        const int st = (int)__shfl_sync(FULL, cur.x, s);
-        cnt = __popc(fm);
-        if ((fm >> lane) & 1u) {
-          const unsigned low = (1u << lane) - 1u;
-          srcl[base_t[t] + __popc(fm & low)] = st + __popc(mm & low);
+      for (int o = 8; o > 0; o >>= 1) any16 |= __shfl_xor_sync(FULL, any16, o);
+      f[wd] = cur[wd].y & __shfl_xor_sync(FULL, any16, 16);
+      tot += __popc(f[wd]);
+    }
+    bool redo = false;
+    if (__any_sync(FULL, tot != 0)) {               // identical decision in every warp: all hold the same 32 entries
+      redo = __any_sync(FULL, tot > ST_KMAX);
+      int nh = 0;
+      if (!redo) {
+        // ---- list the records of this warp's poses (slot order = landmark order)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (t < npw) {
+            const int s = npw * warp + t;
+            int base = t * ST_KMAX;
+#pragma unroll
+            for (int wd = 0; wd < ST_NW; ++wd) {
+              const unsigned fm = __shfl_sync(FULL, f[wd], s), mm = __shfl_sync(FULL, cur[wd].y, s);
+              const int st = (int)__shfl_sync(FULL, cur[wd].x, s);
+              if ((fm >> lane) & 1u) {
+                const unsigned low = (1u << lane) - 1u;
+                srcl[base + __popc(fm & low)] = 6 * (st + __popc(mm & low));      // element offset of the record in a plane
+              }
+              base += __popc(fm);
+            }
+          }
         }
-      }
-      base_t[t + 1] = base_t[t] + cnt;
-    }
-    __syncwarp();
-    {
-      // three records per step: lane (r, part) moves elements 2 part and 2 part + 1 of record pos0 + r with two
-      // 8-byte cp.async (global side: 144 contiguous bytes per record; shared side: the transposed layout)
-      const int total = base_t[4];
-      const int r = lane / 9, part = lane - 9 * r;
-      if (r < 3)
-        for (int pos = r; pos < total; pos += 3) {
-          const int t = (pos >= base_t[1]) + (pos >= base_t[2]) + (pos >= base_t[3]);
-          const int k = pos - (t == 0 ? 0 : (t == 1 ? base_t[1] : (t == 2 ? base_t[2] : base_t[3])));
-          const int s = warp + 8 * t;
-          const int e0 = 2 * part + (r & 1), e1 = 2 * part + 1 - (r & 1);      // neighbouring records start on different banks
-          const double* src = Zp + (int64_t)srcl[pos] * REC;
-          double* dst = stage + (s >> 4) * (REC * PS) + k * 16 + (s & 15);
-          cp_async8(dst + e0 * PS, src + e0);
-          cp_async8(dst + e1 * PS, src + e1);
+        int my_cnt = __shfl_sync(FULL, tot, npw * warp + st_t);
+        if (st_r >= st_nr) my_cnt = 0;
+        unsigned fi[ST_NW], fj[ST_NW];
+#pragma unroll
+        for (int wd = 0; wd < ST_NW; ++wd) {
+          fi[wd] = __shfl_sync(FULL, f[wd], i); fj[wd] = __shfl_sync(FULL, f[wd], 16 + j);
+          if (active) nh += __popc(fi[wd] & fj[wd] & hit_sel);
         }
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
-    __syncthreads();
-    // ---- products: walk the landmarks both poses of this lane's block see
-    const unsigned fi = __shfl_sync(FULL, f, i), fj = __shfl_sync(FULL, f, 16 + j);
-    unsigned hit = active ? (fi & fj & hit_sel) : 0u;
-    while (hit) {
-      const int b = __ffs(hit) - 1;
-      hit &= hit - 1u;
-      const unsigned low = (1u << b) - 1u;
-      const double* ra = sm.rows + __popc(fi & low) * 16 + i;
-      const double* cq = cbase + __popc(fj & low) * 16 + j;
-      double y[REC];
+        // ---- hit list of this lane's block: (row slot, column slot) of every landmark both poses see
+        if (active) {
+            int pi = 0, pj = 0, n = 0;
 #pragma unroll
-      for (int e = 0; e < REC; ++e) y[e] = ra[e * PS];
+            for (int wd = 0; wd < ST_NW; ++wd) {
+              unsigned hit = fi[wd] & fj[wd] & hit_sel;
+              while (hit) {
+                const int b = __ffs(hit) - 1;
+                hit &= hit - 1u;
+                const unsigned low = (1u << b) - 1u;
+                const int a = pi + __popc(fi[wd] & low), bq = pj + __popc(fj[wd] & low);
+                if (n < ST_MAXH) hl[n * ST_THREADS] = (unsigned short)(a | (bq << 8));
+                ++n;
+              }
+              pi += __popc(fi[wd]); pj += __popc(fj[wd]);
+            }
+        }
+        __syncwarp();
+        // ---- three rounds, one column of Z each
+        for (int k = 0; k < 3; ++k) {
+          // the previous round's products are done with the staging area (k == 0: also the vote on the hit-list overflow)
+          if (k == 0) {
+            if (__syncthreads_or(nh > ST_MAXH)) { redo = true; break; }
+          } else {
+            __syncthreads();
+          }
+          {
+            const double* zk = Zk + (int64_t)k * M * 6 + 2 * st_part;
+            const int* sl = srcl + st_t * ST_KMAX;
+            double2* dst = st_dst + st_r * 16;
+#pragma unroll 2
+            for (int kk = st_r; kk < my_cnt; kk += st_nr, dst += st_nr * 16) cp_async16(dst, zk + sl[kk]);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+          }
+#ifdef ST_L2_PREFETCH
+          // pull the records of the NEXT super-chunk into L2 (all three planes) while this one is worked on: a pose's records of a
+          // landmark range are contiguous in the pose-major order; lane s of warp 0 .. 2 (one plane each) walks their 128-byte lines
+          if (k == 0 && single < 0 && warp < 3) {
+            int first = -1, cnt = 0;
 #pragma unroll
-      for (int jj = 0; jj < 6; ++jj) {
-        const double w0 = cq[(3 * jj) * PS], w1 = cq[(3 * jj + 1) * PS], w2 = cq[(3 * jj + 2) * PS];
+            for (int wd = 0; wd < ST_NW; ++wd)
+              if (nxt[wd].y) { if (first < 0) first = (int)nxt[wd].x; cnt += __popc(nxt[wd].y); }
+            if (cnt && (!diag || lane < 16)) {
+              const char* b = reinterpret_cast<const char*>(Zk + ((int64_t)warp * M + first) * 6);
+              const char* e = b + (size_t)cnt * 48;
+              for (const char* q = b; q < e; q += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q));
+            }
+          }
+#endif
+          asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+          __syncthreads();
+          for (int h = 0; h < nh; ++h) {
+            const unsigned pk = hl[h * ST_THREADS];
+            const double2* ra = sm.rows + (pk & 0xffu) * 16 + i;
+            const double2* cq = cbase + (pk >> 8) * 16 + j;
+            const double2 y01 = ra[0], y23 = ra[PS2], y45 = ra[2 * PS2];
+            const double2 w01 = cq[0], w23 = cq[PS2], w45 = cq[2 * PS2];
+            const double y[6] = {y01.x, y01.y, y23.x, y23.y, y45.x, y45.y};
+            const double w[6] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
 #pragma unroll
-        for (int ii = 0; ii < 6; ++ii) acc[6 * ii + jj] = fma(y[3 * ii + 2], w2, fma(y[3 * ii + 1], w1, fma(y[3 * ii], w0, acc[6 * ii + jj])));
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+              for (int cc = 0; cc < 6; ++cc) acc[6 * r + cc] = fma(y[r], w[cc], acc[6 * r + cc]);
+          }
+        }
+        if (!redo && nh) any = true;
       }
-      any = true;
     }
+    // ---- advance
+    if (redo) {
+      if (single < 0) { single = 0; continue; }     // redo this super-chunk one word (<= 32 records, <= 32 hits) at a time
+      // a single word always fits: not reached
+    }
+    if (single >= 0) {
+      if (++single == ST_NW) { single = -1; c0 += ST_NW; }
+    } else {
+      c0 += ST_NW;
     }
   }
   if (diag) {
     // join the two halves of every pose pair: the secondary lane (j, i) parks its sums, transposed, in the staging area
     __syncthreads();
-    double* xch = stage + (primary ? i * 16 + j : j * 16 + i) * 37;
+    double* xch = reinterpret_cast<double*>(sm.rows) + (primary ? i * 16 + j : j * 16 + i) * 37;
     if (active && !primary) {
 #pragma unroll
       for (int r = 0; r < 6; ++r)
@@ -272,7 +342,7 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
 
 // one warp per pose over its (contiguous, pose-major) records: rhs_p += sum_k Z_k u_l(k), and the diagonal block
 // S_pp -= sum_k Z_k Z_k^T (lower triangle) that k_schur_tiles leaves out
-__global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restrict__ pose_obs_ptr, const int* __restrict__ pz_point,
+__global__ void __launch_bounds__(256) k_schur_rhs(int P, int64_t M, const int64_t* __restrict__ pose_obs_ptr, const int* __restrict__ pz_point,
                                                    const double* __restrict__ Zp, const double* __restrict__ ul,
                                                    const int* __restrict__ off_pose, SysView sys) {
   const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -285,9 +355,12 @@ __global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restr
   for (int64_t k = b + lane; k < e; k += 32) {
     const int l = pz_point[k];
     double w[REC];
-    const double2* zp = reinterpret_cast<const double2*>(Zp + k * REC);
 #pragma unroll
-    for (int q = 0; q < 9; ++q) { const double2 v = __ldg(zp + q); w[2 * q] = v.x; w[2 * q + 1] = v.y; }
+    for (int kc = 0; kc < 3; ++kc) {
+      const double2* zp = reinterpret_cast<const double2*>(Zp + ((int64_t)kc * M + k) * 6);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { const double2 v = __ldg(zp + q); w[6 * q + kc] = v.x; w[6 * q + 3 + kc] = v.y; }
+    }
     const double y0 = ul[3 * (int64_t)l], y1 = ul[3 * (int64_t)l + 1], y2 = ul[3 * (int64_t)l + 2];
 #pragma unroll
     for (int q = 0; q < 6; ++q) acc[q] += w[3 * q] * y0 + w[3 * q + 1] * y1 + w[3 * q + 2] * y2;
@@ -321,16 +394,15 @@ __global__ void __launch_bounds__(256) k_schur_rhs(int P, const int64_t* __restr
   }
 }
 
-template <int CH, int KMAX>
 static void launch_tiles(fg_ctx* c, const SysView& sys) {
   DevGraph& d = c->d;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_schur_tiles<CH, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchurSmem<CH, KMAX>));
+    cudaFuncSetAttribute(k_schur_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SchurSmem));
     attr_set = true;
   }
-  k_schur_tiles<CH, KMAX><<<d.n_tiles, ST_THREADS, sizeof(SchurSmem<CH, KMAX>), FGS(c->stream)>>>(d.tile_desc, (int)d.n[T_POSE], d.pc_lo, d.pc_n, d.pc_ptr, d.pc_ent,
-                                                                                 d.Zp, d.off[T_POSE], sys);
+  k_schur_tiles<<<d.n_tiles, ST_THREADS, sizeof(SchurSmem), FGS(c->stream)>>>(d.tile_desc, (int)d.n[T_POSE], d.pc_lo, d.pc_n, d.pc_ptr, d.pc_ent,
+                                                                             d.Zp, d.n_obs, d.off[T_POSE], sys);
 }
 
 void launch_schur(fg_ctx* c, double lambda) {
@@ -344,11 +416,11 @@ void launch_schur(fg_ctx* c, double lambda) {
   if (d.n_obs) k_zmat<<<cdiv(d.n_obs, 256), 256, 0, FGS(st)>>>(d.n_obs, d.obs_point, d.obs_ppos, d.W, d.Cf, d.Zp);
   if (c->kev[2]) cudaEventRecord(c->kev[2], st);
   if (d.n_tiles) {
-    launch_tiles<32, 24>(c, sys);                        // d.schur_ch == 32 (build_schur_tables)
+    launch_tiles(c, sys);                                // table chunks of 32 landmarks (d.schur_ch, build_schur_tables)
   }
   if (c->kev[3]) cudaEventRecord(c->kev[3], st);
   const int P = (int)d.n[T_POSE];
-  if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pz_point, d.Zp, d.ul, d.off[T_POSE], sys);
+  if (d.n_obs) k_schur_rhs<<<cdiv((int64_t)P * 32, 256), 256, 0, FGS(st)>>>(P, d.n_obs, d.pose_obs_ptr, d.pz_point, d.Zp, d.ul, d.off[T_POSE], sys);
 }
 
 }  // namespace fg
