@@ -864,6 +864,8 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<double>(c, &d.gl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Vinv, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.tl, nullptr, (size_t)3 * L))) return rc;
     if ((rc = dev_upload(c, &d.calib, h.calib.data() + 9 * cid, 9)) || (rc = dev_upload(c, &d.sensor, h.sensor.data() + 12 * sid, 12))) return rc;
+    std::copy(h.calib.begin() + 9 * cid, h.calib.begin() + 9 * cid + 9, d.cal.K);
+    std::copy(h.sensor.begin() + 12 * sid, h.sensor.begin() + 12 * sid + 12, d.cal.S);
     if ((rc = dev_upload<double>(c, &d.ul, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Cf, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.Zp, nullptr, (size_t)18 * M))) return rc;
     {

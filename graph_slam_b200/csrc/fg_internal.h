@@ -226,6 +226,7 @@ struct DevGraph {
   double* Vinv = nullptr;           // 6 L
   double* tl = nullptr;             // 3 L  : sum_o W_o^T delta_p (back-substitution scratch)
   double* calib = nullptr;          // 9
+  struct ProjCal { double K[9], S[12]; } cal;   // host copy of calib / sensor: passed to the projection kernels by value (constant bank)
   double* sensor = nullptr;         // 12
   // reduced system
   double* L = nullptr;              // panels being factored

@@ -606,11 +606,11 @@ __global__ void __launch_bounds__(BTE_T) k_between_ends(const int* __restrict__ 
 // single landmark has more).  The W records (144 B each) of a warp's 32 consecutive observations are transposed through a
 // warp-private piece of shared memory (no block barrier) so that the global store is coalesced: a thread writing its own
 // record would cost 32 cache-line wavefronts per store instruction.
-struct ProjCal { double K[9], S[12]; };
+typedef DevGraph::ProjCal ProjCal;
 template <bool JAC>
-__global__ void __launch_bounds__(256, JAC ? 2 : 3) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+__global__ void __launch_bounds__(256, JAC ? 3 : 4) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
-                                                  Vals vals, const double* __restrict__ calib, const double* __restrict__ sensor,
+                                                  Vals vals, const __grid_constant__ ProjCal cal,
                                                   double* __restrict__ W, double* V, double* gl, double* part) {
   __shared__ double wbuf[JAC ? 8 : 1][JAC ? 32 * 19 : 1];
   __shared__ RunMergeSmem<9> ms;
@@ -623,17 +623,13 @@ __global__ void __launch_bounds__(256, JAC ? 2 : 3) k_proj_obs(const int64_t* __
     const int l = act ? obs_point[o] : -1;
     double r[2], Jp[12], Jl[6], w = 0.0;
     if (act) {
-      double X[12], K[9], S[12], p[3];
+      double X[12], p[3];
       load_pose(vals.v[T_POSE], obs_pose[o], X);
-#pragma unroll
-      for (int i = 0; i < 9; ++i) K[i] = __ldg(calib + i);
-#pragma unroll
-      for (int i = 0; i < 12; ++i) S[i] = __ldg(sensor + i);
       p[0] = vals.v[T_POINT][3 * (int64_t)l]; p[1] = vals.v[T_POINT][3 * (int64_t)l + 1]; p[2] = vals.v[T_POINT][3 * (int64_t)l + 2];
       double2 uvv = __ldg(reinterpret_cast<const double2*>(obs_uv) + o);
       double uv[2] = {uvv.x, uvv.y};
       w = obs_w[o];
-      projection_eval<JAC>(X, p, uv, K, S, r, Jp, Jl);
+      projection_eval<JAC>(X, p, uv, cal.K, cal.S, r, Jp, Jl);
       e += w * (r[0] * r[0] + r[1] * r[1]);
     }
     if (JAC) {
@@ -698,52 +694,65 @@ __global__ void k_merge_dup(int n, const int* __restrict__ prim, const int* __re
   }
 }
 
-// one warp per pose: U_pp = sum w Jp^T Jp, g_p = sum w Jp^T r over the pose's observations (recomputed)
+// U_pp = sum w Jp^T Jp, g_p = sum w Jp^T r over the pose's observations (recomputed).  PP_W warps per pose, each over a
+// contiguous quarter of the pose's list (a pose has ~2000 observations at C5: one warp per pose is 5000 long warps, 2.1 waves of
+// the resident 2368, and the last wave runs 11 % full); the quarters are added in order through shared memory.
+#define PP_W 4
 __global__ void __launch_bounds__(256, 2) k_proj_pose(int P, const int64_t* __restrict__ pose_obs_ptr, const int64_t* __restrict__ pose_obs,
                                                    const int* __restrict__ obs_point, const double* __restrict__ obs_uv,
-                                                   const double* __restrict__ obs_w, Vals vals, const double* __restrict__ calib,
-                                                   const double* __restrict__ sensor, const int* __restrict__ off_pose,
-                                                   SysView sys, double* g_r) {
-  int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= P) return;
-  int64_t b = pose_obs_ptr[wid], e = pose_obs_ptr[wid + 1];
-  if (b == e) return;
-  double X[12], K[9], S[12];
-  load_pose(vals.v[T_POSE], wid, X);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) K[i] = __ldg(calib + i);
-#pragma unroll
-  for (int i = 0; i < 12; ++i) S[i] = __ldg(sensor + i);
+                                                   const double* __restrict__ obs_w, Vals vals, const __grid_constant__ ProjCal cal,
+                                                   const int* __restrict__ off_pose, SysView sys, double* g_r) {
+  __shared__ double part[256 / 32][28];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pib = warp / PP_W, q = warp % PP_W;                 // pose within the block, quarter of its list
+  const int wid = blockIdx.x * (256 / 32 / PP_W) + pib;
+  const bool live = wid < P;
+  int64_t b = 0, e = 0;
+  if (live) { b = pose_obs_ptr[wid]; e = pose_obs_ptr[wid + 1]; }
+  const int64_t len = (e - b + PP_W - 1) / PP_W;
+  const int64_t qb = b + q * len, qe = min(e, qb + len);
   double acc[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-  for (int64_t k = b + lane; k < e; k += 32) {
-    int64_t o = pose_obs[k];
-    int l = obs_point[o];
-    double p[3] = {vals.v[T_POINT][3 * (int64_t)l], vals.v[T_POINT][3 * (int64_t)l + 1], vals.v[T_POINT][3 * (int64_t)l + 2]};
-    double uv[2] = {obs_uv[2 * o], obs_uv[2 * o + 1]};
-    double w = obs_w[o], r[2], Jp[12], Jl[6];
-    projection_eval<true>(X, p, uv, K, S, r, Jp, Jl);
-    int q = 0;
+  if (qb < qe) {
+    double X[12];
+    load_pose(vals.v[T_POSE], wid, X);
+    for (int64_t k = qb + lane; k < qe; k += 32) {
+      int64_t o = pose_obs[k];
+      int l = obs_point[o];
+      double p[3] = {vals.v[T_POINT][3 * (int64_t)l], vals.v[T_POINT][3 * (int64_t)l + 1], vals.v[T_POINT][3 * (int64_t)l + 2]};
+      double uv[2] = {obs_uv[2 * o], obs_uv[2 * o + 1]};
+      double w = obs_w[o], r[2], Jp[12], Jl[6];
+      projection_eval<true>(X, p, uv, cal.K, cal.S, r, Jp, Jl);
+      int t = 0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int j = 0; j <= i; ++j) acc[q++] += w * (Jp[i] * Jp[j] + Jp[6 + i] * Jp[6 + j]);
+        for (int j = 0; j <= i; ++j) acc[t++] += w * (Jp[i] * Jp[j] + Jp[6 + i] * Jp[6 + j]);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) acc[21 + i] += w * (Jp[i] * r[0] + Jp[6 + i] * r[1]);
+      for (int i = 0; i < 6; ++i) acc[21 + i] += w * (Jp[i] * r[0] + Jp[6 + i] * r[1]);
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 27; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane == 0) {
-    int o = off_pose[wid], ld;
-    int64_t base = sys_find(sys, o, o, &ld);
-    int q = 0;
+  for (int i = 0; i < 27; ++i) {
+    const double v = warp_sum(acc[i]);
+    if (lane == 0) part[warp][i] = v;
+  }
+  __syncthreads();
+  if (q == 0 && live && b < e && lane < 27) {
+    double v = part[warp][lane];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) sys.L[base + i + (int64_t)j * ld] += acc[q++];      // the only writer of this block in this kernel
-#pragma unroll
-    for (int i = 0; i < 6; ++i) g_r[o + i] += acc[21 + i];
+    for (int k = 1; k < PP_W; ++k) v += part[warp + k][lane];
+    const int o = off_pose[wid];
+    if (lane < 21) {
+      int t = lane, i = 0;
+      while (t > i) { t -= i + 1; ++i; }                       // lower-triangle index -> (i, j = t)
+      int ld;
+      const int64_t base = sys_find(sys, o, o, &ld);
+      sys.L[base + i + (int64_t)t * ld] += v;                   // the only writer of this block in this kernel
+    } else {
+      g_r[o + lane - 21] += v;
+    }
   }
 }
 
@@ -1075,12 +1084,12 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
     k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, FGS(st)>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, slots(cdiv(L, 256)));
     if (d.n_obs) {
       if (JAC && c->kev[0]) cudaEventRecord(c->kev[0], st);
-      k_proj_obs<JAC><<<d.n_oblk, 256, 0, FGS(st)>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.W, d.V, d.gl, slots(d.n_oblk));
+      k_proj_obs<JAC><<<d.n_oblk, 256, 0, FGS(st)>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.cal, d.W, d.V, d.gl, slots(d.n_oblk));
       if (JAC && c->kev[1]) cudaEventRecord(c->kev[1], st);
       if (JAC && d.n_dup) k_merge_dup<<<cdiv(d.n_dup, 128), 128, 0, FGS(st)>>>(d.n_dup, d.dup_prim, d.dup_sec, d.W);
       if (JAC) {
         int P = (int)d.n[T_POSE];
-        k_proj_pose<<<cdiv((int64_t)P * 32, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.calib, d.sensor, d.off[T_POSE], sys, d.g_r);
+        k_proj_pose<<<cdiv((int64_t)P * 32 * PP_W, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.cal, d.off[T_POSE], sys, d.g_r);
       }
     }
   }
