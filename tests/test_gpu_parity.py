@@ -188,6 +188,32 @@ def test_duplicate_pose_landmark_factors_match_oracle():
     check(spec, 1e-7, 1e-6, solver='schur')
 
 
+def test_loop_closure_covisibility_matches_oracle():
+    """Landmarks re-observed after a long gap (loop closure): pose pairs far apart in the sequence share landmarks, so the reduced
+    Hessian has blocks far off the band -- separators of the nested dissection grow, Schur tiles appear far from the diagonal
+    and walk landmark ranges in which most of their poses see nothing (untested for fill and table limits)."""
+    spec = synth.make_config('C4', seed=3, scale=0.06)
+    rng = np.random.default_rng(5)
+    P, L = spec['n_poses'], len(spec['point_init'])
+    first = np.full(L, P, dtype=np.int64); last = np.zeros(L, dtype=np.int64)
+    np.minimum.at(first, spec['proj_point'], spec['proj_pose']); np.maximum.at(last, spec['proj_point'], spec['proj_pose'])
+    K = synth.CAL_SR4K
+    add_p, add_l, add_uv = [], [], []
+    for l in rng.permutation(L)[:2500]:
+        far = np.array([q for q in range(P) if q < first[l] - 40 or q > last[l] + 40])
+        if len(far) == 0: continue
+        uv, z = synth._project(spec['truth_R'][far], spec['truth_t'][far], spec['truth_point'][l][None, :], K, spec['Rs'], spec['ts'])
+        ok = (z > 0.5) & (np.abs(uv[:, 0] - K[3]) < 160.0) & (np.abs(uv[:, 1] - K[4]) < 140.0)      # really visible from there
+        if not ok.any(): continue
+        pick = rng.choice(np.nonzero(ok)[0], size=min(3, int(ok.sum())), replace=False)
+        add_p.append(far[pick]); add_l.append(np.full(len(pick), l)); add_uv.append(uv[pick] + rng.normal(size=(len(pick), 2)))
+    add_p = np.concatenate(add_p); assert len(add_p) > 100
+    spec['proj_pose'] = np.concatenate([spec['proj_pose'], add_p.astype(np.int32)])
+    spec['proj_point'] = np.concatenate([spec['proj_point'], np.concatenate(add_l).astype(np.int32)])
+    spec['proj_uv'] = np.concatenate([spec['proj_uv'], np.concatenate(add_uv)])
+    check(spec, 1e-7, 1e-6, solver='schur')
+
+
 def oracle_marginal(g, kind, idx):
     """Dense oracle: block of the inverse of the full (undamped) normal equations, landmarks included."""
     H, grad, err = g.normal_equations()
