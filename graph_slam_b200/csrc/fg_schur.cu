@@ -6,17 +6,18 @@
 // (gtsam/gtsam_graph.cpp:370-448); in GTSAM this is the elimination of every Point3 before the poses.
 //
 // Symmetric form.  With V_l + lambda I = G G^T (3x3 Cholesky) and C = G^-T,  W Vinv W^T = (W C)(W C)^T, so one array
-// Z_o = W_o C_l (6x3 per observation, 144 B) serves both sides of the product.  k_zmat writes Z in POSE-major order:
-// the observations of one pose are contiguous and sorted by landmark.
+// Z_o = W_o C_l (6x3 per observation, 144 B) serves both sides of the product.  k_zmat writes Z in POSE-major order (the
+// observations of one pose are contiguous and sorted by landmark) as three planes, one per column of the 6 x 3 record.
 //
 // k_schur_tiles: output-stationary, deterministic, no atomics, no pair lists.  One CTA owns a 16 x 16 tile of 6x6
 // blocks (16 consecutive row poses x 16 consecutive column poses); ONE LANE owns one block and keeps its 36 sums in
-// registers.  The landmarks are cut into chunks of CH consecutive ids.  Per chunk the CTA stages the Z records of its
-// 32 poses in shared memory, each lane intersects the landmark bit masks of its two poses and walks the set bits:
-//     S(p_i, q_j) += Z_(p_i, l) Z_(q_j, l)^T       (108 DFMA per hit, operands from shared memory).
-// Shared-memory layout [element e][record k][pose i] with an odd plane stride: the 16 lanes of a half-warp sit on a
-// wrapped diagonal of the tile (distinct i, distinct j), so every operand read is bank-conflict free whatever records
-// the lanes are at.  HBM/L2 traffic is one record per (pose, landmark, tile) instead of two per pair.
+// registers.  The landmarks are walked in super-chunks of 96 consecutive ids (three 32-landmark table words).  Per
+// super-chunk every lane intersects the landmark bit masks of its two poses once and lists its hits; then, one column k of
+// Z at a time, the CTA stages that column of the records its 32 poses have in common with the other side of the tile
+// (48 B per record) and every lane adds z_p^k (z_q^k)^T for its hits (36 DFMA per hit and column, operands by 16-byte
+// shared-memory reads).  Shared-memory layout [slot][pose][48 B]: the 8 lanes of a quarter-warp sit on a wrapped diagonal
+// of an 8 x 8 sub-tile (distinct row pose mod 8, distinct column pose mod 8), so every operand read is bank-conflict free
+// whatever records the lanes are at.  HBM/L2 traffic is one record per (pose, landmark, tile) instead of two per pair.
 #include "fg_internal.h"
 
 namespace fg {
@@ -103,9 +104,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 #define ST_KMAX 56         // record slots per pose and super-chunk
 #define ST_MAXH 32         // hits per lane and super-chunk the hit list has room for
 struct SchurSmem {
-  static constexpr int PS2 = ST_KMAX * 16 + 3;       // plane stride in double2 units; = 3 mod 8 spreads the staging writes over the banks
-  double2 rows[3 * PS2];                             // [element pair][slot][pose]: ONE column of Z (6 doubles) per record
-  double2 cols[3 * PS2];
+  static constexpr int NC = 3 * ST_KMAX * 16;        // 16-byte cells per side
+  double2 rows[NC];                                  // [slot][pose][element pair]: ONE column of Z (6 doubles, 48 contiguous bytes) per record;
+  double2 cols[NC];                                  // cell index = 3 (16 slot + pose) + pair, so the bank group of a read is (3 pose + pair) mod 8
   unsigned short hits[ST_MAXH * ST_THREADS];         // per lane: (row slot | column slot << 8) of every hit of the super-chunk
   int src[ST_THREADS / 32][4 * ST_KMAX];             // per warp: pose-major record index of every record it stages
 };
@@ -123,7 +124,6 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
               const int* __restrict__ off_pose, SysView sys) {
   extern __shared__ __align__(16) unsigned char st_raw[];
   SchurSmem& sm = *reinterpret_cast<SchurSmem*>(st_raw);
-  constexpr int PS2 = SchurSmem::PS2;
   const unsigned FULL = 0xffffffffu;
   const int4 td = tiles[blockIdx.x];
   const int gi = td.x, gj = td.y, cb = td.z, ce = td.w;
@@ -160,7 +160,7 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
   const int npw = diag ? 2 : 4;
   const int st_t = lane % npw, st_part = (lane / npw) % 3, st_r = lane / (3 * npw), st_nr = diag ? 5 : 2;
   const int st_s = npw * warp + st_t;
-  double2* st_dst = (st_s >> 4 ? sm.cols : sm.rows) + st_part * PS2 + (st_s & 15);
+  double2* st_dst = (st_s >> 4 ? sm.cols : sm.rows) + 3 * (st_s & 15) + st_part;
 
   auto fetch = [&](int c) -> uint2 {
     const int r = c - m_lo;
@@ -251,9 +251,9 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
           {
             const double* zk = Zk + (int64_t)k * M * 6 + 2 * st_part;
             const int* sl = srcl + st_t * ST_KMAX;
-            double2* dst = st_dst + st_r * 16;
+            double2* dst = st_dst + st_r * 48;
 #pragma unroll 2
-            for (int kk = st_r; kk < my_cnt; kk += st_nr, dst += st_nr * 16) cp_async16(dst, zk + sl[kk]);
+            for (int kk = st_r; kk < my_cnt; kk += st_nr, dst += st_nr * 48) cp_async16(dst, zk + sl[kk]);
             asm volatile("cp.async.commit_group;\n" ::: "memory");
           }
 #ifdef ST_L2_PREFETCH
@@ -275,10 +275,10 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
           __syncthreads();
           for (int h = 0; h < nh; ++h) {
             const unsigned pk = hl[h * ST_THREADS];
-            const double2* ra = sm.rows + (pk & 0xffu) * 16 + i;
-            const double2* cq = cbase + (pk >> 8) * 16 + j;
-            const double2 y01 = ra[0], y23 = ra[PS2], y45 = ra[2 * PS2];
-            const double2 w01 = cq[0], w23 = cq[PS2], w45 = cq[2 * PS2];
+            const double2* ra = sm.rows + ((pk & 0xffu) * 16 + i) * 3;
+            const double2* cq = cbase + ((pk >> 8) * 16 + j) * 3;
+            const double2 y01 = ra[0], y23 = ra[1], y45 = ra[2];
+            const double2 w01 = cq[0], w23 = cq[1], w45 = cq[2];
             const double y[6] = {y01.x, y01.y, y23.x, y23.y, y45.x, y45.y};
             const double w[6] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
 #pragma unroll
