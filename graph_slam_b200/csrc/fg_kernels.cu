@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(BTE_T) k_between_ends(const int* __restrict__ 
 // record would cost 32 cache-line wavefronts per store instruction.
 typedef DevGraph::ProjCal ProjCal;
 template <bool JAC>
-__global__ void __launch_bounds__(256, JAC ? 3 : 4) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
+__global__ void __launch_bounds__(256, JAC ? 3 : 5) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
                                                   Vals vals, const __grid_constant__ ProjCal cal,
                                                   double* __restrict__ W, double* V, double* gl, double* part) {

@@ -241,42 +241,49 @@ k_schur_tiles(const int4* __restrict__ tiles, int P, const int* __restrict__ pc_
         }
         __syncwarp();
         // ---- three rounds, one column of Z each
+        auto issue = [&](int k, double2* to) {           // cp.async of column k of this warp's records, one commit group
+          const double* zk = Zk + (int64_t)k * M * 6 + 2 * st_part;
+          const int* sl = srcl + st_t * ST_KMAX;
+          double2* dst = to + st_r * 48;
+#pragma unroll 2
+          for (int kk = st_r; kk < my_cnt; kk += st_nr, dst += st_nr * 48) cp_async16(dst, zk + sl[kk]);
+          asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
         for (int k = 0; k < 3; ++k) {
-          // the previous round's products are done with the staging area (k == 0: also the vote on the hit-list overflow)
-          if (k == 0) {
-            if (__syncthreads_or(nh > ST_MAXH)) { redo = true; break; }
+          const double2* rbase = sm.rows;
+          const double2* qbase = cbase;
+          if (!diag) {
+            // the previous round's products are done with the staging area (k == 0: also the vote on the hit-list overflow)
+            if (k == 0) {
+              if (__syncthreads_or(nh > ST_MAXH)) { redo = true; break; }
+            } else {
+              __syncthreads();
+            }
+            issue(k, st_dst);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
           } else {
+            // a diagonal tile stages 16 poses, so the column area is a second buffer: column 1 is on its way while column 0 is
+            // multiplied, column 2 (back in the row area) while column 1 is
+            if (k == 0) {
+              if (__syncthreads_or(nh > ST_MAXH)) { redo = true; break; }
+              issue(0, st_dst);
+              issue(1, st_dst + SchurSmem::NC);
+              asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            } else if (k == 1) {
+              __syncthreads();                       // column 0's products are done with the row area
+              issue(2, st_dst);
+              asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+              rbase = qbase = sm.cols;
+            } else {
+              asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            }
             __syncthreads();
           }
-          {
-            const double* zk = Zk + (int64_t)k * M * 6 + 2 * st_part;
-            const int* sl = srcl + st_t * ST_KMAX;
-            double2* dst = st_dst + st_r * 48;
-#pragma unroll 2
-            for (int kk = st_r; kk < my_cnt; kk += st_nr, dst += st_nr * 48) cp_async16(dst, zk + sl[kk]);
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
-          }
-#ifdef ST_L2_PREFETCH
-          // pull the records of the NEXT super-chunk into L2 (all three planes) while this one is worked on: a pose's records of a
-          // landmark range are contiguous in the pose-major order; lane s of warp 0 .. 2 (one plane each) walks their 128-byte lines
-          if (k == 0 && single < 0 && warp < 3) {
-            int first = -1, cnt = 0;
-#pragma unroll
-            for (int wd = 0; wd < ST_NW; ++wd)
-              if (nxt[wd].y) { if (first < 0) first = (int)nxt[wd].x; cnt += __popc(nxt[wd].y); }
-            if (cnt && (!diag || lane < 16)) {
-              const char* b = reinterpret_cast<const char*>(Zk + ((int64_t)warp * M + first) * 6);
-              const char* e = b + (size_t)cnt * 48;
-              for (const char* q = b; q < e; q += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q));
-            }
-          }
-#endif
-          asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-          __syncthreads();
           for (int h = 0; h < nh; ++h) {
             const unsigned pk = hl[h * ST_THREADS];
-            const double2* ra = sm.rows + ((pk & 0xffu) * 16 + i) * 3;
-            const double2* cq = cbase + ((pk >> 8) * 16 + j) * 3;
+            const double2* ra = rbase + ((pk & 0xffu) * 16 + i) * 3;
+            const double2* cq = qbase + ((pk >> 8) * 16 + j) * 3;
             const double2 y01 = ra[0], y23 = ra[1], y45 = ra[2];
             const double2 w01 = cq[0], w23 = cq[1], w45 = cq[2];
             const double y[6] = {y01.x, y01.y, y23.x, y23.y, y45.x, y45.y};
