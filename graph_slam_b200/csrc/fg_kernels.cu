@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(256, JAC ? 3 : 5) k_proj_obs(const int64_t* __
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
                                                   Vals vals, const __grid_constant__ ProjCal cal,
                                                   double* __restrict__ W, double* V, double* gl, double* part) {
-  __shared__ double wbuf[JAC ? 8 : 1][JAC ? 32 * 19 : 1];
+  __shared__ __align__(16) double wbuf[JAC ? 8 : 1][JAC ? 32 * 18 : 2];   // 144-byte records back to back: 16-byte accesses of 8 lanes hit bank groups (lane + piece) mod 8
   __shared__ RunMergeSmem<9> ms;
   const int64_t s0 = oblk_ptr[blockIdx.x], s1 = oblk_ptr[blockIdx.x + 1];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -633,23 +633,23 @@ __global__ void __launch_bounds__(256, JAC ? 3 : 5) k_proj_obs(const int64_t* __
       e += w * (r[0] * r[0] + r[1] * r[1]);
     }
     if (JAC) {
-      double* wb = wbuf[wp];
+      double2* wb = reinterpret_cast<double2*>(wbuf[wp]);
       if (act) {
+        double wr[18];
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            wb[lane * 19 + 3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
+            wr[3 * i + c] = w * (Jp[i] * Jl[c] + Jp[6 + i] * Jl[3 + c]);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) wb[lane * 9 + q] = make_double2(wr[2 * q], wr[2 * q + 1]);
       }
       __syncwarp();
       {
         const int64_t o0 = base + 32 * wp;                                  // first observation of this warp
         const int n2 = (int)max((int64_t)0, min((int64_t)32, s1 - o0)) * 9;    // 16-byte pieces to store
         double2* dst = reinterpret_cast<double2*>(W + o0 * 18);
-        for (int i = lane; i < n2; i += 32) {
-          const int rr = (2 * i) / 18, pos = 2 * i - 18 * rr;
-          dst[i] = make_double2(wb[rr * 19 + pos], wb[rr * 19 + pos + 1]);
-        }
+        for (int i = lane; i < n2; i += 32) dst[i] = wb[i];
       }
       __syncwarp();
       // V (upper: 00 01 02 11 12 22) and gl
@@ -773,7 +773,7 @@ __global__ void k_damp_rhs(SysView sys, const double* __restrict__ g_r, double l
 __global__ void __launch_bounds__(256) k_lm_backsub_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                         const double* __restrict__ W, const double* __restrict__ delta,
                                                         const int* __restrict__ off_pose, double* tl) {
-  __shared__ double wbuf[8][32 * 19];
+  __shared__ __align__(16) double wbuf[8][32 * 18];
   __shared__ RunMergeSmem<3> ms;
   const int64_t s0 = oblk_ptr[blockIdx.x], s1 = oblk_ptr[blockIdx.x + 1];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(256) k_lm_backsub_obs(const int64_t* __restric
     const bool act = o < s1;
     const int l = act ? obs_point[o] : -1;
     double t3[3] = {0, 0, 0};
-    double* wb = wbuf[wp];
+    double2* wb = reinterpret_cast<double2*>(wbuf[wp]);
     {
       // coalesced load of the warp's consecutive W records, issued before the dependent gather below
       const int64_t o0 = base + 32 * wp;
@@ -798,12 +798,14 @@ __global__ void __launch_bounds__(256) k_lm_backsub_obs(const int64_t* __restric
       for (int i = 0; i < 6; ++i) dl[i] = act ? d[i] : 0.0;
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
-        const int i = lane + 32 * q, rr = (2 * i) / 18, pos = 2 * i - 18 * rr;
-        if (i < n2) { wb[rr * 19 + pos] = v[q].x; wb[rr * 19 + pos + 1] = v[q].y; }
+        const int i = lane + 32 * q;
+        if (i < n2) wb[i] = v[q];
       }
       __syncwarp();
       if (act) {
-        const double* wr = wb + lane * 19;
+        double wr[18];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { const double2 x = wb[lane * 9 + q]; wr[2 * q] = x.x; wr[2 * q + 1] = x.y; }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
 #pragma unroll

@@ -281,14 +281,12 @@ def test_two_view_bundle_adjust_edge_information():
     ctx.close()
 
 
-def test_dense_visibility_splits_schur_chunks():
-    """Every pose sees every landmark: a pose then holds 32 records in a 32-landmark chunk, more than the 24 slots
-    k_schur_tiles keeps per pose, so every chunk takes the two-half-chunk path (fg_schur.cu)."""
-    rng = np.random.default_rng(21)
+def _dense_spec(n, P, keep=None, seed=21):
+    """P poses in a row that all see the same n landmarks (keep(pose, landmark) -> bool thins the observations)."""
+    rng = np.random.default_rng(seed)
     full = synth.make_config('C4', seed=7, scale=0.02)
     K, Rs, ts = full['K'], full['Rs'], full['ts']
-    n, P = 100, 5
-    xi = np.zeros((P, 6)); xi[:, 3] = 0.06 * np.arange(P); xi[:, 1] = 0.01 * np.arange(P)
+    xi = np.zeros((P, 6)); xi[:, 3] = 0.06 * np.arange(P) * 5.0 / P; xi[:, 1] = 0.01 * np.arange(P) * 5.0 / P
     R, t = lie.se3_exp(xi)
     Rc, tc = lie.pose_compose(R, t, np.broadcast_to(Rs, (P, 3, 3)), np.broadcast_to(ts, (P, 3)))
     pc = np.column_stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.4, 0.4, n), rng.uniform(1.5, 4.0, n)])
@@ -299,14 +297,31 @@ def test_dense_visibility_splits_schur_chunks():
     nz = rng.normal(size=(P, 6)) * 0.01; nz[0] = 0
     dR, dt = lie.se3_exp(nz)
     Ri, ti = lie.pose_compose(R, t, dR, dt)
-    spec = dict(name='dense', seed=0, n_poses=P, K=K, Rs=Rs, ts=ts, pose_init_R=Ri, pose_init_t=ti,
+    pp, pl = np.repeat(np.arange(P), n), np.tile(np.arange(n), P)
+    m = np.ones(len(pp), dtype=bool) if keep is None else np.array([keep(a, b) for a, b in zip(pp, pl)])
+    return dict(name='dense', seed=0, n_poses=P, K=K, Rs=Rs, ts=ts, pose_init_R=Ri, pose_init_t=ti,
                 prior_pose_R=np.eye(3), prior_pose_t=np.zeros(3),
                 point_init=pts + rng.normal(size=pts.shape) * 0.014, point_prior_sigma=0.014,
-                proj_pose=np.repeat(np.arange(P), n).astype(np.int32), proj_point=np.tile(np.arange(n), P).astype(np.int32),
-                proj_uv=uv, proj_sigma=1.0)
+                proj_pose=pp[m].astype(np.int32), proj_point=pl[m].astype(np.int32), proj_uv=uv[m], proj_sigma=1.0)
+
+
+def test_dense_visibility_splits_schur_chunks():
+    """Every pose sees every landmark: a pose then holds 96 records in a 96-landmark round of k_schur_tiles, more than its 56
+    record slots, so every round is redone one 32-landmark word at a time (fg_schur.cu: the `single` path)."""
+    check(_dense_spec(100, 5), 1e-7, 1e-6, solver='schur')
+
+
+def test_shared_landmark_runs_overflow_the_hit_list():
+    """40 of every 96 consecutive landmarks are seen by ALL 20 poses and the rest by two poses each: every pose stays within
+    the 56 record slots of a round, but every pose pair has more than the 32 hits its hit list holds -- the CTA-wide vote
+    sends the round to the word-by-word path."""
+    def keep(pose, l):
+        r = l % 96
+        return r < 40 or pose == 2 + (l % 18) or pose == 2 + ((l + 7) % 18)
+    spec = _dense_spec(480, 20, keep)
+    per_pose = np.bincount(spec['proj_pose'] * 5 + spec['proj_point'] // 96, minlength=100)
+    assert per_pose.max() <= 56 and per_pose.min() >= 40
     check(spec, 1e-7, 1e-6, solver='schur')
-
-
 
 
 @pytest.mark.parametrize('name,scale', [('C2', 0.2), ('C3', 0.1), ('C4', 0.06)])
