@@ -305,8 +305,8 @@ def main():
             r['fp64'] = dict(achieved=tf, peak=fp64_peak[pipe], unit='TFLOP/s', frac=tf / fp64_peak[pipe], pipe=pipe.upper(),
                              flops=flops, peak_source=fp64_peak['source'])
         return r
-    roofs = [roof('k_chol_rs', b_cho, t_cho, 'factorisation phase (k_chol_rs x2 + k_front_syrk): dependency chain of %d levels; the leaf phase streams ~12 GB of descendant panels through L2 per factorisation (profiles/r1_ncu_full_summary.md), fp64 on DMMA' % int(rep.n_levels), flops=f_cho, pipe='dmma'),
-             roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA bound: %d pairs x 216 flop = %.1f TFLOP/s achieved (fp64 DFMA peak measured in this run: %.1f TFLOP/s)' % (
+    roofs = [roof('k_chol_rs', b_cho, t_cho, 'factorisation phase (k_chol_rs x2 + k_front_syrk): dependency chain of %d levels; ~5 GB of descendant panels through L2 per factorisation (profiles/r2_ncu_full_summary.md), fp64 on DMMA' % int(rep.n_levels), flops=f_cho, pipe='dmma'),
+             roof('k_schur_tiles', b_sch, t_sch, 'fp64-FMA work: %d pairs x 216 flop = %.1f TFLOP/s achieved (fp64 DFMA peak measured in this run: %.1f TFLOP/s); the profile says shared-memory bandwidth bounds it (DESIGN 2.1, profiles/r2_ncu_full_summary.md)' % (
                  int(rep.n_schur_pairs), f_sch / (t_sch * 1e-3) / 1e12 if t_sch > 0 else 0.0, fp64_meas[0]), flops=f_sch, pipe='dfma'),
              roof('k_proj_obs<1>', b_obs, t_obs, 'streaming pass over the observations')]
     dominant = max(roofs, key=lambda r: r['ms'])
