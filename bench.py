@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--scale', type=float, default=float(os.environ.get('FG_BENCH_SCALE', '1.0')))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shard', default='blocks', choices=['blocks', 'slice'], help='multi-GPU landmark shards: 96-landmark blocks dealt round-robin, or one contiguous range per rank')
     return ap.parse_args()
 
 
@@ -198,9 +199,13 @@ def main():
             uid = torch.frombuffer(bytearray(abi.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
-        sl = (L * rank // world, L * (rank + 1) // world)
+        if args.shard == 'slice':
+            sl = (L * rank // world, L * (rank + 1) // world)
     t_build = time.perf_counter()
-    abi.load_spec(ctx, spec, landmark_slice=sl)
+    # landmark shards: blocks of 96 consecutive landmarks dealt round-robin (abi.shard_landmarks) -- every rank then holds every
+    # Schur tile with 1/world of its rounds; --shard slice gives each rank one contiguous range (1/world of the tiles)
+    ids = abi.shard_landmarks(L, rank, world) if (world > 1 and args.shard == 'blocks' and L) else None
+    abi.load_spec(ctx, spec, landmark_slice=sl, landmark_ids=ids)
     ctx.finalize()
     t_build = time.perf_counter() - t_build
 
@@ -315,7 +320,7 @@ def main():
                 higher_is_better=True, scaling='strong', vs_baseline=None,
                 dtype='f64', data='synthetic',
                 config=dict(workload=workload_name(args.config, args.scale), projections=len(spec.get('proj_pose', [])),
-                    l2='inputs_exceed_L2' if ab['total'] > 126e6 else 'smaller_than_L2', parallelism='landmark-shard x%d, reduced solve replicated' % world,
+                    l2='inputs_exceed_L2' if ab['total'] > 126e6 else 'smaller_than_L2', parallelism='landmark-shard x%d (%s), reduced solve replicated' % (world, args.shard if world > 1 else 'all'),
                     charts='Pose3 EXPMAP / Rot3 EXPMAP', lm='GTSAM defaults, forced iterations',
                     graph_build_s=t_build),
                 e2e=dict(value=args.steps / dt_e2e, unit='iterations/s', h2d_bytes_per_step=state_bytes,

@@ -24,8 +24,11 @@ def main():
         uid = torch.frombuffer(bytearray(abi.comm_unique_id()), dtype=torch.uint8).cuda()
     dist.broadcast(uid, 0)
     ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
-    lo, hi = L * rank // world, L * (rank + 1) // world
-    abi.load_spec(ctx, spec, landmark_slice=(lo, hi))
+    if os.environ.get('FG_MG_SHARD', 'blocks') == 'slice':
+        ids = np.arange(L * rank // world, L * (rank + 1) // world)
+    else:
+        ids = abi.shard_landmarks(L, rank, world)                                         # what bench.py uses
+    abi.load_spec(ctx, spec, landmark_ids=ids)
     e0 = ctx.error()
     rep = ctx.optimize()
     poses = ctx.get_values(abi.T_POSE)
@@ -37,7 +40,7 @@ def main():
         r0 = ref.error()
         rrep = ref.optimize()
         rposes = ref.get_values(abi.T_POSE)
-        rpts = ref.get_values(abi.T_POINT)[lo:hi]
+        rpts = ref.get_values(abi.T_POINT)[ids]
         d_err0 = abs(e0 - r0) / r0
         d_err = abs(rep.final_error - rrep.final_error) / rrep.final_error
         d_pose = np.abs(poses - rposes).max()

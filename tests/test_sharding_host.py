@@ -22,9 +22,9 @@ WORKER = textwrap.dedent('''
     pims = (abi.Pim * (P - 1))()
     for i in range(P - 1):
         pims[i].dt = 0.1; pims[i].cov[:] = np.eye(15).ravel().tolist()
-    def digest(sl, check_pack=False):
+    def digest(sl, check_pack=False, ids=None):
         ctx = abi.Context(device=-1, rank=rank, nranks=world)
-        abi.load_spec(ctx, spec, landmark_slice=sl, preintegrated=pims)
+        abi.load_spec(ctx, spec, landmark_slice=sl, preintegrated=pims, landmark_ids=ids)
         h = hashlib.sha256()
         for w in list(range(0, 17)) + [49]:
             h.update(ctx.symbolic(w).tobytes())
@@ -51,6 +51,8 @@ WORKER = textwrap.dedent('''
         return h.hexdigest()
     mine = digest((L * rank // world, L * (rank + 1) // world), check_pack=(rank == 0))
     full = digest((0, L))
+    dealt = digest(None, ids=abi.shard_landmarks(L, rank, world))      # blocks of 96 landmarks dealt round-robin (bench.py's shards)
+    assert dealt == full, 'round-robin shard: structure differs from the unsharded one'
 
     out = [None] * world
     dist.all_gather_object(out, (mine, full))
