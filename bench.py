@@ -128,6 +128,7 @@ def cpu_baseline_sample(config, steps=1, spec=None, scale=1.0, warmup=0, one_thr
                   '(oracle/cpu_lm.cpp: linearise, Schur, block-banded Cholesky, back-substitution, retract, error)' %
                   (config, '' if scale == 1.0 else '@%g' % scale, spec['n_poses'], len(spec['point_init']), len(spec['proj_pose']), n, dt, threads))
         out = dict(value=n / dt, unit='iterations/s', cores=threads, kind='port', sample=sample, steps_run=n, warmup_run=warmup,
+                   projections=len(spec['proj_pose']),
                    phases_s=dict(zip(('linearize', 'schur', 'factor', 'solve_retract', 'error'), (ph / n).tolist())))
         if one_thread:                                              # also the single-thread figure (one iteration)
             secs1 = st.iterate(lam, 1)[3]
@@ -165,7 +166,10 @@ def run_reference(args):
                 warmup=base['warmup_run'], steps_requested=args.steps, warmup_requested=args.warmup,
                 ms_per_step=1000.0 / base['value'] if base['value'] else None,
                 higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
-                impl='reference', config=dict(workload=workload_name(args.config, args.scale), note='CPU restatement of the reference path, see cpu_baseline.sample; '
+                impl='reference', config=dict(workload=workload_name(args.config, args.scale), projections=base.get('projections'),
+                                              l2='inputs_exceed_L2', parallelism='%d host threads' % base['cores'],
+                                              charts='Pose3 EXPMAP / Rot3 EXPMAP', lm='GTSAM defaults, forced iterations',
+                                              note='CPU restatement of the reference path, see cpu_baseline.sample; '
                                               'timed region = the five phases of each iteration (setup outside)'),
                 cpu_baseline=base,
                 e2e=dict(value=base['value'], unit='iterations/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
