@@ -578,7 +578,7 @@ int build_schur_tables(fg_ctx* c, int64_t L, int64_t M, int64_t P, const std::ve
   std::vector<int>& ppos = T.ppos; std::vector<int>& pzp = T.pzp; std::vector<int>& pc_lo = T.pc_lo; std::vector<int>& pc_n = T.pc_n;
   std::vector<int64_t>& pc_ptr = T.pc_ptr; std::vector<uint2>& pc_ent = T.pc_ent; std::vector<int4>& tiles = T.tiles;
   if (6 * M >= (int64_t)1 << 31) return fail(c, FG_ERR_INVALID, "more than 2^31 / 6 projection factors on one rank");
-  const int CH = 32;                                     // 32 landmarks per chunk, 24 record slots per pose (fg_schur.cu)
+  const int CH = 32;                                     // table words of 32 landmarks; k_schur_tiles walks three of them per staging round (fg_schur.cu)
   ppos.assign(M, 0); pzp.assign(M, 0);
   for (int64_t k = 0; k < M; ++k) { ppos[pose_obs[k]] = (int)k; pzp[k] = s_point[pose_obs[k]]; }
   pc_lo.assign(P, 0); pc_n.assign(P, 0);

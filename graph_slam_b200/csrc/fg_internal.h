@@ -209,12 +209,12 @@ struct DevGraph {
   double* W = nullptr;              // M x 18 (AoS): w Jp^T Jl per observation
   double* ul = nullptr;             // 3 L : G^-1 g_l with V + lambda I = G G^T (so that W Vinv g = Z u)
   double* Cf = nullptr;             // 6 L : upper-triangular C = G^-T (00 01 02 11 12 22); Vinv = C C^T
-  double* Zp = nullptr;             // M x 18 (AoS, POSE-major order): Z_o = W_o C_l, so that W Vinv W^T = Z Z^T
+  double* Zp = nullptr;             // 3 planes x M x 6 (plane k = column k of Z_o = W_o C_l, POSE-major order): W Vinv W^T = Z Z^T
   int* obs_ppos = nullptr;          // M : position of observation o in pose-major order (index into Zp / pose_obs)
   int* pz_point = nullptr;          // M : landmark of the k-th pose-major observation
   // Schur tiles (fg_schur.cu): 16 x 16 pose tiles of the reduced Hessian, landmarks cut into chunks of schur_ch
   int64_t n_pairs = 0;              // observation pairs (a, b) of a common landmark with pose(b) <= pose(a): Schur work units
-  int schur_ch = 0;                 // landmarks per chunk (24 or 32)
+  int schur_ch = 0;                 // landmarks per table word (32)
   int n_tiles = 0;
   int4* tile_desc = nullptr;        // (row pose group, column pose group, first chunk, end chunk), heaviest first
   int* pc_lo = nullptr;             // P : first chunk in which the pose has an observation
