@@ -1135,6 +1135,7 @@ extern "C" int fg_optimize_g2o(fg_ctx* c, const fg_g2o_params* params, fg_g2o_re
   if (!rep) rep = &local;
   std::memset(rep, 0, sizeof *rep);
   if (p.iterations_per_call < 1 || p.max_trials < 1) return fail(c, FG_ERR_INVALID, "bad g2o parameters");
+  if (c->nranks > 1) return fail(c, FG_ERR_INVALID, "fg_optimize_g2o runs on one GPU: a pose graph has no landmarks to shard");
   int rc = fg_finalize(c);
   if (rc != FG_OK) { rep->status = rc; return rc; }
   CK(cudaSetDevice(c->device));

@@ -1043,7 +1043,14 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
   Vals v;
   for (int t = 0; t < T_COUNT; ++t) v.v[t] = trial ? d.val_new[t] : d.val[t];
   SysView sys = make_view(c, d.U0);
-  const bool pose_side = (c->rank == 0);     // replicated factors are counted once
+  // Pose-side factors are known to every rank but each is evaluated by ONE of them: rank r takes the r-th slice of
+  // every launch; the all-reduce of the packed system (and of chi2) adds the slices up.  One rank: the slice is everything.
+  const int rk = c->rank, nrk = c->nranks;
+  auto slice = [&](int b, int n, int& b2, int& n2) {
+    const int lo = (int)((int64_t)n * rk / nrk), hi = (int)((int64_t)n * (rk + 1) / nrk);
+    b2 = b + lo; n2 = hi - lo;
+  };
+  const bool pose_side = true;
   const int T = 128;
   int np = 0;                                // partial-sum slots handed out so far
   auto slots = [&](int grid) { double* p = d.part + np; np += grid; return p; };
@@ -1052,8 +1059,9 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
   auto classes = [&](int kind, auto&& launch) {
     const std::vector<int>& cp = c->color_ptr[kind];
     if (cp.size() < 2) return;
-    if (!JAC) { if (cp.back() > cp.front()) launch(cp.front(), cp.back() - cp.front()); return; }
-    for (size_t k = 0; k + 1 < cp.size(); ++k) if (cp[k + 1] > cp[k]) launch(cp[k], cp[k + 1] - cp[k]);
+    int b2, n2;
+    if (!JAC) { slice(cp.front(), cp.back() - cp.front(), b2, n2); if (n2 > 0) launch(b2, n2); return; }
+    for (size_t k = 0; k + 1 < cp.size(); ++k) { slice(cp[k], cp[k + 1] - cp[k], b2, n2); if (n2 > 0) launch(b2, n2); }
   };
   if (pose_side) {
     classes(K_PP, [&](int b, int n) {
@@ -1066,14 +1074,16 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
       k_prior_vec<JAC, 6, T_BIAS><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.pb_var + b, d.pb_mean + 6 * (size_t)b, d.pb_info + 36 * (size_t)b, v, d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, T)));
     });
     if (JAC && d.n_bt_eblk) {
-      k_between_ends<<<d.n_bt_eblk, BTE_T, 0, FGS(st)>>>(d.bt_eblk, d.bt_end, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, slots(d.n_bt_eblk), d.pose_chart);
+      int b2, n2;
+      slice(0, d.n_bt_eblk, b2, n2);           // whole blocks: a block holds all the ends of its poses
+      if (n2 > 0) k_between_ends<<<n2, BTE_T, 0, FGS(st)>>>(d.bt_eblk + b2, d.bt_end, d.bt_i, d.bt_j, d.bt_meas, d.bt_info, v, d.off[T_POSE], sys, d.g_r, slots(n2), d.pose_chart);
     } else classes(K_BT, [&](int b, int n) {
       k_between<JAC><<<cdiv(n, T), T, 0, FGS(st)>>>(n, d.bt_i + b, d.bt_j + b, d.bt_meas + 12 * (size_t)b, d.bt_info + 36 * (size_t)b, v, d.off[T_POSE], sys, d.g_r, slots(cdiv(n, T)), d.pose_chart);
     });
     classes(K_GE, [&](int b, int n) {
       k_g2o_edge<JAC><<<cdiv(n, 64), 64, 0, FGS(st)>>>(n, d.ge_i + b, d.ge_j + b, d.ge_meas + 12 * (size_t)b, d.ge_info + 36 * (size_t)b, v, d.off[T_POSE], d.fixed_pose, sys, d.g_r, slots(cdiv(n, 64)));
     });
-    if (JAC && d.n_fixed) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, FGS(st)>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
+    if (JAC && d.n_fixed && rk == 0) k_fix_identity<<<cdiv(6 * d.n_fixed, 64), 64, 0, FGS(st)>>>(d.n_fixed, d.fixed_list, d.off[T_POSE], sys);
     classes(K_IMU, [&](int b, int n) {
       k_imu<JAC><<<cdiv(n, IMU_WPB), 32 * IMU_WPB, 0, FGS(st)>>>(n, d.imu_var + 6 * (size_t)b, d.imu_rec + b, v, d.off[T_POSE], d.off[T_VEC3], d.off[T_BIAS], sys, d.g_r, slots(cdiv(n, IMU_WPB)));
     });
