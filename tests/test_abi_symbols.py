@@ -85,3 +85,18 @@ def test_batch_inserts_are_all_or_nothing(fglib):
     ctx.add_prior_points(q, np.zeros((4, 3)), 0.1)
     assert ctx.l.fg_debug_counts(ctx.h, 0) == 4
     ctx.close()
+
+
+@pytest.mark.parametrize('L,world', [(0, 2), (95, 2), (96, 3), (1000, 8), (500000, 8)])
+def test_landmark_shards_partition_the_landmarks(L, world):
+    """abi.shard_landmarks (bench.py's multi-GPU shards): blocks of 96 consecutive landmarks dealt round-robin -- a partition of
+    0..L-1 into increasing id lists whose sizes differ by at most one block."""
+    shards = [abi.shard_landmarks(L, r, world) for r in range(world)]
+    allids = np.concatenate(shards) if L else np.zeros(0, dtype=np.int64)
+    assert len(allids) == L and np.array_equal(np.sort(allids), np.arange(L))
+    for s in shards:
+        assert np.all(np.diff(s) > 0)
+        if len(s):
+            blocks = s // 96
+            assert np.all((blocks % world) == blocks[0] % world)
+    assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 96
