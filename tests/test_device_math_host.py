@@ -169,3 +169,48 @@ def test_pose_charts(hostmath, rng, chart):
         hostmath.hm_between_chart(p(T12(R, t)), p(T12(R2, t2)), p(T12(Rm, tm)), C.c_int(chart), p(r), p(J1))
         ro, H1, H2 = F.between_pose(R, t, R2, t2, Rm, tm, chart=chart)
         assert np.allclose(r, ro, atol=1e-12) and np.allclose(J1.reshape(6, 6), H1, atol=1e-13)
+
+
+def test_device_lie_math_against_scipy_directly(hostmath, rng):
+    """The device formulas (fg_math.cuh compiled for the host) against scipy, with no oracle in between: se3_exp is the matrix
+    exponential of the 4x4 twist [omega, v], se3_log its logarithm, so3_exp / so3_log are scipy's rotation vectors, and the
+    Between residual is the logarithm of Z^-1 X1^-1 X2 on homogeneous matrices."""
+    from scipy.linalg import expm, logm
+    from scipy.spatial.transform import Rotation
+
+    def hat6(xi):
+        w, v = xi[:3], xi[3:]
+        T = np.zeros((4, 4))
+        T[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]
+        T[:3, 3] = v
+        return T
+
+    def vee6(T):
+        return np.array([T[2, 1], T[0, 2], T[1, 0], T[0, 3], T[1, 3], T[2, 3]])
+
+    def homog12(T12v):
+        H = np.eye(4); H[:3, :3] = T12v[:9].reshape(3, 3); H[:3, 3] = T12v[9:]
+        return H
+
+    for _ in range(50):
+        xi = rng.normal(size=6) * rng.choice([1e-3, 0.3, 1.0, 2.0])
+        if np.linalg.norm(xi[:3]) > 3.0:
+            xi *= 3.0 / np.linalg.norm(xi[:3])
+        T = arr(12); hostmath.hm_se3_exp(p(xi), p(T))
+        E = expm(hat6(xi))
+        assert np.abs(homog12(T) - E).max() < 1e-12
+        R = arr(9); hostmath.hm_so3_exp(p(xi[:3].copy()), p(R))
+        assert np.abs(R.reshape(3, 3) - Rotation.from_rotvec(xi[:3]).as_matrix()).max() < 1e-13
+        x2 = arr(6); hostmath.hm_se3_log(p(T), p(x2))
+        assert np.abs(x2 - vee6(np.real(logm(E)))).max() < 1e-8
+        w2 = arr(3); hostmath.hm_so3_log(p(R), p(w2))
+        assert np.abs(w2 - Rotation.from_matrix(R.reshape(3, 3)).as_rotvec()).max() < 1e-10
+    for _ in range(20):
+        X1 = arr(12); X2 = arr(12); Z = arr(12)
+        for X, s in ((X1, 1.0), (X2, 1.0), (Z, 0.4)):
+            xi = rng.normal(size=6) * s
+            hostmath.hm_se3_exp(p(xi), p(X))
+        r = arr(6); J = arr(36)
+        hostmath.hm_between(p(X1), p(X2), p(Z), p(r), p(J))
+        D = np.linalg.inv(homog12(Z)) @ np.linalg.inv(homog12(X1)) @ homog12(X2)
+        assert np.abs(r - vee6(np.real(logm(D)))).max() < 1e-9
