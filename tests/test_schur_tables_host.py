@@ -89,3 +89,82 @@ def test_tiles_visit_every_observation_pair_once(fglib, scale, sl, dup):
     # heaviest tiles first
     w = t['tiles'][:, 3] - t['tiles'][:, 2]
     assert np.all(np.diff(w) <= 0)
+
+
+def test_tile_kernel_index_arithmetic():
+    """Python mirror of the index arithmetic of k_schur_tiles (fg_schur.cu): (i) the compute-role lane mapping covers the 256
+    blocks of a tile once, a quarter-warp holds 8 distinct row poses and 8 distinct column poses mod 8 (the condition for
+    conflict-free 16-byte reads in the [slot][pose][48 B] layout) and the warps of sub-tiles that share a row or a column of the
+    tile sit on different schedulers; (ii) in a diagonal tile the parity split gives every landmark of every unordered pose
+    pair to exactly one lane; (iii) the staging-role mapping copies every (pose, record, 16-byte part) exactly once, for both
+    tile kinds; (iv) slots and hit lists built the kernel's way address the records both poses hold."""
+    # (i) lane mapping
+    seen = np.zeros((16, 16), dtype=int)
+    for warp in range(8):
+        sub = (warp >> 1) if (warp >> 1) < 2 else 5 - (warp >> 1)
+        for q in range(4):
+            rows, cols = set(), set()
+            for ii in range(8):
+                lane = 8 * q + ii
+                dgn = 4 * (warp & 1) + (lane >> 3)
+                i = 8 * (sub >> 1) + (lane & 7); j = 8 * (sub & 1) + (((lane & 7) + dgn) & 7)
+                seen[i, j] += 1
+                rows.add(i % 8); cols.add(j % 8)
+                # bank group of a 16-byte read of part 0..2 of any slot: (3 * pose + part) mod 8
+            assert len(rows) == 8 and len(cols) == 8
+            assert len({(3 * r) % 8 for r in rows}) == 8
+    assert np.all(seen == 1)
+    sched = {}
+    for warp in range(8):
+        sub = (warp >> 1) if (warp >> 1) < 2 else 5 - (warp >> 1)
+        sched.setdefault(sub, set()).add(warp % 4)
+    for a, b in ((0, 1), (2, 3), (0, 2), (1, 3)):                 # sub-tiles sharing a row / a column of the tile
+        assert sched[a] | sched[b] == {0, 1, 2, 3}
+    # (ii) parity split of a diagonal tile
+    for i in range(16):
+        for j in range(16):
+            if i == j:
+                continue
+            sel = 0x55555555 if i > j else 0xaaaaaaaa
+            other = 0x55555555 if j > i else 0xaaaaaaaa
+            assert sel ^ other == 0xffffffff
+    # (iii) staging role
+    KMAX = 56
+    for diag in (False, True):
+        npw, st_nr = (2, 5) if diag else (4, 2)
+        cnt = np.random.default_rng(1).integers(0, KMAX + 1, size=32)
+        copies = {}
+        for warp in range(8):
+            for lane in range(32):
+                st_t, st_part, st_r = lane % npw, (lane // npw) % 3, lane // (3 * npw)
+                s = npw * warp + st_t
+                my_cnt = cnt[s] if st_r < st_nr else 0
+                for kk in range(st_r, my_cnt, st_nr):
+                    key = (s, kk, st_part)
+                    copies[key] = copies.get(key, 0) + 1
+        n_st = 16 if diag else 32
+        assert all(v == 1 for v in copies.values())
+        assert len(copies) == 3 * int(cnt[:n_st].sum())
+    # (iv) slots and hit lists over three words
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        own_i = [int(x) for x in rng.integers(0, 2 ** 32, size=3)]; own_j = [int(x) for x in rng.integers(0, 2 ** 32, size=3)]
+        other_of_i = [int(x) for x in rng.integers(0, 2 ** 32, size=3)]; other_of_j = [int(x) for x in rng.integers(0, 2 ** 32, size=3)]
+        fi = [own_i[w] & (other_of_i[w] | own_j[w]) for w in range(3)]      # f = own & OR(other side); the other side contains j
+        fj = [own_j[w] & (other_of_j[w] | own_i[w]) for w in range(3)]
+        slots_i = [(w, b) for w in range(3) for b in range(32) if (fi[w] >> b) & 1]   # staged records of pose i in slot order
+        slots_j = [(w, b) for w in range(3) for b in range(32) if (fj[w] >> b) & 1]
+        pi = pj = 0
+        hits = []
+        for w in range(3):
+            hit = fi[w] & fj[w]
+            while hit:
+                b = (hit & -hit).bit_length() - 1
+                hit &= hit - 1
+                low = (1 << b) - 1
+                hits.append((pi + bin(fi[w] & low).count('1'), pj + bin(fj[w] & low).count('1'), w, b))
+            pi += bin(fi[w]).count('1'); pj += bin(fj[w]).count('1')
+        want = [(w, b) for w in range(3) for b in range(32) if ((own_i[w] & own_j[w]) >> b) & 1]
+        assert [(w, b) for _, _, w, b in hits] == want                     # every common landmark, once, in landmark order
+        for a, bq, w, b in hits:
+            assert slots_i[a] == (w, b) and slots_j[bq] == (w, b)        # both slots hold that landmark's records
