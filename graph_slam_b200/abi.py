@@ -461,8 +461,17 @@ def load_spec(ctx, spec, landmark_slice=None, preintegrated=None, landmark_ids=N
         if landmark_slice is not None or landmark_ids is not None:
             a, b = covisibility_band(spec)
             ctx.add_structure_edges(X[a], X[b])
-        ctx.add_projections(X[spec['proj_pose'][m]], symbols('q', spec['proj_point'][m]), spec['proj_uv'][m],
-                            spec['proj_sigma'])
+        if 'proj_cal' in spec:                                   # several (Cal3DS2, body_P_sensor) pairs: slot c holds pair c
+            for cidx, (Kc, Rsc, tsc) in enumerate(spec['cals']):
+                ctx.set_calibration(cidx, np.asarray(Kc, dtype=np.float64))
+                ctx.set_sensor(cidx, pose12(Rsc, tsc)[0])
+                mc = m & (np.asarray(spec['proj_cal']) == cidx)
+                if mc.any():
+                    ctx.add_projections(X[spec['proj_pose'][mc]], symbols('q', spec['proj_point'][mc]), spec['proj_uv'][mc],
+                                        spec['proj_sigma'], cid=cidx, sid=cidx)
+        else:
+            ctx.add_projections(X[spec['proj_pose'][m]], symbols('q', spec['proj_point'][m]), spec['proj_uv'][m],
+                                spec['proj_sigma'])
     if 'plane_init' in spec:
         for l, pl in enumerate(spec['plane_init']):
             ctx.add_plane(symbol('l', l), pl)

@@ -786,9 +786,33 @@ extern "C" int fg_finalize(fg_ctx* c) {
   const int64_t L = h.count(T_POINT), M = (int64_t)h.pj_pose.size(), P = h.count(T_POSE);
   d.n_obs = M;
   if (L) {
-    for (size_t i = 1; i < h.pj_calib.size(); ++i)
-      if (h.pj_calib[i] != h.pj_calib[0] || h.pj_sensor[i] != h.pj_sensor[0])
-        return fail(c, FG_ERR_INVALID, "projection factors must share one calibration and one body_P_sensor");
+    // distinct (calibration, body_P_sensor) pairs in order of first appearance: a graph with one pair (what the reference
+    // builds) passes it to the kernels by value; a mixed graph (GTSAM accepts them) carries an index per observation
+    std::vector<DevGraph::ProjCal> cals;
+    std::vector<unsigned char> cal_of(M, 0);
+    {
+      std::vector<std::pair<int, int>> pairs;
+      for (int64_t o = 0; o < M; ++o) {
+        const std::pair<int, int> key(h.pj_calib[o], h.pj_sensor[o]);
+        size_t k = 0;
+        while (k < pairs.size() && pairs[k] != key) ++k;
+        if (k == pairs.size()) {
+          if (pairs.size() == 255) return fail(c, FG_ERR_INVALID, "more than 255 distinct (calibration, body_P_sensor) pairs");
+          pairs.push_back(key);
+          DevGraph::ProjCal pc;
+          std::copy(h.calib.begin() + 9 * key.first, h.calib.begin() + 9 * key.first + 9, pc.K);
+          std::copy(h.sensor.begin() + 12 * key.second, h.sensor.begin() + 12 * key.second + 12, pc.S);
+          cals.push_back(pc);
+        }
+        cal_of[o] = (unsigned char)k;
+      }
+      if (cals.empty()) {
+        DevGraph::ProjCal pc;
+        std::copy(h.calib.begin(), h.calib.begin() + 9, pc.K);
+        std::copy(h.sensor.begin(), h.sensor.begin() + 12, pc.S);
+        cals.push_back(pc);
+      }
+    }
     int cid = M ? h.pj_calib[0] : 0, sid = M ? h.pj_sensor[0] : 0;
     std::vector<int64_t> lm_ptr(L + 1, 0), pose_ptr(P + 1, 0);
     for (int64_t o = 0; o < M; ++o) { lm_ptr[h.pj_point[o] + 1]++; pose_ptr[h.pj_pose[o] + 1]++; }
@@ -796,10 +820,12 @@ extern "C" int fg_finalize(fg_ctx* c) {
     for (int64_t p = 0; p < P; ++p) pose_ptr[p + 1] += pose_ptr[p];
     std::vector<int> s_pose(M), s_point(M);
     std::vector<double> s_uv(2 * M), s_w(M);
+    std::vector<unsigned char> s_cal(M);
     {
       std::vector<int64_t> cur(lm_ptr.begin(), lm_ptr.end() - 1);
       for (int64_t o = 0; o < M; ++o) {
         int64_t k = cur[h.pj_point[o]]++;
+        s_cal[k] = cal_of[o];
         s_pose[k] = h.pj_pose[o]; s_point[k] = h.pj_point[o];
         s_uv[2 * k] = h.pj_uv[2 * o]; s_uv[2 * k + 1] = h.pj_uv[2 * o + 1]; s_w[k] = h.pj_w[o];
       }
@@ -864,8 +890,9 @@ extern "C" int fg_finalize(fg_ctx* c) {
         (rc = dev_upload<double>(c, &d.gl, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Vinv, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.tl, nullptr, (size_t)3 * L))) return rc;
     if ((rc = dev_upload(c, &d.calib, h.calib.data() + 9 * cid, 9)) || (rc = dev_upload(c, &d.sensor, h.sensor.data() + 12 * sid, 12))) return rc;
-    std::copy(h.calib.begin() + 9 * cid, h.calib.begin() + 9 * cid + 9, d.cal.K);
-    std::copy(h.sensor.begin() + 12 * sid, h.sensor.begin() + 12 * sid + 12, d.cal.S);
+    d.cal = cals[0];
+    d.n_cal = (int)cals.size();
+    if (d.n_cal > 1 && ((rc = dev_upload(c, &d.cals, cals)) || (rc = dev_upload(c, &d.obs_cal, s_cal)))) return rc;
     if ((rc = dev_upload<double>(c, &d.ul, nullptr, (size_t)3 * L)) || (rc = dev_upload<double>(c, &d.Cf, nullptr, (size_t)6 * L)) ||
         (rc = dev_upload<double>(c, &d.Zp, nullptr, (size_t)18 * M))) return rc;
     {

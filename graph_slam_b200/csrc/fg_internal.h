@@ -227,6 +227,9 @@ struct DevGraph {
   double* tl = nullptr;             // 3 L  : sum_o W_o^T delta_p (back-substitution scratch)
   double* calib = nullptr;          // 9
   struct ProjCal { double K[9], S[12]; } cal;   // host copy of calib / sensor: passed to the projection kernels by value (constant bank)
+  int n_cal = 1;                    // distinct (Cal3DS2, body_P_sensor) pairs among the projection factors
+  ProjCal* cals = nullptr;          // n_cal entries; only used (with obs_cal) when n_cal > 1
+  unsigned char* obs_cal = nullptr; // M : index into cals per observation (landmark-sorted order)
   double* sensor = nullptr;         // 12
   // reduced system
   double* L = nullptr;              // panels being factored

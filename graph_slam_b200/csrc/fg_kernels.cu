@@ -607,10 +607,21 @@ __global__ void __launch_bounds__(BTE_T) k_between_ends(const int* __restrict__ 
 // warp-private piece of shared memory (no block barrier) so that the global store is coalesced: a thread writing its own
 // record would cost 32 cache-line wavefronts per store instruction.
 typedef DevGraph::ProjCal ProjCal;
-template <bool JAC>
+// Calibration argument of the projection kernels.  One (Cal3DS2, body_P_sensor) pair in the graph -- what the reference builds:
+// the pair travels by value in the constant bank.  Several pairs: a table in global memory and an index per observation.
+template <bool MULTI> struct CalArg;
+template <> struct CalArg<false> {
+  ProjCal cal;
+  __device__ __forceinline__ const ProjCal& at(int64_t) const { return cal; }
+};
+template <> struct CalArg<true> {
+  const ProjCal* cals; const unsigned char* idx;
+  __device__ __forceinline__ const ProjCal& at(int64_t o) const { return cals[idx[o]]; }
+};
+template <bool JAC, bool MULTI>
 __global__ void __launch_bounds__(256, JAC ? 3 : 5) k_proj_obs(const int64_t* __restrict__ oblk_ptr, const int* __restrict__ obs_pose, const int* __restrict__ obs_point,
                                                   const double* __restrict__ obs_uv, const double* __restrict__ obs_w,
-                                                  Vals vals, const __grid_constant__ ProjCal cal,
+                                                  Vals vals, const __grid_constant__ CalArg<MULTI> ca,
                                                   double* __restrict__ W, double* V, double* gl, double* part) {
   __shared__ __align__(16) double wbuf[JAC ? 8 : 1][JAC ? 32 * 18 : 2];   // 144-byte records back to back: 16-byte accesses of 8 lanes hit bank groups (lane + piece) mod 8
   __shared__ RunMergeSmem<9> ms;
@@ -629,7 +640,8 @@ __global__ void __launch_bounds__(256, JAC ? 3 : 5) k_proj_obs(const int64_t* __
       double2 uvv = __ldg(reinterpret_cast<const double2*>(obs_uv) + o);
       double uv[2] = {uvv.x, uvv.y};
       w = obs_w[o];
-      projection_eval<JAC>(X, p, uv, cal.K, cal.S, r, Jp, Jl);
+      const ProjCal& pc = ca.at(o);
+      projection_eval<JAC>(X, p, uv, pc.K, pc.S, r, Jp, Jl);
       e += w * (r[0] * r[0] + r[1] * r[1]);
     }
     if (JAC) {
@@ -698,9 +710,10 @@ __global__ void k_merge_dup(int n, const int* __restrict__ prim, const int* __re
 // contiguous quarter of the pose's list (a pose has ~2000 observations at C5: one warp per pose is 5000 long warps, 2.1 waves of
 // the resident 2368, and the last wave runs 11 % full); the quarters are added in order through shared memory.
 #define PP_W 4
+template <bool MULTI>
 __global__ void __launch_bounds__(256, 2) k_proj_pose(int P, const int64_t* __restrict__ pose_obs_ptr, const int64_t* __restrict__ pose_obs,
                                                    const int* __restrict__ obs_point, const double* __restrict__ obs_uv,
-                                                   const double* __restrict__ obs_w, Vals vals, const __grid_constant__ ProjCal cal,
+                                                   const double* __restrict__ obs_w, Vals vals, const __grid_constant__ CalArg<MULTI> ca,
                                                    const int* __restrict__ off_pose, SysView sys, double* g_r) {
   __shared__ double part[256 / 32][28];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -723,7 +736,8 @@ __global__ void __launch_bounds__(256, 2) k_proj_pose(int P, const int64_t* __re
       double p[3] = {vals.v[T_POINT][3 * (int64_t)l], vals.v[T_POINT][3 * (int64_t)l + 1], vals.v[T_POINT][3 * (int64_t)l + 2]};
       double uv[2] = {obs_uv[2 * o], obs_uv[2 * o + 1]};
       double w = obs_w[o], r[2], Jp[12], Jl[6];
-      projection_eval<true>(X, p, uv, cal.K, cal.S, r, Jp, Jl);
+      const ProjCal& pc = ca.at(o);
+      projection_eval<true>(X, p, uv, pc.K, pc.S, r, Jp, Jl);
       int t = 0;
 #pragma unroll
       for (int i = 0; i < 6; ++i)
@@ -1096,12 +1110,24 @@ static void run_factors(fg_ctx* c, bool trial, double* target) {
     k_lm_prior<JAC><<<cdiv(L, 256), 256, 0, FGS(st)>>>(L, v.v[T_POINT], d.lm_prior_mean, d.lm_prior_w, d.V, d.gl, slots(cdiv(L, 256)));
     if (d.n_obs) {
       if (JAC && c->kev[0]) cudaEventRecord(c->kev[0], st);
-      k_proj_obs<JAC><<<d.n_oblk, 256, 0, FGS(st)>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, d.cal, d.W, d.V, d.gl, slots(d.n_oblk));
+      if (d.n_cal > 1) {
+        const CalArg<true> ca{d.cals, d.obs_cal};
+        k_proj_obs<JAC, true><<<d.n_oblk, 256, 0, FGS(st)>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, ca, d.W, d.V, d.gl, slots(d.n_oblk));
+      } else {
+        const CalArg<false> ca{d.cal};
+        k_proj_obs<JAC, false><<<d.n_oblk, 256, 0, FGS(st)>>>(d.oblk_ptr, d.obs_pose, d.obs_point, d.obs_uv, d.obs_w, v, ca, d.W, d.V, d.gl, slots(d.n_oblk));
+      }
       if (JAC && c->kev[1]) cudaEventRecord(c->kev[1], st);
       if (JAC && d.n_dup) k_merge_dup<<<cdiv(d.n_dup, 128), 128, 0, FGS(st)>>>(d.n_dup, d.dup_prim, d.dup_sec, d.W);
       if (JAC) {
         int P = (int)d.n[T_POSE];
-        k_proj_pose<<<cdiv((int64_t)P * 32 * PP_W, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, d.cal, d.off[T_POSE], sys, d.g_r);
+        if (d.n_cal > 1) {
+          const CalArg<true> ca{d.cals, d.obs_cal};
+          k_proj_pose<true><<<cdiv((int64_t)P * 32 * PP_W, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, ca, d.off[T_POSE], sys, d.g_r);
+        } else {
+          const CalArg<false> ca{d.cal};
+          k_proj_pose<false><<<cdiv((int64_t)P * 32 * PP_W, 256), 256, 0, FGS(st)>>>(P, d.pose_obs_ptr, d.pose_obs, d.obs_point, d.obs_uv, d.obs_w, v, ca, d.off[T_POSE], sys, d.g_r);
+        }
       }
     }
   }

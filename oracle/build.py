@@ -37,6 +37,9 @@ def from_spec(spec):
                                 info=np.broadcast_to(np.eye(3) / spec['point_prior_sigma'] ** 2, (L, 3, 3)))
         f['proj'] = dict(i=spec['proj_pose'].astype(np.int64), l=spec['proj_point'].astype(np.int64),
                          uv=spec['proj_uv'], sigma=spec['proj_sigma'])
+        if 'proj_cal' in spec:                                   # mixed calibrations: spec['cals'] = [(K, Rs, ts), ...]
+            f['proj']['cal'] = np.asarray(spec['proj_cal'], dtype=np.int64)
+            g.cals = [(tuple(K), Rs, ts) for K, Rs, ts in spec['cals']]
     if 'plane_init' in spec:
         g.plane = spec['plane_init'].copy()
         f['plane'] = dict(i=spec['plane_obs_pose'].astype(np.int64), l=spec['plane_obs_plane'].astype(np.int64),

@@ -96,7 +96,22 @@ class Graph:
                 out.append((res, q['info'], None))
         if 'proj' in f:
             q = f['proj']; i, l = q['i'], q['l']
-            res = F.projection(self.R[i], self.t[i], self.point[l], q['uv'], self.K, self.Rs, self.ts, jac)
+            if 'cal' in q:
+                # several (Cal3DS2, body_P_sensor) pairs in one graph: q['cal'] indexes self.cals per factor
+                n = len(i)
+                r = np.zeros((n, 2)); Jp = np.zeros((n, 2, 6)); Jl = np.zeros((n, 2, 3))
+                for cidx, (Kc, Rsc, tsc) in enumerate(self.cals):
+                    m = q['cal'] == cidx
+                    if not m.any():
+                        continue
+                    rr = F.projection(self.R[i[m]], self.t[i[m]], self.point[l[m]], q['uv'][m], Kc, Rsc, tsc, jac)
+                    if jac:
+                        r[m], Jp[m], Jl[m] = rr
+                    else:
+                        r[m] = rr
+                res = (r, Jp, Jl) if jac else r
+            else:
+                res = F.projection(self.R[i], self.t[i], self.point[l], q['uv'], self.K, self.Rs, self.ts, jac)
             info = np.broadcast_to(np.eye(2) / q['sigma'] ** 2, (len(i), 2, 2))
             out.append((res[0], info, [(6 * i, res[1]), (d['o_pt'] + 3 * l, res[2])]) if jac else (res, info, None))
         if 'plane' in f:

@@ -214,6 +214,31 @@ def test_loop_closure_covisibility_matches_oracle():
     check(spec, 1e-7, 1e-6, solver='schur')
 
 
+def mixed_calibration_spec():
+    """C4 at 3 % with the observations of every third pose taken by a second camera: other Cal3DS2 (focal lengths, skew,
+    principal point, distortion) and other body_P_sensor -- GTSAM accepts projection factors with different K / body_P_sensor in
+    one graph (the reference builds one pair only; round 1 rejected mixed graphs)."""
+    spec = synth.make_config('C4', seed=9, scale=0.03)
+    rng = np.random.default_rng(17)
+    K1 = np.array(spec['K'], dtype=np.float64)
+    K2 = K1 * np.array([1.06, 0.97, 1.0, 1.03, 0.95, 0.8, 0.7, 1.0, 1.0]) + np.array([0, 0, 0.4, 0, 0, 0, 0, 2e-3, -1e-3])
+    dR, dt = lie.se3_exp(np.array([0.03, -0.02, 0.04, 0.01, 0.02, -0.015]))
+    Rs2, ts2 = lie.pose_compose(spec['Rs'], spec['ts'], dR, dt)
+    cam2 = (spec['proj_pose'] % 3) == 1
+    uv2, z = synth._project(spec['truth_R'][spec['proj_pose'][cam2]], spec['truth_t'][spec['proj_pose'][cam2]],
+                            spec['truth_point'][spec['proj_point'][cam2]], K2, Rs2, ts2)
+    assert np.all(z > 0.1)
+    spec['proj_uv'] = spec['proj_uv'].copy()
+    spec['proj_uv'][cam2] = uv2 + rng.normal(size=uv2.shape)
+    spec['proj_cal'] = cam2.astype(np.int64)
+    spec['cals'] = [(K1, spec['Rs'], spec['ts']), (K2, Rs2, ts2)]
+    return spec
+
+
+def test_mixed_calibrations_match_oracle():
+    check(mixed_calibration_spec(), 1e-7, 1e-6, solver='schur')
+
+
 def oracle_marginal(g, kind, idx):
     """Dense oracle: block of the inverse of the full (undamped) normal equations, landmarks included."""
     H, grad, err = g.normal_equations()
