@@ -222,3 +222,28 @@ def test_lm_minimum_of_a_small_pose_graph_against_scipy_least_squares():
     T = poses(sol.x)
     for i in range(P):
         assert np.abs(T[i] - homog(g1.R[i], g1.t[i])).max() < 1e-3
+
+
+def test_mixed_calibration_graph_equals_per_camera_evaluation():
+    """Oracle plumbing of several (Cal3DS2, body_P_sensor) pairs in one graph: the graph's chi2 is the sum of the two cameras'
+    reprojection terms evaluated separately, and the Jacobian blocks land on the factors of the right camera."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gpu_parity import mixed_calibration_spec
+    from oracle import build
+    spec = mixed_calibration_spec()
+    g = build.from_spec(spec)
+    q = g.f['proj']
+    e_proj = 0.0
+    for cidx, (K, Rs, ts) in enumerate(g.cals):
+        m = q['cal'] == cidx
+        r = factors.projection(g.R[q['i'][m]], g.t[q['i'][m]], g.point[q['l'][m]], q['uv'][m], K, Rs, ts, jac=False)
+        e_proj += 0.5 * np.sum(r * r) / q['sigma'] ** 2
+    g_no = build.from_spec({k: v for k, v in spec.items() if k not in ('proj_pose', 'proj_point', 'proj_uv', 'proj_cal', 'cals')} | {'proj_pose': spec['proj_pose'][:0], 'proj_point': spec['proj_point'][:0], 'proj_uv': spec['proj_uv'][:0]})
+    assert abs(g.error() - (g_no.error() + e_proj)) < 1e-9 * g.error()
+    blocks = [b for b in g.linearize(jac=True) if b[2] is not None and b[0].shape[-1] == 2][0]
+    r, _, ((_, Jp), (_, Jl)) = blocks
+    k = int(np.nonzero(q['cal'] == 1)[0][0])
+    K, Rs, ts = g.cals[1]
+    rr, Jpr, Jlr = factors.projection(g.R[q['i'][k]], g.t[q['i'][k]], g.point[q['l'][k]], q['uv'][k], K, Rs, ts, jac=True)
+    assert np.allclose(r[k], rr) and np.allclose(Jp[k], Jpr) and np.allclose(Jl[k], Jlr)
