@@ -16,7 +16,10 @@ Pinning status:
   * BetweenFactor<Pose3>, PriorFactor, GenericProjectionFactor/Cal3DS2,
     CombinedImuFactor / preintegration, LevenbergMarquardt, g2o EdgeSE3:
     PARITY UNPINNED -- the reference holds no golden vectors for them; they are
-    validated by central-difference Jacobian checks and closed-form minimisers.
+    validated by central-difference Jacobian checks and closed-form minimisers
+    (tests/test_oracle_jacobians.py) and against implementations that share nothing
+    with this package (tests/test_oracle_independent.py: scipy expm / logm / Rotation,
+    a scalar camera model, brute-force IMU integration, scipy least_squares).
 
 oracle/cpu_lm.cpp (+ cpu_baseline.py) is a TIMING baseline: an OpenMP C++ port of one LM
 iteration of the BA + IMU graph, checked against this numpy oracle in tests/test_cpu_baseline.py.
